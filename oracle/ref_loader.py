@@ -1,0 +1,127 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference hot-path file.
+
+This module exists to (a) validate ``oracle/gd_oracle.py`` against the real
+reference and (b) generate the golden fixtures under ``tests/golden/``.  It only
+works inside the build container, where ``/root/reference`` is mounted; the GPU
+box has no such path, so nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py``
+may call it.
+
+The reference file ``mmdet3d_gaussian/models/losses/gaussian_distance_loss.py``
+imports exactly two upstream symbols (lines 3-4):
+
+* ``mmdet.models.builder.LOSSES``            -- a registry with a
+  ``register_module()`` decorator (``gaussian_distance_loss.py:251``)
+* ``mmdet.models.losses.utils.weighted_loss`` -- decorator applied at
+  ``gaussian_distance_loss.py:42,109,144,189,201,214,227``
+
+mmdet is NOT installed in this image (and is un-pinned by the reference:
+``setup.py`` has no ``install_requires``), so both are supplied by the stub
+below.  ``weighted_loss`` restates mmdet 2.x ``models/losses/utils.py``
+(``weight_reduce_loss``): ``loss*=weight``; ``avg_factor is None`` ->
+none/mean/sum; ``avg_factor`` given -> ``mean``: ``sum()/avg_factor``,
+``none``: unchanged, ``sum``: ValueError.  (Some mmdet releases add
+``finfo(float32).eps`` to ``avg_factor``; <=1.2e-7 relative, inside tolerance,
+and not reproduced here.)
+"""
+import functools
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get('GD_REFERENCE_ROOT', '/root/reference')
+REFERENCE_FILE = os.path.join(
+    REFERENCE_ROOT, 'mmdet3d_gaussian', 'models', 'losses',
+    'gaussian_distance_loss.py')
+
+
+def reference_available():
+    return os.path.isfile(REFERENCE_FILE)
+
+
+class _StubRegistry:
+    """Minimal stand-in for mmcv's Registry: name -> class, decorator API."""
+
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def _register(cls):
+            self.module_dict[name or cls.__name__] = cls
+            return cls
+        if module is not None:
+            return _register(module)
+        return _register
+
+    def get(self, key):
+        return self.module_dict.get(key)
+
+    def build(self, cfg):
+        cfg = dict(cfg)
+        return self.module_dict[cfg.pop('type')](**cfg)
+
+
+def _weight_reduce_loss(loss, weight=None, reduction='mean', avg_factor=None):
+    """mmdet 2.x ``weight_reduce_loss`` semantics."""
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        if reduction == 'mean':
+            return loss.mean()
+        if reduction == 'sum':
+            return loss.sum()
+        return loss
+    if reduction == 'mean':
+        return loss.sum() / avg_factor
+    if reduction != 'none':
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss
+
+
+def _weighted_loss(loss_func):
+    @functools.wraps(loss_func)
+    def wrapper(pred, target, weight=None, reduction='mean', avg_factor=None,
+                **kwargs):
+        loss = loss_func(pred, target, **kwargs)
+        return _weight_reduce_loss(loss, weight, reduction, avg_factor)
+    return wrapper
+
+
+def _install_stub_mmdet():
+    if 'mmdet.models.builder' in sys.modules and hasattr(
+            sys.modules['mmdet.models.builder'], '_gd_stub'):
+        return
+    names = ['mmdet', 'mmdet.models', 'mmdet.models.builder',
+             'mmdet.models.losses', 'mmdet.models.losses.utils']
+    mods = {n: types.ModuleType(n) for n in names}
+    for n in names:
+        if '.' in n:
+            parent, child = n.rsplit('.', 1)
+            setattr(mods[parent], child, mods[n])
+    mods['mmdet.models.builder'].LOSSES = _StubRegistry('loss')
+    mods['mmdet.models.builder']._gd_stub = True
+    mods['mmdet.models.losses.utils'].weighted_loss = _weighted_loss
+    mods['mmdet.models.losses.utils'].weight_reduce_loss = _weight_reduce_loss
+    sys.modules.update(mods)
+
+
+_CACHED = None
+
+
+def load_reference():
+    """Import the reference loss file by path, unmodified; returns the module."""
+    global _CACHED
+    if _CACHED is not None:
+        return _CACHED
+    if not reference_available():
+        raise FileNotFoundError(
+            f'{REFERENCE_FILE} not found: the reference only exists in the '
+            f'build container')
+    _install_stub_mmdet()
+    spec = importlib.util.spec_from_file_location(
+        '_gd_reference_loss', REFERENCE_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _CACHED = mod
+    return mod
