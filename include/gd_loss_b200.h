@@ -1,0 +1,166 @@
+/* gd_loss_b200.h -- C ABI of the B200 (sm_100a) Gaussian-distance loss library.
+ *
+ * Drop-in boundary for the ONE hot path of zhanggefan/mmdet3d-gaussian:
+ *   mmdet3d_gaussian/models/losses/gaussian_distance_loss.py  (cited as ref:LINE)
+ * The reference is pure PyTorch; its "FFI" is the Python call
+ *   GDLoss.forward(pred, target, weight, avg_factor, reduction_override)  ref:280-310
+ * followed by autograd's backward.  Each entry point below names the piece of
+ * that call it replaces.  The Python binding a maintainer adds is a ctypes stub
+ * (INTEGRATION.md); the shipped one is mmdet3d_gaussian_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary
+ *   - every pointer is DEVICE memory unless the name ends in _host
+ *   - the caller allocates all outputs and the workspace; nothing here
+ *     allocates device memory, synchronises the device or throws (the *_host
+ *     entry point is the documented exception: it owns a staging pipeline)
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*)
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     GD_ERR_* argument error
+ *   - box rows are 7 fp32 (x, y, z, w, h, l, r)                       ref:8
+ */
+#ifndef GD_LOSS_B200_H_
+#define GD_LOSS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_ABI_VERSION 1
+
+/* loss_type: keys of GDLoss.BAG_GD_LOSS                                ref:253-259 */
+enum {
+  GD_LOSS_GWD3D = 0,        /* 'gwd3d'         ref:42-106  */
+  GD_LOSS_KLD3D = 1,        /* 'kld3d'         ref:109-141 */
+  GD_LOSS_JD3D = 2,         /* 'jd3d'          ref:189-198 */
+  GD_LOSS_KLD3D_SYMMAX = 3, /* 'kld3d_symmax'  ref:201-211 */
+  GD_LOSS_KLD3D_SYMMIN = 4, /* 'kld3d_symmin'  ref:214-224 */
+  GD_LOSS_BD3D = 5,         /* 'bd3d'          ref:144-186 */
+  GD_LOSS_KFIOU3D = 6       /* 'kfiou3d'       ref:227-248 */
+};
+
+/* fun: postprocess() non-linearity                                     ref:24-34 */
+enum { GD_FUN_NONE = 0, GD_FUN_LOG1P = 1, GD_FUN_EXPM1 = 2, GD_FUN_NLOG = 3 };
+
+/* weight layout                                                        ref:295-296 */
+enum {
+  GD_WEIGHT_NONE = 0,  /* weight is None                                           */
+  GD_WEIGHT_ROW = 1,   /* [N]                                                      */
+  GD_WEIGHT_ROW7 = 2   /* [N,7]: the kernel takes mean(-1) per row                 */
+};
+
+/* kernel variant */
+enum {
+  GD_VARIANT_AUTO = 0,   /* bulk pipeline when layout allows, else staged          */
+  GD_VARIANT_STAGED = 1, /* LDG/STG staged through shared memory; any stride       */
+  GD_VARIANT_BULK = 2    /* persistent, cp.async.bulk (TMA 1-D) + mbarrier ring    */
+};
+
+enum {
+  GD_ERR_BAD_ARG = -1,       /* null pointer / negative size / unknown enum        */
+  GD_ERR_WORKSPACE = -2,     /* workspace too small                                */
+  GD_ERR_LAYOUT = -3         /* GD_VARIANT_BULK requested on unaligned / strided   */
+};
+
+/* The constructor arguments of GDLoss that reach the distance function
+ * (ref:261-278): loss_type, center_offset, fun, tau, alpha and the one extra
+ * kwarg each distance accepts -- `normalize` for gwd3d (ref:43), `sqrt` for the
+ * others (ref:110,145,190,202,215,228) -- passed as `flag`. */
+typedef struct gd_loss_config {
+  int32_t loss_type;
+  int32_t fun;
+  int32_t flag;
+  float tau;               /* the kernel applies the tau map iff tau >= 1.0   ref:36 */
+  float alpha;
+  float center_offset[3];  /* ref:9-12 */
+} gd_loss_config;
+
+int gd_abi_version(void);
+
+/* Bytes of device workspace gd_loss_* needs for `n` rows.  The workspace must
+ * be zero-filled ONCE when allocated; the kernels leave it zeroed again, so it
+ * can be reused by later calls on the same stream without clearing. */
+size_t gd_loss_workspace_bytes(int64_t n);
+
+/* Fused forward + backward: replaces GDLoss.forward (ref:298-310: preprocess x2,
+ * distance, postprocess, weighted reduction, x loss_weight) AND the autograd
+ * backward to `pred`, in one pass over HBM.
+ *
+ *   pred, target : [n,7] fp32, row strides in ELEMENTS (7 when contiguous;
+ *                  the CenterGDHead call site passes row-strided views,
+ *                  gd_centerpoint_head.py:413-423)
+ *   weight       : per weight_mode; weight_row_stride in elements (1 or 7 when
+ *                  contiguous); ignored for GD_WEIGHT_NONE
+ *   scale        : every known-at-forward scalar folded together:
+ *                  loss_weight * (1/n | 1/avg_factor | 1)            ref:310 + mmdet weight_reduce_loss
+ *   loss_sum     : nullable, 1 fp32 := scale * sum_i w_i * loss_i   (written, not accumulated)
+ *   row_loss     : nullable, [n] fp32 := scale * w_i * loss_i       (reduction='none')
+ *   grad_pred    : nullable, [n,7] fp32 contiguous := scale * w_i * d loss_i / d pred_i
+ *                  (nullable: forward only, e.g. under torch.no_grad)
+ * The sum is deterministic: per-CTA partials in fp64, combined in fixed order
+ * by the last CTA to finish. */
+int gd_loss_fwd_bwd(const gd_loss_config* cfg,
+                    const float* pred, int64_t pred_row_stride,
+                    const float* target, int64_t target_row_stride,
+                    const float* weight, int32_t weight_mode, int64_t weight_row_stride,
+                    int64_t n, float scale,
+                    float* loss_sum, float* row_loss, float* grad_pred,
+                    void* workspace, size_t workspace_bytes,
+                    int32_t variant, void* stream);
+
+/* Autograd fold: grad[i,:] *= *grad_output (0-dim upstream gradient; replaces the
+ * first step of the reference's autograd backward).  Reads the scalar on the
+ * device -- no host sync. */
+int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void* stream);
+
+/* Autograd fold for reduction='none': grad[i,:] *= grad_output[i]. */
+int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_rows,
+                       int64_t grad_output_stride, void* stream);
+
+/* Early-return branch of GDLoss.forward (ref:290-292): when a weight is given
+ * and no element is > 0 the reference returns (pred*weight).sum().  This writes
+ * flag[0] = 1 if any weight element is > 0 else 0 (count elements, any layout
+ * flattened by the caller) so the shim can take that branch. */
+int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* stream);
+
+/* Pairwise matrix (new surface):
+ *   out[i, j] = postprocess(distance(boxes1[i], boxes2[j]))   i<n, j<m
+ * equal to the element-wise path on the broadcast-expanded pairs.  boxes
+ * contiguous [n,7] / [m,7]; out row stride in elements (>= m). */
+int gd_pairwise(const gd_loss_config* cfg,
+                const float* boxes1, int64_t n,
+                const float* boxes2, int64_t m,
+                float* out, int64_t out_row_stride, void* stream);
+
+/* Pairwise with the consumer fused (assigner use): per row i the argmin/min
+ * over j, per column j the argmin over i is left to the caller via the matrix.
+ *   row_min [n] fp32, row_argmin [n] int32; the matrix itself is not written. */
+int gd_pairwise_row_argmin(const gd_loss_config* cfg,
+                           const float* boxes1, int64_t n,
+                           const float* boxes2, int64_t m,
+                           float* row_min, int32_t* row_argmin, void* stream);
+
+/* End-to-end entry with HOST buffers (bench `e2e`): chunks rows, overlaps
+ * H2D of chunk k+1 / kernel of chunk k / D2H of chunk k-1 on internal streams,
+ * returns when loss_host and grad_host are complete.  Host buffers may be
+ * pageable or pinned (pinned is what overlaps).  grad_host nullable. */
+int gd_loss_fwd_bwd_host(const gd_loss_config* cfg,
+                         const float* pred_host, const float* target_host,
+                         const float* weight_host, int32_t weight_mode,
+                         int64_t n, float scale,
+                         float* loss_host, float* grad_host,
+                         int32_t device, int64_t chunk_rows);
+
+/* Number of kernel launches issued by this library in this process (bench
+ * `gpu_launches`). */
+int64_t gd_launch_count(void);
+
+const char* gd_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* GD_LOSS_B200_H_ */

@@ -1,0 +1,96 @@
+"""ctypes binding of ``libgdloss_b200.so`` -- the C ABI in ``include/gd_loss_b200.h``.
+
+There is no fallback of any kind: if the library is missing (and cannot be
+built because nvcc is absent) or a call fails, this raises.  Tensors are passed
+as raw device pointers; work is enqueued on torch's current CUDA stream.
+"""
+import ctypes
+import os
+
+from . import build_ext
+
+LOSS_TYPES = {'gwd3d': 0, 'kld3d': 1, 'jd3d': 2, 'kld3d_symmax': 3,
+              'kld3d_symmin': 4, 'bd3d': 5, 'kfiou3d': 6}
+FUNS = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
+WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
+VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2}
+
+
+class GDLossConfig(ctypes.Structure):
+    """``struct gd_loss_config``."""
+    _fields_ = [('loss_type', ctypes.c_int32), ('fun', ctypes.c_int32),
+                ('flag', ctypes.c_int32), ('tau', ctypes.c_float),
+                ('alpha', ctypes.c_float), ('center_offset', ctypes.c_float * 3)]
+
+
+_vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+_cfgp = ctypes.POINTER(GDLossConfig)
+
+# name -> (restype, argtypes); must list every symbol include/gd_loss_b200.h declares
+SIGNATURES = {
+    'gd_abi_version': (ctypes.c_int, []),
+    'gd_loss_workspace_bytes': (ctypes.c_size_t, [_i64]),
+    'gd_loss_fwd_bwd': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _i32, _i64,
+                                       _i64, _f32, _vp, _vp, _vp, _vp,
+                                       ctypes.c_size_t, _i32, _vp]),
+    'gd_scale_grad': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    'gd_scale_grad_rows': (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp]),
+    'gd_any_positive': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    'gd_pairwise': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    'gd_pairwise_row_argmin': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'gd_loss_fwd_bwd_host': (ctypes.c_int, [_cfgp, _vp, _vp, _vp, _i32, _i64, _f32,
+                                            _vp, _vp, _i32, _i64]),
+    'gd_launch_count': (_i64, []),
+    'gd_error_string': (ctypes.c_char_p, [ctypes.c_int]),
+}
+
+_LIB = None
+_LIB_PATH = None
+
+
+def load(path=None):
+    """Load (building first if needed) the shared library; cached."""
+    global _LIB, _LIB_PATH
+    if _LIB is not None and path is None:
+        return _LIB
+    if path is None:
+        path = os.environ.get('GD_LOSS_B200_LIB')
+    if path is None:
+        path = build_ext.lib_path()
+        if not build_ext.is_current():
+            # build() raises if nvcc is unavailable: no silent fallback
+            path = build_ext.build()
+    if not os.path.exists(path):
+        raise RuntimeError(f'gd_loss_b200: native library {path} is missing; run '
+                           f'`python -m mmdet3d_gaussian_b200.build_ext`')
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.gd_abi_version() != 1:
+        raise RuntimeError('gd_loss_b200: ABI version mismatch')
+    _LIB, _LIB_PATH = lib, path
+    return lib
+
+
+def loaded_path():
+    return _LIB_PATH
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().gd_error_string(code).decode()
+        raise RuntimeError(f'gd_loss_b200.{what} failed ({code}): {msg}')
+
+
+def make_config(loss_type, fun, flag, tau, alpha, center_offset):
+    cfg = GDLossConfig()
+    cfg.loss_type = LOSS_TYPES[loss_type]
+    cfg.fun = FUNS[fun]
+    cfg.flag = 1 if flag else 0
+    cfg.tau = float(tau)
+    cfg.alpha = float(alpha)
+    for i in range(3):
+        cfg.center_offset[i] = float(center_offset[i])
+    return cfg

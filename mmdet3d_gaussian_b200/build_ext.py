@@ -1,0 +1,97 @@
+"""Builds ``libgdloss_b200.so`` (the C-ABI CUDA library) in-tree with nvcc.
+
+sm_100a only (``-gencode arch=compute_100a,code=sm_100a``); nvcc cross-compiles
+without a GPU.  The ``.so`` is git-ignored but travels to the GPU box with the
+repo snapshot.  A content hash of the sources is stored beside the library so a
+stale binary is rebuilt and a current one is not (mtimes do not survive the
+snapshot copy).
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, 'csrc')
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), 'include')
+SOURCES = ['gd_loss_kernels.cu', 'gd_pairwise.cu', 'gd_host_pipeline.cu']
+HEADERS = ['gd_math.cuh', 'gd_common.cuh']
+LIB_NAME = 'libgdloss_b200.so'
+LIB_PRECISE_NAME = 'libgdloss_b200_precise.so'   # -DGD_PRECISE_MATH=1, tests only
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
+              '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3']
+
+
+def lib_path(precise=False):
+    return os.path.join(PKG_DIR, LIB_PRECISE_NAME if precise else LIB_NAME)
+
+
+def _nvcc():
+    exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(exe):
+        raise RuntimeError('nvcc not found: cannot build libgdloss_b200.so')
+    return exe
+
+
+def _source_hash(extra=''):
+    h = hashlib.sha256()
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), 'rb') as f:
+            h.update(name.encode())
+            h.update(f.read())
+    with open(os.path.join(INCLUDE, 'gd_loss_b200.h'), 'rb') as f:
+        h.update(f.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update(extra.encode())
+    return h.hexdigest()
+
+
+def is_current(precise=False):
+    lib = lib_path(precise)
+    stamp = lib + '.hash'
+    if not (os.path.exists(lib) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as f:
+        return f.read().strip() == _source_hash('precise' if precise else '')
+
+
+def build(force=False, precise=False, verbose=False):
+    """Compile the library if missing or stale; returns its path."""
+    lib = lib_path(precise)
+    if not force and is_current(precise):
+        return lib
+    nvcc = _nvcc()
+    build_dir = os.path.join(PKG_DIR, 'build', 'precise' if precise else 'fast')
+    os.makedirs(build_dir, exist_ok=True)
+    defs = ['-DGD_PRECISE_MATH=1'] if precise else []
+
+    def compile_one(src):
+        obj = os.path.join(build_dir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + defs + ['-I', INCLUDE, '-c',
+                                            os.path.join(CSRC, src), '-o', obj]
+        if verbose:
+            cmd += ['-Xptxas', '-v']
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{res.stdout}\n{res.stderr}')
+        if verbose:
+            sys.stderr.write(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    res = subprocess.run([nvcc, '-shared', '-o', lib] + objs + ['-cudart', 'static'],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f'link failed:\n{res.stdout}\n{res.stderr}')
+    with open(lib + '.hash', 'w') as f:
+        f.write(_source_hash('precise' if precise else ''))
+    return lib
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, precise='--precise' in sys.argv,
+                verbose='-v' in sys.argv))

@@ -1,0 +1,712 @@
+// Per-pair Gaussian-distance math: value and analytic d/d(pred) in registers.
+//
+// One call evaluates one (pred, target) box pair for one of the seven distance
+// types of the reference (mmdet3d_gaussian/models/losses/gaussian_distance_loss.py,
+// cited as ref:LINE) and, when GRAD, the hand-derived gradient w.r.t. the seven
+// pred columns, replacing the reference's autograd chain of ~160-250 small ops.
+//
+// Formulation.  The reference builds R, S, Sigma = R S^2 R^T with batched 2x2
+// matmuls (ref:86-88,116-117,149-150).  Here everything is written in the pred
+// box's own frame: with half extents a=w/2, b=h/2, e=l/2 (A=a^2 ...; C,D,F for
+// the target), yaw difference dl = r_p - r_t, s2 = sin^2 dl:
+//
+//   tr(Sigma_p Sigma_t)     = (AC+BD) cos^2 + (AD+BC) sin^2             (ref:88-90)
+//   det(Sigma_p + Sigma_t)  = (A+C)(B+D) + (A-B)(C-D) s2                (ref:155-157,235-236)
+//   Sigma_t in pred frame   = [[C c^2 + D s^2, (D-C) s c], [., C s^2 + D c^2]]
+//
+// and terms that are differences of nearly equal quantities when the boxes
+// almost coincide are evaluated from differences/ratios instead (SURVEY.md
+// section 7 "hard parts"), e.g. A+B+C+D-2 sqrt(U) = (a_p-a_t)^2+(b_p-b_t)^2+2 eta with
+// eta = (A-B)(C-D) s2 / (V + sqrt(U)), V = a_p a_t + b_p b_t.  Against the fp64
+// oracle this is at least as accurate as the reference's own fp32 evaluation.
+//
+// The file compiles for the device (nvcc, T=float) and, for formula
+// verification only, on the host (tests/host_math builds it with g++ in float
+// and double).  The shipped library contains no host compute path.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#ifndef GD_PRECISE_MATH
+#define GD_PRECISE_MATH 0
+#endif
+
+#if defined(__CUDACC__)
+#define GD_HD __host__ __device__ __forceinline__
+#else
+#define GD_HD inline
+#endif
+
+namespace gd {
+
+enum LossType : int {
+  kGwd = 0,      // 'gwd3d'         ref:42-106
+  kKld = 1,      // 'kld3d'         ref:109-141
+  kJd = 2,       // 'jd3d'          ref:189-198
+  kSymMax = 3,   // 'kld3d_symmax'  ref:201-211
+  kSymMin = 4,   // 'kld3d_symmin'  ref:214-224
+  kBd = 5,       // 'bd3d'          ref:144-186
+  kKfiou = 6,    // 'kfiou3d'       ref:227-248
+  kNumLossTypes = 7
+};
+
+enum Fun : int { kFunNone = 0, kFunLog1p = 1, kFunExpm1 = 2, kFunNlog = 3 };  // ref:24-34
+
+template <typename T>
+struct PairParams {
+  T off[3];      // center_offset                      ref:12
+  T alpha2;      // alpha^2                            ref:99
+  T inv_alpha2;  // 1/alpha^2                          ref:137,182
+  T tau;         // only used when tau_on              ref:36-37
+  int fun;       // Fun
+  int tau_on;    // tau >= 1.0 decided on the host     ref:36
+  int flag;      // 'normalize' (gwd) or 'sqrt' (others)   ref:43,110,145
+};
+
+// ---------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Mth;
+
+template <>
+struct Mth<double> {
+  static GD_HD double rcp(double x) { return 1.0 / x; }
+  static GD_HD double sqrt(double x) { return ::sqrt(x); }
+  static GD_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static GD_HD void sincos(double x, double* s, double* c) {
+    *s = ::sin(x);
+    *c = ::cos(x);
+  }
+  static GD_HD double log(double x) { return ::log(x); }
+  static GD_HD double log1p(double x) { return ::log1p(x); }
+  static GD_HD double expm1(double x) { return ::expm1(x); }
+  static GD_HD double exp(double x) { return ::exp(x); }
+  static GD_HD double rcbrt(double x) { return 1.0 / ::cbrt(x); }
+  // S - log(r1 r2 r3), r_i = 1 + q_i, S = sum q_i; plain evaluation is accurate
+  // enough in double.
+  static GD_HD double sum_minus_log_ratios(double S, double pair, double r1, double r2,
+                                           double r3) {
+    (void)pair;
+    return S - (::log(r1) + ::log(r2) + ::log(r3));
+  }
+  static GD_HD double inf() { return HUGE_VAL; }
+};
+
+template <>
+struct Mth<float> {
+  // Device arithmetic: MUFU approximations (rcp/sqrt/rsqrt.approx.ftz: <= 1-2 ulp)
+  // instead of the IEEE-rounded sequences (each ~8 instructions + a slow-path
+  // call).  The parity budget is 1e-5 relative; these cost ~1e-7 per operation
+  // and keep the kernel on the HBM side of the roofline.  -DGD_PRECISE_MATH=1
+  // restores the IEEE versions (used by the tests to bound the difference).
+  static GD_HD float rcp(float x) {
+#if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#elif defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+  }
+  static GD_HD float sqrt(float x) {
+#if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#elif defined(__CUDA_ARCH__)
+    return __fsqrt_rn(x);
+#else
+    return ::sqrtf(x);
+#endif
+  }
+  static GD_HD float rsqrt(float x) {
+#if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#elif defined(__CUDA_ARCH__)
+    return __frcp_rn(__fsqrt_rn(x));
+#else
+    return 1.0f / ::sqrtf(x);
+#endif
+  }
+  static GD_HD void sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    ::sincosf(x, s, c);
+#else
+    *s = ::sinf(x);
+    *c = ::cosf(x);
+#endif
+  }
+  static GD_HD float log(float x) { return ::logf(x); }
+  static GD_HD float log1p(float x) { return ::log1pf(x); }
+  static GD_HD float expm1(float x) { return ::expm1f(x); }
+  static GD_HD float exp(float x) { return ::expf(x); }
+  static GD_HD float rcbrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return ::rcbrtf(x);
+#else
+    return 1.0f / ::cbrtf(x);
+#endif
+  }
+  // S - log(y) with S = q1+q2+q3, y = r1 r2 r3, r_i = 1+q_i the extent ratios, and
+  // pair = y - 1 - S (the mixed products of the q_i).  This is the log-det part of
+  // the KLD shape term; together with sum q_i^2/2 it vanishes QUADRATICALLY as the
+  // boxes coincide, so it must be accurate in a relative sense for |q| << 1, where
+  // the naive S - log(y) loses everything -- and it must not cancel for |q| >> 1
+  // (degenerate 1e-7 extents, ref:13-14) either.
+  //   y = 2^k m, m in [sqrt(1/2), sqrt(2));  s = f/(2+f);  log(m) = 2s + 2 s^3 P(s^2)
+  //   k == 0 (y near 1): f = x := S + pair (exact small quantity, not y - 1);
+  //            x - log(1+x) = x s - 2 s^3 P(s^2), result = that - pair
+  //   k != 0: result = S - k ln2 - 2s - tail directly (it is O(0.06) or larger)
+  // y is formed as a product of ratios so it stays accurate when x is within
+  // rounding of -1.
+  static GD_HD float sum_minus_log_ratios(float S, float pair, float r1, float r2,
+                                          float r3) {
+    const float y = r1 * r2 * r3;
+    if (!(y > 1.0e-37f) || !(y < 3.0e38f)) {   // product under/overflowed, or nan
+      return S - (::logf(r1) + ::logf(r2) + ::logf(r3));
+    }
+    uint32_t yb;
+    memcpy(&yb, &y, 4);
+    const int k = (int)((int32_t)(yb - 0x3f3504f3u) >> 23);
+    const uint32_t mb = yb - ((uint32_t)k << 23);
+    float m;
+    memcpy(&m, &mb, 4);
+    const float x = S + pair;
+    const float f = (k == 0) ? x : (m - 1.0f);
+    const float s = f * rcp(2.0f + f);
+    const float z = s * s;
+    // |s| <= 0.1716, z <= 0.02944: 6 terms -> truncation < 2e-9 relative to 1/3
+    float p = 1.0f / 13.0f;
+    p = fmaf(p, z, 1.0f / 11.0f);
+    p = fmaf(p, z, 1.0f / 9.0f);
+    p = fmaf(p, z, 1.0f / 7.0f);
+    p = fmaf(p, z, 1.0f / 5.0f);
+    p = fmaf(p, z, 1.0f / 3.0f);
+    const float tail = 2.0f * s * z * p;
+    const float kf = (float)k;
+    float r = fmaf(-kf, 0.693145751953125f, S);          // ln2 hi (k*hi exact)
+    r = fmaf(-kf, 1.428606765330187e-06f, r);            // ln2 lo
+    const float direct = (r - 2.0f * s) - tail;
+    return (k == 0) ? (fmaf(x, s, -tail) - pair) : direct;
+  }
+  static GD_HD float inf() { return HUGE_VALF; }
+};
+
+// torch.clamp(min, max) semantics (NaN propagates); returns the gradient mask
+// of the CLOSED interval (clamp passes grad on [min,max]).
+template <typename T>
+GD_HD T clamp_extent(T v, T* mask) {
+  const T lo = (T)1e-7, hi = (T)1e7;           // ref:13-14
+  *mask = (v >= lo && v <= hi) ? (T)1 : (T)0;
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// sqrt(clamp(x, 0)) and its derivative factor 1/(2 sqrt(x)):
+// 0 below zero (clamp blocks), +inf at exactly zero (ref:95,99,139,184,197;
+// torch autograd convention probed in SURVEY.md appendix A).
+template <typename T>
+GD_HD T sqrt_clamp0(T x, T* dfac) {
+  if (x < (T)0) {
+    *dfac = (T)0;
+    return (T)0;
+  }
+  *dfac = (T)0.5 * Mth<T>::rsqrt(x);           // +inf at x == 0
+  return Mth<T>::sqrt(x);
+}
+
+// post map ref:24-39: f = log1p | expm1 | nlog | identity, then tau >= 1 ->
+// 1 - tau/(tau+f) = f/(tau+f).  Returns value, multiplies *dfac by d out / d in.
+template <typename T>
+GD_HD T post_map(T d, const PairParams<T>& P, T* dfac) {
+  T f = d, df = (T)1;
+  if (P.fun == kFunLog1p) {
+    f = Mth<T>::log1p(d);                      // ref:26
+    df = Mth<T>::rcp((T)1 + d);
+  } else if (P.fun == kFunExpm1) {
+    f = Mth<T>::expm1(d);                      // ref:28
+    df = f + (T)1;
+  } else if (P.fun == kFunNlog) {
+    T arg = (T)1 - d + (T)1e-7;                // ref:30
+    f = -Mth<T>::log(arg);
+    df = Mth<T>::rcp(arg);
+  }
+  if (P.tau_on) {                              // ref:36-37
+    T inv = Mth<T>::rcp(P.tau + f);
+    df = df * P.tau * inv * inv;
+    f = f * inv;
+  }
+  *dfac = *dfac * df;
+  return f;
+}
+
+// ---------------------------------------------------------------------------
+// a1: the two boxes reduced to what every distance needs         ref:8-21
+// ---------------------------------------------------------------------------
+template <typename T>
+struct PairGeom {
+  T dx, dy, dz;             // c_p - c_t, centre = xyz + off * UNCLAMPED extents (ref:12)
+  T ap, bp, ep;             // pred half extents (clamped, ref:13-14, x0.5 ref:19-20)
+  T at, bt, et;             // target half extents
+  T ma, mb, me;             // clamp gradient masks of the pred extents
+  T sp, cp;                 // sin / cos of pred yaw              (ref:16-17)
+  T sd, cd;                 // sin / cos of (r_p - r_t)
+};
+
+template <typename T, bool NEED_PRED_ROT>
+GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P) {
+  PairGeom<T> g;
+  g.dx = (p[0] - t[0]) + P.off[0] * (p[3] - t[3]);
+  g.dy = (p[1] - t[1]) + P.off[1] * (p[4] - t[4]);
+  g.dz = (p[2] - t[2]) + P.off[2] * (p[5] - t[5]);
+  T dummy;
+  g.ap = (T)0.5 * clamp_extent(p[3], &g.ma);
+  g.bp = (T)0.5 * clamp_extent(p[4], &g.mb);
+  g.ep = (T)0.5 * clamp_extent(p[5], &g.me);
+  g.at = (T)0.5 * clamp_extent(t[3], &dummy);
+  g.bt = (T)0.5 * clamp_extent(t[4], &dummy);
+  g.et = (T)0.5 * clamp_extent(t[5], &dummy);
+  Mth<T>::sincos(p[6] - t[6], &g.sd, &g.cd);
+  if (NEED_PRED_ROT) {
+    Mth<T>::sincos(p[6], &g.sp, &g.cp);
+  } else {
+    g.sp = (T)0;
+    g.cp = (T)1;
+  }
+  return g;
+}
+
+// Local gradient (before the outer chain factor): w.r.t. centre difference in
+// the global frame, the three pred half extents and the pred yaw.
+template <typename T>
+struct LocalGrad {
+  T gdx, gdy, gdz, ga, gb, ge, gr;
+};
+
+template <typename T>
+GD_HD void store_grad(const PairGeom<T>& g, const PairParams<T>& P,
+                      const LocalGrad<T>& L, T fac, T* out) {
+  // d/dw = 0.5 * [1e-7 <= w <= 1e7] * d/da + off_x * d/dc_x   
+  out[0] = fac * L.gdx;
+  out[1] = fac * L.gdy;
+  out[2] = fac * L.gdz;
+  out[3] = fac * ((T)0.5 * g.ma * L.ga + P.off[0] * L.gdx);
+  out[4] = fac * ((T)0.5 * g.mb * L.gb + P.off[1] * L.gdy);
+  out[5] = fac * ((T)0.5 * g.me * L.ge + P.off[2] * L.gdz);
+  out[6] = fac * L.gr;
+}
+
+// ---------------------------------------------------------------------------
+// a2: GWD                                                        ref:42-106
+// ---------------------------------------------------------------------------
+template <typename T, bool GRAD>
+GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+  const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
+  const T s2 = g.sd * g.sd, c2 = g.cd * g.cd;
+  const T K = (g.ap * g.bp) * (g.at * g.bt);                       // ref:91-92
+  // U = tr(Sigma_p Sigma_t) + 2 sqrt(det det): all terms positive    ref:88-95
+  const T U = (A * C + B * D) * c2 + (A * D + B * C) * s2 + (T)2 * K;
+  T kU;                                                            // 1/(2 sqrt U)
+  const T rU = sqrt_clamp0(U, &kU);                                // ref:95
+  const T V = g.ap * g.at + g.bp * g.bt;
+  const T amb = (g.ap - g.bp) * (g.ap + g.bp);                     // A - B
+  const T cmd = (g.at - g.bt) * (g.at + g.bt);                     // C - D
+  const T eps = amb * cmd * s2;                                    // V^2 - U
+  const T eta = eps * Mth<T>::rcp(V + rU);                         // V - sqrt U
+  const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
+  const T W = da * da + db * db + (T)2 * eta + de * de;            // ref:81-97
+  const T d2 = g.dx * g.dx + g.dy * g.dy + g.dz * g.dz + P.alpha2 * W;  // ref:79,99
+  T k;                                                             // 1/(2 d)
+  T d = sqrt_clamp0(d2, &k);                                       // ref:99
+  T inv_n = (T)1;
+  if (P.flag) {                                                    // ref:101-104
+    // 1 / (2 (K e_p e_t)^(1/6)), product split so it cannot overflow
+    const T vp = Mth<T>::sqrt(g.ap * g.bp * g.ep);
+    const T vt = Mth<T>::sqrt(g.at * g.bt * g.et);
+    inv_n = (T)0.5 * Mth<T>::rcbrt(vp * vt);
+  }
+  const T gval = d * inv_n;
+  T fac = (T)1;
+  const T out = post_map(gval, P, &fac);
+  if (GRAD) {
+    const T irU = (T)2 * kU;                                       // 1/sqrt U
+    const T rot = cmd * s2;                                        // (C-D) s2
+    // dW/da_p = [2 (a_p-a_t) V - 2 a_p (eta - (C-D) s2)] / sqrt U  
+    const T dWa = (T)2 * (da * V - g.ap * (eta - rot)) * irU;
+    const T dWb = (T)2 * (db * V - g.bp * (eta + rot)) * irU;
+    const T dWr = amb * cmd * ((T)2 * g.sd * g.cd) * irU;
+    const T kn = k * inv_n;                                        // 1/(2 d n)
+    LocalGrad<T> L;
+    L.gdx = (T)2 * g.dx * kn;
+    L.gdy = (T)2 * g.dy * kn;
+    L.gdz = (T)2 * g.dz * kn;
+    L.ga = P.alpha2 * dWa * kn;
+    L.gb = P.alpha2 * dWb * kn;
+    L.ge = P.alpha2 * (T)2 * de * kn;
+    L.gr = P.alpha2 * dWr * kn;
+    if (P.flag) {                                                  // d ln n / da = 1/(6a)
+      const T g6 = gval * (T)(1.0 / 6.0);
+      L.ga -= g6 * Mth<T>::rcp(g.ap);
+      L.gb -= g6 * Mth<T>::rcp(g.bp);
+      L.ge -= g6 * Mth<T>::rcp(g.ep);
+    }
+    store_grad(g, P, L, fac, grad);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// a3: KLD, both directions, in the pred frame                   ref:109-141
+// ---------------------------------------------------------------------------
+// Shared pieces of KL(t||p) ("fwd", what kld3d_loss(pred, target) computes:
+// it inverts Sigma_p, ref:114-116) and KL(p||t) ("rev", kld3d_loss(target,
+// pred), needed by jd / symmax / symmin, ref:193,207,220).
+template <typename T>
+struct KldCommon {
+  T u, v;            // centre difference rotated into the pred frame   (ref:119-123)
+  T iA, iB, iE;      // 1/A, 1/B, 1/E
+  T cmd;             // C - D
+  T s2, s2x2;        // sin^2 dl, sin(2 dl)
+};
+
+template <typename T>
+GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
+                LocalGrad<T>* L, T* ul, T* vl) {
+  // value: 0.5 (u^2/A + v^2/B + dz^2/E)/alpha^2 + 0.5 tr(Sp^-1 St) + 0.5 F/E
+  //        + ln(a_p b_p e_p / a_t b_t e_t) - 1.5                   ref:122-137
+  const T u = g.cp * g.dx + g.sp * g.dy;
+  const T v = -g.sp * g.dx + g.cp * g.dy;
+  const T iap = Mth<T>::rcp(g.ap), ibp = Mth<T>::rcp(g.bp), iep = Mth<T>::rcp(g.ep);
+  const T iA = iap * iap, iB = ibp * ibp, iE = iep * iep;
+  const T s2 = g.sd * g.sd;
+  const T cmd = (g.at - g.bt) * (g.at + g.bt);
+  // delta_i = (t_i - p_i)/p_i ; C/A = (1+delta_a)^2 ...
+  const T qa = (g.at - g.ap) * iap, qb = (g.bt - g.bp) * ibp, qe = (g.et - g.ep) * iep;
+  const T ra = g.at * iap, rb = g.bt * ibp, re = g.et * iep;       // = 1 + q
+  const T maha = (T)0.5 * (u * u * iA + v * v * iB + g.dz * g.dz * iE) * P.inv_alpha2;
+  // sum(delta + delta^2/2) - log((1+da)(1+db)(1+de)) with a single log:
+  const T pair = qa * qb + qa * qe + qb * qe + qa * qb * qe;       // Pi(1+d) - 1 - sum d
+  const T shape = (T)0.5 * (qa * qa + qb * qb + qe * qe)
+      + Mth<T>::sum_minus_log_ratios(qa + qb + qe, pair, ra, rb, re)
+      + (T)0.5 * cmd * s2 * (iB - iA);
+  if (want_grad) {
+    const T s2x2 = (T)2 * g.sd * g.cd;
+    const T rot = cmd * s2;
+    const T lu = u * iA * P.inv_alpha2, lv = v * iB * P.inv_alpha2;
+    *ul = lu;                                  // gradient w.r.t. (u, v): pred frame
+    *vl = lv;
+    L->gdz = g.dz * iE * P.inv_alpha2;
+    L->ga = iap * (-qa * ((T)2 + qa) + rot * iA - u * u * iA * P.inv_alpha2);
+    L->gb = ibp * (-qb * ((T)2 + qb) - rot * iB - v * v * iB * P.inv_alpha2);
+    L->ge = iep * (-qe * ((T)2 + qe) - g.dz * g.dz * iE * P.inv_alpha2);
+    L->gr = (iA - iB) * (u * v * P.inv_alpha2 - (T)0.5 * cmd * s2x2);
+  }
+  return maha + shape;
+}
+
+template <typename T>
+GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
+                LocalGrad<T>* L, T* ul, T* vl) {
+  // KL with Sigma_t inverted (kld3d_loss(target, pred)); gradient still w.r.t. pred.
+  const T u = g.cp * g.dx + g.sp * g.dy;
+  const T v = -g.sp * g.dx + g.cp * g.dy;
+  // rotate into the target frame: (u', v') = R(dl) (u, v)
+  const T ut = g.cd * u - g.sd * v;
+  const T vt = g.sd * u + g.cd * v;
+  const T iat = Mth<T>::rcp(g.at), ibt = Mth<T>::rcp(g.bt), iet = Mth<T>::rcp(g.et);
+  const T iC = iat * iat, iD = ibt * ibt, iF = iet * iet;
+  const T s2 = g.sd * g.sd;
+  const T amb = (g.ap - g.bp) * (g.ap + g.bp);
+  const T qa = (g.ap - g.at) * iat, qb = (g.bp - g.bt) * ibt, qe = (g.ep - g.et) * iet;
+  const T ra = g.ap * iat, rb = g.bp * ibt, re = g.ep * iet;       // = 1 + q
+  const T maha = (T)0.5 * (ut * ut * iC + vt * vt * iD + g.dz * g.dz * iF) * P.inv_alpha2;
+  const T pair = qa * qb + qa * qe + qb * qe + qa * qb * qe;
+  const T shape = (T)0.5 * (qa * qa + qb * qb + qe * qe)
+      + Mth<T>::sum_minus_log_ratios(qa + qb + qe, pair, ra, rb, re)
+      + (T)0.5 * amb * s2 * (iD - iC);
+  if (want_grad) {
+    const T s2x2 = (T)2 * g.sd * g.cd;
+    const T A = g.ap * g.ap, B = g.bp * g.bp;
+    // gradient w.r.t. (u', v') rotated back into the pred frame: R(-dl)
+    const T lut = ut * iC * P.inv_alpha2, lvt = vt * iD * P.inv_alpha2;
+    *ul = g.cd * lut + g.sd * lvt;
+    *vl = -g.sd * lut + g.cd * lvt;
+    L->gdz = g.dz * iF * P.inv_alpha2;
+    L->ga = Mth<T>::rcp(g.ap) * (qa * ((T)2 + qa) + A * s2 * (iD - iC));
+    L->gb = Mth<T>::rcp(g.bp) * (qb * ((T)2 + qb) + B * s2 * (iC - iD));
+    L->ge = Mth<T>::rcp(g.ep) * (qe * ((T)2 + qe));
+    L->gr = (T)0.5 * amb * s2x2 * (iD - iC);
+  }
+  return maha + shape;
+}
+
+template <typename T>
+GD_HD void rotate_centre_grad(const PairGeom<T>& g, T ul, T vl, LocalGrad<T>* L) {
+  // pred frame -> global frame: R(r_p)
+  L->gdx = g.cp * ul - g.sp * vl;
+  L->gdy = g.sp * ul + g.cp * vl;
+}
+
+template <typename T, int LOSS, bool GRAD>
+GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+  LocalGrad<T> L;
+  T ul = (T)0, vl = (T)0;
+  T fac = (T)1;
+  T val;
+  if (LOSS == kKld) {
+    val = kld_fwd(g, P, GRAD, &L, &ul, &vl);
+    if (P.flag) {                                                  // ref:138-139
+      T k;
+      val = sqrt_clamp0(val, &k);
+      fac = k;
+    }
+  } else {
+    LocalGrad<T> Lr;
+    T ulr = (T)0, vlr = (T)0;
+    T f = kld_fwd(g, P, GRAD, &L, &ul, &vl);
+    T r = kld_rev(g, P, GRAD, &Lr, &ulr, &vlr);
+    T wf, wr;                                  // d val / d f, d val / d r
+    if (LOSS == kJd) {                                             // ref:191-197
+      val = (T)0.5 * (f + r);
+      wf = wr = (T)0.5;
+      if (P.flag) {
+        T k;
+        val = sqrt_clamp0(val, &k);
+        wf *= k;
+        wr *= k;
+      }
+    } else {                                                       // ref:204-223
+      T kf = (T)1, kr = (T)1;
+      if (P.flag) {
+        f = sqrt_clamp0(f, &kf);
+        r = sqrt_clamp0(r, &kr);
+      }
+      // torch.max / torch.min backward: exact ties split 1/2 - 1/2 (appendix A)
+      const bool take_f = (LOSS == kSymMax) ? (f > r) : (f < r);
+      const bool tie = (f == r);
+      val = tie ? f : (take_f ? f : r);
+      if (f != f || r != r) val = f + r;       // NaN propagates like torch.max/min
+      wf = tie ? (T)0.5 * kf : (take_f ? kf : (T)0);
+      wr = tie ? (T)0.5 * kr : (take_f ? (T)0 : kr);
+    }
+    if (GRAD) {
+      ul = wf * ul + wr * ulr;
+      vl = wf * vl + wr * vlr;
+      L.gdz = wf * L.gdz + wr * Lr.gdz;
+      L.ga = wf * L.ga + wr * Lr.ga;
+      L.gb = wf * L.gb + wr * Lr.gb;
+      L.ge = wf * L.ge + wr * Lr.ge;
+      L.gr = wf * L.gr + wr * Lr.gr;
+    }
+  }
+  const T out = post_map(val, P, &fac);
+  if (GRAD) {
+    rotate_centre_grad(g, ul, vl, &L);
+    store_grad(g, P, L, fac, grad);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// a4: Bhattacharyya                                             ref:144-186
+// ---------------------------------------------------------------------------
+template <typename T, bool GRAD>
+GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+  const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
+  const T E = g.ep * g.ep, F = g.et * g.et;
+  const T s2 = g.sd * g.sd, c2 = g.cd * g.cd, sc = g.sd * g.cd;
+  const T u = g.cp * g.dx + g.sp * g.dy;
+  const T v = -g.sp * g.dx + g.cp * g.dy;
+  const T amb = (g.ap - g.bp) * (g.ap + g.bp);
+  const T cmd = (g.at - g.bt) * (g.at + g.bt);
+  // Sigma_t in the pred frame
+  const T t00 = C * c2 + D * s2, t11 = C * s2 + D * c2, t01 = -cmd * sc;
+  // M = (Sigma_p + Sigma_t)/2 in the pred frame                    ref:152
+  const T M00 = (T)0.5 * (A + t00), M11 = (T)0.5 * (B + t11), M01 = (T)0.5 * t01;
+  const T Ml = (T)0.5 * (E + F);                                   // ref:153
+  const T eps = amb * cmd * s2;
+  const T detN = (A + C) * (B + D) + eps;                          // det(Sp+St)
+  const T det_raw = (T)0.25 * detN;                                // ref:155-157
+  const bool clamped = !(det_raw >= (T)1e-7);                      // ref:158
+  const T det = clamped ? (T)1e-7 : det_raw;
+  const T idet = Mth<T>::rcp(det);
+  const T iMl = Mth<T>::rcp(Ml);
+  const T Q2 = u * u * M11 - (T)2 * u * v * M01 + v * v * M00;     // d^T adj(M) d
+  const T maha = (T)0.125 * (Q2 * idet + g.dz * g.dz * iMl) * P.inv_alpha2;  // ref:170-172,182
+  // shape: 0.5 ln det + 0.5 ln Ml - 0.25 ln(ABE) - 0.25 ln(CDF)    ref:174-180
+  const T K = (g.ap * g.bp) * (g.at * g.bt);
+  const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
+  const T xe = de * de * Mth<T>::rcp((T)2 * g.ep * g.et);          // Ml/(e_p e_t) - 1
+  T shape;
+  if (!clamped) {
+    // det/(sqrt(AB) sqrt(CD)) = (1+xa)(1+xb) + eps/(4K),  xa = (a_p-a_t)^2/(2 a_p a_t)
+    const T xa = da * da * Mth<T>::rcp((T)2 * g.ap * g.at);
+    const T xb = db * db * Mth<T>::rcp((T)2 * g.bp * g.bt);
+    const T q = xa + xb + xa * xb + (T)0.25 * eps * Mth<T>::rcp(K);
+    const T qq = q + xe + q * xe;              // (1+q)(1+xe) - 1
+    shape = (qq < (T)1e37) ? (T)0.5 * Mth<T>::log1p(qq)
+                           : (T)0.5 * (Mth<T>::log1p(q) + Mth<T>::log1p(xe));  // 1e7-vs-1e-7 extents
+  } else {
+    shape = (T)0.5 * (Mth<T>::log((T)1e-7) - Mth<T>::log(K)) + (T)0.5 * Mth<T>::log1p(xe);
+  }
+  T val = maha + shape;
+  T fac = (T)1;
+  if (P.flag) {                                                    // ref:183-184
+    T k;
+    val = sqrt_clamp0(val, &k);
+    fac = k;
+  }
+  const T out = post_map(val, P, &fac);
+  if (GRAD) {
+    const T c8 = (T)0.125 * P.inv_alpha2 * idet;                   // 1/(8 alpha^2 det)
+    LocalGrad<T> L;
+    // centre: M^-1 d / (4 alpha^2) in the pred frame, then rotate
+    const T ul = (T)2 * c8 * (M11 * u - M01 * v);
+    const T vl = (T)2 * c8 * (M00 * v - M01 * u);
+    rotate_centre_grad(g, ul, vl, &L);
+    L.gdz = (T)0.25 * g.dz * iMl * P.inv_alpha2;
+    const T iap = Mth<T>::rcp(g.ap), ibp = Mth<T>::rcp(g.bp), iep = Mth<T>::rcp(g.ep);
+    T sa, sb, gam;                             // shape parts and d/d det_raw factor
+    if (!clamped) {
+      const T idN = Mth<T>::rcp(detN);
+      // a_p M11/det/2... - 1/(2 a_p) = [(A - t00)(B + t11) + t01^2] / (2 a_p detN)
+      const T Amt = da * (g.ap + g.at) + cmd * s2;                 // A - t00
+      const T Bmt = db * (g.bp + g.bt) - cmd * s2;                 // B - t11
+      sa = (T)0.5 * (Amt * (B + t11) + t01 * t01) * idN * iap;
+      sb = (T)0.5 * (Bmt * (A + t00) + t01 * t01) * idN * ibp;
+      gam = -Q2 * c8 * idet;                   // Mahalanobis part of d/d det
+      L.gr = -amb * (u * v * c8 + (gam + (T)0.5 * idet) * M01);
+    } else {
+      sa = -(T)0.5 * iap;
+      sb = -(T)0.5 * ibp;
+      gam = (T)0;
+      L.gr = -amb * (u * v * c8);
+    }
+    L.ga = g.ap * (v * v * c8 + gam * M11) + sa;
+    L.gb = g.bp * (u * u * c8 + gam * M00) + sb;
+    L.ge = -(T)0.125 * g.dz * g.dz * iMl * iMl * P.inv_alpha2 * g.ep
+        + (T)0.25 * de * (g.ep + g.et) * iep * iMl;
+    store_grad(g, P, L, fac, grad);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// a7: KFIoU (ignores centres, alpha, sqrt; tau forced 0)         ref:227-248
+// ---------------------------------------------------------------------------
+template <typename T, bool GRAD>
+GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T* grad) {
+  PairParams<T> P = Pin;
+  P.tau_on = 0;                                                    // ref:247
+  const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
+  const T E = g.ep * g.ep, F = g.et * g.et;
+  const T s2 = g.sd * g.sd, c2 = g.cd * g.cd;
+  const T amb = (g.ap - g.bp) * (g.ap + g.bp);
+  const T cmd = (g.at - g.bt) * (g.at + g.bt);
+  const T detN = (A + C) * (B + D) + amb * cmd * s2;               // ref:234-236
+  const T Zraw = detN * (E + F);                                   // ref:237-238
+  const bool zc = !(Zraw >= (T)1e-7);                              // ref:243
+  const T Z = zc ? (T)1e-7 : Zraw;
+  const T volp = g.ap * g.bp * g.ep, volt = g.at * g.bt * g.et;    // ref:240-241
+  const T irZ = Mth<T>::rcp(Mth<T>::sqrt(Z));
+  const T I = volp * volt * irZ;                                   // ref:243
+  const T Uraw = volp + volt - I;
+  const bool uc = !(Uraw >= (T)1e-7);                              // ref:245
+  const T Uc = uc ? (T)1e-7 : Uraw;
+  const T iU = Mth<T>::rcp(Uc);
+  const T kf = I * iU;                                             // ref:246
+  const T cK = (T)4.656854249492381;
+  T fac = (T)1;
+  const T out = post_map((T)1 - cK * kf, P, &fac);                 // ref:247
+  if (GRAD) {
+    // d ln I / dx = d ln volp / dx - 0.5 [Z unclamped] d ln Z / dx
+    const T t00 = C * c2 + D * s2, t11 = C * s2 + D * c2;
+    const T hz = zc ? (T)0 : (T)0.5 * Mth<T>::rcp(Z);
+    const T iap = Mth<T>::rcp(g.ap), ibp = Mth<T>::rcp(g.bp), iep = Mth<T>::rcp(g.ep);
+    const T EF = E + F;
+    const T dIa = I * (iap - hz * EF * (T)2 * g.ap * (B + t11));
+    const T dIb = I * (ibp - hz * EF * (T)2 * g.bp * (A + t00));
+    const T dIe = I * (iep - hz * (T)2 * g.ep * detN);
+    const T dIr = I * (-hz * EF * amb * cmd * ((T)2 * g.sd * g.cd));
+    const T mu = uc ? (T)0 : (T)1;
+    // k = I/U: dk = (dI U - I dU)/U^2, dU = mu (dvol - dI)
+    const T c = -cK * iU;                      // d(1 - cK k)/dk * 1/U
+    LocalGrad<T> L;
+    L.gdx = L.gdy = L.gdz = (T)0;
+    L.ga = c * (dIa - kf * mu * (volp * iap - dIa));
+    L.gb = c * (dIb - kf * mu * (volp * ibp - dIb));
+    L.ge = c * (dIe - kf * mu * (volp * iep - dIe));
+    L.gr = c * (dIr + kf * mu * dIr);
+    store_grad(g, P, L, fac, grad);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// dispatchers
+// ---------------------------------------------------------------------------
+template <typename T, int LOSS, bool GRAD>
+GD_HD T core_eval(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+  if (LOSS == kGwd) return gwd_core<T, GRAD>(g, P, grad);
+  if (LOSS == kBd) return bd_core<T, GRAD>(g, P, grad);
+  if (LOSS == kKfiou) return kfiou_core<T, GRAD>(g, P, grad);
+  return kld_family_core<T, LOSS, GRAD>(g, P, grad);
+}
+
+// element-wise path: one (pred row, target row) pair, value + d/d pred
+template <typename T, int LOSS, bool GRAD>
+GD_HD T pair_eval(const T* p, const T* t, const PairParams<T>& P, T* grad) {
+  constexpr bool kNeedRot = !(LOSS == kGwd || LOSS == kKfiou);
+  const PairGeom<T> g = make_geom<T, kNeedRot>(p, t, P);
+  return core_eval<T, LOSS, GRAD>(g, P, grad);
+}
+
+// ---------------------------------------------------------------------------
+// a12: pairwise N x M path.  Everything that depends on ONE box is computed
+// once per box (BoxGauss); the per-pair work is the geometry difference and the
+// same value cores as above.  sin/cos of the yaw difference come from the
+// angle-difference identities instead of a per-pair sincos.
+// ---------------------------------------------------------------------------
+template <typename T>
+struct BoxGauss {
+  T cx, cy, cz;     // centre incl. center_offset * unclamped extents   ref:12
+  T a, b, e;        // clamped half extents                             ref:13-14,19-20
+  T s, c;           // sin / cos yaw                                    ref:16-17
+};
+
+template <typename T>
+GD_HD BoxGauss<T> box_gauss(const T* row, const PairParams<T>& P) {
+  BoxGauss<T> b;
+  T m;
+  b.cx = row[0] + P.off[0] * row[3];
+  b.cy = row[1] + P.off[1] * row[4];
+  b.cz = row[2] + P.off[2] * row[5];
+  b.a = (T)0.5 * clamp_extent(row[3], &m);
+  b.b = (T)0.5 * clamp_extent(row[4], &m);
+  b.e = (T)0.5 * clamp_extent(row[5], &m);
+  Mth<T>::sincos(row[6], &b.s, &b.c);
+  return b;
+}
+
+template <typename T, int LOSS>
+GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P) {
+  PairGeom<T> g;
+  g.dx = p.cx - t.cx;
+  g.dy = p.cy - t.cy;
+  g.dz = p.cz - t.cz;
+  g.ap = p.a; g.bp = p.b; g.ep = p.e;
+  g.at = t.a; g.bt = t.b; g.et = t.e;
+  g.ma = g.mb = g.me = (T)0;
+  g.sp = p.s; g.cp = p.c;
+  g.sd = p.s * t.c - p.c * t.s;       // sin(r_p - r_t)
+  g.cd = p.c * t.c + p.s * t.s;       // cos(r_p - r_t)
+  return core_eval<T, LOSS, false>(g, P, (T*)0);
+}
+
+}  // namespace gd

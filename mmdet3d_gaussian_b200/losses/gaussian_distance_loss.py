@@ -1,0 +1,138 @@
+"""Drop-in ``GDLoss`` backed by the sm_100a kernels.
+
+Host-side mirror of the reference module
+``mmdet3d_gaussian/models/losses/gaussian_distance_loss.py`` (``ref:LINE``):
+same registry name, constructor (ref:261-278), ``forward`` signature
+(ref:280-286), assertions and error behaviour; the arithmetic of ref:8-248 and of
+mmdet's ``weighted_loss`` wrapper runs in one fused CUDA kernel
+(``csrc/gd_loss_kernels.cu``) reached through the C ABI.
+"""
+from copy import deepcopy
+
+import torch
+from torch import nn
+
+from .. import _lib, ops
+from ..registry import register_everywhere
+
+# loss_type -> (name of the one extra kwarg the distance accepts, its default)
+_FLAG = {'gwd3d': ('normalize', True),        # ref:43
+         'kld3d': ('sqrt', True),             # ref:110
+         'jd3d': ('sqrt', True),              # ref:190
+         'kld3d_symmax': ('sqrt', True),      # ref:202-203
+         'kld3d_symmin': ('sqrt', True),      # ref:215-216
+         'bd3d': ('sqrt', True),              # ref:145
+         'kfiou3d': ('sqrt', False)}          # ref:228 (accepted, ignored)
+
+
+def _scale_and_mode(reduction, avg_factor, n, loss_weight):
+    """mmdet ``weight_reduce_loss`` folded into one scalar.
+    Returns (scale, rows_out)."""
+    if avg_factor is None:
+        if reduction == 'mean':
+            # loss.mean(): divides by N (not by sum of weights); mean of empty is nan
+            return (loss_weight / n if n > 0 else float('nan')), False
+        if reduction == 'sum':
+            return loss_weight, False
+        return loss_weight, True
+    if reduction == 'mean':
+        return loss_weight / float(avg_factor), False
+    if reduction == 'none':
+        return loss_weight, True
+    raise ValueError('avg_factor can not be used with reduction="sum"')
+
+
+@register_everywhere
+class GDLoss(nn.Module):
+    """Gaussian-distance box regression loss (GWD / KLD / JD / sym-KLD / BCD / KFIoU).
+
+    Args mirror the reference (ref:261-263).  ``**kwargs`` are forwarded to the
+    distance: ``normalize`` for ``gwd3d``, ``sqrt`` for the others.  One extra,
+    backwards-compatible key is consumed here: ``variant`` ('auto' | 'staged' |
+    'bulk') selects the kernel variant.
+    """
+
+    BAG_GD_LOSS = tuple(_lib.LOSS_TYPES)          # ref:253-259
+
+    def __init__(self, loss_type, center_offset=(0, 0, 0.5), fun='log1p',
+                 tau=1.0, alpha=1.0, reduction='mean', loss_weight=1.0, **kwargs):
+        super().__init__()
+        assert reduction in ['none', 'sum', 'mean']               # ref:265
+        assert loss_type in self.BAG_GD_LOSS                      # ref:266
+        if loss_type not in ['kfiou3d']:
+            assert fun in ['log1p', 'none']                       # ref:267-268
+        else:
+            assert fun in ['nlog', 'expm1', 'none']               # ref:269-270
+        self.loss_type = loss_type
+        self.center_offset = center_offset
+        self.fun = fun
+        self.tau = tau
+        self.alpha = alpha
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+        self.variant = kwargs.pop('variant', 'auto')
+        self.kwargs = kwargs                                      # ref:278
+
+    def _config(self, extra):
+        name, default = _FLAG[self.loss_type]
+        unknown = set(extra) - {name}
+        if unknown:
+            # the reference forwards **kwargs into the distance function, which
+            # raises TypeError on names it does not accept (ref:301-310)
+            raise TypeError(f'{self.loss_type}_loss() got an unexpected keyword '
+                            f'argument {sorted(unknown)[0]!r}')
+        return _lib.make_config(self.loss_type, self.fun, extra.get(name, default),
+                                self.tau, self.alpha, self.center_offset)
+
+    def forward(self, pred, target, weight=None, avg_factor=None,
+                reduction_override=None, **kwargs):
+        assert reduction_override in (None, 'none', 'mean', 'sum')   # ref:287
+        reduction = (
+            reduction_override if reduction_override else self.reduction)  # ref:288-289
+        if (weight is not None) and (reduction != 'none') and (
+                not ops.any_positive(weight)):                    # ref:290-291
+            return (pred * weight).sum()                          # ref:292
+        _kwargs = deepcopy(self.kwargs)                           # ref:293
+        _kwargs.update(kwargs)                                    # ref:294
+        cfg = self._config(_kwargs)
+        n = pred.numel() // 7
+        scale, rows_out = _scale_and_mode(reduction, avg_factor, n, self.loss_weight)
+        return ops.gd_loss(pred, target, weight, cfg, scale, rows_out=rows_out,
+                           variant=self.variant)
+
+    def extra_repr(self):
+        return (f'loss_type={self.loss_type!r}, fun={self.fun!r}, tau={self.tau}, '
+                f'alpha={self.alpha}, reduction={self.reduction!r}, '
+                f'loss_weight={self.loss_weight}')
+
+
+class GDPairwiseDistance(nn.Module):
+    """Batched pairwise matrix ``D[i,j] = post(distance(boxes1[i], boxes2[j]))``
+    (new surface): same ``loss_type`` / ``fun`` / ``tau`` /
+    ``alpha`` / ``center_offset`` / ``normalize|sqrt`` meaning as ``GDLoss``; no
+    weights, no reduction, no gradient."""
+
+    def __init__(self, loss_type, center_offset=(0, 0, 0.5), fun='log1p', tau=1.0,
+                 alpha=1.0, **kwargs):
+        super().__init__()
+        assert loss_type in _lib.LOSS_TYPES
+        if loss_type != 'kfiou3d':
+            assert fun in ['log1p', 'none']
+        else:
+            assert fun in ['nlog', 'expm1', 'none']
+        name, default = _FLAG[loss_type]
+        unknown = set(kwargs) - {name}
+        if unknown:
+            raise TypeError(f'unexpected keyword argument {sorted(unknown)[0]!r}')
+        self.loss_type = loss_type
+        self.cfg = _lib.make_config(loss_type, fun, kwargs.get(name, default), tau,
+                                    alpha, center_offset)
+
+    @torch.no_grad()
+    def forward(self, boxes1, boxes2):
+        return ops.pairwise_distance(boxes1, boxes2, self.cfg)
+
+    @torch.no_grad()
+    def row_argmin(self, boxes1, boxes2):
+        """``(min_j D[i,j], argmin_j D[i,j])`` without writing the matrix."""
+        return ops.pairwise_row_argmin(boxes1, boxes2, self.cfg)

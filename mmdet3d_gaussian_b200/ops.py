@@ -1,0 +1,229 @@
+"""Torch-facing operators over the C ABI (``include/gd_loss_b200.h``).
+
+PyTorch is plumbing here: it owns the device memory, the stream and the autograd
+graph edge.  All arithmetic happens in the CUDA library; there is no eager or CPU
+fallback -- non-CUDA tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_WORKSPACES = {}
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name} must be a torch.Tensor, got {type(t)}')
+    if not t.is_cuda:
+        raise RuntimeError(
+            f'gd_loss_b200: {name} is on {t.device}; this implementation is CUDA-only '
+            f'(sm_100a) and has no CPU fallback')
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(device):
+    """Zero-initialised scratch (ticket + per-CTA partials), one per (device, stream).
+    The kernels leave it zeroed, so it is cleared exactly once."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        nbytes = _lib.load().gd_loss_workspace_bytes(0)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _rows7(t):
+    """[..., 7] -> [N, 7] fp32 with unit inner stride (row stride free)."""
+    t = t.reshape(-1, 7)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.shape[0] > 0 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _row_stride(t):
+    """Row stride in elements of a [N,7] tensor (7 when there is at most one row)."""
+    return t.stride(0) if t.shape[0] > 1 else 7
+
+
+def _launch(cfg, pred, target, weight, wmode, scale, want_sum, want_rows, want_grad,
+            variant):
+    lib = _lib.load()
+    n = pred.shape[0]
+    dev = pred.device
+    loss = torch.empty((), dtype=torch.float32, device=dev) if want_sum else None
+    rows = torch.empty((n,), dtype=torch.float32, device=dev) if want_rows else None
+    grad = torch.empty((n, 7), dtype=torch.float32, device=dev) if want_grad else None
+    ws = _workspace(dev) if want_sum else None
+    wstride = 0
+    if wmode == _lib.WEIGHT_ROW:
+        wstride = weight.stride(0) if n > 1 else 1
+    elif wmode == _lib.WEIGHT_ROW7:
+        wstride = _row_stride(weight)
+    with torch.cuda.device(dev):
+        code = lib.gd_loss_fwd_bwd(
+            ctypes.byref(cfg), _ptr(pred), _row_stride(pred), _ptr(target),
+            _row_stride(target), _ptr(weight), wmode, wstride, n, float(scale),
+            _ptr(loss), _ptr(rows), _ptr(grad), _ptr(ws),
+            ws.numel() if ws is not None else 0, _lib.VARIANTS[variant], _stream_ptr())
+    _lib.check(code, 'gd_loss_fwd_bwd')
+    return loss, rows, grad
+
+
+class _GDLossFunction(torch.autograd.Function):
+    """Fused forward+backward.  The gradient w.r.t. ``pred`` is produced by the
+    forward launch (one HBM pass, 88 B/pair) with every known-at-forward scalar
+    folded in; ``backward`` only folds the incoming ``grad_output`` (a kernel that
+    exits immediately when it is exactly 1)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, cfg, wmode, scale, rows_out, variant):
+        need_grad = bool(ctx.needs_input_grad[0])
+        loss, rows, grad = _launch(cfg, pred, target, weight, wmode, scale,
+                                   not rows_out, rows_out, need_grad, variant)
+        ctx.gd = (cfg, wmode, scale, rows_out, variant)
+        ctx.grad_buf = grad
+        ctx.save_for_backward(pred, target, weight)
+        ctx.set_materialize_grads(False)
+        return rows if rows_out else loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if grad_out is None or not ctx.needs_input_grad[0]:
+            return (None,) * 8
+        cfg, wmode, scale, rows_out, variant = ctx.gd
+        pred, target, weight = ctx.saved_tensors
+        grad = ctx.grad_buf
+        ctx.grad_buf = None
+        if grad is None:
+            # second backward through the same node (retain_graph=True) or grad
+            # mode was off at forward time: regenerate with the fused kernel
+            _, _, grad = _launch(cfg, pred, target, weight, wmode, scale, False, False,
+                                 True, variant)
+        lib = _lib.load()
+        n = grad.shape[0]
+        go = grad_out.detach()
+        if go.dtype != torch.float32:
+            go = go.float()
+        with torch.cuda.device(grad.device):
+            if rows_out:
+                go = go.reshape(-1)
+                code = lib.gd_scale_grad_rows(_ptr(grad), n, _ptr(go),
+                                              go.stride(0) if n > 1 else 1, _stream_ptr())
+                _lib.check(code, 'gd_scale_grad_rows')
+            else:
+                code = lib.gd_scale_grad(_ptr(grad), n, _ptr(go), _stream_ptr())
+                _lib.check(code, 'gd_scale_grad')
+        return (grad,) + (None,) * 7
+
+
+def gd_loss(pred, target, weight, cfg, scale, rows_out=False, variant='auto'):
+    """``scale * sum_i w_i loss_i`` (0-dim) or ``scale * w_i * loss_i`` ([N]).
+
+    ``pred``/``target``: ``[..., 7]``; ``weight``: ``None``, ``[N]`` or ``[N,7]``
+    (mean over the last dim, reference ``gaussian_distance_loss.py:295-296``)."""
+    _require_cuda(pred, 'pred')
+    _require_cuda(target, 'target')
+    if target.requires_grad:
+        raise NotImplementedError(
+            'gd_loss_b200: gradients w.r.t. `target` are not produced (the reference '
+            'call sites build targets without grad); detach the target')
+    out_shape_rows = pred.shape[:-1]
+    in_dtype = pred.dtype
+    p2 = _rows7(pred)
+    t2 = _rows7(target.detach())
+    if p2.shape != t2.shape:
+        raise ValueError(f'pred {tuple(pred.shape)} and target {tuple(target.shape)} differ')
+    n = p2.shape[0]
+    wmode, w2 = _lib.WEIGHT_NONE, None
+    if weight is not None:
+        _require_cuda(weight, 'weight')
+        w = weight.detach()
+        if w.dtype != torch.float32:
+            w = w.float()
+        if w.shape == pred.shape:
+            wmode, w2 = _lib.WEIGHT_ROW7, w.reshape(-1, 7)
+            if n > 0 and w2.stride(1) != 1:
+                w2 = w2.contiguous()
+        elif w.numel() == n and w.shape == pred.shape[:-1]:
+            wmode, w2 = _lib.WEIGHT_ROW, w.reshape(-1)
+        else:
+            raise ValueError(f'weight shape {tuple(weight.shape)} must be '
+                             f'{tuple(pred.shape)} or {tuple(pred.shape[:-1])}')
+    out = _GDLossFunction.apply(p2, t2, w2, cfg, wmode, scale, rows_out, variant)
+    if rows_out and len(out_shape_rows) != 1:
+        out = out.reshape(out_shape_rows)
+    if in_dtype != torch.float32 and in_dtype.is_floating_point:
+        out = out.to(in_dtype)
+    return out
+
+
+def any_positive(weight):
+    """``bool(torch.any(weight > 0))`` -- the early-return probe of
+    ``GDLoss.forward`` (reference ``gaussian_distance_loss.py:290``); like the
+    reference it costs one device->host sync."""
+    _require_cuda(weight, 'weight')
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    flag = torch.empty((1,), dtype=torch.int32, device=w.device)
+    with torch.cuda.device(w.device):
+        code = _lib.load().gd_any_positive(_ptr(w), w.numel(), _ptr(flag), _stream_ptr())
+    _lib.check(code, 'gd_any_positive')
+    return bool(flag.item())
+
+
+def _boxes(t, name):
+    _require_cuda(t, name)
+    if t.dim() != 2 or t.shape[1] != 7:
+        raise ValueError(f'{name} must be [K,7], got {tuple(t.shape)}')
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def pairwise_distance(boxes1, boxes2, cfg, out=None):
+    """``[N,M]`` matrix ``out[i,j] = post(distance(boxes1[i], boxes2[j]))``."""
+    b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
+    n, m = b1.shape[0], b2.shape[0]
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        code = _lib.load().gd_pairwise(ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m,
+                                       _ptr(out), out.stride(0) if n > 1 else max(m, 1),
+                                       _stream_ptr())
+    _lib.check(code, 'gd_pairwise')
+    return out
+
+
+def pairwise_row_argmin(boxes1, boxes2, cfg):
+    """Per row of the (never materialised) matrix: ``(min_j, argmin_j)``."""
+    b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
+    n, m = b1.shape[0], b2.shape[0]
+    if m == 0:
+        raise ValueError('pairwise_row_argmin needs at least one column box')
+    vmin = torch.empty((n,), dtype=torch.float32, device=b1.device)
+    idx = torch.empty((n,), dtype=torch.int32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        code = _lib.load().gd_pairwise_row_argmin(ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m,
+                                                  _ptr(vmin), _ptr(idx), _stream_ptr())
+    _lib.check(code, 'gd_pairwise_row_argmin')
+    return vmin, idx.long()
+
+
+def launch_count():
+    return int(_lib.load().gd_launch_count())

@@ -1,0 +1,384 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).
+
+Everything goes through the public ``GDLoss`` module -> ctypes -> C ABI
+(``libgdloss_b200.so``) -> CUDA kernels; the oracle (``oracle/gd_oracle.py``,
+fp64 on CPU) and the golden vectors written from the unmodified reference
+(``tests/golden/gd_golden.npz``) are only the checkers.
+
+Parity rule, tolerance from BASELINE.json north_star (1e-5
+relative in fp32):
+  * reduced loss:            |ours - ref| <= 1e-5 |ref|
+  * per-row loss / row grad: ||ours - ref|| <= 1e-5 max(||ref||, row floor)
+  * rows whose fp64 reference gradient is non-finite are excluded and counted.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from mmdet3d_gaussian_b200 import GDLoss, GDPairwiseDistance, build_loss, ops, synth
+from mmdet3d_gaussian_b200 import _lib
+from oracle import gd_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+ALL_TYPES = ('gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'kld3d_symmin', 'bd3d', 'kfiou3d')
+VARIANTS = ('bulk', 'staged')
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _need_cuda():
+    assert torch.cuda.is_available(), 'these tests need a CUDA device'
+    assert _lib.loaded_path() is None or 'libgdloss_b200' in _lib.loaded_path()
+    _lib.load()
+    yield
+
+
+def dev(t):
+    return None if t is None else t.cuda()
+
+
+def run_ours(kwargs, pred, target, weight=None, avg_factor=None, override=None,
+             variant='auto', grad_output=None, **fw):
+    mod = GDLoss(variant=variant, **kwargs)
+    p = pred.detach().clone().cuda().requires_grad_(True)
+    out = mod(p, dev(target), dev(weight), avg_factor=avg_factor,
+              reduction_override=override, **fw)
+    if out.dim() == 0:
+        out.backward(grad_output)
+    else:
+        out.backward(torch.ones_like(out) if grad_output is None else grad_output)
+    return out.detach().cpu().double().numpy(), p.grad.cpu().double().numpy()
+
+
+def run_oracle(kwargs, pred, target, weight=None, avg_factor=None, override=None):
+    mod = gd_oracle.GDLossOracle(**kwargs)
+    w = None if weight is None else weight.double()
+    loss, grad = gd_oracle.loss_and_grad(mod, pred.double(), target.double(), w,
+                                         avg_factor=avg_factor, reduction_override=override)
+    return loss.numpy(), grad.numpy()
+
+
+def row_check(ours_loss, ours_grad, ref_loss, ref_grad, rtol=RTOL, loss_floor=1e-3,
+              grad_floor=1e-2, what=''):
+    """Returns number of excluded (non-finite reference) rows; asserts the rest."""
+    fin = np.isfinite(ref_grad).all(axis=1) & np.isfinite(ref_loss)
+    el = np.abs(ours_loss - ref_loss)[fin] / np.maximum(np.abs(ref_loss[fin]), loss_floor)
+    gn = np.linalg.norm(ref_grad[fin], axis=1)
+    eg = np.linalg.norm(ours_grad[fin] - ref_grad[fin], axis=1) / np.maximum(gn, grad_floor)
+    assert el.size == 0 or el.max() <= rtol, f'{what}: row loss err {el.max():.3e}'
+    assert eg.size == 0 or eg.max() <= rtol, f'{what}: row grad err {eg.max():.3e}'
+    return int((~fin).sum())
+
+
+# ---------------------------------------------------------------------------
+# 1. golden vectors written by the unmodified reference
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_golden_vectors(golden, variant):
+    z, manifest = golden
+    checked = excluded = 0
+    for e in manifest:
+        cid, inputs = e['id'], e['inputs']
+        pred = torch.from_numpy(z[f'in/{inputs}/pred'])
+        target = torch.from_numpy(z[f'in/{inputs}/target'])
+        weight = (torch.from_numpy(z[f'case/{cid}/weight'])
+                  if e['weight_mode'] is not None else None)
+        if 'raises' in e:
+            with pytest.raises((ValueError, RuntimeError)):
+                run_ours(e['kwargs'], pred, target, weight, e['avg_factor'], e['override'],
+                         variant)
+            continue
+        ours_l, ours_g = run_ours(e['kwargs'], pred, target, weight, e['avg_factor'],
+                                  e['override'], variant)
+        ref_l, ref_g = z[f'case/{cid}/loss_f64'], z[f'case/{cid}/grad_f64']
+        lt = e['kwargs']['loss_type']
+        # kfiou has an inherent 1 - c*k cancellation (the reference's own fp32 error is
+        # 1e-3 on these sets); the near-tie max/min rows of symmax/symmin can pick the
+        # other branch.  Both get the documented looser floor.
+        loose = lt == 'kfiou3d' or inputs in ('edge',) or \
+            (lt in ('kld3d_symmax', 'kld3d_symmin') and inputs != 'kitti_s0.3')
+        rtol = 2e-3 if loose else RTOL
+        if ref_l.ndim == 0:
+            assert abs(ours_l - ref_l) <= rtol * max(abs(ref_l), 1e-6), (e, ours_l, ref_l)
+            fin = np.isfinite(ref_g).all(1)
+            scale = max(np.abs(ref_g[fin]).max(), 1e-12)
+            err = np.linalg.norm(ours_g[fin] - ref_g[fin], axis=1) / np.maximum(
+                np.linalg.norm(ref_g[fin], axis=1), 1e-2 * scale)
+            assert err.max() <= rtol, (e, err.max())
+        else:
+            sc = max(np.abs(ref_l[np.isfinite(ref_l)]).max(), 1e-6)
+            excluded += row_check(ours_l, ours_g, ref_l, ref_g, rtol,
+                                  loss_floor=1e-3 * sc, grad_floor=1e-2, what=str(e))
+        checked += 1
+    assert checked >= 280
+    print(f'golden[{variant}]: {checked} cases, {excluded} non-finite reference rows excluded')
+
+
+# ---------------------------------------------------------------------------
+# 2. fresh seeded inputs vs the fp64 oracle, all distances x options (C1 size)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('loss_type', ('gwd3d', 'kld3d', 'bd3d', 'jd3d'))
+@pytest.mark.parametrize('sigma', (0.3, 0.05, 0.005))
+def test_rows_vs_oracle(loss_type, sigma):
+    n = 100_000 if sigma == 0.3 else 20_000
+    pred, target, _ = synth.make_pairs(n, 'kitti', seed=3, sigma=sigma)
+    for fun, tau in (('log1p', 0.0), ('none', 1.0)):
+        kw = dict(loss_type=loss_type, fun=fun, tau=tau, reduction='none', loss_weight=5.0)
+        ref_l, ref_g = run_oracle(kw, pred, target)
+        for variant in VARIANTS:
+            l, g = run_ours(kw, pred, target, variant=variant)
+            row_check(l, g, ref_l, ref_g, RTOL, loss_floor=1e-6, grad_floor=1e-6,
+                      what=f'{loss_type}/{fun}/tau{tau}/s{sigma}/{variant}')
+
+
+@pytest.mark.parametrize('loss_type', ALL_TYPES)
+def test_reduced_vs_oracle_c1(loss_type):
+    """Config C1 shape: N=100k, weights [N], avg_factor, loss_weight=5."""
+    pred, target, w = synth.make_pairs(100_000, 'kitti', seed=0, weights='bernoulli')
+    fun = 'none' if loss_type == 'kfiou3d' else 'log1p'
+    af = float(max(int((w > 0).sum()), 1))
+    for tau in (0.0, 1.0):
+        kw = dict(loss_type=loss_type, fun=fun, tau=tau, loss_weight=5.0)
+        ref_l, ref_g = run_oracle(kw, pred, target, w, af)
+        l, g = run_ours(kw, pred, target, w, af)
+        assert abs(l - ref_l) <= RTOL * abs(ref_l)
+        gn = np.linalg.norm(ref_g, axis=1)
+        tol = 2e-4 if loss_type == 'kfiou3d' else RTOL
+        err = np.linalg.norm(g - ref_g, axis=1) / np.maximum(gn, 1e-3 * gn.max())
+        assert err.max() <= tol, (loss_type, tau, err.max())
+
+
+# ---------------------------------------------------------------------------
+# 3. the drop-in surface: shapes, strides, alignment, tails, reductions, autograd
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('n', (0, 1, 2, 3, 4, 5, 255, 256, 257, 1023, 4099))
+def test_tail_sizes(n):
+    pred, target, w = synth.make_pairs(max(n, 1), 'waymo', seed=n, weights='bernoulli')
+    pred, target, w = pred[:n], target[:n], w[:n] + 0.1
+    kw = dict(loss_type='bd3d', fun='log1p', tau=1.0, reduction='sum')
+    if n == 0:
+        out = GDLoss(**kw)(pred.cuda().requires_grad_(True), target.cuda())
+        assert out.item() == 0.0
+        out = GDLoss(**dict(kw, reduction='mean'))(pred.cuda(), target.cuda())
+        assert math.isnan(out.item())            # torch: mean of empty is nan
+        return
+    ref_l, ref_g = run_oracle(kw, pred, target, w)
+    for variant in ('auto', 'staged'):
+        l, g = run_ours(kw, pred, target, w, variant=variant)
+        assert abs(l - ref_l) <= RTOL * abs(ref_l)
+        assert np.abs(g - ref_g).max() <= RTOL * max(np.abs(ref_g).max(), 1e-6)
+
+
+def test_strided_and_unaligned_views():
+    """CenterGDHead passes [..., :7] views of width-9 / width-11 rows
+    (gd_centerpoint_head.py:413-423); offset views are only 4-byte aligned."""
+    n = 3000
+    pred, target, _ = synth.make_pairs(n, 'nuscenes', seed=4)
+    kw = dict(loss_type='gwd3d', fun='log1p', tau=0.0, reduction='mean', loss_weight=2.0)
+    ref_l, ref_g = run_oracle(kw, pred, target, None, 17.0)
+    wide_p = torch.randn(n, 9).cuda()
+    wide_p[:, :7] = pred.cuda()
+    wide_t = torch.randn(n, 11).cuda()
+    wide_t[:, :7] = target.cuda()
+    wide_p.requires_grad_(True)
+    out = GDLoss(**kw)(wide_p[..., :7], wide_t[..., :7], avg_factor=17.0)
+    out.backward()
+    assert abs(out.item() - ref_l) <= RTOL * abs(ref_l)
+    g = wide_p.grad.cpu().double().numpy()
+    assert np.abs(g[:, :7] - ref_g).max() <= RTOL * np.abs(ref_g).max()
+    assert np.all(g[:, 7:] == 0)
+    # unaligned base pointer: rows 1.. of a contiguous buffer (28 B offset)
+    p = pred.cuda().clone().requires_grad_(True)
+    out2 = GDLoss(**kw)(p[1:], target.cuda()[1:], avg_factor=17.0)
+    out2.backward()
+    ref_l2, ref_g2 = run_oracle(kw, pred[1:], target[1:], None, 17.0)
+    assert abs(out2.item() - ref_l2) <= RTOL * abs(ref_l2)
+    assert np.abs(p.grad.cpu().double().numpy()[1:] - ref_g2).max() <= RTOL * np.abs(ref_g2).max()
+    # explicit bulk request on a layout it cannot take must fail loudly, not fall back
+    with pytest.raises(RuntimeError):
+        GDLoss(variant='bulk', **kw)(p[1:], target.cuda()[1:])
+    # batched [B, K, 7] input
+    p3 = pred.cuda().reshape(30, 100, 7)
+    out3 = GDLoss(**kw)(p3, target.cuda().reshape(30, 100, 7), avg_factor=17.0)
+    assert abs(out3.item() - ref_l) <= RTOL * abs(ref_l)
+
+
+def test_early_return_and_weight_shapes():
+    pred, target, _ = synth.make_pairs(500, 'kitti', seed=8)
+    p = pred.cuda().requires_grad_(True)
+    w0 = torch.zeros(500, 7).cuda()
+    out = GDLoss('gwd3d', loss_weight=5.0)(p, target.cuda(), w0, avg_factor=3)   # ref:290-292
+    out.backward()
+    assert out.item() == 0.0 and torch.equal(p.grad, w0)
+    with pytest.raises(RuntimeError):                 # [N] zero weights: reference raises too
+        GDLoss('gwd3d')(p, target.cuda(), torch.zeros(500).cuda())
+    rows = GDLoss('gwd3d', reduction='none')(p, target.cuda(), w0)   # 'none' skips the early return
+    assert rows.shape == (500,) and float(rows.abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        GDLoss('kld3d', reduction='sum')(p, target.cuda(), avg_factor=2.0)
+    with pytest.raises(ValueError):
+        GDLoss('kld3d')(p, target.cuda(), torch.ones(500, 1).cuda())
+    with pytest.raises(TypeError):
+        GDLoss('kld3d', normalize=True)(p, target.cuda())
+    with pytest.raises(AssertionError):
+        GDLoss('gwd3d', fun='expm1')
+    with pytest.raises(AssertionError):
+        GDLoss('gwd3d')(p, target.cuda(), reduction_override='max')
+    with pytest.raises(NotImplementedError):
+        GDLoss('gwd3d')(p, target.cuda().requires_grad_(True))
+    with pytest.raises(RuntimeError):
+        GDLoss('gwd3d')(pred, target)                 # CPU tensors: no fallback
+
+
+def test_autograd_contract():
+    pred, target, w = synth.make_pairs(4096 + 3, 'kitti', seed=12, weights='bernoulli')
+    kw = dict(loss_type='kld3d', fun='log1p', tau=1.0, loss_weight=5.0)
+    ref_l, ref_g = run_oracle(kw, pred, target, w, 100.0)
+    # arbitrary upstream scalar (fp16 loss scaling): grad_output = 1024
+    l, g = run_ours(kw, pred, target, w, 100.0, grad_output=torch.tensor(1024.0).cuda())
+    assert np.abs(g - 1024.0 * ref_g).max() <= RTOL * 1024.0 * np.abs(ref_g).max()
+    # composed graph: (2*loss + 1).backward()
+    p = pred.cuda().requires_grad_(True)
+    mod = GDLoss(**kw)
+    (2.0 * mod(p * 1.0, target.cuda(), w.cuda(), avg_factor=100.0) + 1.0).backward()
+    assert np.abs(p.grad.cpu().double().numpy() - 2.0 * ref_g).max() <= RTOL * 2 * np.abs(ref_g).max()
+    # retain_graph: second backward regenerates the gradient
+    p2 = pred.cuda().requires_grad_(True)
+    out = mod(p2, target.cuda(), w.cuda(), avg_factor=100.0)
+    out.backward(retain_graph=True)
+    g1 = p2.grad.clone()
+    p2.grad = None
+    out.backward()
+    assert torch.equal(g1, p2.grad)
+    # reduction='none' with a vector grad_output
+    kwn = dict(kw, reduction='none')
+    go = torch.rand(pred.shape[0]).cuda() + 0.5
+    ln, gn = run_ours(kwn, pred, target, w, grad_output=go)
+    omod = gd_oracle.GDLossOracle(**kwn)
+    _, ogn = gd_oracle.loss_and_grad(omod, pred.double(), target.double(), w.double(),
+                                     grad_output=go.cpu().double())
+    assert np.abs(gn - ogn.numpy()).max() <= RTOL * np.abs(ogn.numpy()).max()
+    # no_grad / eval: forward only, same value
+    with torch.no_grad():
+        l0 = mod(pred.cuda(), target.cuda(), w.cuda(), avg_factor=100.0)
+    assert abs(l0.item() - ref_l) <= RTOL * abs(ref_l)
+    # registry + state-free module
+    built = build_loss(dict(type='GDLoss', loss_type='gwd3d', fun='log1p', tau=0.0,
+                            loss_weight=5.0))
+    assert isinstance(built, GDLoss) and len(built.state_dict()) == 0
+
+
+# ---------------------------------------------------------------------------
+# 4. size-independent properties at BASELINE.json's full size (C2: 2^24 pairs)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('loss_type', ('kld3d', 'bd3d', 'gwd3d'))
+def test_full_size_properties(loss_type):
+    n = 1 << 24
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=0, device='cuda')
+    kw = dict(loss_type=loss_type, fun='log1p', tau=0.0, reduction='sum')
+    mod = GDLoss(**kw)
+    p = pred.requires_grad_(True)
+    total = mod(p, target, w)
+    total.backward()
+    g_full = p.grad
+    # (a) determinism: bit-identical on a second run
+    p.grad = None
+    total2 = mod(p, target, w)
+    total2.backward()
+    assert torch.equal(total, total2) and torch.equal(g_full, p.grad)
+    # (b) shard additivity (the multi-GPU partition): sum of 8 row shards == whole
+    parts = [mod(pred.detach()[i * (n // 8):(i + 1) * (n // 8)],
+                 target[i * (n // 8):(i + 1) * (n // 8)],
+                 w[i * (n // 8):(i + 1) * (n // 8)]).double() for i in range(8)]
+    assert abs(sum(parts).item() - total.double().item()) <= 1e-6 * abs(total.item())
+    # (c) staged and bulk variants agree bit-for-bit per row (same math, different data path)
+    rows_b = GDLoss(**dict(kw, reduction='none', variant='bulk'))(pred.detach(), target, w)
+    rows_s = GDLoss(**dict(kw, reduction='none', variant='staged'))(pred.detach(), target, w)
+    assert torch.equal(rows_b, rows_s)
+    # (d) checksum of rows == reduced value; linearity in loss_weight
+    assert abs(rows_b.double().sum().item() - total.double().item()) <= 1e-6 * abs(total.item())
+    t5 = GDLoss(**dict(kw, loss_weight=5.0))(pred.detach(), target, w)
+    assert abs(t5.item() - 5.0 * total.item()) <= 2e-6 * abs(t5.item())
+    # (e) identity: distance(box, box) == 0 exactly, for every row
+    ident = GDLoss(**dict(kw, reduction='none'))(target, target)
+    assert float(ident.abs().max()) == 0.0
+    # (f) sampled rows vs the fp64 oracle
+    idx = torch.randint(0, n, (20000,), device='cuda')
+    rl, rg = run_oracle(dict(kw, reduction='none'), pred.detach()[idx].cpu(),
+                        target[idx].cpu(), w[idx].cpu())
+    row_check(rows_b[idx].cpu().double().numpy(), g_full[idx].cpu().double().numpy(),
+              rl, rg, RTOL, 1e-6, 1e-6, what=f'{loss_type} full size sample')
+
+
+# ---------------------------------------------------------------------------
+# 5. pairwise matrix + indices
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('loss_type', ALL_TYPES)
+def test_pairwise_vs_oracle(loss_type):
+    b1, _, _ = synth.make_pairs(700, 'waymo', seed=21)
+    b2 = synth.make_targets(37, 'waymo', seed=22)
+    fun = 'none' if loss_type == 'kfiou3d' else 'log1p'
+    pw = GDPairwiseDistance(loss_type, fun=fun, tau=1.0)
+    mat = pw(b1.cuda(), b2.cuda())
+    ref = gd_oracle.pairwise_distance(b1.double(), b2.double(), loss_type, fun=fun, tau=1.0)
+    tol = 2e-4 if loss_type == 'kfiou3d' else RTOL
+    err = (mat.cpu().double() - ref).abs() / ref.abs().clamp_min(1e-3)
+    assert err.max().item() <= tol, err.max().item()
+    # fused arg-reduction == argmin of OUR matrix, bit-exact (values and indices)
+    vmin, idx = pw.row_argmin(b1.cuda(), b2.cuda())
+    tv, ti = mat.min(dim=1)
+    assert torch.equal(idx, ti) and torch.equal(vmin, tv)
+    # vs the fp64 oracle indices, with the tie-margin audit of SURVEY.md section 7
+    top2 = ref.topk(2, dim=1, largest=False).values
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5 * top2[:, 1].abs().clamp_min(1e-3)
+    assert torch.equal(idx.cpu()[clear], ref.argmin(1)[clear])
+    assert clear.float().mean().item() > 0.95
+
+
+def test_pairwise_c4_consistency():
+    """Config C4 shape (200k anchors x 256 GT): matrix rows equal the element-wise
+    kernel on the expanded pairs; fused argmin is bit-exact with the matrix."""
+    anchors = synth.make_anchor_grid(200_000, 'waymo', device='cuda')
+    gts = synth.make_targets(256, 'waymo', seed=5, device='cuda')
+    gts[:, 0] = gts[:, 0] * 2 - 70
+    pw = GDPairwiseDistance('gwd3d', fun='log1p', tau=1.0)
+    mat = pw(anchors, gts)
+    vmin, idx = pw.row_argmin(anchors, gts)
+    tv, ti = mat.min(dim=1)
+    assert torch.equal(idx, ti) and torch.equal(vmin, tv)
+    rows = torch.randint(0, 200_000, (64,), device='cuda')
+    el = GDLoss('gwd3d', fun='log1p', tau=1.0, reduction='none')
+    for r in rows.tolist()[:16]:
+        ref = el(anchors[r:r + 1].expand(256, 7).contiguous(), gts)
+        assert torch.allclose(mat[r], ref, rtol=RTOL, atol=1e-7)
+    # per-GT best anchor (column argmin) from the matrix vs the fp64 oracle on a slice
+    sl = anchors[:4096].cpu().double()
+    ref = gd_oracle.pairwise_distance(sl, gts.cpu().double(), 'gwd3d', fun='log1p', tau=1.0)
+    ours = mat[:4096].cpu().double()
+    assert ((ours - ref).abs() / ref.abs().clamp_min(1e-3)).max().item() <= RTOL
+
+
+# ---------------------------------------------------------------------------
+# 6. host-buffer entry point (bench e2e path)
+# ---------------------------------------------------------------------------
+def test_host_pipeline_matches_device_path():
+    import ctypes
+    n = 300_000 + 2
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=31, weights='bernoulli')
+    pred, target, w = pred.pin_memory(), target.pin_memory(), w.pin_memory()
+    grad = torch.empty(n, 7).pin_memory()
+    loss = torch.zeros(1).pin_memory()
+    cfg = _lib.make_config('bd3d', 'log1p', True, 0.0, 1.0, (0, 0, 0.5))
+    lib = _lib.load()
+    code = lib.gd_loss_fwd_bwd_host(ctypes.byref(cfg), pred.data_ptr(), target.data_ptr(),
+                                    w.data_ptr(), _lib.WEIGHT_ROW, n, 5.0 / n,
+                                    loss.data_ptr(), grad.data_ptr(), 0, 65536)
+    _lib.check(code, 'gd_loss_fwd_bwd_host')
+    p = pred.cuda().requires_grad_(True)
+    out = GDLoss('bd3d', fun='log1p', tau=0.0, loss_weight=5.0)(p, target.cuda(), w.cuda())
+    out.backward()
+    assert abs(loss.item() - out.item()) <= 1e-6 * abs(out.item())
+    assert torch.equal(grad, p.grad.cpu())

@@ -1,0 +1,162 @@
+"""CPU tests of the kernel's per-pair math (csrc/gd_math.cuh), host-compiled.
+
+TEST-ONLY build (tests/host_math/harness.cpp, g++): the float64 instantiation
+pins the hand-derived closed forms and analytic gradients to the fp64 oracle's
+autograd (<= 1e-9), the float32 instantiation previews the device arithmetic
+and is required to beat the 1e-5 parity budget (and the reference's own fp32
+error) on the sigma in {0.3, 0.05, 0.005} distributions.  The shipped library has
+no host compute path; nothing here is reachable from the product.
+"""
+import ctypes
+import itertools
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from mmdet3d_gaussian_b200 import synth
+from oracle import gd_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LT = ['gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'kld3d_symmin', 'bd3d', 'kfiou3d']
+FUN = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
+
+
+@pytest.fixture(scope='module')
+def hostlib():
+    out = os.path.join(tempfile.mkdtemp(prefix='gd_host_math_'), 'gd_host_math.so')
+    subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-shared', '-fPIC',
+                    '-x', 'c++', os.path.join(HERE, 'host_math', 'harness.cpp'), '-o', out],
+                   check=True)
+    return ctypes.CDLL(out)
+
+
+def host_eval(lib, lt, pred, target, off, alpha, tau, fun, flag, dt):
+    n = pred.shape[0]
+    npdt = np.float64 if dt == 'f64' else np.float32
+    p = np.ascontiguousarray(pred.numpy().astype(npdt))
+    t = np.ascontiguousarray(target.numpy().astype(npdt))
+    ol, og = np.zeros(n, npdt), np.zeros((n, 7), npdt)
+    getattr(lib, 'gd_host_eval_' + dt)(
+        ctypes.c_int(LT.index(lt)), ctypes.c_long(n), p.ctypes.data_as(ctypes.c_void_p),
+        t.ctypes.data_as(ctypes.c_void_p), (ctypes.c_double * 3)(*off), ctypes.c_double(alpha),
+        ctypes.c_double(tau), ctypes.c_int(FUN[fun]), ctypes.c_int(int(flag)),
+        ol.ctypes.data_as(ctypes.c_void_p), og.ctypes.data_as(ctypes.c_void_p))
+    return ol.astype(np.float64), og.astype(np.float64)
+
+
+def oracle_eval(lt, pred, target, off, alpha, tau, fun, flag, dtype=torch.float64):
+    kw = {'normalize' if lt == 'gwd3d' else 'sqrt': flag}
+    m = gd_oracle.GDLossOracle(lt, center_offset=off, fun=fun, tau=tau, alpha=alpha,
+                               reduction='none', **kw)
+    loss, g = gd_oracle.loss_and_grad(m, pred.to(dtype), target.to(dtype))
+    return loss.double().numpy(), g.double().numpy()
+
+
+@pytest.mark.parametrize('lt', LT)
+def test_closed_forms_and_gradients_fp64(hostlib, lt):
+    funs = ['nlog', 'expm1', 'none'] if lt == 'kfiou3d' else ['log1p', 'none']
+    for sigma in (None, 0.05):
+        pred, target, _ = synth.make_pairs(1500, 'kitti', seed=5, sigma=sigma)
+        for fun, tau, alpha, flag, off in itertools.product(
+                funs, (0.0, 1.0, 2.5), (1.0, 0.5), (True, False),
+                ((0, 0, 0.5), (0.1, -0.2, 0.3))):
+            a = (lt, pred, target, off, alpha, tau, fun, flag)
+            ol, og = host_eval(hostlib, *a, 'f64')
+            rl, rg = oracle_eval(*a)
+            el = np.max(np.abs(ol - rl) / np.maximum(np.abs(rl), 1e-3))
+            eg = np.max(np.abs(og - rg) / np.maximum(np.abs(rg).max(1, keepdims=True), 1e-3))
+            assert el < 1e-9 and eg < 1e-8, (a[0], a[3:], sigma, el, eg)
+
+
+@pytest.mark.parametrize('lt', ['gwd3d', 'kld3d', 'jd3d', 'bd3d'])
+@pytest.mark.parametrize('sigma', [0.3, 0.05, 0.005])
+def test_fp32_arithmetic_within_budget(hostlib, lt, sigma):
+    """Per-row error of the kernel's float32 formulation vs fp64, next to the
+    reference formulation's own float32 error (the oracle run in float32)."""
+    pred, target, _ = synth.make_pairs(50_000, 'kitti', seed=5, sigma=sigma)
+    a = (lt, pred, target, (0, 0, 0.5), 1.0, 0.0, 'log1p', True)
+    ol, og = host_eval(hostlib, *a, 'f32')
+    rl, rg = oracle_eval(*a)
+    fl, fg = oracle_eval(*a, dtype=torch.float32)
+    fin = np.isfinite(rg).all(1) & np.isfinite(fg).all(1)
+
+    def errs(l, g):
+        el = np.abs(l - rl)[fin] / np.maximum(np.abs(rl[fin]), 1e-30)
+        eg = np.linalg.norm(g - rg, axis=1)[fin] / np.maximum(
+            np.linalg.norm(rg, axis=1)[fin], 1e-30)
+        return el.max(), eg.max()
+    ours, ref32 = errs(ol, og), errs(fl, fg)
+    assert ours[0] <= 5e-6 and ours[1] <= 5e-6, (ours, ref32)
+    assert ours[0] <= ref32[0] and ours[1] <= ref32[1], (ours, ref32)
+
+
+def test_identity_is_exact_zero_fp32(hostlib):
+    _, target, _ = synth.make_pairs(2000, 'nuscenes', seed=1)
+    for lt in ('gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'kld3d_symmin', 'bd3d'):
+        ol, _ = host_eval(hostlib, lt, target, target, (0, 0, 0.5), 1.0, 0.0, 'log1p', True,
+                          'f32')
+        assert np.all(ol == 0.0), lt
+
+
+def test_degenerate_extents_stay_finite(hostlib):
+    """Extents at/below the 1e-7 clamp and at the 1e7 ceiling (reachable from the
+    shipped Waymo configs) must not overflow the fp32 formulation."""
+    p = torch.tensor([[0., 0., 0., 1e-7, 2e-8, -1.0, 0.3],
+                      [0., 0., 0., 2e7, 1e7, 1e7, 0.3],
+                      [1., 2., 3., 1.6, 3.9, 1.5, 0.1]])
+    t = torch.tensor([[0.1, 0.2, 0., 1.6, 3.9, 1.5, 0.1],
+                      [0.1, 0.2, 0., 1e-7, 1e-7, 1e-7, 0.1],
+                      [0., 0., 0., 1e-7, 2e-8, -1.0, 0.3]])
+    for lt in ('gwd3d', 'kld3d', 'jd3d', 'bd3d', 'kfiou3d'):
+        fun = 'none' if lt == 'kfiou3d' else 'log1p'
+        a = (lt, p, t, (0, 0, 0.5), 1.0, 0.0, fun, lt == 'gwd3d')
+        ol, _ = host_eval(hostlib, *a, 'f32')
+        rl, _ = oracle_eval(*a)
+        ok = np.isfinite(rl)
+        assert np.all(np.isfinite(ol[ok])), (lt, ol, rl)
+        assert np.allclose(ol[ok], rl[ok], rtol=2e-4, atol=1e-6), (lt, ol, rl)
+
+
+def test_sum_minus_log_ratios(hostlib):
+    fn = hostlib.gd_host_sum_minus_log_ratios_f32
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float] * 5
+    rng = np.random.default_rng(0)
+    for scale in (1e-4, 1e-2, 0.3, 2.0, 1e4):
+        q = np.abs(rng.normal(0, scale, (2000, 3))) if scale > 1 else \
+            rng.normal(0, scale, (2000, 3)).clip(-0.95, None)
+        r = (1.0 + q).astype(np.float32)
+        q = (r.astype(np.float64) - 1.0)                      # exact q for the rounded ratios
+        S = q.sum(1)
+        pair = q[:, 0] * q[:, 1] + q[:, 0] * q[:, 2] + q[:, 1] * q[:, 2] + q.prod(1)
+        # the quantity the kernel needs: sum(q + q^2/2) - log(prod r)
+        want = S + 0.5 * (q * q).sum(1) - np.log(r.astype(np.float64)).sum(1)
+        got = np.array([fn(np.float32(a), np.float32(b), *map(np.float32, c))
+                        for a, b, c in zip(S, pair, r)]) + 0.5 * (q * q).sum(1)
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+        assert rel.max() < 5e-6, (scale, rel.max())
+
+
+@pytest.mark.parametrize('lt', LT)
+def test_pairwise_value_path(hostlib, lt):
+    """Per-box precompute + angle-difference identities == element-wise oracle."""
+    b1, _, _ = synth.make_pairs(60, 'waymo', seed=2)
+    b2 = synth.make_targets(13, 'waymo', seed=3)
+    fun = 'none' if lt == 'kfiou3d' else 'log1p'
+    ref = gd_oracle.pairwise_distance(b1.double(), b2.double(), lt, fun=fun, tau=1.0).numpy()
+    for dt, tol in (('f64', 1e-10), ('f32', 2e-4 if lt == 'kfiou3d' else 1e-5)):
+        npdt = np.float64 if dt == 'f64' else np.float32
+        a1 = np.ascontiguousarray(b1.numpy().astype(npdt))
+        a2 = np.ascontiguousarray(b2.numpy().astype(npdt))
+        out = np.zeros((60, 13), npdt)
+        getattr(hostlib, 'gd_host_pairwise_' + dt)(
+            ctypes.c_int(LT.index(lt)), ctypes.c_long(60), ctypes.c_long(13),
+            a1.ctypes.data_as(ctypes.c_void_p), a2.ctypes.data_as(ctypes.c_void_p),
+            (ctypes.c_double * 3)(0, 0, 0.5), ctypes.c_double(1.0), ctypes.c_double(1.0),
+            ctypes.c_int(FUN[fun]), ctypes.c_int(1), out.ctypes.data_as(ctypes.c_void_p))
+        err = np.abs(out - ref) / np.maximum(np.abs(ref), 1e-3)
+        assert err.max() < tol, (dt, err.max())
