@@ -59,6 +59,15 @@ enum {
   GD_VARIANT_BULK = 2    /* persistent, cp.async.bulk (TMA 1-D) + mbarrier ring    */
 };
 
+/* flags of gd_loss_fwd_bwd */
+enum {
+  /* Rows whose (mean) weight is exactly 0 contribute exactly 0 loss and 0 gradient,
+   * even if their distance is inf/nan.  With non-negative weights this makes the
+   * all-zero-weight batch equal to the reference's early return (ref:290-292)
+   * without the host sync that `torch.any(weight > 0)` costs there. */
+  GD_FLAG_MASK_ZERO_WEIGHT = 1
+};
+
 enum {
   GD_ERR_BAD_ARG = -1,       /* null pointer / negative size / unknown enum        */
   GD_ERR_WORKSPACE = -2,     /* workspace too small                                */
@@ -109,7 +118,7 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg,
                     int64_t n, float scale,
                     float* loss_sum, float* row_loss, float* grad_pred,
                     void* workspace, size_t workspace_bytes,
-                    int32_t variant, void* stream);
+                    int32_t variant, int32_t flags, void* stream);
 
 /* Autograd fold: grad[i,:] *= *grad_output (0-dim upstream gradient; replaces the
  * first step of the reference's autograd backward).  Reads the scalar on the

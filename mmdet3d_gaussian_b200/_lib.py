@@ -14,6 +14,7 @@ LOSS_TYPES = {'gwd3d': 0, 'kld3d': 1, 'jd3d': 2, 'kld3d_symmax': 3,
 FUNS = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
 WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
 VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2}
+FLAG_MASK_ZERO_WEIGHT = 1
 
 
 class GDLossConfig(ctypes.Structure):
@@ -32,7 +33,7 @@ SIGNATURES = {
     'gd_loss_workspace_bytes': (ctypes.c_size_t, [_i64]),
     'gd_loss_fwd_bwd': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _i32, _i64,
                                        _i64, _f32, _vp, _vp, _vp, _vp,
-                                       ctypes.c_size_t, _i32, _vp]),
+                                       ctypes.c_size_t, _i32, _i32, _vp]),
     'gd_scale_grad': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     'gd_scale_grad_rows': (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp]),
     'gd_any_positive': (ctypes.c_int, [_vp, _i64, _vp, _vp]),

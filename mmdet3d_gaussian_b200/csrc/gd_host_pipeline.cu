@@ -132,7 +132,7 @@ extern "C" int gd_loss_fwd_bwd_host(const gd_loss_config* cfg, const float* pred
     }
     rc = gd_loss_fwd_bwd(cfg, sl.pred, 7, sl.target, 7, sl.weight, weight_mode, wcols, rows, scale,
                          sl.loss, nullptr, grad_host ? sl.grad : nullptr, sl.ws, sl.ws_bytes,
-                         GD_VARIANT_AUTO, sl.stream);
+                         GD_VARIANT_AUTO, 0, sl.stream);
     if (rc != 0) break;
     if (grad_host)
       e = cudaMemcpyAsync(grad_host + r0 * 7, sl.grad, (size_t)rows * kRowBytes,

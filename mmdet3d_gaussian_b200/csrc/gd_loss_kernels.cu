@@ -52,6 +52,7 @@ struct LossArgs {
   long long pstride, tstride, wstride;   // row strides in elements
   long long n;
   int wmode;
+  int mask_zero_w;                        // GD_FLAG_MASK_ZERO_WEIGHT
   float scale;
   float* loss_sum;
   float* row_loss;
@@ -114,7 +115,14 @@ __device__ __forceinline__ float row_weight_smem(const float* sw, int wmode, int
 template <int LOSS, bool GRAD>
 __device__ __forceinline__ float eval_row(const float* p, const float* t, float w,
                                           const LossArgs& a, float* g, float* rl) {
-  const float l = gd::pair_eval<float, LOSS, GRAD>(p, t, a.pp, g);
+  float l = gd::pair_eval<float, LOSS, GRAD>(p, t, a.pp, g);
+  if (a.mask_zero_w && w == 0.0f) {        // masked row: exactly zero, nan/inf do not leak
+    l = 0.0f;
+    if (GRAD) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) g[c] = 0.0f;
+    }
+  }
   const float ws = w * a.scale;
   if (GRAD) {
 #pragma unroll
@@ -456,9 +464,9 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg, const float* pred, int64_t pred_r
                     const float* target, int64_t target_row_stride, const float* weight,
                     int32_t weight_mode, int64_t weight_row_stride, int64_t n, float scale,
                     float* loss_sum, float* row_loss, float* grad_pred, void* workspace,
-                    size_t workspace_bytes, int32_t variant, void* stream) {
+                    size_t workspace_bytes, int32_t variant, int32_t flags, void* stream) {
   using namespace gdk;
-  if (!config_ok(cfg) || n < 0 || weight_mode < GD_WEIGHT_NONE || weight_mode > GD_WEIGHT_ROW7 ||
+  if (!config_ok(cfg) || n < 0 || (flags & ~GD_FLAG_MASK_ZERO_WEIGHT) || weight_mode < GD_WEIGHT_NONE || weight_mode > GD_WEIGHT_ROW7 ||
       variant < GD_VARIANT_AUTO || variant > GD_VARIANT_BULK)
     return GD_ERR_BAD_ARG;
   if (n > 0 && (!pred || !target || (weight_mode != GD_WEIGHT_NONE && !weight)))
@@ -492,6 +500,7 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg, const float* pred, int64_t pred_r
   a.wstride = weight_row_stride;
   a.n = n;
   a.wmode = weight_mode;
+  a.mask_zero_w = (flags & GD_FLAG_MASK_ZERO_WEIGHT) ? 1 : 0;
   a.scale = scale;
   a.loss_sum = loss_sum;
   a.row_loss = row_loss;

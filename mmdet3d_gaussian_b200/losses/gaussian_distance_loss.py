@@ -47,9 +47,16 @@ class GDLoss(nn.Module):
     """Gaussian-distance box regression loss (GWD / KLD / JD / sym-KLD / BCD / KFIoU).
 
     Args mirror the reference (ref:261-263).  ``**kwargs`` are forwarded to the
-    distance: ``normalize`` for ``gwd3d``, ``sqrt`` for the others.  One extra,
-    backwards-compatible key is consumed here: ``variant`` ('auto' | 'staged' |
-    'bulk') selects the kernel variant.
+    distance: ``normalize`` for ``gwd3d``, ``sqrt`` for the others.  Two extra,
+    backwards-compatible keys are consumed here and never reach the distance:
+
+    * ``variant`` ('auto' | 'staged' | 'bulk') selects the kernel variant;
+    * ``host_sync`` (default True).  True keeps the reference's early return
+      (ref:290-292) exactly, including its device->host sync
+      (``torch.any(weight > 0)``).  False never syncs: rows whose weight is exactly
+      0 are masked inside the kernel (0 loss, 0 gradient).  For non-negative
+      weights the two agree on every finite row; the all-zero batch returns 0
+      with zero gradients either way.
     """
 
     BAG_GD_LOSS = tuple(_lib.LOSS_TYPES)          # ref:253-259
@@ -71,6 +78,7 @@ class GDLoss(nn.Module):
         self.reduction = reduction
         self.loss_weight = loss_weight
         self.variant = kwargs.pop('variant', 'auto')
+        self.host_sync = bool(kwargs.pop('host_sync', True))
         self.kwargs = kwargs                                      # ref:278
 
     def _config(self, extra):
@@ -89,7 +97,7 @@ class GDLoss(nn.Module):
         assert reduction_override in (None, 'none', 'mean', 'sum')   # ref:287
         reduction = (
             reduction_override if reduction_override else self.reduction)  # ref:288-289
-        if (weight is not None) and (reduction != 'none') and (
+        if self.host_sync and (weight is not None) and (reduction != 'none') and (
                 not ops.any_positive(weight)):                    # ref:290-291
             return (pred * weight).sum()                          # ref:292
         _kwargs = deepcopy(self.kwargs)                           # ref:293
@@ -98,7 +106,8 @@ class GDLoss(nn.Module):
         n = pred.numel() // 7
         scale, rows_out = _scale_and_mode(reduction, avg_factor, n, self.loss_weight)
         return ops.gd_loss(pred, target, weight, cfg, scale, rows_out=rows_out,
-                           variant=self.variant)
+                           variant=self.variant,
+                           mask_zero_weight=not self.host_sync)
 
     def extra_repr(self):
         return (f'loss_type={self.loss_type!r}, fun={self.fun!r}, tau={self.tau}, '

@@ -58,7 +58,7 @@ def _row_stride(t):
 
 
 def _launch(cfg, pred, target, weight, wmode, scale, want_sum, want_rows, want_grad,
-            variant):
+            variant, flags=0):
     lib = _lib.load()
     n = pred.shape[0]
     dev = pred.device
@@ -76,7 +76,8 @@ def _launch(cfg, pred, target, weight, wmode, scale, want_sum, want_rows, want_g
             ctypes.byref(cfg), _ptr(pred), _row_stride(pred), _ptr(target),
             _row_stride(target), _ptr(weight), wmode, wstride, n, float(scale),
             _ptr(loss), _ptr(rows), _ptr(grad), _ptr(ws),
-            ws.numel() if ws is not None else 0, _lib.VARIANTS[variant], _stream_ptr())
+            ws.numel() if ws is not None else 0, _lib.VARIANTS[variant], flags,
+            _stream_ptr())
     _lib.check(code, 'gd_loss_fwd_bwd')
     return loss, rows, grad
 
@@ -88,11 +89,11 @@ class _GDLossFunction(torch.autograd.Function):
     exits immediately when it is exactly 1)."""
 
     @staticmethod
-    def forward(ctx, pred, target, weight, cfg, wmode, scale, rows_out, variant):
+    def forward(ctx, pred, target, weight, cfg, wmode, scale, rows_out, variant, flags):
         need_grad = bool(ctx.needs_input_grad[0])
         loss, rows, grad = _launch(cfg, pred, target, weight, wmode, scale,
-                                   not rows_out, rows_out, need_grad, variant)
-        ctx.gd = (cfg, wmode, scale, rows_out, variant)
+                                   not rows_out, rows_out, need_grad, variant, flags)
+        ctx.gd = (cfg, wmode, scale, rows_out, variant, flags)
         ctx.grad_buf = grad
         ctx.save_for_backward(pred, target, weight)
         ctx.set_materialize_grads(False)
@@ -101,8 +102,8 @@ class _GDLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         if grad_out is None or not ctx.needs_input_grad[0]:
-            return (None,) * 8
-        cfg, wmode, scale, rows_out, variant = ctx.gd
+            return (None,) * 9
+        cfg, wmode, scale, rows_out, variant, flags = ctx.gd
         pred, target, weight = ctx.saved_tensors
         grad = ctx.grad_buf
         ctx.grad_buf = None
@@ -110,7 +111,7 @@ class _GDLossFunction(torch.autograd.Function):
             # second backward through the same node (retain_graph=True) or grad
             # mode was off at forward time: regenerate with the fused kernel
             _, _, grad = _launch(cfg, pred, target, weight, wmode, scale, False, False,
-                                 True, variant)
+                                 True, variant, flags)
         lib = _lib.load()
         n = grad.shape[0]
         go = grad_out.detach()
@@ -125,10 +126,11 @@ class _GDLossFunction(torch.autograd.Function):
             else:
                 code = lib.gd_scale_grad(_ptr(grad), n, _ptr(go), _stream_ptr())
                 _lib.check(code, 'gd_scale_grad')
-        return (grad,) + (None,) * 7
+        return (grad,) + (None,) * 8
 
 
-def gd_loss(pred, target, weight, cfg, scale, rows_out=False, variant='auto'):
+def gd_loss(pred, target, weight, cfg, scale, rows_out=False, variant='auto',
+            mask_zero_weight=False):
     """``scale * sum_i w_i loss_i`` (0-dim) or ``scale * w_i * loss_i`` ([N]).
 
     ``pred``/``target``: ``[..., 7]``; ``weight``: ``None``, ``[N]`` or ``[N,7]``
@@ -161,7 +163,8 @@ def gd_loss(pred, target, weight, cfg, scale, rows_out=False, variant='auto'):
         else:
             raise ValueError(f'weight shape {tuple(weight.shape)} must be '
                              f'{tuple(pred.shape)} or {tuple(pred.shape[:-1])}')
-    out = _GDLossFunction.apply(p2, t2, w2, cfg, wmode, scale, rows_out, variant)
+    flags = _lib.FLAG_MASK_ZERO_WEIGHT if mask_zero_weight else 0
+    out = _GDLossFunction.apply(p2, t2, w2, cfg, wmode, scale, rows_out, variant, flags)
     if rows_out and len(out_shape_rows) != 1:
         out = out.reshape(out_shape_rows)
     if in_dtype != torch.float32 and in_dtype.is_floating_point:

@@ -69,24 +69,24 @@ def test_argument_validation_without_gpu(lib):
     call = lib.gd_loss_fwd_bwd
     # negative n, null pointers, unknown enums, missing workspace: rejected up front
     assert call(ctypes.byref(cfg), one, 7, one, 7, null, 0, 0, -1, 1.0, null, null, null,
-                null, 0, 0, null) == -1
+                null, 0, 0, 0, null) == -1
     assert call(ctypes.byref(cfg), null, 7, one, 7, null, 0, 0, 8, 1.0, null, null, null,
-                null, 0, 0, null) == -1
+                null, 0, 0, 0, null) == -1
     assert call(ctypes.byref(cfg), one, 7, one, 7, null, 1, 1, 8, 1.0, null, null, null,
-                null, 0, 0, null) == -1
+                null, 0, 0, 0, null) == -1
     assert call(ctypes.byref(cfg), one, 7, one, 7, null, 0, 0, 8, 1.0, one, null, null,
-                null, 0, 0, null) == -2
+                null, 0, 0, 0, null) == -2
     assert call(ctypes.byref(cfg), one, 7, one, 7, null, 0, 0, 8, 1.0, null, null, null,
-                null, 0, 7, null) == -1
+                null, 0, 7, 0, null) == -1
     bad = _lib.make_config('gwd3d', 'log1p', True, 0.0, 1.0, (0, 0, 0.5))
     bad.loss_type = 9
     assert call(ctypes.byref(bad), one, 7, one, 7, null, 0, 0, 8, 1.0, null, null, null,
-                null, 0, 0, null) == -1
+                null, 0, 0, 0, null) == -1
     # bulk variant on a strided / unaligned layout is an error, not a silent fallback
     assert call(ctypes.byref(cfg), one, 9, one, 7, null, 0, 0, 8, 1.0, null, null, null,
-                null, 0, 2, null) == -3
+                null, 0, 2, 0, null) == -3
     assert call(ctypes.byref(cfg), ctypes.c_void_p(20), 7, one, 7, null, 0, 0, 8, 1.0, null,
-                null, null, null, 0, 2, null) == -3
+                null, null, null, 0, 2, 0, null) == -3
     assert lib.gd_pairwise(ctypes.byref(cfg), one, 4, one, 4, one, 3, null) == -1
     assert lib.gd_pairwise_row_argmin(ctypes.byref(cfg), one, 4, one, 0, one, one, null) == -1
     assert b'bad argument' in lib.gd_error_string(-1)

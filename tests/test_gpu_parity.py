@@ -233,6 +233,29 @@ def test_early_return_and_weight_shapes():
         GDLoss('gwd3d')(pred, target)                 # CPU tensors: no fallback
 
 
+def test_host_sync_free_mode():
+    """host_sync=False: no early-return probe, zero-weight rows masked in-kernel."""
+    pred, target, w = synth.make_pairs(5000, 'kitti', seed=14, weights='bernoulli')
+    kw = dict(loss_type='gwd3d', fun='log1p', tau=0.0, loss_weight=5.0)
+    ref_l, ref_g = run_oracle(kw, pred, target, w, 100.0)
+    l, g = run_ours(dict(kw, host_sync=False), pred, target, w, 100.0)
+    assert abs(l - ref_l) <= RTOL * abs(ref_l)
+    assert np.abs(g - ref_g).max() <= RTOL * np.abs(ref_g).max()
+    # all-zero [N,7] weights: same value and gradient as the reference's early return
+    z7 = torch.zeros(5000, 7)
+    l0, g0 = run_ours(dict(kw, host_sync=False), pred, target, z7, 3.0)
+    assert l0 == 0.0 and np.all(g0 == 0.0)
+    # identical boxes give inf/nan row gradients in the reference; masked when w == 0
+    p2 = pred.clone()
+    p2[:100] = target[:100]
+    wz = torch.ones(5000)
+    wz[:100] = 0.0
+    l1, g1 = run_ours(dict(kw, host_sync=False), p2, target, wz, 100.0)
+    assert np.isfinite(l1) and np.isfinite(g1).all() and np.all(g1[:100] == 0.0)
+    l2, g2 = run_ours(kw, p2, target, wz, 100.0)       # faithful mode: 0 * nan = nan leaks
+    assert not np.isfinite(g2[:100]).all()
+
+
 def test_autograd_contract():
     pred, target, w = synth.make_pairs(4096 + 3, 'kitti', seed=12, weights='bernoulli')
     kw = dict(loss_type='kld3d', fun='log1p', tau=1.0, loss_weight=5.0)
