@@ -56,7 +56,9 @@ enum {
 enum {
   GD_VARIANT_AUTO = 0,   /* bulk pipeline when layout allows, else staged          */
   GD_VARIANT_STAGED = 1, /* LDG/STG staged through shared memory; any stride       */
-  GD_VARIANT_BULK = 2    /* persistent, cp.async.bulk (TMA 1-D) + mbarrier ring    */
+  GD_VARIANT_BULK = 2,   /* persistent per-warp cp.async.bulk (TMA 1-D) + mbarrier
+                            rings, 4 rows per lane                                 */
+  GD_VARIANT_BULK_R2 = 3 /* same, 2 rows per lane / twice the warps (tuning aid)   */
 };
 
 /* flags of gd_loss_fwd_bwd */

@@ -16,8 +16,10 @@ from concurrent.futures import ThreadPoolExecutor
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), 'include')
-SOURCES = ['gd_loss_kernels.cu', 'gd_pairwise.cu', 'gd_host_pipeline.cu']
-HEADERS = ['gd_math.cuh', 'gd_common.cuh']
+SOURCES = ['gd_loss_api.cu', 'gd_loss_inst_gwd.cu', 'gd_loss_inst_kld.cu', 'gd_loss_inst_jd.cu',
+           'gd_loss_inst_symmax.cu', 'gd_loss_inst_symmin.cu', 'gd_loss_inst_bd.cu',
+           'gd_loss_inst_kfiou.cu', 'gd_pairwise.cu', 'gd_host_pipeline.cu']
+HEADERS = ['gd_math.cuh', 'gd_common.cuh', 'gd_loss_kernels.cuh']
 LIB_NAME = 'libgdloss_b200.so'
 LIB_PRECISE_NAME = 'libgdloss_b200_precise.so'   # -DGD_PRECISE_MATH=1, tests only
 
@@ -81,7 +83,7 @@ def build(force=False, precise=False, verbose=False):
             sys.stderr.write(res.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
     res = subprocess.run([nvcc, '-shared', '-o', lib] + objs + ['-cudart', 'static'],
                          capture_output=True, text=True)

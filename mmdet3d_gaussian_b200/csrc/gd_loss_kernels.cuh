@@ -1,0 +1,483 @@
+// Fused forward+backward Gaussian-distance loss kernels for B200 (sm_100a).
+//
+// Replaces, in ONE pass over HBM (88 algorithmic bytes per box pair: pred 28 +
+// target 28 + weight 4 read, grad 28 written), what the reference does with
+// ~160-250 eager torch ops and autograd: GDLoss.forward
+// (mmdet3d_gaussian/models/losses/gaussian_distance_loss.py:280-310, "ref")
+// = preprocess x2 (ref:8-21) -> distance (ref:42-248) -> postprocess (ref:24-39)
+// -> weighted reduction (mmdet weight_reduce_loss) -> x loss_weight, plus
+// d loss / d pred.
+//
+// Two kernels, same per-row math (gd_math.cuh):
+//   * gd_warp_kernel   -- persistent, one CTA per SM.  Every WARP runs its own
+//                         2-stage ring of [32*R-row] tiles (R rows per lane):
+//                         lane 0 fills a stage with 1-D bulk async copies (TMA
+//                         engine, cp.async.bulk + mbarrier complete_tx), lanes read
+//                         their rows from shared memory at stride 7 (odd => no bank
+//                         conflicts), stage the gradient rows in shared memory and
+//                         lane 0 writes them back with a bulk store.  No CTA-wide
+//                         barrier in the loop; per-tile bookkeeping is amortised
+//                         over R rows.  fun / tau / flag / weight mode are
+//                         compile-time for the common configurations.  Needs
+//                         contiguous, 16-byte aligned tensors.
+//   * gd_staged_kernel -- CTA tiles with plain (vector when possible) loads and
+//                         stores; takes any row stride / alignment (the
+//                         CenterGDHead call site passes row-strided views).
+// The AoS [N,7] layout is the reference's contract; the transpose to
+// one-row-per-thread happens in shared memory, never in HBM.
+//
+// Loss sum: per-thread fp32 -> warp shuffle -> per-CTA fp64 partial -> the last
+// CTA (atomic ticket, one atomic per CTA) adds the partials in fixed order, so
+// the result is deterministic for a given grid.
+#pragma once
+#include "gd_common.cuh"
+
+namespace gdk {
+
+struct LossArgs {
+  const float* pred;
+  const float* target;
+  const float* weight;
+  long long pstride, tstride, wstride;   // row strides in elements
+  long long n;
+  int wmode;
+  int mask_zero_w;                        // GD_FLAG_MASK_ZERO_WEIGHT
+  float scale;
+  float* loss_sum;
+  float* row_loss;
+  float* grad;
+  double* partials;                       // [grid]
+  unsigned int* ticket;                   // zero on entry, zero again on exit
+  gd::PairParams<float> pp;
+};
+
+// ---------------------------------------------------------------------------
+// deterministic grid-wide sum
+// ---------------------------------------------------------------------------
+constexpr int kMaxWarps = 32;
+
+__device__ __forceinline__ void finish_sum(float acc, const LossArgs& a) {
+  __shared__ float s_warp[kMaxWarps];
+  __shared__ double s_dwarp[kMaxWarps];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = (int)(blockDim.x >> 5), nthreads = (int)blockDim.x;
+  acc = warp_sum(acc);
+  if (lane == 0) s_warp[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += (double)s_warp[w];
+    a.partials[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int t = atomicAdd(a.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int i = tid; i < gridDim.x; i += nthreads) s += __ldcg(a.partials + i);
+    s = warp_sum(s);
+    if (lane == 0) s_dwarp[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < nwarps; ++w) tot += s_dwarp[w];
+      *a.loss_sum = (float)(tot * (double)a.scale);
+      *a.ticket = 0u;                     // leave the workspace reusable
+    }
+  }
+}
+
+// weight of one row: None -> 1, [N] -> w, [N,7] -> mean(-1)          ref:295-296
+__device__ __forceinline__ float row_weight_smem(const float* sw, int wmode, int r) {
+  if (wmode == GD_WEIGHT_ROW) return sw[r];
+  if (wmode == GD_WEIGHT_ROW7) {
+    const float* w = sw + 7 * r;
+    return (((((w[0] + w[1]) + w[2]) + w[3]) + w[4]) + w[5] + w[6]) / 7.0f;
+  }
+  return 1.0f;
+}
+
+// One row, registers only.  Returns w_i * loss_i (unscaled) for the sum;
+// g[] <- scale * w_i * dloss_i/dpred_i, *rl <- scale * w_i * loss_i.
+template <int LOSS, bool GRAD>
+__device__ __forceinline__ float eval_row(const float* p, const float* t, float w,
+                                          const gd::PairParams<float>& pp, float scale,
+                                          bool mask_zero_w, float* g, float* rl) {
+  const float ws = w * scale;
+  float l = gd::pair_eval<float, LOSS, GRAD>(p, t, pp, ws, g);
+  if (mask_zero_w && w == 0.0f) {          // masked row: exactly zero, nan/inf do not leak
+    l = 0.0f;
+    if (GRAD) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) g[c] = 0.0f;
+    }
+  }
+  *rl = l * ws;
+  return l * w;
+}
+
+// ---------------------------------------------------------------------------
+// staged kernel: any stride / alignment
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_rows(float* __restrict__ s, const float* __restrict__ g,
+                                          long long stride, int cols, long long row0, int rows,
+                                          int tid) {
+  const int nel = rows * cols;
+  if (stride == cols) {
+    const float* base = g + row0 * cols;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+      const int nv = nel >> 2;
+      const float4* b4 = reinterpret_cast<const float4*>(base);
+      float4* s4 = reinterpret_cast<float4*>(s);
+      for (int i = tid; i < nv; i += kThreads) s4[i] = __ldcs(b4 + i);
+      for (int i = (nv << 2) + tid; i < nel; i += kThreads) s[i] = __ldcs(base + i);
+    } else {
+      for (int i = tid; i < nel; i += kThreads) s[i] = __ldcs(base + i);
+    }
+  } else {
+    for (int i = tid; i < nel; i += kThreads) {
+      const int r = i / cols, c = i - r * cols;
+      s[i] = __ldcs(g + (row0 + r) * stride + c);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_rows(float* __restrict__ g, const float* __restrict__ s,
+                                           int cols, long long row0, int rows, int tid) {
+  const int nel = rows * cols;
+  float* base = g + row0 * cols;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+    const int nv = nel >> 2;
+    float4* b4 = reinterpret_cast<float4*>(base);
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    for (int i = tid; i < nv; i += kThreads) __stcs(b4 + i, s4[i]);
+    for (int i = (nv << 2) + tid; i < nel; i += kThreads) __stcs(base + i, s[i]);
+  } else {
+    for (int i = tid; i < nel; i += kThreads) __stcs(base + i, s[i]);
+  }
+}
+
+template <int LOSS, bool GRAD>
+__global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
+  __shared__ __align__(16) float s_pred[kTile * 7];    // reused for the gradient tile
+  __shared__ __align__(16) float s_tgt[kTile * 7];
+  __shared__ __align__(16) float s_w[kTile * 7];       // [N,7] weights only
+  const int tid = threadIdx.x;
+  const long long ntiles = (a.n + kTile - 1) / kTile;
+  float acc = 0.0f;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kTile;
+    const int rows = (int)min((long long)kTile, a.n - row0);
+    load_rows(s_pred, a.pred, a.pstride, 7, row0, rows, tid);
+    load_rows(s_tgt, a.target, a.tstride, 7, row0, rows, tid);
+    if (a.wmode == GD_WEIGHT_ROW7) load_rows(s_w, a.weight, a.wstride, 7, row0, rows, tid);
+    float w1 = 1.0f;
+    if (a.wmode == GD_WEIGHT_ROW && tid < rows) w1 = __ldcs(a.weight + (row0 + tid) * a.wstride);
+    __syncthreads();
+    if (tid < rows) {
+      float p[7], t[7], g[7], rl;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        p[c] = s_pred[7 * tid + c];
+        t[c] = s_tgt[7 * tid + c];
+      }
+      const float w = (a.wmode == GD_WEIGHT_ROW7) ? row_weight_smem(s_w, a.wmode, tid) : w1;
+      acc += eval_row<LOSS, GRAD>(p, t, w, a.pp, a.scale, a.mask_zero_w != 0, g, &rl);
+      if (a.row_loss) __stcs(a.row_loss + row0 + tid, rl);
+      if (GRAD) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) s_pred[7 * tid + c] = g[c];   // own row only: no hazard
+      }
+    }
+    __syncthreads();
+    if (GRAD) store_rows(a.grad, s_pred, 7, row0, rows, tid);
+    __syncthreads();
+  }
+  if (a.loss_sum) finish_sum(acc, a);
+}
+
+// ---------------------------------------------------------------------------
+// warp pipeline kernel: persistent, every warp owns a 2-stage ring of tiles
+// ---------------------------------------------------------------------------
+constexpr int kWarpStages = 2;
+
+struct WarpLayout {
+  int wtile;      // bytes of one weight tile
+  int stage;      // bytes of one input stage (pred | target | weight)
+  int out;        // bytes of the output buffer (grad | row loss)
+  int per_warp;   // shared memory bytes one warp needs
+};
+
+__host__ __device__ inline WarpLayout warp_layout(int rows_per_lane, int wmode, bool grad,
+                                                  bool rows) {
+  const int trows = 32 * rows_per_lane;
+  WarpLayout L;
+  L.wtile = wmode == GD_WEIGHT_ROW7 ? trows * kRowBytes : (wmode == GD_WEIGHT_ROW ? trows * 4 : 0);
+  L.stage = 2 * trows * kRowBytes + L.wtile;
+  L.out = (grad ? trows * kRowBytes : 0) + (rows ? trows * 4 : 0);
+  L.per_warp = kWarpStages * L.stage + L.out + 16;      // + two mbarriers
+  return L;
+}
+
+// SPEC < 0: fun / tau_on / flag / mask come from the arguments at run time.
+// SPEC >= 0: bits [1:0] fun, [2] tau_on, [3] flag are compile-time constants (the
+// per-row branches and constant loads disappear).
+// WM < 0: weight mode at run time, else compile-time.
+template <int LOSS, bool GRAD, int R, int SPEC, int WM>
+__global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const LossArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kTileRows = 32 * R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wmode = WM >= 0 ? WM : a.wmode;
+  const bool want_rows = a.row_loss != nullptr;
+  gd::PairParams<float> pp = a.pp;
+  const bool mask_zero = a.mask_zero_w != 0;
+  if (SPEC >= 0) {
+    pp.fun = SPEC & 3;
+    pp.tau_on = (SPEC >> 2) & 1;
+    pp.flag = (SPEC >> 3) & 1;
+  }
+  const WarpLayout L = warp_layout(R, wmode, GRAD, want_rows);
+  unsigned char* base = smem + (size_t)warp * L.per_warp;
+  unsigned char* out_base = base + kWarpStages * L.stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_base + L.out);
+  float* og = reinterpret_cast<float*>(out_base);
+  float* orow = reinterpret_cast<float*>(out_base + (GRAD ? kTileRows * kRowBytes : 0));
+
+  // rows the bulk path can move: a multiple of 4 rows keeps every copy a multiple of 16 B
+  const long long n_main = a.n & ~3LL;
+  const long long ntiles = (n_main + kTileRows - 1) / kTileRows;
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int my_n = ntiles > gwarp ? (int)((ntiles - 1 - gwarp) / nwarps) + 1 : 0;
+  const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
+  uint64_t policy = 0;
+
+  auto issue = [&](int i) {               // lane 0 only
+    const long long row0 = (gwarp + (long long)i * nwarps) * kTileRows;
+    const uint32_t rows = (uint32_t)min((long long)kTileRows, n_main - row0);
+    const int s = i & (kWarpStages - 1);
+    unsigned char* st = base + s * L.stage;
+    const uint32_t box_bytes = rows * kRowBytes;
+    const uint32_t w_bytes = wmode ? rows * wcols * 4u : 0u;
+    mbar_arrive_expect_tx(&bars[s], 2 * box_bytes + w_bytes);
+    bulk_load(st, a.pred + row0 * 7, box_bytes, &bars[s], policy);
+    bulk_load(st + kTileRows * kRowBytes, a.target + row0 * 7, box_bytes, &bars[s], policy);
+    if (wmode)
+      bulk_load(st + 2 * kTileRows * kRowBytes, a.weight + row0 * wcols, w_bytes, &bars[s], policy);
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kWarpStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    policy = policy_evict_first();
+    const int pre = my_n < kWarpStages ? my_n : kWarpStages;
+    for (int i = 0; i < pre; ++i) issue(i);
+  }
+  __syncwarp();
+
+  float acc = 0.0f;
+  for (int i = 0; i < my_n; ++i) {
+    const int s = i & (kWarpStages - 1);
+    const long long row0 = (gwarp + (long long)i * nwarps) * kTileRows;
+    const int rows = (int)min((long long)kTileRows, n_main - row0);
+    const unsigned char* st = base + s * L.stage;
+    const float* sp = reinterpret_cast<const float*>(st);
+    const float* stg = reinterpret_cast<const float*>(st + kTileRows * kRowBytes);
+    const float* sw = reinterpret_cast<const float*>(st + 2 * kTileRows * kRowBytes);
+
+    mbar_wait(&bars[s], (uint32_t)((i / kWarpStages) & 1));
+    float p[R][7], t[R][7], w[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      // word 7r+c -> bank (7 lane + c) mod 32: conflict free.  Rows past a partial
+      // tile's end read stale shared memory; they are never evaluated or stored.
+      const int r = lane + 32 * k;
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        p[k][c] = sp[7 * r + c];
+        t[k][c] = stg[7 * r + c];
+      }
+      w[k] = row_weight_smem(sw, wmode, r);
+    }
+    // the previous tile's store must have finished READING the output buffer
+    if (lane == 0 && L.out && i > 0) bulk_wait_read<0>();
+    __syncwarp();                          // stage s consumed by every lane; out buffer free
+    if (lane == 0 && i + kWarpStages < my_n) issue(i + kWarpStages);
+
+    if (rows == kTileRows) {
+      // Full tile (all but at most one tile per kernel): the R rows of this lane go
+      // through the branch-free FAST math as one straight-line block, so their
+      // instruction streams interleave; rows it flags (clamped / degenerate
+      // extents, huge yaw, masked weight, ...) are redone on the robust path.
+      float g[R][7], rl[R], lw[R];
+      bool rare[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        rare[k] = mask_zero && w[k] == 0.0f;
+        const float ws = w[k] * a.scale;
+        const float l = gd::pair_eval_fast<float, LOSS, GRAD>(p[k], t[k], pp, ws, g[k], &rare[k]);
+        rl[k] = l * ws;
+        lw[k] = l * w[k];
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (rare[k])
+          lw[k] = eval_row<LOSS, GRAD>(p[k], t[k], w[k], pp, a.scale, mask_zero, g[k], &rl[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int r = lane + 32 * k;
+        acc += lw[k];
+        if (GRAD) {
+#pragma unroll
+          for (int c = 0; c < 7; ++c) og[7 * r + c] = g[k][c];
+        }
+        if (want_rows) orow[r] = rl[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int r = lane + 32 * k;
+        if (r < rows) {
+          float g[7], rl;
+          acc += eval_row<LOSS, GRAD>(p[k], t[k], w[k], pp, a.scale, mask_zero, g, &rl);
+          if (GRAD) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) og[7 * r + c] = g[c];
+          }
+          if (want_rows) orow[r] = rl;
+        }
+      }
+    }
+    if (L.out) {
+      fence_proxy_async_smem();            // generic-proxy writes -> visible to the bulk engine
+      __syncwarp();
+      if (lane == 0) {
+        if (GRAD) bulk_store(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes);
+        if (want_rows) bulk_store(a.row_loss + row0, orow, (uint32_t)rows * 4u);
+        bulk_commit();
+      }
+    }
+  }
+
+  // <= 3 leftover rows (n % 4): block 0 warp 0, straight from global memory
+  if (blockIdx.x == 0 && tid < (int)(a.n - n_main)) {
+    const long long r = n_main + tid;
+    float p[7], t[7], g[7], rl, w = 1.0f;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      p[c] = a.pred[r * 7 + c];
+      t[c] = a.target[r * 7 + c];
+    }
+    if (wmode == GD_WEIGHT_ROW) w = a.weight[r];
+    if (wmode == GD_WEIGHT_ROW7) w = row_weight_smem(a.weight + r * 7, GD_WEIGHT_ROW7, 0);
+    acc += eval_row<LOSS, GRAD>(p, t, w, pp, a.scale, mask_zero, g, &rl);
+    if (GRAD) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) a.grad[r * 7 + c] = g[c];
+    }
+    if (want_rows) a.row_loss[r] = rl;
+  }
+  if (lane == 0 && L.out) bulk_wait_all<0>();
+  if (a.loss_sum) finish_sum(acc, a);
+}
+
+// ---------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------
+template <int LOSS, bool GRAD>
+int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
+  gd_staged_kernel<LOSS, GRAD><<<grid, kThreads, 0, stream>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+constexpr int kSmemBudget = 227 * 1024 - 1024;   // opt-in max per CTA minus static + slack
+
+template <int LOSS, bool GRAD, int R, int SPEC, int WM>
+int launch_warp_inst(const LossArgs& a, int max_grid, cudaStream_t stream) {
+  auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const WarpLayout L = warp_layout(R, a.wmode, GRAD, a.row_loss != nullptr);
+  constexpr int kWarpCap = R >= 4 ? 12 : 24;
+  int warps = kSmemBudget / L.per_warp;
+  if (warps > kWarpCap) warps = kWarpCap;
+  if (warps < 1) return GD_ERR_BAD_ARG;
+  const long long ntiles = ((a.n & ~3LL) + 32 * R - 1) / (32 * R);
+  long long grid = (ntiles + warps - 1) / warps;
+  const long long sms = device_info().sm_count;
+  if (grid > sms) grid = sms;               // persistent: one CTA per SM
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) grid = 1;
+  if (grid < sms && warps > 4) {            // small batch: spread tiles over more SMs
+    warps = 4;
+    grid = (ntiles + warps - 1) / warps;
+    if (grid > sms) grid = sms;
+    if (grid < 1) grid = 1;
+  }
+  kern<<<(int)grid, warps * 32, (size_t)warps * L.per_warp, stream>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+// Specialised instantiations exist for the shipped configurations (fun in
+// {none, log1p}, flag = default true, weights None / [N]); anything else takes the
+// run-time-parameter instantiation of the same kernel.
+template <int LOSS, bool GRAD, int R>
+int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
+  constexpr bool kHasSpec = GRAD && (LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd);
+  if constexpr (kHasSpec) {
+    const gd::PairParams<float>& pp = a.pp;
+    const bool spec_ok = pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p) &&
+                         a.wmode != GD_WEIGHT_ROW7 && !a.row_loss;
+    if (spec_ok) {
+      const int spec = pp.fun | (pp.tau_on << 2) | (1 << 3);
+#define GD_SPEC_CASE(S)                                                                 \
+  case S:                                                                               \
+    return a.wmode == GD_WEIGHT_ROW ? launch_warp_inst<LOSS, GRAD, R, S, 1>(a, max_grid, stream) \
+                                    : launch_warp_inst<LOSS, GRAD, R, S, 0>(a, max_grid, stream);
+      switch (spec) {
+        GD_SPEC_CASE(8) GD_SPEC_CASE(9) GD_SPEC_CASE(12) GD_SPEC_CASE(13)
+        default: break;
+      }
+#undef GD_SPEC_CASE
+    }
+  }
+  return launch_warp_inst<LOSS, GRAD, R, -1, -1>(a, max_grid, stream);
+}
+
+template <int LOSS>
+int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t stream) {
+  const bool grad = a.grad != nullptr;
+  if (variant == GD_VARIANT_BULK) {
+    return grad ? launch_warp<LOSS, true, 4>(a, max_grid, stream)
+                : launch_warp<LOSS, false, 4>(a, max_grid, stream);
+  }
+  if (variant == GD_VARIANT_BULK_R2) {
+    return grad ? launch_warp<LOSS, true, 2>(a, max_grid, stream)
+                : launch_warp<LOSS, false, 2>(a, max_grid, stream);
+  }
+  long long grid = (a.n + kTile - 1) / kTile;
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) grid = 1;
+  return grad ? launch_staged<LOSS, true>(a, (int)grid, stream)
+              : launch_staged<LOSS, false>(a, (int)grid, stream);
+}
+
+constexpr int kMaxGrid = 65536;           // partials capacity of the workspace
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace gdk
+

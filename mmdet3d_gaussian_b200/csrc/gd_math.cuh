@@ -87,12 +87,18 @@ struct Mth<double> {
   static GD_HD double rcbrt(double x) { return 1.0 / ::cbrt(x); }
   // S - log(r1 r2 r3), r_i = 1 + q_i, S = sum q_i; plain evaluation is accurate
   // enough in double.
+  template <bool FAST>
   static GD_HD double sum_minus_log_ratios(double S, double pair, double r1, double r2,
-                                           double r3) {
+                                           double r3, bool* rare) {
     (void)pair;
+    (void)rare;
     return S - (::log(r1) + ::log(r2) + ::log(r3));
   }
   static GD_HD double inf() { return HUGE_VAL; }
+  // FAST-path stand-ins (the double instantiation only checks formulas)
+  static GD_HD void sincos_fast(double x, double* s, double* c) { sincos(x, s, c); }
+  static GD_HD double log1p_pos(double x) { return ::log1p(x); }
+  static GD_HD double rsixthroot(double x) { return ::pow(x, -1.0 / 6.0); }
 };
 
 template <>
@@ -166,10 +172,13 @@ struct Mth<float> {
   //   k != 0: result = S - k ln2 - 2s - tail directly (it is O(0.06) or larger)
   // y is formed as a product of ratios so it stays accurate when x is within
   // rounding of -1.
+  template <bool FAST>
   static GD_HD float sum_minus_log_ratios(float S, float pair, float r1, float r2,
-                                          float r3) {
+                                          float r3, bool* rare) {
     const float y = r1 * r2 * r3;
-    if (!(y > 1.0e-37f) || !(y < 3.0e38f)) {   // product under/overflowed, or nan
+    if (FAST) {                                // caller re-runs the row on the robust path
+      *rare |= !(y > 1.0e-30f && y < 1.0e30f);
+    } else if (!(y > 1.0e-37f) || !(y < 3.0e38f)) {   // product under/overflowed, or nan
       return S - (::logf(r1) + ::logf(r2) + ::logf(r3));
     }
     uint32_t yb;
@@ -197,6 +206,68 @@ struct Mth<float> {
     return (k == 0) ? (fmaf(x, s, -tail) - pair) : direct;
   }
   static GD_HD float inf() { return HUGE_VALF; }
+
+  // ---- branch-free helpers of the FAST path (rows pre-screened as "nice") ----
+  // sin/cos for |x| <= ~1e4: 3-term Cody-Waite reduction by pi/2 + degree-7/8
+  // minimax polynomials on [-pi/4, pi/4]; ~1 ulp, no slow path, no branch.
+  static GD_HD void sincos_fast(float x, float* sn, float* cs) {
+#if defined(__CUDA_ARCH__)
+    const int q = __float2int_rn(x * 0.63661974668502807617f);
+#else
+    const int q = (int)::rintf(x * 0.63661974668502807617f);
+#endif
+    const float k = (float)q;
+    float r = fmaf(k, -1.5707962512969970703f, x);
+    r = fmaf(k, -7.5497894158615963534e-08f, r);
+    r = fmaf(k, -5.3903029534742383927e-15f, r);
+    const float z = r * r;
+    float ps = fmaf(z, -1.9515295891e-4f, 8.3327032626e-3f);
+    ps = fmaf(z, ps, -1.6666662693e-1f);
+    const float sr = fmaf(r * z, ps, r);
+    float pc = fmaf(z, 2.44331570e-5f, -1.38878601e-3f);
+    pc = fmaf(z, pc, 4.16667275e-2f);
+    pc = fmaf(z, pc, -4.99999970e-1f);
+    const float cr = fmaf(z, pc, 1.0f);
+    const float s0 = (q & 1) ? cr : sr;
+    const float c0 = (q & 1) ? sr : cr;
+    *sn = (q & 2) ? -s0 : s0;
+    *cs = ((q + 1) & 2) ? -c0 : c0;
+  }
+  // log(1+x) for 0 <= x < ~1e30, branch free, ~1 ulp (same range reduction and
+  // series as sum_minus_log_ratios).
+  static GD_HD float log1p_pos(float x) {
+    const float y = 1.0f + x;
+    uint32_t yb;
+    memcpy(&yb, &y, 4);
+    const int k = (int)((int32_t)(yb - 0x3f3504f3u) >> 23);
+    const uint32_t mb = yb - ((uint32_t)k << 23);
+    float m;
+    memcpy(&m, &mb, 4);
+    const float f = (k == 0) ? x : (m - 1.0f);
+    const float s = f * rcp(2.0f + f);
+    const float z = s * s;
+    float p = 1.0f / 13.0f;
+    p = fmaf(p, z, 1.0f / 11.0f);
+    p = fmaf(p, z, 1.0f / 9.0f);
+    p = fmaf(p, z, 1.0f / 7.0f);
+    p = fmaf(p, z, 1.0f / 5.0f);
+    p = fmaf(p, z, 1.0f / 3.0f);
+    const float kf = (float)k;
+    const float lo = fmaf(kf, 1.428606765330187e-06f, 2.0f * s * z * p);
+    return fmaf(kf, 0.693145751953125f, fmaf(2.0f, s, lo));
+  }
+  // x^(-1/6) for normal positive x: one MUFU.LG2 + one MUFU.EX2 (rel. err ~5e-7)
+  static GD_HD float rsixthroot(float x) {
+#if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    l *= -(1.0f / 6.0f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return r;
+#else
+    return rcbrt(sqrt(x));
+#endif
+  }
 };
 
 // torch.clamp(min, max) semantics (NaN propagates); returns the gradient mask
@@ -213,21 +284,25 @@ GD_HD T clamp_extent(T v, T* mask) {
 // torch autograd convention probed in SURVEY.md appendix A).
 template <typename T>
 GD_HD T sqrt_clamp0(T x, T* dfac) {
-  if (x < (T)0) {
-    *dfac = (T)0;
-    return (T)0;
-  }
-  *dfac = (T)0.5 * Mth<T>::rsqrt(x);           // +inf at x == 0
-  return Mth<T>::sqrt(x);
+  const bool neg = x < (T)0;                   // NaN falls through and propagates
+  const T xc = neg ? (T)0 : x;
+  const T k = (T)0.5 * Mth<T>::rsqrt(xc);      // +inf at x == 0
+  *dfac = neg ? (T)0 : k;
+  return Mth<T>::sqrt(xc);
 }
 
 // post map ref:24-39: f = log1p | expm1 | nlog | identity, then tau >= 1 ->
 // 1 - tau/(tau+f) = f/(tau+f).  Returns value, multiplies *dfac by d out / d in.
-template <typename T>
-GD_HD T post_map(T d, const PairParams<T>& P, T* dfac) {
+template <typename T, bool FAST>
+GD_HD T post_map(T d, const PairParams<T>& P, T* dfac, bool* rare) {
   T f = d, df = (T)1;
   if (P.fun == kFunLog1p) {
-    f = Mth<T>::log1p(d);                      // ref:26
+    if (FAST) {
+      *rare |= !(d < (T)1e30);                 // inf / nan distance: robust path
+      f = Mth<T>::log1p_pos(d);
+    } else {
+      f = Mth<T>::log1p(d);                    // ref:26
+    }
     df = Mth<T>::rcp((T)1 + d);
   } else if (P.fun == kFunExpm1) {
     f = Mth<T>::expm1(d);                      // ref:28
@@ -259,12 +334,39 @@ struct PairGeom {
   T sd, cd;                 // sin / cos of (r_p - r_t)
 };
 
-template <typename T, bool NEED_PRED_ROT>
-GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P) {
+// FAST: the caller promises to re-run the row on the robust path when *rare is
+// set.  A row is "nice" when all six extents lie in [1e-4, 1e4] (clamps inactive,
+// gradient masks 1, no overflow in products of ratios) and both yaws are within
+// +-1e4 rad (branch-free range reduction); NaNs fail every test and land on the
+// robust path too.
+template <typename T, bool NEED_PRED_ROT, bool FAST>
+GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool* rare) {
   PairGeom<T> g;
   g.dx = (p[0] - t[0]) + P.off[0] * (p[3] - t[3]);
   g.dy = (p[1] - t[1]) + P.off[1] * (p[4] - t[4]);
   g.dz = (p[2] - t[2]) + P.off[2] * (p[5] - t[5]);
+  if (FAST) {
+    const T lo = (T)1e-4, hi = (T)1e4;
+    bool ok = p[3] >= lo && p[4] >= lo && p[5] >= lo && t[3] >= lo && t[4] >= lo && t[5] >= lo;
+    ok = ok && p[3] <= hi && p[4] <= hi && p[5] <= hi && t[3] <= hi && t[4] <= hi && t[5] <= hi;
+    ok = ok && (p[6] >= -hi && p[6] <= hi && t[6] >= -hi && t[6] <= hi);
+    *rare |= !ok;
+    g.ap = (T)0.5 * p[3];
+    g.bp = (T)0.5 * p[4];
+    g.ep = (T)0.5 * p[5];
+    g.at = (T)0.5 * t[3];
+    g.bt = (T)0.5 * t[4];
+    g.et = (T)0.5 * t[5];
+    g.ma = g.mb = g.me = (T)1;
+    Mth<T>::sincos_fast(p[6] - t[6], &g.sd, &g.cd);
+    if (NEED_PRED_ROT) {
+      Mth<T>::sincos_fast(p[6], &g.sp, &g.cp);
+    } else {
+      g.sp = (T)0;
+      g.cp = (T)1;
+    }
+    return g;
+  }
   T dummy;
   g.ap = (T)0.5 * clamp_extent(p[3], &g.ma);
   g.bp = (T)0.5 * clamp_extent(p[4], &g.mb);
@@ -305,8 +407,8 @@ GD_HD void store_grad(const PairGeom<T>& g, const PairParams<T>& P,
 // ---------------------------------------------------------------------------
 // a2: GWD                                                        ref:42-106
 // ---------------------------------------------------------------------------
-template <typename T, bool GRAD>
-GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+template <typename T, bool GRAD, bool FAST>
+GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
   const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd;
   const T K = (g.ap * g.bp) * (g.at * g.bt);                       // ref:91-92
@@ -327,13 +429,17 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
   T inv_n = (T)1;
   if (P.flag) {                                                    // ref:101-104
     // 1 / (2 (K e_p e_t)^(1/6)), product split so it cannot overflow
-    const T vp = Mth<T>::sqrt(g.ap * g.bp * g.ep);
-    const T vt = Mth<T>::sqrt(g.at * g.bt * g.et);
-    inv_n = (T)0.5 * Mth<T>::rcbrt(vp * vt);
+    if (FAST) {
+      inv_n = (T)0.5 * Mth<T>::rsixthroot((g.ap * g.bp * g.ep) * (g.at * g.bt * g.et));
+    } else {
+      const T vp = Mth<T>::sqrt(g.ap * g.bp * g.ep);
+      const T vt = Mth<T>::sqrt(g.at * g.bt * g.et);
+      inv_n = (T)0.5 * Mth<T>::rcbrt(vp * vt);
+    }
   }
   const T gval = d * inv_n;
   T fac = (T)1;
-  const T out = post_map(gval, P, &fac);
+  const T out = post_map<T, FAST>(gval, P, &fac, rare);
   if (GRAD) {
     const T irU = (T)2 * kU;                                       // 1/sqrt U
     const T rot = cmd * s2;                                        // (C-D) s2
@@ -356,7 +462,7 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
       L.gb -= g6 * Mth<T>::rcp(g.bp);
       L.ge -= g6 * Mth<T>::rcp(g.ep);
     }
-    store_grad(g, P, L, fac, grad);
+    store_grad(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -375,9 +481,9 @@ struct KldCommon {
   T s2, s2x2;        // sin^2 dl, sin(2 dl)
 };
 
-template <typename T>
+template <typename T, bool FAST>
 GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
-                LocalGrad<T>* L, T* ul, T* vl) {
+                LocalGrad<T>* L, T* ul, T* vl, bool* rare) {
   // value: 0.5 (u^2/A + v^2/B + dz^2/E)/alpha^2 + 0.5 tr(Sp^-1 St) + 0.5 F/E
   //        + ln(a_p b_p e_p / a_t b_t e_t) - 1.5                   ref:122-137
   const T u = g.cp * g.dx + g.sp * g.dy;
@@ -393,7 +499,7 @@ GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   // sum(delta + delta^2/2) - log((1+da)(1+db)(1+de)) with a single log:
   const T pair = qa * qb + qa * qe + qb * qe + qa * qb * qe;       // Pi(1+d) - 1 - sum d
   const T shape = (T)0.5 * (qa * qa + qb * qb + qe * qe)
-      + Mth<T>::sum_minus_log_ratios(qa + qb + qe, pair, ra, rb, re)
+      + Mth<T>::template sum_minus_log_ratios<FAST>(qa + qb + qe, pair, ra, rb, re, rare)
       + (T)0.5 * cmd * s2 * (iB - iA);
   if (want_grad) {
     const T s2x2 = (T)2 * g.sd * g.cd;
@@ -410,9 +516,9 @@ GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   return maha + shape;
 }
 
-template <typename T>
+template <typename T, bool FAST>
 GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
-                LocalGrad<T>* L, T* ul, T* vl) {
+                LocalGrad<T>* L, T* ul, T* vl, bool* rare) {
   // KL with Sigma_t inverted (kld3d_loss(target, pred)); gradient still w.r.t. pred.
   const T u = g.cp * g.dx + g.sp * g.dy;
   const T v = -g.sp * g.dx + g.cp * g.dy;
@@ -428,7 +534,7 @@ GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   const T maha = (T)0.5 * (ut * ut * iC + vt * vt * iD + g.dz * g.dz * iF) * P.inv_alpha2;
   const T pair = qa * qb + qa * qe + qb * qe + qa * qb * qe;
   const T shape = (T)0.5 * (qa * qa + qb * qb + qe * qe)
-      + Mth<T>::sum_minus_log_ratios(qa + qb + qe, pair, ra, rb, re)
+      + Mth<T>::template sum_minus_log_ratios<FAST>(qa + qb + qe, pair, ra, rb, re, rare)
       + (T)0.5 * amb * s2 * (iD - iC);
   if (want_grad) {
     const T s2x2 = (T)2 * g.sd * g.cd;
@@ -453,14 +559,15 @@ GD_HD void rotate_centre_grad(const PairGeom<T>& g, T ul, T vl, LocalGrad<T>* L)
   L->gdy = g.sp * ul + g.cp * vl;
 }
 
-template <typename T, int LOSS, bool GRAD>
-GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+template <typename T, int LOSS, bool GRAD, bool FAST>
+GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
+                        bool* rare) {
   LocalGrad<T> L;
   T ul = (T)0, vl = (T)0;
   T fac = (T)1;
   T val;
   if (LOSS == kKld) {
-    val = kld_fwd(g, P, GRAD, &L, &ul, &vl);
+    val = kld_fwd<T, FAST>(g, P, GRAD, &L, &ul, &vl, rare);
     if (P.flag) {                                                  // ref:138-139
       T k;
       val = sqrt_clamp0(val, &k);
@@ -469,8 +576,8 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
   } else {
     LocalGrad<T> Lr;
     T ulr = (T)0, vlr = (T)0;
-    T f = kld_fwd(g, P, GRAD, &L, &ul, &vl);
-    T r = kld_rev(g, P, GRAD, &Lr, &ulr, &vlr);
+    T f = kld_fwd<T, FAST>(g, P, GRAD, &L, &ul, &vl, rare);
+    T r = kld_rev<T, FAST>(g, P, GRAD, &Lr, &ulr, &vlr, rare);
     T wf, wr;                                  // d val / d f, d val / d r
     if (LOSS == kJd) {                                             // ref:191-197
       val = (T)0.5 * (f + r);
@@ -505,10 +612,10 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
       L.gr = wf * L.gr + wr * Lr.gr;
     }
   }
-  const T out = post_map(val, P, &fac);
+  const T out = post_map<T, FAST>(val, P, &fac, rare);
   if (GRAD) {
     rotate_centre_grad(g, ul, vl, &L);
-    store_grad(g, P, L, fac, grad);
+    store_grad(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -516,8 +623,8 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
 // ---------------------------------------------------------------------------
 // a4: Bhattacharyya                                             ref:144-186
 // ---------------------------------------------------------------------------
-template <typename T, bool GRAD>
-GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
+template <typename T, bool GRAD, bool FAST>
+GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
   const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
   const T E = g.ep * g.ep, F = g.et * g.et;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd, sc = g.sd * g.cd;
@@ -533,7 +640,11 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
   const T eps = amb * cmd * s2;
   const T detN = (A + C) * (B + D) + eps;                          // det(Sp+St)
   const T det_raw = (T)0.25 * detN;                                // ref:155-157
-  const bool clamped = !(det_raw >= (T)1e-7);                      // ref:158
+  bool clamped = !(det_raw >= (T)1e-7);                            // ref:158
+  if (FAST) {                              // clamp active (or nan): robust path redoes the row
+    *rare |= clamped;
+    clamped = false;
+  }
   const T det = clamped ? (T)1e-7 : det_raw;
   const T idet = Mth<T>::rcp(det);
   const T iMl = Mth<T>::rcp(Ml);
@@ -550,8 +661,13 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
     const T xb = db * db * Mth<T>::rcp((T)2 * g.bp * g.bt);
     const T q = xa + xb + xa * xb + (T)0.25 * eps * Mth<T>::rcp(K);
     const T qq = q + xe + q * xe;              // (1+q)(1+xe) - 1
-    shape = (qq < (T)1e37) ? (T)0.5 * Mth<T>::log1p(qq)
-                           : (T)0.5 * (Mth<T>::log1p(q) + Mth<T>::log1p(xe));  // 1e7-vs-1e-7 extents
+    if (FAST) {
+      *rare |= !(qq >= (T)0 && qq < (T)1e30);
+      shape = (T)0.5 * Mth<T>::log1p_pos(qq);
+    } else {
+      shape = (qq < (T)1e37) ? (T)0.5 * Mth<T>::log1p(qq)
+                             : (T)0.5 * (Mth<T>::log1p(q) + Mth<T>::log1p(xe));  // 1e7-vs-1e-7 extents
+    }
   } else {
     shape = (T)0.5 * (Mth<T>::log((T)1e-7) - Mth<T>::log(K)) + (T)0.5 * Mth<T>::log1p(xe);
   }
@@ -562,7 +678,7 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
     val = sqrt_clamp0(val, &k);
     fac = k;
   }
-  const T out = post_map(val, P, &fac);
+  const T out = post_map<T, FAST>(val, P, &fac, rare);
   if (GRAD) {
     const T c8 = (T)0.125 * P.inv_alpha2 * idet;                   // 1/(8 alpha^2 det)
     LocalGrad<T> L;
@@ -592,7 +708,7 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
     L.gb = g.bp * (u * u * c8 + gam * M00) + sb;
     L.ge = -(T)0.125 * g.dz * g.dz * iMl * iMl * P.inv_alpha2 * g.ep
         + (T)0.25 * de * (g.ep + g.et) * iep * iMl;
-    store_grad(g, P, L, fac, grad);
+    store_grad(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -600,8 +716,9 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
 // ---------------------------------------------------------------------------
 // a7: KFIoU (ignores centres, alpha, sqrt; tau forced 0)         ref:227-248
 // ---------------------------------------------------------------------------
-template <typename T, bool GRAD>
-GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T* grad) {
+template <typename T, bool GRAD, bool FAST>
+GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* grad,
+                   bool* rare) {
   PairParams<T> P = Pin;
   P.tau_on = 0;                                                    // ref:247
   const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
@@ -622,8 +739,48 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T* grad) {
   const T iU = Mth<T>::rcp(Uc);
   const T kf = I * iU;                                             // ref:246
   const T cK = (T)4.656854249492381;
+  const T R0 = (T)5.656854249492381;           // 4 sqrt(2) = cK + 1
+  if (!zc && !uc) {
+    // No clamp active: 1 - cK I/U is a difference of nearly equal numbers when the
+    // boxes almost coincide (I/U -> 1/cK).  With R = (vol_p+vol_t) sqrt(Z)/(vol_p vol_t)
+    // = U/I + 1 one has  R = R0 sqrt(1+xi),  1+xi = (1+x1)(1+q)(1+xe)  with the small
+    // non-negative-ish pieces below, and  1 - cK I/U = (R - R0)/(R - 1)
+    //                                   = R0 xi / ((sqrt(1+xi) + 1)(R - 1)).
+    const T K = (g.ap * g.bp) * (g.at * g.bt);
+    const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
+    const T i4K = (T)0.25 * Mth<T>::rcp(K);
+    const T dv = da * g.bp * g.ep + g.at * (db * g.ep + g.bt * de);   // vol_p - vol_t, no cancellation
+    const T i4vv = (T)0.25 * Mth<T>::rcp(volp * volt);
+    const T x1 = dv * dv * i4vv;
+    const T xa = da * da * Mth<T>::rcp((T)2 * g.ap * g.at);
+    const T xb = db * db * Mth<T>::rcp((T)2 * g.bp * g.bt);
+    const T xe = de * de * Mth<T>::rcp((T)2 * g.ep * g.et);
+    const T q = xa + xb + xa * xb + amb * cmd * s2 * i4K;
+    const T xi = x1 + q + xe + x1 * q + x1 * xe + q * xe + x1 * q * xe;
+    const T sq = Mth<T>::sqrt((T)1 + xi);
+    const T Rm1 = R0 * sq - (T)1;
+    const T iRm1 = Mth<T>::rcp(Rm1);
+    T fac = (T)1;
+    const T out = post_map<T, false>(R0 * xi * Mth<T>::rcp(sq + (T)1) * iRm1, P, &fac, rare);
+    if (GRAD) {
+      // d/dx = cK R0 sqrt(1+xi) / (2 (R-1)^2) * [dx1/(1+x1) + dq/(1+q) + dxe/(1+xe)]
+      const T coef = (T)0.5 * cK * R0 * sq * iRm1 * iRm1;
+      const T i1 = Mth<T>::rcp((T)1 + x1), iq = Mth<T>::rcp((T)1 + q), ie = Mth<T>::rcp((T)1 + xe);
+      const T iap = Mth<T>::rcp(g.ap), ibp = Mth<T>::rcp(g.bp), iep = Mth<T>::rcp(g.ep);
+      const T dx1v = dv * (volp + volt) * i4vv * i1;       // (dx1/dvol_p) vol_p / (1+x1)
+      const T rot = cmd * s2 * (A + B);
+      LocalGrad<T> L;
+      L.gdx = L.gdy = L.gdz = (T)0;
+      L.ga = coef * iap * (dx1v + ((B + D) * da * (g.ap + g.at) + rot) * i4K * iq);
+      L.gb = coef * ibp * (dx1v + ((A + C) * db * (g.bp + g.bt) - rot) * i4K * iq);
+      L.ge = coef * iep * (dx1v + (T)0.5 * de * (g.ep + g.et) * Mth<T>::rcp(g.ep * g.et) * ie);
+      L.gr = coef * amb * cmd * ((T)2 * g.sd * g.cd) * i4K * iq;
+      store_grad(g, P, L, fac * gscale, grad);
+    }
+    return out;
+  }
   T fac = (T)1;
-  const T out = post_map((T)1 - cK * kf, P, &fac);                 // ref:247
+  const T out = post_map<T, false>((T)1 - cK * kf, P, &fac, rare);  // ref:247
   if (GRAD) {
     // d ln I / dx = d ln volp / dx - 0.5 [Z unclamped] d ln Z / dx
     const T t00 = C * c2 + D * s2, t11 = C * s2 + D * c2;
@@ -643,7 +800,7 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T* grad) {
     L.gb = c * (dIb - kf * mu * (volp * ibp - dIb));
     L.ge = c * (dIe - kf * mu * (volp * iep - dIe));
     L.gr = c * (dIr + kf * mu * dIr);
-    store_grad(g, P, L, fac, grad);
+    store_grad(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -651,20 +808,41 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T* grad) {
 // ---------------------------------------------------------------------------
 // dispatchers
 // ---------------------------------------------------------------------------
-template <typename T, int LOSS, bool GRAD>
-GD_HD T core_eval(const PairGeom<T>& g, const PairParams<T>& P, T* grad) {
-  if (LOSS == kGwd) return gwd_core<T, GRAD>(g, P, grad);
-  if (LOSS == kBd) return bd_core<T, GRAD>(g, P, grad);
-  if (LOSS == kKfiou) return kfiou_core<T, GRAD>(g, P, grad);
-  return kld_family_core<T, LOSS, GRAD>(g, P, grad);
+template <typename T, int LOSS, bool GRAD, bool FAST>
+GD_HD T core_eval(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
+  if (LOSS == kGwd) return gwd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  if (LOSS == kBd) return bd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  if (LOSS == kKfiou) return kfiou_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  return kld_family_core<T, LOSS, GRAD, FAST>(g, P, gscale, grad, rare);
 }
 
-// element-wise path: one (pred row, target row) pair, value + d/d pred
+// element-wise path, ROBUST version: one (pred row, target row) pair for ANY input
+// (clamped / degenerate extents, huge yaws, nan): returns the loss value and
+// writes grad[0..6] = gscale * d value / d pred (gscale folds weight * scale into
+// the single chain-rule factor instead of seven extra multiplies).
 template <typename T, int LOSS, bool GRAD>
-GD_HD T pair_eval(const T* p, const T* t, const PairParams<T>& P, T* grad) {
+GD_HD T pair_eval(const T* p, const T* t, const PairParams<T>& P, T gscale, T* grad) {
   constexpr bool kNeedRot = !(LOSS == kGwd || LOSS == kKfiou);
-  const PairGeom<T> g = make_geom<T, kNeedRot>(p, t, P);
-  return core_eval<T, LOSS, GRAD>(g, P, grad);
+  bool unused = false;
+  const PairGeom<T> g = make_geom<T, kNeedRot, false>(p, t, P, &unused);
+  return core_eval<T, LOSS, GRAD, false>(g, P, gscale, grad, &unused);
+}
+
+// element-wise path, FAST version: straight-line code (no branch, no clamp, no
+// slow path) so that several rows of one thread interleave in the scheduler.
+// Identical formulas; *rare is set when the row is not "nice" (see make_geom) or
+// hits a guard inside the distance -- the caller must then call pair_eval on it.
+// kfiou3d has no fast variant (it is not a headline loss): always rare = true.
+template <typename T, int LOSS, bool GRAD>
+GD_HD T pair_eval_fast(const T* p, const T* t, const PairParams<T>& P, T gscale, T* grad,
+                       bool* rare) {
+  constexpr bool kNeedRot = !(LOSS == kGwd || LOSS == kKfiou);
+  if (LOSS == kKfiou) {
+    *rare = true;
+    return (T)0;
+  }
+  const PairGeom<T> g = make_geom<T, kNeedRot, true>(p, t, P, rare);
+  return core_eval<T, LOSS, GRAD, true>(g, P, gscale, grad, rare);
 }
 
 // ---------------------------------------------------------------------------
@@ -706,7 +884,8 @@ GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<
   g.sp = p.s; g.cp = p.c;
   g.sd = p.s * t.c - p.c * t.s;       // sin(r_p - r_t)
   g.cd = p.c * t.c + p.s * t.s;       // cos(r_p - r_t)
-  return core_eval<T, LOSS, false>(g, P, (T*)0);
+  bool unused = false;
+  return core_eval<T, LOSS, false, false>(g, P, (T)1, (T*)0, &unused);
 }
 
 }  // namespace gd

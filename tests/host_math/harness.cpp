@@ -24,18 +24,61 @@ static void run(int loss, long n, const T* pred, const T* target, const double* 
     const T* t = target + 7 * i;
     T* g = out_grad + 7 * i;
     switch (loss) {
-      case 0: out_loss[i] = gd::pair_eval<T, 0, true>(p, t, P, g); break;
-      case 1: out_loss[i] = gd::pair_eval<T, 1, true>(p, t, P, g); break;
-      case 2: out_loss[i] = gd::pair_eval<T, 2, true>(p, t, P, g); break;
-      case 3: out_loss[i] = gd::pair_eval<T, 3, true>(p, t, P, g); break;
-      case 4: out_loss[i] = gd::pair_eval<T, 4, true>(p, t, P, g); break;
-      case 5: out_loss[i] = gd::pair_eval<T, 5, true>(p, t, P, g); break;
-      case 6: out_loss[i] = gd::pair_eval<T, 6, true>(p, t, P, g); break;
+      case 0: out_loss[i] = gd::pair_eval<T, 0, true>(p, t, P, (T)1, g); break;
+      case 1: out_loss[i] = gd::pair_eval<T, 1, true>(p, t, P, (T)1, g); break;
+      case 2: out_loss[i] = gd::pair_eval<T, 2, true>(p, t, P, (T)1, g); break;
+      case 3: out_loss[i] = gd::pair_eval<T, 3, true>(p, t, P, (T)1, g); break;
+      case 4: out_loss[i] = gd::pair_eval<T, 4, true>(p, t, P, (T)1, g); break;
+      case 5: out_loss[i] = gd::pair_eval<T, 5, true>(p, t, P, (T)1, g); break;
+      case 6: out_loss[i] = gd::pair_eval<T, 6, true>(p, t, P, (T)1, g); break;
     }
   }
 }
 
+// FAST path: returns per-row rare flags; rows flagged rare carry unspecified values
+template <typename T>
+static void run_fast(int loss, long n, const T* pred, const T* target, const double* off,
+                     double alpha, double tau, int fun, int flag, T* out_loss, T* out_grad,
+                     int* out_rare) {
+  gd::PairParams<T> P;
+  for (int i = 0; i < 3; ++i) P.off[i] = (T)(float)off[i];
+  P.alpha2 = (T)(alpha * alpha);
+  P.inv_alpha2 = (T)(1.0 / (alpha * alpha));
+  P.tau = (T)tau;
+  P.tau_on = tau >= 1.0;
+  P.fun = fun;
+  P.flag = flag;
+  for (long i = 0; i < n; ++i) {
+    const T* p = pred + 7 * i;
+    const T* t = target + 7 * i;
+    T* g = out_grad + 7 * i;
+    bool rare = false;
+    switch (loss) {
+      case 0: out_loss[i] = gd::pair_eval_fast<T, 0, true>(p, t, P, (T)1, g, &rare); break;
+      case 1: out_loss[i] = gd::pair_eval_fast<T, 1, true>(p, t, P, (T)1, g, &rare); break;
+      case 2: out_loss[i] = gd::pair_eval_fast<T, 2, true>(p, t, P, (T)1, g, &rare); break;
+      case 3: out_loss[i] = gd::pair_eval_fast<T, 3, true>(p, t, P, (T)1, g, &rare); break;
+      case 4: out_loss[i] = gd::pair_eval_fast<T, 4, true>(p, t, P, (T)1, g, &rare); break;
+      case 5: out_loss[i] = gd::pair_eval_fast<T, 5, true>(p, t, P, (T)1, g, &rare); break;
+      case 6: out_loss[i] = gd::pair_eval_fast<T, 6, true>(p, t, P, (T)1, g, &rare); break;
+    }
+    out_rare[i] = rare ? 1 : 0;
+  }
+}
+
 extern "C" {
+void gd_host_eval_fast_f64(int loss, long n, const double* pred, const double* target,
+                           const double* off, double alpha, double tau, int fun, int flag,
+                           double* out_loss, double* out_grad, int* out_rare) {
+  run_fast<double>(loss, n, pred, target, off, alpha, tau, fun, flag, out_loss, out_grad,
+                   out_rare);
+}
+void gd_host_eval_fast_f32(int loss, long n, const float* pred, const float* target,
+                           const double* off, double alpha, double tau, int fun, int flag,
+                           float* out_loss, float* out_grad, int* out_rare) {
+  run_fast<float>(loss, n, pred, target, off, alpha, tau, fun, flag, out_loss, out_grad,
+                  out_rare);
+}
 void gd_host_eval_f64(int loss, long n, const double* pred, const double* target,
                       const double* off, double alpha, double tau, int fun, int flag,
                       double* out_loss, double* out_grad) {
@@ -47,7 +90,8 @@ void gd_host_eval_f32(int loss, long n, const float* pred, const float* target,
   run<float>(loss, n, pred, target, off, alpha, tau, fun, flag, out_loss, out_grad);
 }
 float gd_host_sum_minus_log_ratios_f32(float S, float pair, float r1, float r2, float r3) {
-  return gd::Mth<float>::sum_minus_log_ratios(S, pair, r1, r2, r3);
+  bool rare = false;
+  return gd::Mth<float>::sum_minus_log_ratios<false>(S, pair, r1, r2, r3, &rare);
 }
 }
 

@@ -57,7 +57,7 @@ def test_sass_is_sm100a_with_bulk_copies():
                          text=True).stdout
     assert 'sm_100a' in elf
     sass = subprocess.run([cuobjdump, '-sass', '-fun',
-                           '_ZN3gdk14gd_bulk_kernelILi1ELb1ELi3EEEvNS_8LossArgsE',
+                           '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1EEEvNS_8LossArgsE',
                            build_ext.lib_path()], capture_output=True, text=True).stdout
     assert 'UBLKCP' in sass and 'SYNCS' in sass
 

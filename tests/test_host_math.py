@@ -72,13 +72,13 @@ def test_closed_forms_and_gradients_fp64(hostlib, lt):
             assert el < 1e-9 and eg < 1e-8, (a[0], a[3:], sigma, el, eg)
 
 
-@pytest.mark.parametrize('lt', ['gwd3d', 'kld3d', 'jd3d', 'bd3d'])
+@pytest.mark.parametrize('lt', ['gwd3d', 'kld3d', 'jd3d', 'bd3d', 'kfiou3d'])
 @pytest.mark.parametrize('sigma', [0.3, 0.05, 0.005])
 def test_fp32_arithmetic_within_budget(hostlib, lt, sigma):
     """Per-row error of the kernel's float32 formulation vs fp64, next to the
     reference formulation's own float32 error (the oracle run in float32)."""
     pred, target, _ = synth.make_pairs(50_000, 'kitti', seed=5, sigma=sigma)
-    a = (lt, pred, target, (0, 0, 0.5), 1.0, 0.0, 'log1p', True)
+    a = (lt, pred, target, (0, 0, 0.5), 1.0, 0.0, 'none' if lt == 'kfiou3d' else 'log1p', True)
     ol, og = host_eval(hostlib, *a, 'f32')
     rl, rg = oracle_eval(*a)
     fl, fg = oracle_eval(*a, dtype=torch.float32)
@@ -92,6 +92,56 @@ def test_fp32_arithmetic_within_budget(hostlib, lt, sigma):
     ours, ref32 = errs(ol, og), errs(fl, fg)
     assert ours[0] <= 5e-6 and ours[1] <= 5e-6, (ours, ref32)
     assert ours[0] <= ref32[0] and ours[1] <= ref32[1], (ours, ref32)
+
+
+def host_eval_fast(lib, lt, pred, target, off, alpha, tau, fun, flag, dt):
+    n = pred.shape[0]
+    npdt = np.float64 if dt == 'f64' else np.float32
+    p = np.ascontiguousarray(pred.numpy().astype(npdt))
+    t = np.ascontiguousarray(target.numpy().astype(npdt))
+    ol, og, rr = np.zeros(n, npdt), np.zeros((n, 7), npdt), np.zeros(n, np.int32)
+    getattr(lib, 'gd_host_eval_fast_' + dt)(
+        ctypes.c_int(LT.index(lt)), ctypes.c_long(n), p.ctypes.data_as(ctypes.c_void_p),
+        t.ctypes.data_as(ctypes.c_void_p), (ctypes.c_double * 3)(*off), ctypes.c_double(alpha),
+        ctypes.c_double(tau), ctypes.c_int(FUN[fun]), ctypes.c_int(int(flag)),
+        ol.ctypes.data_as(ctypes.c_void_p), og.ctypes.data_as(ctypes.c_void_p),
+        rr.ctypes.data_as(ctypes.c_void_p))
+    return ol.astype(np.float64), og.astype(np.float64), rr
+
+
+@pytest.mark.parametrize('lt', LT[:6])
+def test_fast_path_formulas_and_screening(hostlib, lt):
+    """The branch-free FAST path (what the kernel's hot loop runs): same values and
+    gradients as the oracle on ordinary rows, and every degenerate row is flagged
+    `rare` (so the kernel redoes it on the robust path) instead of silently wrong."""
+    pred, target, _ = synth.make_pairs(3000, 'nuscenes', seed=9)
+    for fun, tau, alpha, flag in itertools.product(('log1p', 'none'), (0.0, 1.0), (1.0, 0.5),
+                                                   (True, False)):
+        a = (lt, pred, target, (0, 0, 0.5), alpha, tau, fun, flag)
+        ol, og, rr = host_eval_fast(hostlib, *a, 'f64')
+        rl, rg = oracle_eval(*a)
+        assert rr.sum() == 0
+        assert np.max(np.abs(ol - rl) / np.maximum(np.abs(rl), 1e-3)) < 1e-9
+        assert np.max(np.abs(og - rg) / np.maximum(np.abs(rg).max(1, keepdims=True), 1e-3)) < 1e-8
+    a = (lt, pred, target, (0, 0, 0.5), 1.0, 0.0, 'log1p', True)
+    ol, og, rr = host_eval_fast(hostlib, *a, 'f32')
+    rl, rg = oracle_eval(*a)
+    assert rr.sum() == 0
+    assert np.max(np.abs(ol - rl) / np.maximum(np.abs(rl), 1e-30)) < 5e-6
+    assert np.max(np.linalg.norm(og - rg, axis=1) / np.linalg.norm(rg, axis=1)) < 5e-6
+    # degenerate rows must be screened out
+    bad_p, bad_t = pred[:8].clone(), target[:8].clone()
+    bad_p[0, 3] = 1e-7
+    bad_p[1, 4] = -1.0
+    bad_t[2, 5] = 5e-5
+    bad_p[3, 3] = 2e7
+    bad_p[4, 6] = 3e4
+    bad_t[5, 6] = -2e4
+    bad_p[6, 5] = float('nan')
+    bad_t[7, 3] = float('inf')
+    _, _, rr = host_eval_fast(hostlib, lt, bad_p, bad_t, (0, 0, 0.5), 1.0, 0.0, 'log1p', True,
+                              'f32')
+    assert rr.tolist() == [1] * 8
 
 
 def test_identity_is_exact_zero_fp32(hostlib):
@@ -148,7 +198,7 @@ def test_pairwise_value_path(hostlib, lt):
     b2 = synth.make_targets(13, 'waymo', seed=3)
     fun = 'none' if lt == 'kfiou3d' else 'log1p'
     ref = gd_oracle.pairwise_distance(b1.double(), b2.double(), lt, fun=fun, tau=1.0).numpy()
-    for dt, tol in (('f64', 1e-10), ('f32', 2e-4 if lt == 'kfiou3d' else 1e-5)):
+    for dt, tol in (('f64', 1e-10), ('f32', 1e-5)):
         npdt = np.float64 if dt == 'f64' else np.float32
         a1 = np.ascontiguousarray(b1.numpy().astype(npdt))
         a2 = np.ascontiguousarray(b2.numpy().astype(npdt))

@@ -19,8 +19,8 @@ tail -5 $OUT/pytest_gpu.log
 echo "== bench"
 timeout -s KILL 600 python bench.py --steps 100 --warmup 5 > $OUT/bench_auto.json 2> $OUT/bench_auto.err
 echo "bench auto exit $?"
-timeout -s KILL 300 python bench.py --steps 100 --warmup 5 --variant staged --no-e2e --no-cpu > $OUT/bench_staged.json 2> $OUT/bench_staged.err
-echo "bench staged exit $?"
+timeout -s KILL 300 python bench.py --steps 100 --warmup 5 --variant bulk_r2 --no-e2e --no-cpu > $OUT/bench_r2.json 2> $OUT/bench_r2.err
+echo "bench r2 exit $?"
 GD_LOSS_B200_LIB=$PWD/mmdet3d_gaussian_b200/libgdloss_b200_precise.so timeout -s KILL 300 python bench.py --steps 100 --warmup 5 --no-e2e --no-cpu > $OUT/bench_precise.json 2> $OUT/bench_precise.err
 echo "bench precise exit $?"
 timeout -s KILL 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
@@ -34,7 +34,7 @@ echo "== ncu"
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
   --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:gd_bulk_kernel \
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:gd_warp_kernel \
   -s 12 -c 4 -o $OUT/prof_bulk -f python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT
