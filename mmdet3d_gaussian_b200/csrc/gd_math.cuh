@@ -757,6 +757,7 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* 
     const T xe = de * de * Mth<T>::rcp((T)2 * g.ep * g.et);
     const T q = xa + xb + xa * xb + amb * cmd * s2 * i4K;
     const T xi = x1 + q + xe + x1 * q + x1 * xe + q * xe + x1 * q * xe;
+    if (xi < (T)1e30) {                        // else (1e7-vs-1e-7 extents): plain form below
     const T sq = Mth<T>::sqrt((T)1 + xi);
     const T Rm1 = R0 * sq - (T)1;
     const T iRm1 = Mth<T>::rcp(Rm1);
@@ -778,6 +779,7 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* 
       store_grad(g, P, L, fac * gscale, grad);
     }
     return out;
+    }
   }
   T fac = (T)1;
   const T out = post_map<T, false>((T)1 - cK * kf, P, &fac, rare);  // ref:247
