@@ -308,9 +308,9 @@ GD_HD T post_map(T d, const PairParams<T>& P, T* dfac, bool* rare) {
     f = Mth<T>::expm1(d);                      // ref:28
     df = f + (T)1;
   } else if (P.fun == kFunNlog) {
-    T arg = (T)1 - d + (T)1e-7;                // ref:30
-    f = -Mth<T>::log(arg);
-    df = Mth<T>::rcp(arg);
+    // -log(1 - d + 1e-7) (ref:30) as -log1p(1e-7 - d): no rounding of 1 - d for small d
+    f = -Mth<T>::log1p((T)1e-7 - d);
+    df = Mth<T>::rcp((T)1 - d + (T)1e-7);
   }
   if (P.tau_on) {                              // ref:36-37
     T inv = Mth<T>::rcp(P.tau + f);
@@ -337,7 +337,8 @@ struct PairGeom {
 // FAST: the caller promises to re-run the row on the robust path when *rare is
 // set.  A row is "nice" when all six extents lie in [1e-4, 1e4] (clamps inactive,
 // gradient masks 1, no overflow in products of ratios) and both yaws are within
-// +-1e4 rad (branch-free range reduction); NaNs fail every test and land on the
+// +-16 rad (so r_p - r_t is formed with an absolute error below 1e-6 rad and the
+// branch-free range reduction is exact); NaNs fail every test and land on the
 // robust path too.
 template <typename T, bool NEED_PRED_ROT, bool FAST>
 GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool* rare) {
@@ -349,7 +350,8 @@ GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool
     const T lo = (T)1e-4, hi = (T)1e4;
     bool ok = p[3] >= lo && p[4] >= lo && p[5] >= lo && t[3] >= lo && t[4] >= lo && t[5] >= lo;
     ok = ok && p[3] <= hi && p[4] <= hi && p[5] <= hi && t[3] <= hi && t[4] <= hi && t[5] <= hi;
-    ok = ok && (p[6] >= -hi && p[6] <= hi && t[6] >= -hi && t[6] <= hi);
+    const T ymax = (T)16;
+    ok = ok && (p[6] >= -ymax && p[6] <= ymax && t[6] >= -ymax && t[6] <= ymax);
     *rare |= !ok;
     g.ap = (T)0.5 * p[3];
     g.bp = (T)0.5 * p[4];
@@ -374,12 +376,25 @@ GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool
   g.at = (T)0.5 * clamp_extent(t[3], &dummy);
   g.bt = (T)0.5 * clamp_extent(t[4], &dummy);
   g.et = (T)0.5 * clamp_extent(t[5], &dummy);
-  Mth<T>::sincos(p[6] - t[6], &g.sd, &g.cd);
-  if (NEED_PRED_ROT) {
-    Mth<T>::sincos(p[6], &g.sp, &g.cp);
+  const T ybig = (T)16;
+  if (p[6] >= -ybig && p[6] <= ybig && t[6] >= -ybig && t[6] <= ybig) {
+    // ordinary yaws: the difference is formed first so that sin(r_p - r_t) keeps its
+    // RELATIVE accuracy when the boxes are nearly parallel
+    Mth<T>::sincos(p[6] - t[6], &g.sd, &g.cd);
+    if (NEED_PRED_ROT) {
+      Mth<T>::sincos(p[6], &g.sp, &g.cp);
+    } else {
+      g.sp = (T)0;
+      g.cp = (T)1;
+    }
   } else {
-    g.sp = (T)0;
-    g.cp = (T)1;
+    // huge yaws: r_p - r_t would lose its low bits in float, so take sin/cos of
+    // each angle (as the reference does, ref:16-17) and use the difference identities
+    T st, ct;
+    Mth<T>::sincos(p[6], &g.sp, &g.cp);
+    Mth<T>::sincos(t[6], &st, &ct);
+    g.sd = g.sp * ct - g.cp * st;
+    g.cd = g.cp * ct + g.sp * st;
   }
   return g;
 }

@@ -53,8 +53,9 @@ class ShardedGDLoss(torch.nn.Module):
         if reduction == 'mean' and avg_factor is None:
             local = self.loss_module(pred, target, weight, reduction_override='sum',
                                      **kwargs)
-            packed = torch.stack([local.detach().float(),
-                                  torch.tensor(float(n_local), device=local.device)])
+            packed = torch.stack([local.detach(),
+                                  torch.tensor(float(n_local), device=local.device,
+                                               dtype=local.dtype)])
             if dist.is_available() and dist.is_initialized():
                 dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
             n_global = packed[1]

@@ -274,7 +274,6 @@ def test_mixed_nice_and_degenerate_rows(loss_type):
     ref_l, ref_g = run_oracle(kw, pred, target, w)
     for variant in VARIANTS:
         l, gr = run_ours(kw, pred, target, w, variant=variant)
-        # yaw 1e5 in fp32 has an ulp of 0.008 rad: compare those rows loosely
         hard = np.zeros(n, bool)
         hard[idx.numpy()] = True
         row_check(l[~hard], gr[~hard], ref_l[~hard], ref_g[~hard], RTOL, 1e-6, 1e-6,
@@ -282,7 +281,7 @@ def test_mixed_nice_and_degenerate_rows(loss_type):
         fin = np.isfinite(ref_g).all(1) & np.isfinite(ref_l) & hard
         assert np.isfinite(l[fin]).all(), f'{loss_type}/{variant}: non-finite on degenerate rows'
         el = np.abs(l - ref_l)[fin] / np.maximum(np.abs(ref_l[fin]), 1e-3)
-        assert el.max() <= 2e-3, (loss_type, variant, el.max())
+        assert el.max() <= 1e-4, (loss_type, variant, el.max())
 
 
 def test_host_sync_free_mode():
@@ -369,10 +368,11 @@ def test_full_size_properties(loss_type):
                  target[i * (n // 8):(i + 1) * (n // 8)],
                  w[i * (n // 8):(i + 1) * (n // 8)]).double() for i in range(8)]
     assert abs(sum(parts).item() - total.double().item()) <= 1e-6 * abs(total.item())
-    # (c) staged and bulk variants agree bit-for-bit per row (same math, different data path)
+    # (c) the bulk variant (branch-free FAST math) and the staged variant (robust math)
+    # evaluate the same formulas with different elementary functions: equal to ~1e-6
     rows_b = GDLoss(**dict(kw, reduction='none', variant='bulk'))(pred.detach(), target, w)
     rows_s = GDLoss(**dict(kw, reduction='none', variant='staged'))(pred.detach(), target, w)
-    assert torch.equal(rows_b, rows_s)
+    assert torch.allclose(rows_b, rows_s, rtol=5e-6, atol=1e-7)
     # (d) checksum of rows == reduced value; linearity in loss_weight
     assert abs(rows_b.double().sum().item() - total.double().item()) <= 1e-6 * abs(total.item())
     t5 = GDLoss(**dict(kw, loss_weight=5.0))(pred.detach(), target, w)

@@ -135,7 +135,7 @@ def test_fast_path_formulas_and_screening(hostlib, lt):
     bad_p[1, 4] = -1.0
     bad_t[2, 5] = 5e-5
     bad_p[3, 3] = 2e7
-    bad_p[4, 6] = 3e4
+    bad_p[4, 6] = 17.0
     bad_t[5, 6] = -2e4
     bad_p[6, 5] = float('nan')
     bad_t[7, 3] = float('inf')
