@@ -873,6 +873,7 @@ struct BoxGauss {
   T cx, cy, cz;     // centre incl. center_offset * unclamped extents   ref:12
   T a, b, e;        // clamped half extents                             ref:13-14,19-20
   T s, c;           // sin / cos yaw                                    ref:16-17
+  int nice;         // extents in [1e-4, 1e4]: the FAST cores may be used for this box
 };
 
 template <typename T>
@@ -885,12 +886,15 @@ GD_HD BoxGauss<T> box_gauss(const T* row, const PairParams<T>& P) {
   b.a = (T)0.5 * clamp_extent(row[3], &m);
   b.b = (T)0.5 * clamp_extent(row[4], &m);
   b.e = (T)0.5 * clamp_extent(row[5], &m);
-  Mth<T>::sincos(row[6], &b.s, &b.c);
+  Mth<T>::sincos(row[6], &b.s, &b.c);        // once per box: accurate version, any magnitude
+  const T lo = (T)1e-4, hi = (T)1e4;
+  b.nice = (row[3] >= lo && row[3] <= hi && row[4] >= lo && row[4] <= hi && row[5] >= lo &&
+            row[5] <= hi) ? 1 : 0;
   return b;
 }
 
-template <typename T, int LOSS>
-GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P) {
+template <typename T>
+GD_HD PairGeom<T> geom_from_gauss(const BoxGauss<T>& p, const BoxGauss<T>& t) {
   PairGeom<T> g;
   g.dx = p.cx - t.cx;
   g.dy = p.cy - t.cy;
@@ -901,6 +905,27 @@ GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<
   g.sp = p.s; g.cp = p.c;
   g.sd = p.s * t.c - p.c * t.s;       // sin(r_p - r_t)
   g.cd = p.c * t.c + p.s * t.s;       // cos(r_p - r_t)
+  return g;
+}
+
+// robust value (any input)
+template <typename T, int LOSS>
+GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P) {
+  const PairGeom<T> g = geom_from_gauss(p, t);
+  bool unused = false;
+  return core_eval<T, LOSS, false, false>(g, P, (T)1, (T*)0, &unused);
+}
+
+// value through the branch-free FAST cores when both boxes are nice and no guard
+// trips, else through the robust cores (a cold branch).
+template <typename T, int LOSS>
+GD_HD T pair_value_auto(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P) {
+  const PairGeom<T> g = geom_from_gauss(p, t);
+  if (LOSS != kKfiou) {
+    bool rare = !(p.nice && t.nice);
+    const T v = core_eval<T, LOSS, false, true>(g, P, (T)1, (T*)0, &rare);
+    if (!rare) return v;
+  }
   bool unused = false;
   return core_eval<T, LOSS, false, false>(g, P, (T)1, (T*)0, &unused);
 }

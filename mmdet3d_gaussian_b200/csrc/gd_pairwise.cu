@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(
     float* o = out + row0 * out_stride + j;
 #pragma unroll 2
     for (int r = 0; r < rows; ++r) {
-      const float v = gd::pair_value<float, LOSS>(s_rows[r], t, pp);
+      const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t, pp);
       if (WRITE && live) __stcs(o + (long long)r * out_stride, v);
       if (ARGMIN) {
         unsigned long long k = live ? pack_key(v, (unsigned int)j) : ~0ull;

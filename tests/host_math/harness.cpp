@@ -113,13 +113,13 @@ static void run_pairwise(int loss, long n, long m, const T* b1, const T* b2, con
       const gd::BoxGauss<T> t = gd::box_gauss(b2 + 7 * j, P);
       T v = 0;
       switch (loss) {
-        case 0: v = gd::pair_value<T, 0>(p, t, P); break;
-        case 1: v = gd::pair_value<T, 1>(p, t, P); break;
-        case 2: v = gd::pair_value<T, 2>(p, t, P); break;
-        case 3: v = gd::pair_value<T, 3>(p, t, P); break;
-        case 4: v = gd::pair_value<T, 4>(p, t, P); break;
-        case 5: v = gd::pair_value<T, 5>(p, t, P); break;
-        case 6: v = gd::pair_value<T, 6>(p, t, P); break;
+        case 0: v = gd::pair_value_auto<T, 0>(p, t, P); break;
+        case 1: v = gd::pair_value_auto<T, 1>(p, t, P); break;
+        case 2: v = gd::pair_value_auto<T, 2>(p, t, P); break;
+        case 3: v = gd::pair_value_auto<T, 3>(p, t, P); break;
+        case 4: v = gd::pair_value_auto<T, 4>(p, t, P); break;
+        case 5: v = gd::pair_value_auto<T, 5>(p, t, P); break;
+        case 6: v = gd::pair_value_auto<T, 6>(p, t, P); break;
       }
       out[i * m + j] = v;
     }
