@@ -28,10 +28,15 @@ def time_launch(fn, reps):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', choices=['all', 'elementwise', 'pairwise'], default='all')
+    ap.add_argument('--max-log2n', type=int, default=26)
+    args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device('cuda', 0)
     torch.cuda.set_device(dev)
-    nmax = 1 << 26
+    nmax = 1 << (args.max_log2n if args.only != 'pairwise' else 10)
     pred, target, weight = synth.make_pairs(nmax, 'kitti', seed=0, device=dev)
     grad = torch.empty(nmax, 7, device=dev)
     rows = torch.empty(nmax, device=dev)
@@ -40,7 +45,7 @@ def main():
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = {'elementwise': [], 'pairwise': []}
     types = ['gwd3d', 'kld3d', 'bd3d']
-    for e in list(range(10, 27, 2)):
+    for e in ([] if args.only == 'pairwise' else list(range(10, args.max_log2n + 1, 2))):
         n = 1 << e
         for lt in types + (['jd3d', 'kld3d_symmax', 'kld3d_symmin', 'kfiou3d'] if e == 24 else []):
             fun = 'none' if lt == 'kfiou3d' else 'log1p'
@@ -70,7 +75,7 @@ def main():
     mat = torch.empty(200_000, 256, device=dev)
     vmin = torch.empty(200_000, device=dev)
     idx = torch.empty(200_000, dtype=torch.int32, device=dev)
-    for lt in types:
+    for lt in ([] if args.only == 'elementwise' else types):
         cfg = _lib.make_config(lt, 'log1p', True, 1.0, 1.0, (0, 0, 0.5))
         ms = time_launch(lambda: _lib.check(lib.gd_pairwise(
             ctypes.byref(cfg), anchors.data_ptr(), 200_000, gts.data_ptr(), 256,
