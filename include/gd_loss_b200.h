@@ -127,6 +127,10 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg,
  * device -- no host sync. */
 int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void* stream);
 
+/* Same fold for a gradient buffer of any shape: buf[0..count) *= *scalar (head front
+ * ends, whose gradient rows are wider than 7). */
+int gd_scale_buffer(float* buf, int64_t count, const float* scalar, void* stream);
+
 /* Autograd fold for reduction='none': grad[i,:] *= grad_output[i]. */
 int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_rows,
                        int64_t grad_output_stride, void* stream);
@@ -153,6 +157,83 @@ int gd_pairwise_row_argmin(const gd_loss_config* cfg,
                            const float* boxes1, int64_t n,
                            const float* boxes2, int64_t m,
                            float* row_min, int32_t* row_argmin, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Head front ends: positive-row gather + box decode +
+ * GD loss + gradient w.r.t. the RAW network outputs in one launch.
+ * ------------------------------------------------------------------------- */
+
+/* where the gradient rows go (anchor front end) */
+enum {
+  GD_GRAD_NONE = 0,     /* forward only                                                */
+  GD_GRAD_COMPACT = 1,  /* index mode: [num_pos,7], row k belongs to pos_inds[k]       */
+  GD_GRAD_SCATTER = 2,  /* index mode: rows pos_inds[k] of a caller-ZEROED [T,7]        */
+  GD_GRAD_DENSE = 3     /* mask mode: every row of [T,7] is written (0 for negatives)  */
+};
+
+/* Replaces GDAnchor3DHead.loss_single's GD branch
+ * (mmdet3d_gaussian/models/dense_heads/gd_anchor3d_head.py:102-112 positive-row
+ * selection and gathers, :128-131 weights, :133-136 bbox_coder.decode x2 -- upstream
+ * mmdet3d DeltaXYZWLHRBBoxCoder.decode --, :137-141 GDLoss) and its backward.
+ *
+ *   anchors       : [anchor_rows,7]; row i of the batch uses anchors[i % anchor_rows]
+ *                   (anchor_list.repeat(mini_batch,1), :110-111)
+ *   deltas_pred   : [T,7] bbox_pred after permute/reshape (:97-98), row stride in elements
+ *   deltas_target : [T,7] bbox_targets (:99)
+ *   bbox_weights  : nullable [T,7] (:100); with decode_weight_host[7] (HOST memory, the
+ *                   train_cfg 'decode_weight' broadcast to 7) the row weight is
+ *                   mean_c(bbox_weights[i,c] * decode_weight[c]).  Null => weight None.
+ *   row selection : EITHER pos_inds[num_pos] (int64, the reference's nonzero result)
+ *                   OR labels[T] (int64) + num_classes: positive <=> 0 <= label < num_classes
+ *                   (:102-104) decided in-kernel -- no nonzero, no host sync.
+ *   scale         : loss_weight / avg_factor (as gd_loss_fwd_bwd)
+ *   loss_sum      : nullable, 1 fp32 := scale * sum_pos w_i loss_i
+ *   grad_deltas   : per grad_mode; = scale * w_i * d loss_i / d deltas_pred[i]
+ * No positives => loss 0 and zero gradient (the reference's `pos_bbox_pred.sum()`
+ * branch, :160-161). */
+int gd_anchor_decoded_loss_fwd_bwd(const gd_loss_config* cfg,
+                                   const float* anchors, int64_t anchor_rows,
+                                   const float* deltas_pred, int64_t deltas_pred_row_stride,
+                                   const float* deltas_target, int64_t deltas_target_row_stride,
+                                   const float* bbox_weights, int64_t bbox_weights_row_stride,
+                                   const float* decode_weight_host,
+                                   const int64_t* pos_inds, int64_t num_pos,
+                                   const int64_t* labels, int64_t num_classes,
+                                   int64_t total_rows, float scale,
+                                   float* loss_sum, float* grad_deltas, int32_t grad_mode,
+                                   void* workspace, size_t workspace_bytes,
+                                   int32_t flags, void* stream);
+
+/* CenterPointBBoxCoderRev.__init__ constants
+ * (mmdet3d_gaussian/core/bbox/coders/centerpoint_bbox_coders.py:9-20) */
+typedef struct gd_center_coder {
+  double pc_range[2];       /* pc_range[0], pc_range[1]      */
+  double voxel_size[2];     /* voxel_size[0], voxel_size[1]  */
+  int32_t out_size_factor;
+  int32_t norm_bbox;        /* dims = exp(pred)              */
+} gd_center_coder;
+
+/* Replaces CenterGDHead.loss's GD branch
+ * (mmdet3d_gaussian/models/dense_heads/gd_centerpoint_head.py:421-423
+ * CenterPointBBoxYawCoder.decode(locs, preds, correct_yaw=False)[..., :7] --
+ * core/bbox/coders/centerpoint_bbox_yaw_coders.py:18-56 --, :433-434 GDLoss) and
+ * its backward.
+ *   preds  : [n, >=7] gathered head outputs (reg2, height, dim3, yaw, ...), row stride
+ *   locs   : [n, 2] int64 (x_ind, y_ind) = pos_ind[..., 1:], row stride in elements
+ *   target : [n, >=7] real-world boxes (anno_boxes / encode()[..., :7]), row stride
+ *   weight : as gd_loss_fwd_bwd (the reference passes none)
+ *   grad_preds : nullable [n, grad_cols >= 7] with row stride; columns >= 7 are zeroed */
+int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_center_coder* coder,
+                                   const float* preds, int64_t preds_row_stride,
+                                   const int64_t* locs, int64_t locs_row_stride,
+                                   const float* target, int64_t target_row_stride,
+                                   const float* weight, int32_t weight_mode,
+                                   int64_t weight_row_stride,
+                                   int64_t n, float scale,
+                                   float* loss_sum, float* grad_preds,
+                                   int64_t grad_row_stride, int32_t grad_cols,
+                                   void* workspace, size_t workspace_bytes,
+                                   int32_t flags, void* stream);
 
 /* End-to-end entry with HOST buffers (bench `e2e`): chunks rows, overlaps
  * H2D of chunk k+1 / kernel of chunk k / D2H of chunk k-1 on internal streams,

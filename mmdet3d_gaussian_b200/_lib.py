@@ -15,6 +15,7 @@ FUNS = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
 WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
 VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3}
 FLAG_MASK_ZERO_WEIGHT = 1
+GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3
 
 
 class GDLossConfig(ctypes.Structure):
@@ -22,6 +23,12 @@ class GDLossConfig(ctypes.Structure):
     _fields_ = [('loss_type', ctypes.c_int32), ('fun', ctypes.c_int32),
                 ('flag', ctypes.c_int32), ('tau', ctypes.c_float),
                 ('alpha', ctypes.c_float), ('center_offset', ctypes.c_float * 3)]
+
+
+class GDCenterCoder(ctypes.Structure):
+    """``struct gd_center_coder``."""
+    _fields_ = [('pc_range', ctypes.c_double * 2), ('voxel_size', ctypes.c_double * 2),
+                ('out_size_factor', ctypes.c_int32), ('norm_bbox', ctypes.c_int32)]
 
 
 _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
@@ -35,10 +42,17 @@ SIGNATURES = {
                                        _i64, _f32, _vp, _vp, _vp, _vp,
                                        ctypes.c_size_t, _i32, _i32, _vp]),
     'gd_scale_grad': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    'gd_scale_buffer': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     'gd_scale_grad_rows': (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp]),
     'gd_any_positive': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     'gd_pairwise': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     'gd_pairwise_row_argmin': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'gd_anchor_decoded_loss_fwd_bwd': (ctypes.c_int, [
+        _cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, ctypes.POINTER(ctypes.c_float),
+        _vp, _i64, _vp, _i64, _i64, _f32, _vp, _vp, _i32, _vp, ctypes.c_size_t, _i32, _vp]),
+    'gd_center_decoded_loss_fwd_bwd': (ctypes.c_int, [
+        _cfgp, ctypes.POINTER(GDCenterCoder), _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32,
+        _i64, _i64, _f32, _vp, _vp, _i64, _i32, _vp, ctypes.c_size_t, _i32, _vp]),
     'gd_loss_fwd_bwd_host': (ctypes.c_int, [_cfgp, _vp, _vp, _vp, _i32, _i64, _f32,
                                             _vp, _vp, _i32, _i64]),
     'gd_launch_count': (_i64, []),
@@ -83,6 +97,16 @@ def check(code, what):
     if code != 0:
         msg = load().gd_error_string(code).decode()
         raise RuntimeError(f'gd_loss_b200.{what} failed ({code}): {msg}')
+
+
+def make_center_coder(pc_range, out_size_factor, voxel_size, norm_bbox=True):
+    c = GDCenterCoder()
+    for i in range(2):
+        c.pc_range[i] = float(pc_range[i])
+        c.voxel_size[i] = float(voxel_size[i])
+    c.out_size_factor = int(out_size_factor)
+    c.norm_bbox = 1 if norm_bbox else 0
+    return c
 
 
 def make_config(loss_type, fun, flag, tau, alpha, center_offset):

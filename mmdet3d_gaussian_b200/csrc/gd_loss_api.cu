@@ -163,6 +163,20 @@ int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void*
   return (int)cudaGetLastError();
 }
 
+int gd_scale_buffer(float* buf, int64_t count, const float* scalar, void* stream) {
+  using namespace gdk;
+  if (count < 0 || (count > 0 && (!buf || !scalar))) return GD_ERR_BAD_ARG;
+  if (count == 0) return 0;
+  long long grid = (count / 4 + kThreads - 1) / kThreads;
+  const long long cap = (long long)device_info().sm_count * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  gd_scale_grad_kernel<<<(int)grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      buf, count, scalar);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
 int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_rows,
                        int64_t grad_output_stride, void* stream) {
   using namespace gdk;

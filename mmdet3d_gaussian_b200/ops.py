@@ -230,3 +230,183 @@ def pairwise_row_argmin(boxes1, boxes2, cfg):
 
 def launch_count():
     return int(_lib.load().gd_launch_count())
+
+
+# ---------------------------------------------------------------------------
+# head front ends: gather + decode + loss + gradient to the raw outputs (f1)
+# ---------------------------------------------------------------------------
+def _rows_f32(t, name, min_cols=7):
+    _require_cuda(t, name)
+    if t.dim() != 2 or t.shape[1] < min_cols:
+        raise ValueError(f'{name} must be [K,>={min_cols}], got {tuple(t.shape)}')
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.shape[0] > 0 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _stride0(t):
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+def _fold_grad_output(grad, grad_out):
+    """grad *= grad_out (0-dim) on the device; the kernel exits at once when it is 1."""
+    go = grad_out.detach()
+    if go.dtype != torch.float32:
+        go = go.float()
+    with torch.cuda.device(grad.device):
+        code = _lib.load().gd_scale_buffer(_ptr(grad), grad.numel(), _ptr(go), _stream_ptr())
+    _lib.check(code, 'gd_scale_buffer')
+
+
+class _AnchorDecodedLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bbox_pred, anchors, bbox_targets, bbox_weights, decode_weight, pos_inds,
+                labels, num_classes, cfg, scale, flags):
+        lib = _lib.load()
+        dev = bbox_pred.device
+        total = bbox_pred.shape[0]
+        need_grad = bool(ctx.needs_input_grad[0])
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        grad, mode = None, _lib.GRAD_NONE
+        if need_grad:
+            if labels is not None:
+                grad, mode = torch.empty((total, 7), dtype=torch.float32, device=dev), _lib.GRAD_DENSE
+            else:
+                grad, mode = torch.zeros((total, 7), dtype=torch.float32, device=dev), _lib.GRAD_SCATTER
+        ws = _workspace(dev)
+        dw = None
+        if bbox_weights is not None:
+            dw = (ctypes.c_float * 7)(*[float(x) for x in decode_weight])
+        with torch.cuda.device(dev):
+            code = lib.gd_anchor_decoded_loss_fwd_bwd(
+                ctypes.byref(cfg), _ptr(anchors), anchors.shape[0], _ptr(bbox_pred),
+                _stride0(bbox_pred), _ptr(bbox_targets), _stride0(bbox_targets),
+                _ptr(bbox_weights), _stride0(bbox_weights) if bbox_weights is not None else 7,
+                dw, _ptr(pos_inds), pos_inds.numel() if pos_inds is not None else 0,
+                _ptr(labels), int(num_classes or 0), total, float(scale), _ptr(loss), _ptr(grad),
+                mode, _ptr(ws), ws.numel(), flags, _stream_ptr())
+        _lib.check(code, 'gd_anchor_decoded_loss_fwd_bwd')
+        ctx.grad_buf = grad
+        ctx.set_materialize_grads(False)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if grad_out is None or not ctx.needs_input_grad[0]:
+            return (None,) * 11
+        grad = ctx.grad_buf
+        ctx.grad_buf = None
+        if grad is None:
+            raise RuntimeError('gd_loss_b200: the fused head loss supports one backward pass '
+                               'per forward (retain_graph re-use is not supported)')
+        _fold_grad_output(grad, grad_out)
+        return (grad,) + (None,) * 10
+
+
+def anchor_decoded_loss(anchors, bbox_pred, bbox_targets, bbox_weights, decode_weight, cfg,
+                        scale, pos_inds=None, labels=None, num_classes=None,
+                        mask_zero_weight=True):
+    """Fused GD branch of ``GDAnchor3DHead.loss_single``
+    (reference ``gd_anchor3d_head.py:102-141``); see ``gd_anchor_decoded_loss_fwd_bwd``
+    in ``include/gd_loss_b200.h``.  Returns the 0-dim loss; differentiable w.r.t.
+    ``bbox_pred`` (dense ``[T,7]`` gradient, zero off the positives)."""
+    if (pos_inds is None) == (labels is None):
+        raise ValueError('pass exactly one of pos_inds / labels')
+    anchors = _rows_f32(anchors.detach(), 'anchors').contiguous()[:, :7].contiguous()
+    bp = _rows_f32(bbox_pred, 'bbox_pred')
+    bt = _rows_f32(bbox_targets.detach(), 'bbox_targets')
+    if bp.shape[0] != bt.shape[0]:
+        raise ValueError('bbox_pred and bbox_targets row counts differ')
+    bw = None
+    if decode_weight is not None and bbox_weights is not None:
+        bw = _rows_f32(bbox_weights.detach(), 'bbox_weights')
+        if bw.shape[0] != bp.shape[0]:
+            raise ValueError('bbox_weights row count differs from bbox_pred')
+        if not hasattr(decode_weight, '__len__'):
+            decode_weight = [decode_weight] * 7
+        if len(decode_weight) != 7:
+            raise ValueError('decode_weight must be a scalar or 7 values')
+    if pos_inds is not None:
+        _require_cuda(pos_inds, 'pos_inds')
+        pos_inds = pos_inds.detach().reshape(-1).to(torch.int64).contiguous()
+    else:
+        _require_cuda(labels, 'labels')
+        if num_classes is None:
+            raise ValueError('labels mode needs num_classes')
+        labels = labels.detach().reshape(-1).to(torch.int64).contiguous()
+        if labels.numel() != bp.shape[0]:
+            raise ValueError('labels must have one entry per bbox_pred row')
+    flags = _lib.FLAG_MASK_ZERO_WEIGHT if mask_zero_weight else 0
+    return _AnchorDecodedLossFunction.apply(bp, anchors, bt, bw, decode_weight, pos_inds,
+                                            labels, num_classes, cfg, scale, flags)
+
+
+class _CenterDecodedLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, locs, target, weight, wmode, coder, cfg, scale, flags):
+        lib = _lib.load()
+        dev = pred.device
+        n, cols = pred.shape
+        need_grad = bool(ctx.needs_input_grad[0])
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        grad = torch.empty((n, cols), dtype=torch.float32, device=dev) if need_grad else None
+        ws = _workspace(dev)
+        wstride = 0
+        if wmode == _lib.WEIGHT_ROW:
+            wstride = weight.stride(0) if n > 1 else 1
+        elif wmode == _lib.WEIGHT_ROW7:
+            wstride = _stride0(weight)
+        with torch.cuda.device(dev):
+            code = lib.gd_center_decoded_loss_fwd_bwd(
+                ctypes.byref(cfg), ctypes.byref(coder), _ptr(pred), _stride0(pred), _ptr(locs),
+                locs.stride(0) if n > 1 else 2, _ptr(target), _stride0(target), _ptr(weight),
+                wmode, wstride, n, float(scale), _ptr(loss), _ptr(grad), cols, cols, _ptr(ws),
+                ws.numel(), flags, _stream_ptr())
+        _lib.check(code, 'gd_center_decoded_loss_fwd_bwd')
+        ctx.grad_buf = grad
+        ctx.set_materialize_grads(False)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if grad_out is None or not ctx.needs_input_grad[0]:
+            return (None,) * 9
+        grad = ctx.grad_buf
+        ctx.grad_buf = None
+        if grad is None:
+            raise RuntimeError('gd_loss_b200: the fused head loss supports one backward pass '
+                               'per forward (retain_graph re-use is not supported)')
+        _fold_grad_output(grad, grad_out)
+        return (grad,) + (None,) * 8
+
+
+def center_decoded_loss(pred, pos_ind, target_box, weight, coder, cfg, scale,
+                        mask_zero_weight=True):
+    """Fused GD branch of ``CenterGDHead.loss`` (reference
+    ``gd_centerpoint_head.py:413-434``); see ``gd_center_decoded_loss_fwd_bwd``.
+    ``pred`` ``[P,C>=7]`` gathered head outputs, ``pos_ind`` ``[P,3]`` int64
+    (batch, x, y), ``target_box`` ``[P,>=7]``.  Differentiable w.r.t. ``pred``."""
+    p = _rows_f32(pred, 'pred')
+    t = _rows_f32(target_box.detach(), 'target_box')
+    _require_cuda(pos_ind, 'pos_ind')
+    if pos_ind.dim() != 2 or pos_ind.shape[1] != 3 or pos_ind.shape[0] != p.shape[0]:
+        raise ValueError(f'pos_ind must be [{p.shape[0]},3] (batch, x, y)')
+    if t.shape[0] != p.shape[0]:
+        raise ValueError('pred and target_box row counts differ')
+    locs = pos_ind.detach().to(torch.int64)[:, 1:]          # (x_ind, y_ind), a strided view
+    if locs.stride(1) != 1:
+        locs = locs.contiguous()
+    wmode, w2 = _lib.WEIGHT_NONE, None
+    if weight is not None:
+        _require_cuda(weight, 'weight')
+        w = weight.detach().float()
+        if w.dim() == 2 and w.shape == (p.shape[0], 7):
+            wmode, w2 = _lib.WEIGHT_ROW7, (w if w.stride(1) == 1 else w.contiguous())
+        elif w.numel() == p.shape[0]:
+            wmode, w2 = _lib.WEIGHT_ROW, w.reshape(-1)
+        else:
+            raise ValueError('weight must be [P] or [P,7]')
+    flags = _lib.FLAG_MASK_ZERO_WEIGHT if mask_zero_weight else 0
+    return _CenterDecodedLossFunction.apply(p, locs, t, w2, wmode, coder, cfg, scale, flags)

@@ -281,6 +281,83 @@ def pairwise_distance(boxes1, boxes2, loss_type, center_offset=(0, 0, 0.5),
 
 
 # --------------------------------------------------------------------------
+# f1: the decoders the reference runs in front of the loss, and the two head
+# call sites restated end to end.
+# --------------------------------------------------------------------------
+def decode_delta_xyzwlhr(anchors, deltas):
+    """Upstream mmdet3d ``DeltaXYZWLHRBBoxCoder.decode`` (called at
+    ``models/dense_heads/gd_anchor3d_head.py:133-136``).  mmdet3d is NOT in the
+    reference checkout and is un-pinned by it, so this decoder is **parity
+    unpinned**; the positional arithmetic below is the same in every mmdet3d
+    release that ships the coder (the releases only rename columns 3/4)."""
+    a0, a1, a2, a3, a4, a5, a6 = torch.split(anchors[..., :7], 1, dim=-1)
+    d0, d1, d2, d3, d4, d5, d6 = torch.split(deltas[..., :7], 1, dim=-1)
+    a2 = a2 + a5 / 2
+    diagonal = torch.sqrt(a4 ** 2 + a3 ** 2)
+    x = d0 * diagonal + a0
+    y = d1 * diagonal + a1
+    z = d2 * a5 + a2
+    e4 = torch.exp(d4) * a4
+    e3 = torch.exp(d3) * a3
+    e5 = torch.exp(d5) * a5
+    r = d6 + a6
+    z = z - e5 / 2
+    return torch.cat([x, y, z, e3, e4, e5, r], dim=-1)
+
+
+def decode_centerpoint_yaw(locs, preds, pc_range, out_size_factor, voxel_size,
+                           norm_bbox=True):
+    """``CenterPointBBoxYawCoder.decode(locs, preds, correct_yaw=False)``
+    (``core/bbox/coders/centerpoint_bbox_yaw_coders.py:18-56``; constants from
+    ``centerpoint_bbox_coders.py:9-20``).  Pinned against the unmodified
+    reference class by ``oracle/make_golden.py`` (``gd_decode_golden.npz``)."""
+    x = (preds[..., 0] + locs[..., 0]) * out_size_factor * voxel_size[0] \
+        + pc_range[0]                                              # coder:30-31
+    y = (preds[..., 1] + locs[..., 1]) * out_size_factor * voxel_size[1] \
+        + pc_range[1]                                              # coder:32-33
+    z = preds[..., 2]                                              # coder:34
+    dim = preds[..., 3:6]                                          # coder:35
+    if norm_bbox:
+        dim = dim.exp()                                            # coder:36-37
+    yaw = preds[..., 6]                                            # coder:38
+    others = preds[..., 9:]                                        # coder:51
+    return torch.cat((x.unsqueeze(-1), y.unsqueeze(-1), z.unsqueeze(-1), dim,
+                      yaw.unsqueeze(-1), others), dim=-1)          # coder:53-55
+
+
+def anchor_head_gd_loss(module, anchors, bbox_pred, bbox_targets, bbox_weights,
+                        pos_inds, decode_weight=None, avg_factor=None):
+    """The GD branch of ``GDAnchor3DHead.loss_single``
+    (``gd_anchor3d_head.py:107-141``): ``anchors`` is ``[A0,7]`` and repeats over
+    the mini-batch (:110-111); ``bbox_pred/bbox_targets/bbox_weights`` are
+    ``[T,7]``; returns the scalar the head adds into ``loss_bbox``."""
+    total = bbox_pred.shape[0]
+    pos_pred = bbox_pred[pos_inds]                                 # head:107
+    pos_targets = bbox_targets[pos_inds]                           # head:108
+    pos_weights = bbox_weights[pos_inds]                           # head:109
+    reps = -(-total // anchors.shape[0])
+    pos_anchors = anchors.repeat(reps, 1)[:total][pos_inds]        # head:110-112
+    if len(pos_inds) == 0:
+        return pos_pred.sum()                                      # head:160-161
+    weight = None
+    if decode_weight:                                              # head:128-131
+        weight = pos_weights * bbox_weights.new_tensor(decode_weight)
+    pred_dec = decode_delta_xyzwlhr(pos_anchors, pos_pred)         # head:133-134
+    tgt_dec = decode_delta_xyzwlhr(pos_anchors, pos_targets)       # head:135-136
+    return module(pred_dec, tgt_dec, weight, avg_factor=avg_factor)  # head:137-141
+
+
+def center_head_gd_loss(module, pred, pos_ind, target_box, coder, avg_factor=None):
+    """The GD branch of ``CenterGDHead.loss``
+    (``gd_centerpoint_head.py:413-434``): ``pred`` ``[P,C]`` gathered head
+    outputs, ``pos_ind`` ``[P,3]`` (batch, x, y), ``target_box`` ``[P,>=7]``;
+    ``coder`` = dict(pc_range, out_size_factor, voxel_size, norm_bbox)."""
+    target_gd = target_box[..., :7]                                # head:415
+    pred_gd = decode_centerpoint_yaw(pos_ind[..., 1:], pred, **coder)[..., :7]  # head:421-422
+    return module(pred_gd, target_gd, avg_factor=avg_factor)       # head:433-434
+
+
+# --------------------------------------------------------------------------
 # helper used by tests and bench: loss + d loss / d pred in one call
 # --------------------------------------------------------------------------
 def loss_and_grad(module, pred, target, weight=None, avg_factor=None,

@@ -125,3 +125,46 @@ def load_reference():
     spec.loader.exec_module(mod)
     _CACHED = mod
     return mod
+
+
+# ---------------------------------------------------------------------------
+# CenterPointBBoxYawCoder: the decoder the reference runs
+# in front of the loss in CenterGDHead.loss (gd_centerpoint_head.py:421-423).
+# ---------------------------------------------------------------------------
+CODER_DIR = os.path.join(REFERENCE_ROOT, 'mmdet3d_gaussian', 'core', 'bbox', 'coders')
+_CODER = None
+
+
+def load_reference_center_coder():
+    """Import ``core/bbox/coders/centerpoint_bbox_coders.py`` and
+    ``centerpoint_bbox_yaw_coders.py`` by path, unmodified, under a stub
+    ``mmdet.core.bbox`` (``BaseBBoxCoder`` = plain base class, ``BBOX_CODERS`` =
+    registry with ``register_module()``); returns ``CenterPointBBoxYawCoder``."""
+    global _CODER
+    if _CODER is not None:
+        return _CODER
+    if not os.path.isdir(CODER_DIR):
+        raise FileNotFoundError(f'{CODER_DIR} not found: build container only')
+    _install_stub_mmdet()
+    for name in ('mmdet.core', 'mmdet.core.bbox', 'mmdet.core.bbox.builder'):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            sys.modules[name] = mod
+            parent, child = name.rsplit('.', 1)
+            setattr(sys.modules[parent], child, mod)
+    sys.modules['mmdet.core.bbox'].BaseBBoxCoder = type('BaseBBoxCoder', (), {})
+    sys.modules['mmdet.core.bbox.builder'].BBOX_CODERS = _StubRegistry('bbox_coder')
+    pkg = types.ModuleType('_gd_ref_coders')
+    pkg.__path__ = [CODER_DIR]               # a package whose __init__ is NOT executed
+    sys.modules['_gd_ref_coders'] = pkg
+
+    def _load(stem):
+        spec = importlib.util.spec_from_file_location(
+            f'_gd_ref_coders.{stem}', os.path.join(CODER_DIR, stem + '.py'))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    pkg.CenterPointBBoxCoderRev = _load('centerpoint_bbox_coders').CenterPointBBoxCoderRev
+    _CODER = _load('centerpoint_bbox_yaw_coders').CenterPointBBoxYawCoder
+    return _CODER

@@ -137,3 +137,93 @@ void gd_host_pairwise_f32(int loss, long n, long m, const float* b1, const float
   run_pairwise<float>(loss, n, m, b1, b2, off, alpha, tau, fun, flag, out);
 }
 }
+
+// ---- decode front ends (csrc/gd_decode.cuh) --------------------------------
+#include "../../mmdet3d_gaussian_b200/csrc/gd_decode.cuh"
+
+template <typename T>
+static gd::PairParams<T> mk_params(const double* off, double alpha, double tau, int fun, int flag) {
+  gd::PairParams<T> P;
+  for (int i = 0; i < 3; ++i) P.off[i] = (T)(float)off[i];
+  P.alpha2 = (T)(alpha * alpha);
+  P.inv_alpha2 = (T)(1.0 / (alpha * alpha));
+  P.tau = (T)tau;
+  P.tau_on = tau >= 1.0;
+  P.fun = fun;
+  P.flag = flag;
+  return P;
+}
+
+template <typename T>
+static void run_anchor(int loss, long n, const T* an, const T* dp, const T* dt, const double* off,
+                       double alpha, double tau, int fun, int flag, T* out_loss, T* out_grad) {
+  const gd::PairParams<T> P = mk_params<T>(off, alpha, tau, fun, flag);
+  for (long i = 0; i < n; ++i) {
+    const T *a = an + 7 * i, *p = dp + 7 * i, *t = dt + 7 * i;
+    T* g = out_grad + 7 * i;
+    switch (loss) {
+      case 0: out_loss[i] = gd::anchor_pair_eval<T, 0, true>(a, p, t, P, (T)1, g); break;
+      case 1: out_loss[i] = gd::anchor_pair_eval<T, 1, true>(a, p, t, P, (T)1, g); break;
+      case 2: out_loss[i] = gd::anchor_pair_eval<T, 2, true>(a, p, t, P, (T)1, g); break;
+      case 3: out_loss[i] = gd::anchor_pair_eval<T, 3, true>(a, p, t, P, (T)1, g); break;
+      case 4: out_loss[i] = gd::anchor_pair_eval<T, 4, true>(a, p, t, P, (T)1, g); break;
+      case 5: out_loss[i] = gd::anchor_pair_eval<T, 5, true>(a, p, t, P, (T)1, g); break;
+      case 6: out_loss[i] = gd::anchor_pair_eval<T, 6, true>(a, p, t, P, (T)1, g); break;
+    }
+  }
+}
+
+template <typename T>
+static void run_center(int loss, long n, const T* pr, long pstride, const long long* locs,
+                       const T* tg, long tstride, const double* coder, int norm_bbox,
+                       const double* off, double alpha, double tau, int fun, int flag,
+                       T* out_loss, T* out_grad) {
+  const gd::PairParams<T> P = mk_params<T>(off, alpha, tau, fun, flag);
+  gd::CenterDecodeParams D;
+  D.sx = coder[0];
+  D.sy = coder[1];
+  D.x0 = coder[2];
+  D.y0 = coder[3];
+  D.norm_bbox = norm_bbox;
+  for (long i = 0; i < n; ++i) {
+    const T *p = pr + pstride * i, *t = tg + tstride * i;
+    const long long lx = locs[2 * i], ly = locs[2 * i + 1];
+    T* g = out_grad + 7 * i;
+    switch (loss) {
+      case 0: out_loss[i] = gd::center_pair_eval<T, 0, true>(p, lx, ly, t, D, P, (T)1, g); break;
+      case 1: out_loss[i] = gd::center_pair_eval<T, 1, true>(p, lx, ly, t, D, P, (T)1, g); break;
+      case 2: out_loss[i] = gd::center_pair_eval<T, 2, true>(p, lx, ly, t, D, P, (T)1, g); break;
+      case 3: out_loss[i] = gd::center_pair_eval<T, 3, true>(p, lx, ly, t, D, P, (T)1, g); break;
+      case 4: out_loss[i] = gd::center_pair_eval<T, 4, true>(p, lx, ly, t, D, P, (T)1, g); break;
+      case 5: out_loss[i] = gd::center_pair_eval<T, 5, true>(p, lx, ly, t, D, P, (T)1, g); break;
+      case 6: out_loss[i] = gd::center_pair_eval<T, 6, true>(p, lx, ly, t, D, P, (T)1, g); break;
+    }
+  }
+}
+
+extern "C" {
+void gd_host_anchor_f64(int loss, long n, const double* an, const double* dp, const double* dt,
+                        const double* off, double alpha, double tau, int fun, int flag,
+                        double* out_loss, double* out_grad) {
+  run_anchor<double>(loss, n, an, dp, dt, off, alpha, tau, fun, flag, out_loss, out_grad);
+}
+void gd_host_anchor_f32(int loss, long n, const float* an, const float* dp, const float* dt,
+                        const double* off, double alpha, double tau, int fun, int flag,
+                        float* out_loss, float* out_grad) {
+  run_anchor<float>(loss, n, an, dp, dt, off, alpha, tau, fun, flag, out_loss, out_grad);
+}
+void gd_host_center_f64(int loss, long n, const double* pr, long pstride, const long long* locs,
+                        const double* tg, long tstride, const double* coder, int norm_bbox,
+                        const double* off, double alpha, double tau, int fun, int flag,
+                        double* out_loss, double* out_grad) {
+  run_center<double>(loss, n, pr, pstride, locs, tg, tstride, coder, norm_bbox, off, alpha, tau,
+                     fun, flag, out_loss, out_grad);
+}
+void gd_host_center_f32(int loss, long n, const float* pr, long pstride, const long long* locs,
+                        const float* tg, long tstride, const double* coder, int norm_bbox,
+                        const double* off, double alpha, double tau, int fun, int flag,
+                        float* out_loss, float* out_grad) {
+  run_center<float>(loss, n, pr, pstride, locs, tg, tstride, coder, norm_bbox, off, alpha, tau,
+                    fun, flag, out_loss, out_grad);
+}
+}

@@ -130,3 +130,74 @@ def test_no_cpu_fallback():
         GDLoss('gwd3d')(torch.zeros(4, 7), torch.zeros(4, 7))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         GDPairwiseDistance('gwd3d')(torch.zeros(4, 7), torch.zeros(4, 7))
+
+
+def test_head_front_end_argument_validation_without_gpu(lib):
+    cfg = _lib.make_config('gwd3d', 'log1p', True, 1.0, 1.0, (0, 0, 0.5))
+    null, one = ctypes.c_void_p(0), ctypes.c_void_p(16)
+    dw = (ctypes.c_float * 7)(*[1.0] * 7)
+    anchor = lib.gd_anchor_decoded_loss_fwd_bwd
+
+    def call_anchor(pos=one, npos=4, labels=null, grad=one, mode=_lib.GRAD_SCATTER, bw=null,
+                    dwp=None, arows=4, loss=null, ws=null, wsb=0, total=16):
+        return anchor(ctypes.byref(cfg), one, arows, one, 7, one, 7, bw, 7, dwp, pos, npos,
+                      labels, 3, total, 1.0, loss, grad, mode, ws, wsb, 0, null)
+    # well-formed empty calls are accepted in every mode (nothing is launched)
+    assert call_anchor(pos=null, npos=0, labels=one, mode=_lib.GRAD_DENSE, total=0) == 0
+    assert call_anchor(npos=0, mode=_lib.GRAD_SCATTER) == 0
+    assert call_anchor(npos=0, mode=_lib.GRAD_COMPACT) == 0
+    assert call_anchor(npos=0, grad=null, mode=_lib.GRAD_NONE) == 0
+    assert call_anchor(arows=0) == -1                          # no anchors
+    assert call_anchor(pos=null) == -1                         # index mode without indices
+    assert call_anchor(labels=one) == -1                       # both selectors
+    assert call_anchor(mode=_lib.GRAD_DENSE) == -1             # dense needs labels
+    assert call_anchor(pos=null, npos=0, labels=one, mode=_lib.GRAD_COMPACT) == -1
+    assert call_anchor(grad=null) == -1                        # gradient requested, no buffer
+    assert call_anchor(bw=one, dwp=None) == -1                 # weights without decode_weight
+    assert call_anchor(bw=one, dwp=dw, loss=one) == -2         # loss_sum without workspace
+    assert call_anchor(mode=9) == -1
+
+    coder = _lib.make_center_coder((-51.2, -51.2), 4, (0.2, 0.2))
+    assert ctypes.sizeof(_lib.GDCenterCoder) == 40
+    center = lib.gd_center_decoded_loss_fwd_bwd
+
+    def call_center(c=ctypes.byref(coder), preds=one, n=4, wmode=0, w=null, grad=one, gstride=11,
+                    gcols=11, loss=null):
+        return center(ctypes.byref(cfg), c, preds, 11, one, 3, one, 11, w, wmode, 1, n, 1.0,
+                      loss, grad, gstride, gcols, null, 0, 0, null)
+    assert call_center(c=None) == -1
+    assert call_center(preds=null) == -1
+    assert call_center(n=-1) == -1
+    assert call_center(wmode=1) == -1                          # weight mode without weights
+    assert call_center(gcols=6) == -1                          # gradient rows narrower than 7
+    assert call_center(gstride=9) == -1                        # stride < columns
+    assert call_center(loss=one) == -2
+    assert lib.gd_scale_buffer(null, 8, one, null) == -1
+    assert lib.gd_scale_buffer(null, 0, null, null) == 0
+
+
+def test_head_modules_validate_on_the_host():
+    from mmdet3d_gaussian_b200 import GDAnchorHeadLoss, GDCenterHeadLoss
+    from mmdet3d_gaussian_b200.heads import _scale
+    cfg = dict(type='GDLoss', loss_type='gwd3d', fun='log1p', tau=1.0, loss_weight=5.0)
+    head = GDAnchorHeadLoss(cfg, decode_weight=1)
+    assert isinstance(head.loss_decoded_bbox, GDLoss) and len(head.state_dict()) == 0
+    assert _scale(head.loss_decoded_bbox, 10.0, None) == 0.5
+    assert _scale(head.loss_decoded_bbox, None, 4) == 1.25
+    with pytest.raises(ValueError):
+        _scale(head.loss_decoded_bbox, None, None)             # labels mode needs avg_factor
+    with pytest.raises(NotImplementedError):
+        _scale(GDLoss('gwd3d', reduction='none'), None, 4)
+    with pytest.raises(ValueError):
+        GDAnchorHeadLoss(dict(type='SmoothL1Loss'))
+    z = torch.zeros(4, 7)
+    with pytest.raises(ValueError, match='exactly one'):
+        head(z, z, z, z, avg_factor=1.0)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        head(z, z, z, z, pos_inds=torch.zeros(1, dtype=torch.long), avg_factor=1.0)
+    center = GDCenterHeadLoss(dict(cfg, tau=0.0), dict(
+        type='CenterPointBBoxYawCoder', pc_range=(-51.2, -51.2), out_size_factor=4,
+        voxel_size=(0.2, 0.2), code_size=9))
+    assert center.coder.norm_bbox == 1 and center.coder.out_size_factor == 4
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        center(torch.zeros(4, 11), torch.zeros(4, 3, dtype=torch.long), torch.zeros(4, 11))
