@@ -158,6 +158,47 @@ int gd_pairwise_row_argmin(const gd_loss_config* cfg,
                            const float* boxes2, int64_t m,
                            float* row_min, int32_t* row_argmin, void* stream);
 
+/* flags of gd_pairwise_assign */
+enum {
+  GD_PAIR_SIMILARITY = 1   /* the optional matrix holds 1 - value ("larger is closer", the
+                              iou_calculator convention of mmdet assigners); the minima
+                              are always minima of the distance value                   */
+};
+
+/* Bytes of device workspace gd_pairwise_assign needs for m columns.  Zero-filled ONCE
+ * when allocated; the kernel leaves it zeroed again. */
+size_t gd_pairwise_workspace_bytes(int64_t m);
+
+/* Pairwise distances with BOTH assigner reductions fused (SURVEY.md section 8 row f2;
+ * what a MaxIoUAssigner-style consumer takes from an N x M cost matrix, cf. the
+ * reference's IoU-based core/bbox/assigners/sim_ota_3d_assigner.py:91-123):
+ *   row_min[i], row_argmin[i] = min / argmin over j of D[i,j]     (per anchor: closest GT)
+ *   col_min[j], col_argmin[j] = min / argmin over i of D[i,j]     (per GT: closest anchor)
+ * NaN is the minimum (torch.min semantics); ties go to the lowest index.  `out` is
+ * optional: when null the matrix is never written.  The reductions and the matrix come
+ * from the same per-pair instruction sequence, so they are bit-consistent. */
+int gd_pairwise_assign(const gd_loss_config* cfg,
+                       const float* boxes1, int64_t n,
+                       const float* boxes2, int64_t m,
+                       float* row_min, int32_t* row_argmin,
+                       float* col_min, int32_t* col_argmin,
+                       float* out, int64_t out_row_stride, int32_t flags,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* MaxIoUAssigner-style labels from the fused minima, with similarity = 1 - distance
+ * (for tau >= 1 that is tau / (tau + f(d)) in (0, 1], an IoU-like score).  Restates
+ * upstream mmdet MaxIoUAssigner.assign_wrt_overlaps with gt_max_assign_all=False
+ * (mmdet is not in the reference checkout: parity unpinned, contract in DESIGN.md):
+ *   assigned = -1;  neg_lo <= sim < neg_hi -> 0;  sim >= pos_thr -> row_argmin + 1;
+ *   match_low_quality: for each GT j in order with (1 - col_min[j]) >= min_pos:
+ *                      assigned[col_argmin[j]] = j + 1   (the last GT wins)
+ * assigned_gt_inds [n] int64, max_overlaps [n] fp32 (nullable) = 1 - row_min. */
+int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin, int64_t n,
+                          const float* col_min, const int32_t* col_argmin, int64_t m,
+                          float pos_thr, float neg_lo, float neg_hi, float min_pos,
+                          int32_t match_low_quality, int64_t* assigned_gt_inds,
+                          float* max_overlaps, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Head front ends: positive-row gather + box decode +
  * GD loss + gradient w.r.t. the RAW network outputs in one launch.

@@ -6,9 +6,11 @@ the reference's registry name, constructor and ``forward``; the math runs in
 hand-written CUDA kernels behind a C ABI (``include/gd_loss_b200.h``).  See
 DESIGN.md.
 """
+from .assigners import GDMaxSimAssigner, GDSimilarity3D
 from .heads import GDAnchorHeadLoss, GDCenterHeadLoss
 from .losses import GDLoss, GDPairwiseDistance
 from .registry import LOSSES, build_loss
 
-__all__ = ['GDLoss', 'GDPairwiseDistance', 'GDAnchorHeadLoss', 'GDCenterHeadLoss', 'LOSSES', 'build_loss']
+__all__ = ['GDLoss', 'GDPairwiseDistance', 'GDAnchorHeadLoss', 'GDCenterHeadLoss',
+           'GDSimilarity3D', 'GDMaxSimAssigner', 'LOSSES', 'build_loss']
 __version__ = '0.1.0'

@@ -15,6 +15,7 @@ FUNS = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
 WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
 VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3}
 FLAG_MASK_ZERO_WEIGHT = 1
+PAIR_SIMILARITY = 1
 GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3
 
 
@@ -47,6 +48,11 @@ SIGNATURES = {
     'gd_any_positive': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     'gd_pairwise': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     'gd_pairwise_row_argmin': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    'gd_pairwise_workspace_bytes': (ctypes.c_size_t, [_i64]),
+    'gd_pairwise_assign': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp,
+                                          _i64, _i32, _vp, ctypes.c_size_t, _vp]),
+    'gd_assign_from_minima': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _f32, _f32, _f32, _f32,
+                                             _i32, _vp, _vp, _vp]),
     'gd_anchor_decoded_loss_fwd_bwd': (ctypes.c_int, [
         _cfgp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, ctypes.POINTER(ctypes.c_float),
         _vp, _i64, _vp, _i64, _i64, _f32, _vp, _vp, _i32, _vp, ctypes.c_size_t, _i32, _vp]),

@@ -18,8 +18,11 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), 'include')
 SOURCES = ['gd_loss_api.cu', 'gd_loss_inst_gwd.cu', 'gd_loss_inst_kld.cu', 'gd_loss_inst_jd.cu',
            'gd_loss_inst_symmax.cu', 'gd_loss_inst_symmin.cu', 'gd_loss_inst_bd.cu',
-           'gd_loss_inst_kfiou.cu', 'gd_pairwise.cu', 'gd_host_pipeline.cu', 'gd_decoded.cu']
-HEADERS = ['gd_math.cuh', 'gd_common.cuh', 'gd_loss_kernels.cuh', 'gd_decode.cuh']
+           'gd_loss_inst_kfiou.cu', 'gd_pairwise.cu', 'gd_host_pipeline.cu', 'gd_decoded.cu',
+           'gd_pairwise_inst_gwd.cu', 'gd_pairwise_inst_kld.cu', 'gd_pairwise_inst_jd.cu',
+           'gd_pairwise_inst_symmax.cu', 'gd_pairwise_inst_symmin.cu', 'gd_pairwise_inst_bd.cu',
+           'gd_pairwise_inst_kfiou.cu']
+HEADERS = ['gd_math.cuh', 'gd_common.cuh', 'gd_loss_kernels.cuh', 'gd_decode.cuh', 'gd_pairwise.cuh']
 LIB_NAME = 'libgdloss_b200.so'
 LIB_PRECISE_NAME = 'libgdloss_b200_precise.so'   # -DGD_PRECISE_MATH=1, tests only
 

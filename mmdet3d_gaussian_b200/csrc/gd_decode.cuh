@@ -113,6 +113,7 @@ GD_HD T anchor_pair_eval(const T* a, const T* dp, const T* dt, const PairParams<
   g.bt = (T)0.5 * clamp_extent(te[1], &dummy);
   g.et = (T)0.5 * clamp_extent(te[2], &dummy);
   geom_set_yaw<T, kNeedRot>(&g, dp[6] + a[6], dt[6] + a[6], dp[6] - dt[6]);
+  geom_derive(&g);
   T gb[7];
   bool unused = false;
   const T val = core_eval<T, LOSS, GRAD, false>(g, P, gscale, gb, &unused);
@@ -159,6 +160,7 @@ GD_HD T center_pair_eval(const T* pr, long long loc_x, long long loc_y, const T*
   g.bt = (T)0.5 * clamp_extent(t[4], &dummy);
   g.et = (T)0.5 * clamp_extent(t[5], &dummy);
   geom_set_yaw<T, kNeedRot>(&g, pr[6], t[6], pr[6] - t[6]);
+  geom_derive(&g);
   T gb[7];
   bool unused = false;
   const T val = core_eval<T, LOSS, GRAD, false>(g, P, gscale, gb, &unused);

@@ -332,7 +332,39 @@ struct PairGeom {
   T ma, mb, me;             // clamp gradient masks of the pred extents
   T sp, cp;                 // sin / cos of pred yaw              (ref:16-17)
   T sd, cd;                 // sin / cos of (r_p - r_t)
+  // Quantities that depend on ONE box only.  The element-wise path derives them per
+  // pair (geom_derive, same arithmetic as before); the pairwise path computes them
+  // once per box (BoxGauss) so the N x M inner loop does not repeat them.
+  T A, B, E, C, D, F;       // squared half extents (pred: A B E, target: C D F)
+  T abp, abt;               // a_p b_p, a_t b_t                    (ref:91-92)
+  T amb, cmd;               // A - B, C - D formed as (a-b)(a+b)
+  T iap, ibp, iep;          // 1 / pred half extents
+  T iat, ibt, iet;          // 1 / target half extents
+  T r6p, r6t;               // (a b e)^(-1/6) per box, valid iff has_r6
+  bool has_r6;
 };
+
+template <typename T>
+GD_HD void geom_derive(PairGeom<T>* g) {
+  g->A = g->ap * g->ap;
+  g->B = g->bp * g->bp;
+  g->E = g->ep * g->ep;
+  g->C = g->at * g->at;
+  g->D = g->bt * g->bt;
+  g->F = g->et * g->et;
+  g->abp = g->ap * g->bp;
+  g->abt = g->at * g->bt;
+  g->amb = (g->ap - g->bp) * (g->ap + g->bp);
+  g->cmd = (g->at - g->bt) * (g->at + g->bt);
+  g->iap = Mth<T>::rcp(g->ap);
+  g->ibp = Mth<T>::rcp(g->bp);
+  g->iep = Mth<T>::rcp(g->ep);
+  g->iat = Mth<T>::rcp(g->at);
+  g->ibt = Mth<T>::rcp(g->bt);
+  g->iet = Mth<T>::rcp(g->et);
+  g->r6p = g->r6t = (T)0;
+  g->has_r6 = false;
+}
 
 // FAST: the caller promises to re-run the row on the robust path when *rare is
 // set.  A row is "nice" when all six extents lie in [1e-4, 1e4] (clamps inactive,
@@ -367,6 +399,7 @@ GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool
       g.sp = (T)0;
       g.cp = (T)1;
     }
+    geom_derive(&g);
     return g;
   }
   T dummy;
@@ -396,6 +429,7 @@ GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool
     g.sd = g.sp * ct - g.cp * st;
     g.cd = g.cp * ct + g.sp * st;
   }
+  geom_derive(&g);
   return g;
 }
 
@@ -424,16 +458,16 @@ GD_HD void store_grad(const PairGeom<T>& g, const PairParams<T>& P,
 // ---------------------------------------------------------------------------
 template <typename T, bool GRAD, bool FAST>
 GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
-  const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
+  const T A = g.A, B = g.B, C = g.C, D = g.D;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd;
-  const T K = (g.ap * g.bp) * (g.at * g.bt);                       // ref:91-92
+  const T K = g.abp * g.abt;                                       // ref:91-92
   // U = tr(Sigma_p Sigma_t) + 2 sqrt(det det): all terms positive    ref:88-95
   const T U = (A * C + B * D) * c2 + (A * D + B * C) * s2 + (T)2 * K;
   T kU;                                                            // 1/(2 sqrt U)
   const T rU = sqrt_clamp0(U, &kU);                                // ref:95
   const T V = g.ap * g.at + g.bp * g.bt;
-  const T amb = (g.ap - g.bp) * (g.ap + g.bp);                     // A - B
-  const T cmd = (g.at - g.bt) * (g.at + g.bt);                     // C - D
+  const T amb = g.amb;                                             // A - B
+  const T cmd = g.cmd;                                             // C - D
   const T eps = amb * cmd * s2;                                    // V^2 - U
   const T eta = eps * Mth<T>::rcp(V + rU);                         // V - sqrt U
   const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
@@ -444,8 +478,10 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
   T inv_n = (T)1;
   if (P.flag) {                                                    // ref:101-104
     // 1 / (2 (K e_p e_t)^(1/6)), product split so it cannot overflow
-    if (FAST) {
-      inv_n = (T)0.5 * Mth<T>::rsixthroot((g.ap * g.bp * g.ep) * (g.at * g.bt * g.et));
+    if (g.has_r6) {                            // pairwise: per-box factors
+      inv_n = (T)0.5 * (g.r6p * g.r6t);
+    } else if (FAST) {
+      inv_n = (T)0.5 * Mth<T>::rsixthroot((g.abp * g.ep) * (g.abt * g.et));
     } else {
       const T vp = Mth<T>::sqrt(g.ap * g.bp * g.ep);
       const T vt = Mth<T>::sqrt(g.at * g.bt * g.et);
@@ -473,9 +509,9 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
     L.gr = P.alpha2 * dWr * kn;
     if (P.flag) {                                                  // d ln n / da = 1/(6a)
       const T g6 = gval * (T)(1.0 / 6.0);
-      L.ga -= g6 * Mth<T>::rcp(g.ap);
-      L.gb -= g6 * Mth<T>::rcp(g.bp);
-      L.ge -= g6 * Mth<T>::rcp(g.ep);
+      L.ga -= g6 * g.iap;
+      L.gb -= g6 * g.ibp;
+      L.ge -= g6 * g.iep;
     }
     store_grad(g, P, L, fac * gscale, grad);
   }
@@ -503,10 +539,10 @@ GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   //        + ln(a_p b_p e_p / a_t b_t e_t) - 1.5                   ref:122-137
   const T u = g.cp * g.dx + g.sp * g.dy;
   const T v = -g.sp * g.dx + g.cp * g.dy;
-  const T iap = Mth<T>::rcp(g.ap), ibp = Mth<T>::rcp(g.bp), iep = Mth<T>::rcp(g.ep);
+  const T iap = g.iap, ibp = g.ibp, iep = g.iep;
   const T iA = iap * iap, iB = ibp * ibp, iE = iep * iep;
   const T s2 = g.sd * g.sd;
-  const T cmd = (g.at - g.bt) * (g.at + g.bt);
+  const T cmd = g.cmd;
   // delta_i = (t_i - p_i)/p_i ; C/A = (1+delta_a)^2 ...
   const T qa = (g.at - g.ap) * iap, qb = (g.bt - g.bp) * ibp, qe = (g.et - g.ep) * iep;
   const T ra = g.at * iap, rb = g.bt * ibp, re = g.et * iep;       // = 1 + q
@@ -540,10 +576,10 @@ GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   // rotate into the target frame: (u', v') = R(dl) (u, v)
   const T ut = g.cd * u - g.sd * v;
   const T vt = g.sd * u + g.cd * v;
-  const T iat = Mth<T>::rcp(g.at), ibt = Mth<T>::rcp(g.bt), iet = Mth<T>::rcp(g.et);
+  const T iat = g.iat, ibt = g.ibt, iet = g.iet;
   const T iC = iat * iat, iD = ibt * ibt, iF = iet * iet;
   const T s2 = g.sd * g.sd;
-  const T amb = (g.ap - g.bp) * (g.ap + g.bp);
+  const T amb = g.amb;
   const T qa = (g.ap - g.at) * iat, qb = (g.bp - g.bt) * ibt, qe = (g.ep - g.et) * iet;
   const T ra = g.ap * iat, rb = g.bp * ibt, re = g.ep * iet;       // = 1 + q
   const T maha = (T)0.5 * (ut * ut * iC + vt * vt * iD + g.dz * g.dz * iF) * P.inv_alpha2;
@@ -553,15 +589,15 @@ GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
       + (T)0.5 * amb * s2 * (iD - iC);
   if (want_grad) {
     const T s2x2 = (T)2 * g.sd * g.cd;
-    const T A = g.ap * g.ap, B = g.bp * g.bp;
+    const T A = g.A, B = g.B;
     // gradient w.r.t. (u', v') rotated back into the pred frame: R(-dl)
     const T lut = ut * iC * P.inv_alpha2, lvt = vt * iD * P.inv_alpha2;
     *ul = g.cd * lut + g.sd * lvt;
     *vl = -g.sd * lut + g.cd * lvt;
     L->gdz = g.dz * iF * P.inv_alpha2;
-    L->ga = Mth<T>::rcp(g.ap) * (qa * ((T)2 + qa) + A * s2 * (iD - iC));
-    L->gb = Mth<T>::rcp(g.bp) * (qb * ((T)2 + qb) + B * s2 * (iC - iD));
-    L->ge = Mth<T>::rcp(g.ep) * (qe * ((T)2 + qe));
+    L->ga = g.iap * (qa * ((T)2 + qa) + A * s2 * (iD - iC));
+    L->gb = g.ibp * (qb * ((T)2 + qb) + B * s2 * (iC - iD));
+    L->ge = g.iep * (qe * ((T)2 + qe));
     L->gr = (T)0.5 * amb * s2x2 * (iD - iC);
   }
   return maha + shape;
@@ -640,13 +676,13 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
 // ---------------------------------------------------------------------------
 template <typename T, bool GRAD, bool FAST>
 GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
-  const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
-  const T E = g.ep * g.ep, F = g.et * g.et;
+  const T A = g.A, B = g.B, C = g.C, D = g.D;
+  const T E = g.E, F = g.F;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd, sc = g.sd * g.cd;
   const T u = g.cp * g.dx + g.sp * g.dy;
   const T v = -g.sp * g.dx + g.cp * g.dy;
-  const T amb = (g.ap - g.bp) * (g.ap + g.bp);
-  const T cmd = (g.at - g.bt) * (g.at + g.bt);
+  const T amb = g.amb;
+  const T cmd = g.cmd;
   // Sigma_t in the pred frame
   const T t00 = C * c2 + D * s2, t11 = C * s2 + D * c2, t01 = -cmd * sc;
   // M = (Sigma_p + Sigma_t)/2 in the pred frame                    ref:152
@@ -666,15 +702,15 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
   const T Q2 = u * u * M11 - (T)2 * u * v * M01 + v * v * M00;     // d^T adj(M) d
   const T maha = (T)0.125 * (Q2 * idet + g.dz * g.dz * iMl) * P.inv_alpha2;  // ref:170-172,182
   // shape: 0.5 ln det + 0.5 ln Ml - 0.25 ln(ABE) - 0.25 ln(CDF)    ref:174-180
-  const T K = (g.ap * g.bp) * (g.at * g.bt);
+  const T K = g.abp * g.abt;
   const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
-  const T xe = de * de * Mth<T>::rcp((T)2 * g.ep * g.et);          // Ml/(e_p e_t) - 1
+  const T xe = de * de * ((T)0.5 * g.iep * g.iet);                 // Ml/(e_p e_t) - 1
   T shape;
   if (!clamped) {
     // det/(sqrt(AB) sqrt(CD)) = (1+xa)(1+xb) + eps/(4K),  xa = (a_p-a_t)^2/(2 a_p a_t)
-    const T xa = da * da * Mth<T>::rcp((T)2 * g.ap * g.at);
-    const T xb = db * db * Mth<T>::rcp((T)2 * g.bp * g.bt);
-    const T q = xa + xb + xa * xb + (T)0.25 * eps * Mth<T>::rcp(K);
+    const T xa = da * da * ((T)0.5 * g.iap * g.iat);
+    const T xb = db * db * ((T)0.5 * g.ibp * g.ibt);
+    const T q = xa + xb + xa * xb + (T)0.25 * eps * ((g.iap * g.ibp) * (g.iat * g.ibt));
     const T qq = q + xe + q * xe;              // (1+q)(1+xe) - 1
     if (FAST) {
       *rare |= !(qq >= (T)0 && qq < (T)1e30);
@@ -702,7 +738,7 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
     const T vl = (T)2 * c8 * (M00 * v - M01 * u);
     rotate_centre_grad(g, ul, vl, &L);
     L.gdz = (T)0.25 * g.dz * iMl * P.inv_alpha2;
-    const T iap = Mth<T>::rcp(g.ap), ibp = Mth<T>::rcp(g.bp), iep = Mth<T>::rcp(g.ep);
+    const T iap = g.iap, ibp = g.ibp, iep = g.iep;
     T sa, sb, gam;                             // shape parts and d/d det_raw factor
     if (!clamped) {
       const T idN = Mth<T>::rcp(detN);
@@ -873,6 +909,11 @@ struct BoxGauss {
   T cx, cy, cz;     // centre incl. center_offset * unclamped extents   ref:12
   T a, b, e;        // clamped half extents                             ref:13-14,19-20
   T s, c;           // sin / cos yaw                                    ref:16-17
+  T A, B, E;        // squared half extents
+  T ab;             // a b
+  T amb;            // (a - b)(a + b)
+  T r6;             // (a b e)^(-1/6): the box's factor of the gwd normaliser   ref:101-104
+  T ia, ib, ie;     // reciprocal half extents
   int nice;         // extents in [1e-4, 1e4]: the FAST cores may be used for this box
 };
 
@@ -887,6 +928,15 @@ GD_HD BoxGauss<T> box_gauss(const T* row, const PairParams<T>& P) {
   b.b = (T)0.5 * clamp_extent(row[4], &m);
   b.e = (T)0.5 * clamp_extent(row[5], &m);
   Mth<T>::sincos(row[6], &b.s, &b.c);        // once per box: accurate version, any magnitude
+  b.A = b.a * b.a;
+  b.B = b.b * b.b;
+  b.E = b.e * b.e;
+  b.ab = b.a * b.b;
+  b.amb = (b.a - b.b) * (b.a + b.b);
+  b.r6 = Mth<T>::rcbrt(Mth<T>::sqrt(b.ab * b.e));   // finite for every clamped extent
+  b.ia = Mth<T>::rcp(b.a);
+  b.ib = Mth<T>::rcp(b.b);
+  b.ie = Mth<T>::rcp(b.e);
   const T lo = (T)1e-4, hi = (T)1e4;
   b.nice = (row[3] >= lo && row[3] <= hi && row[4] >= lo && row[4] <= hi && row[5] >= lo &&
             row[5] <= hi) ? 1 : 0;
@@ -905,6 +955,14 @@ GD_HD PairGeom<T> geom_from_gauss(const BoxGauss<T>& p, const BoxGauss<T>& t) {
   g.sp = p.s; g.cp = p.c;
   g.sd = p.s * t.c - p.c * t.s;       // sin(r_p - r_t)
   g.cd = p.c * t.c + p.s * t.s;       // cos(r_p - r_t)
+  g.A = p.A; g.B = p.B; g.E = p.E;
+  g.C = t.A; g.D = t.B; g.F = t.E;
+  g.abp = p.ab; g.abt = t.ab;
+  g.amb = p.amb; g.cmd = t.amb;
+  g.iap = p.ia; g.ibp = p.ib; g.iep = p.ie;
+  g.iat = t.ia; g.ibt = t.ib; g.iet = t.ie;
+  g.r6p = p.r6; g.r6t = t.r6;
+  g.has_r6 = true;
   return g;
 }
 

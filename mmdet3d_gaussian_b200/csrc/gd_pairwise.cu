@@ -1,127 +1,57 @@
-// Pairwise N x M Gaussian-distance matrix for B200 (sm_100a).
-//
-// New surface (the reference has only IoU matrices,
-// core/bbox/assigners/sim_ota_3d_assigner.py:91-93): out[i,j] =
-// postprocess(distance(boxes1[i], boxes2[j])), equal to the element-wise loss
-// path of gaussian_distance_loss.py on the broadcast-expanded pairs.
-//
-// Mapping: thread <-> column j.  A CTA owns kRowsPerCta rows of boxes1; it
-// converts them once to BoxGauss (centre, half extents, sin/cos yaw) in shared
-// memory, each thread converts its own column box once into registers, and the
-// inner loop over rows reads the row Gaussian as a shared-memory broadcast and
-// writes out[i, j0 + tid] -- consecutive threads write consecutive floats, so
-// the 4 B/pair output stream is fully coalesced.  FP32 CUDA-core math, no
-// tensor cores (not a contraction).  The fused arg-reduction variant reduces
-// (value, column) keys with warp shuffles + shared memory and need not write the
-// matrix at all.
-#include "gd_common.cuh"
+// C ABI of the pairwise N x M Gaussian-distance kernels (gd_pairwise.cuh; one
+// instantiation per loss type in gd_pairwise_inst_*.cu).
+#include "gd_pairwise.cuh"
 
 namespace gdk {
+extern template int launch_pairwise<gd::kGwd>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kKld>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kJd>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kSymMax>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kSymMin>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kBd>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kKfiou>(const PairwiseArgs&, cudaStream_t);
 
-constexpr int kRowsPerCta = 64;
-constexpr int kWarps = kThreads / 32;
-
-// (value, column) packed so that an unsigned 64-bit min is "smaller value, then
-// lower column"; NaN maps below everything (torch.min / argmin propagate NaN).
-__device__ __forceinline__ unsigned long long pack_key(float v, unsigned int j) {
-  unsigned int b = __float_as_uint(v);
-  b ^= (b >> 31) ? 0xffffffffu : 0x80000000u;
-  if (v != v) b = 0u;
-  return ((unsigned long long)b << 32) | j;
+// --- MaxIoUAssigner-style labels from the fused minima (similarity = 1 - distance) ---
+__global__ void __launch_bounds__(kThreads) gd_assign_lowq_kernel(
+    const float* __restrict__ col_min, const int* __restrict__ col_argmin, long long m,
+    long long n, float min_pos, long long* __restrict__ assigned) {
+  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= m) return;
+  const float sim = 1.0f - col_min[j];
+  const long long anchor = col_argmin[j];
+  // mmdet walks the GTs in order and overwrites: the highest GT index wins
+  if (sim >= min_pos && anchor >= 0 && anchor < n)
+    atomicMax(reinterpret_cast<unsigned long long*>(assigned + anchor), (unsigned long long)(j + 1));
 }
-__device__ __forceinline__ float unpack_value(unsigned long long k) {
-  unsigned int b = (unsigned int)(k >> 32);
-  if (b == 0u) return __uint_as_float(0x7fc00000u);
-  b ^= (b >> 31) ? 0x80000000u : 0xffffffffu;
-  return __uint_as_float(b);
+
+__global__ void __launch_bounds__(kThreads) gd_assign_rows_kernel(
+    const float* __restrict__ row_min, const int* __restrict__ row_argmin, long long n,
+    float pos_thr, float neg_lo, float neg_hi, long long* __restrict__ assigned,
+    float* __restrict__ max_overlaps) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const float sim = 1.0f - row_min[i];
+  long long lab = -1;                                   // ignore
+  if (sim >= neg_lo && sim < neg_hi) lab = 0;           // negative
+  if (sim >= pos_thr) lab = (long long)row_argmin[i] + 1;
+  const long long lowq = assigned[i];                   // set by gd_assign_lowq_kernel, else 0
+  if (lowq > 0) lab = lowq;
+  assigned[i] = lab;
+  if (max_overlaps) max_overlaps[i] = sim;
 }
 
-// One kernel for both uses so the matrix and the fused arg-reduction run the
-// SAME per-pair instruction sequence (indices derived from either are then
-// bit-identical): WRITE stores the matrix, ARGMIN keeps per-row minima.
-template <int LOSS, bool WRITE, bool ARGMIN>
-__global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(
-    const float* __restrict__ b1, long long n, const float* __restrict__ b2, long long m,
-    float* __restrict__ out, long long out_stride, float* __restrict__ row_min,
-    int* __restrict__ row_argmin, const gd::PairParams<float> pp) {
-  __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
-  __shared__ unsigned long long s_best[ARGMIN ? kRowsPerCta : 1][kWarps];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long row0 = (long long)blockIdx.x * kRowsPerCta;
-  const int rows = (int)min((long long)kRowsPerCta, n - row0);
-  if (tid < rows) s_rows[tid] = gd::box_gauss(b1 + (row0 + tid) * 7, pp);
-  if (ARGMIN) {
-    for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads)
-      (&s_best[0][0])[i] = ~0ull;
+static int dispatch_pairwise(const gd_loss_config* cfg, const PairwiseArgs& a, cudaStream_t st) {
+  switch (cfg->loss_type) {
+    case GD_LOSS_GWD3D: return launch_pairwise<gd::kGwd>(a, st);
+    case GD_LOSS_KLD3D: return launch_pairwise<gd::kKld>(a, st);
+    case GD_LOSS_JD3D: return launch_pairwise<gd::kJd>(a, st);
+    case GD_LOSS_KLD3D_SYMMAX: return launch_pairwise<gd::kSymMax>(a, st);
+    case GD_LOSS_KLD3D_SYMMIN: return launch_pairwise<gd::kSymMin>(a, st);
+    case GD_LOSS_BD3D: return launch_pairwise<gd::kBd>(a, st);
+    case GD_LOSS_KFIOU3D: return launch_pairwise<gd::kKfiou>(a, st);
   }
-  __syncthreads();
-  // whole-CTA column chunks so that every lane takes part in the warp reductions
-  for (long long c0 = (long long)blockIdx.y * kThreads; c0 < m;
-       c0 += (long long)gridDim.y * kThreads) {
-    const long long j = c0 + tid;
-    const bool live = j < m;
-    gd::BoxGauss<float> t;
-    if (live) t = gd::box_gauss(b2 + j * 7, pp);
-    else t = s_rows[0];                    // any valid box: result is discarded
-    float* o = out + row0 * out_stride + j;
-#pragma unroll 2
-    for (int r = 0; r < rows; ++r) {
-      const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t, pp);
-      if (WRITE && live) __stcs(o + (long long)r * out_stride, v);
-      if (ARGMIN) {
-        unsigned long long k = live ? pack_key(v, (unsigned int)j) : ~0ull;
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, sh);
-          k = other < k ? other : k;
-        }
-        if (lane == 0 && k < s_best[r][warp]) s_best[r][warp] = k;
-      }
-    }
-  }
-  if (ARGMIN) {
-    __syncthreads();
-    if (tid < rows) {
-      unsigned long long k = s_best[tid][0];
-#pragma unroll
-      for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
-      row_min[row0 + tid] = unpack_value(k);
-      row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
-    }
-  }
+  return GD_ERR_BAD_ARG;
 }
-
-template <int LOSS>
-int launch_pairwise(const float* b1, long long n, const float* b2, long long m, float* out,
-                    long long out_stride, float* row_min, int* row_argmin,
-                    const gd::PairParams<float>& pp, cudaStream_t st) {
-  const long long gx = (n + kRowsPerCta - 1) / kRowsPerCta;
-  if (gx > 2147483647LL || m > 0xffffffffLL) return GD_ERR_BAD_ARG;
-  if (row_argmin) {                        // fused arg-reduction: one CTA walks all columns
-    dim3 grid((unsigned)gx, 1);
-    if (out)
-      gd_pairwise_kernel<LOSS, true, true><<<grid, kThreads, 0, st>>>(
-          b1, n, b2, m, out, out_stride, row_min, row_argmin, pp);
-    else
-      gd_pairwise_kernel<LOSS, false, true><<<grid, kThreads, 0, st>>>(
-          b1, n, b2, m, out, out_stride, row_min, row_argmin, pp);
-  } else {
-    long long gy = (m + kThreads - 1) / kThreads;
-    if (gy > 65535) gy = 65535;
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    gd_pairwise_kernel<LOSS, true, false><<<grid, kThreads, 0, st>>>(
-        b1, n, b2, m, out, out_stride, row_min, row_argmin, pp);
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
-}
-
-template <int LOSS>
-int launch_argmin(const float* b1, long long n, const float* b2, long long m, float* row_min,
-                  int* row_argmin, const gd::PairParams<float>& pp, cudaStream_t st) {
-  return launch_pairwise<LOSS>(b1, n, b2, m, nullptr, m, row_min, row_argmin, pp, st);
-}
-
 }  // namespace gdk
 
 extern "C" {
@@ -132,18 +62,15 @@ int gd_pairwise(const gd_loss_config* cfg, const float* boxes1, int64_t n, const
   if (!config_ok(cfg) || n < 0 || m < 0 || out_row_stride < m) return GD_ERR_BAD_ARG;
   if (n == 0 || m == 0) return 0;
   if (!boxes1 || !boxes2 || !out) return GD_ERR_BAD_ARG;
-  const gd::PairParams<float> pp = make_pair_params(*cfg);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (cfg->loss_type) {
-    case GD_LOSS_GWD3D: return launch_pairwise<gd::kGwd>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-    case GD_LOSS_KLD3D: return launch_pairwise<gd::kKld>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-    case GD_LOSS_JD3D: return launch_pairwise<gd::kJd>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-    case GD_LOSS_KLD3D_SYMMAX: return launch_pairwise<gd::kSymMax>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-    case GD_LOSS_KLD3D_SYMMIN: return launch_pairwise<gd::kSymMin>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-    case GD_LOSS_BD3D: return launch_pairwise<gd::kBd>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-    case GD_LOSS_KFIOU3D: return launch_pairwise<gd::kKfiou>(boxes1, n, boxes2, m, out, out_row_stride, nullptr, nullptr, pp, st);
-  }
-  return GD_ERR_BAD_ARG;
+  PairwiseArgs a{};
+  a.b1 = boxes1;
+  a.n = n;
+  a.b2 = boxes2;
+  a.m = m;
+  a.out = out;
+  a.out_stride = out_row_stride;
+  a.pp = make_pair_params(*cfg);
+  return dispatch_pairwise(cfg, a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int gd_pairwise_row_argmin(const gd_loss_config* cfg, const float* boxes1, int64_t n,
@@ -153,18 +80,74 @@ int gd_pairwise_row_argmin(const gd_loss_config* cfg, const float* boxes1, int64
   if (!config_ok(cfg) || n < 0 || m <= 0) return GD_ERR_BAD_ARG;
   if (n == 0) return 0;
   if (!boxes1 || !boxes2 || !row_min || !row_argmin) return GD_ERR_BAD_ARG;
-  const gd::PairParams<float> pp = make_pair_params(*cfg);
+  PairwiseArgs a{};
+  a.b1 = boxes1;
+  a.n = n;
+  a.b2 = boxes2;
+  a.m = m;
+  a.out_stride = m;
+  a.row_min = row_min;
+  a.row_argmin = row_argmin;
+  a.pp = make_pair_params(*cfg);
+  return dispatch_pairwise(cfg, a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t gd_pairwise_workspace_bytes(int64_t m) {
+  return 256 + sizeof(unsigned long long) * (size_t)(m > 0 ? m : 0);
+}
+
+int gd_pairwise_assign(const gd_loss_config* cfg, const float* boxes1, int64_t n,
+                       const float* boxes2, int64_t m, float* row_min, int32_t* row_argmin,
+                       float* col_min, int32_t* col_argmin, float* out, int64_t out_row_stride,
+                       int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace gdk;
+  if (!config_ok(cfg) || n < 0 || m <= 0 || (flags & ~GD_PAIR_SIMILARITY)) return GD_ERR_BAD_ARG;
+  if (out && out_row_stride < m) return GD_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < gd_pairwise_workspace_bytes(m)) return GD_ERR_WORKSPACE;
+  if (n == 0) return 0;
+  if (!boxes1 || !boxes2 || !row_min || !row_argmin || !col_min || !col_argmin)
+    return GD_ERR_BAD_ARG;
+  PairwiseArgs a{};
+  a.b1 = boxes1;
+  a.n = n;
+  a.b2 = boxes2;
+  a.m = m;
+  a.out = out;
+  a.out_stride = out ? out_row_stride : m;
+  a.similarity = (flags & GD_PAIR_SIMILARITY) ? 1 : 0;
+  a.row_min = row_min;
+  a.row_argmin = row_argmin;
+  a.ticket = reinterpret_cast<unsigned int*>(workspace);
+  a.col_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  a.col_min = col_min;
+  a.col_argmin = col_argmin;
+  a.pp = make_pair_params(*cfg);
+  return dispatch_pairwise(cfg, a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin, int64_t n,
+                          const float* col_min, const int32_t* col_argmin, int64_t m,
+                          float pos_thr, float neg_lo, float neg_hi, float min_pos,
+                          int32_t match_low_quality, int64_t* assigned_gt_inds,
+                          float* max_overlaps, void* stream) {
+  using namespace gdk;
+  if (n < 0 || m < 0) return GD_ERR_BAD_ARG;
+  if (n == 0) return 0;
+  if (!row_min || !row_argmin || !assigned_gt_inds) return GD_ERR_BAD_ARG;
+  if (match_low_quality && m > 0 && (!col_min || !col_argmin)) return GD_ERR_BAD_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (cfg->loss_type) {
-    case GD_LOSS_GWD3D: return launch_argmin<gd::kGwd>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
-    case GD_LOSS_KLD3D: return launch_argmin<gd::kKld>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
-    case GD_LOSS_JD3D: return launch_argmin<gd::kJd>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
-    case GD_LOSS_KLD3D_SYMMAX: return launch_argmin<gd::kSymMax>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
-    case GD_LOSS_KLD3D_SYMMIN: return launch_argmin<gd::kSymMin>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
-    case GD_LOSS_BD3D: return launch_argmin<gd::kBd>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
-    case GD_LOSS_KFIOU3D: return launch_argmin<gd::kKfiou>(boxes1, n, boxes2, m, row_min, row_argmin, pp, st);
+  cudaError_t e = cudaMemsetAsync(assigned_gt_inds, 0, sizeof(int64_t) * (size_t)n, st);
+  if (e != cudaSuccess) return (int)e;
+  if (match_low_quality && m > 0) {
+    gd_assign_lowq_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+        col_min, col_argmin, m, n, min_pos, reinterpret_cast<long long*>(assigned_gt_inds));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  return GD_ERR_BAD_ARG;
+  gd_assign_rows_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+      row_min, row_argmin, n, pos_thr, neg_lo, neg_hi,
+      reinterpret_cast<long long*>(assigned_gt_inds), max_overlaps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -1,0 +1,5 @@
+// One pairwise instantiation per translation unit so the build parallelises.
+#include "gd_pairwise.cuh"
+namespace gdk {
+template int launch_pairwise<gd::kKfiou>(const PairwiseArgs&, cudaStream_t);
+}  // namespace gdk

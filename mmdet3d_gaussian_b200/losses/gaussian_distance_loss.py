@@ -80,6 +80,7 @@ class GDLoss(nn.Module):
         self.variant = kwargs.pop('variant', 'auto')
         self.host_sync = bool(kwargs.pop('host_sync', True))
         self.kwargs = kwargs                                      # ref:278
+        self._cfg_cache = {}
 
     def _config(self, extra):
         name, default = _FLAG[self.loss_type]
@@ -89,8 +90,12 @@ class GDLoss(nn.Module):
             # raises TypeError on names it does not accept (ref:301-310)
             raise TypeError(f'{self.loss_type}_loss() got an unexpected keyword '
                             f'argument {sorted(unknown)[0]!r}')
-        return _lib.make_config(self.loss_type, self.fun, extra.get(name, default),
-                                self.tau, self.alpha, self.center_offset)
+        key = (self.loss_type, self.fun, bool(extra.get(name, default)), float(self.tau),
+               float(self.alpha), tuple(float(x) for x in self.center_offset))
+        cfg = self._cfg_cache.get(key)
+        if cfg is None:
+            cfg = self._cfg_cache[key] = _lib.make_config(*key)
+        return cfg
 
     def forward(self, pred, target, weight=None, avg_factor=None,
                 reduction_override=None, **kwargs):
@@ -100,7 +105,7 @@ class GDLoss(nn.Module):
         if self.host_sync and (weight is not None) and (reduction != 'none') and (
                 not ops.any_positive(weight)):                    # ref:290-291
             return (pred * weight).sum()                          # ref:292
-        _kwargs = deepcopy(self.kwargs)                           # ref:293
+        _kwargs = deepcopy(self.kwargs) if (self.kwargs or kwargs) else {}   # ref:293
         _kwargs.update(kwargs)                                    # ref:294
         cfg = self._config(_kwargs)
         n = pred.numel() // 7
@@ -140,6 +145,12 @@ class GDPairwiseDistance(nn.Module):
     @torch.no_grad()
     def forward(self, boxes1, boxes2):
         return ops.pairwise_distance(boxes1, boxes2, self.cfg)
+
+    @torch.no_grad()
+    def assign(self, boxes1, boxes2, want_matrix=False):
+        """Row and column ``(min, argmin)`` in one launch, matrix optional:
+        ``(row_min, row_argmin, col_min, col_argmin, matrix | None)``."""
+        return ops.pairwise_assign(boxes1, boxes2, self.cfg, want_matrix=want_matrix)
 
     @torch.no_grad()
     def row_argmin(self, boxes1, boxes2):

@@ -22,14 +22,40 @@ def _require_cuda(t, name):
             f'(sm_100a) and has no CPU fallback')
 
 
+def _raw_stream(index=None):
+    """cudaStream_t of torch's current stream on device ``index`` as an int (the raw
+    getter: ``torch.cuda.current_stream()`` costs ~10 us of Python per call, which is more
+    than the kernel launch itself at training sizes)."""
+    if index is None:
+        index = torch._C._cuda_getDevice()
+    return torch._C._cuda_getCurrentRawStream(index)
+
+
 def _stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(_raw_stream())
+
+
+class _on_device:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current."""
+    __slots__ = ('ctx',)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index == torch._C._cuda_getDevice() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _workspace(device):
     """Zero-initialised scratch (ticket + per-CTA partials), one per (device, stream).
     The kernels leave it zeroed, so it is cleared exactly once."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, _raw_stream(device.index))
     ws = _WORKSPACES.get(key)
     if ws is None:
         nbytes = _lib.load().gd_loss_workspace_bytes(0)
@@ -71,7 +97,7 @@ def _launch(cfg, pred, target, weight, wmode, scale, want_sum, want_rows, want_g
         wstride = weight.stride(0) if n > 1 else 1
     elif wmode == _lib.WEIGHT_ROW7:
         wstride = _row_stride(weight)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         code = lib.gd_loss_fwd_bwd(
             ctypes.byref(cfg), _ptr(pred), _row_stride(pred), _ptr(target),
             _row_stride(target), _ptr(weight), wmode, wstride, n, float(scale),
@@ -117,7 +143,7 @@ class _GDLossFunction(torch.autograd.Function):
         go = grad_out.detach()
         if go.dtype != torch.float32:
             go = go.float()
-        with torch.cuda.device(grad.device):
+        with _on_device(grad.device):
             if rows_out:
                 go = go.reshape(-1)
                 code = lib.gd_scale_grad_rows(_ptr(grad), n, _ptr(go),
@@ -183,7 +209,7 @@ def any_positive(weight):
     if not w.is_contiguous():
         w = w.contiguous()
     flag = torch.empty((1,), dtype=torch.int32, device=w.device)
-    with torch.cuda.device(w.device):
+    with _on_device(w.device):
         code = _lib.load().gd_any_positive(_ptr(w), w.numel(), _ptr(flag), _stream_ptr())
     _lib.check(code, 'gd_any_positive')
     return bool(flag.item())
@@ -205,7 +231,7 @@ def pairwise_distance(boxes1, boxes2, cfg, out=None):
     n, m = b1.shape[0], b2.shape[0]
     if out is None:
         out = torch.empty((n, m), dtype=torch.float32, device=b1.device)
-    with torch.cuda.device(b1.device):
+    with _on_device(b1.device):
         code = _lib.load().gd_pairwise(ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m,
                                        _ptr(out), out.stride(0) if n > 1 else max(m, 1),
                                        _stream_ptr())
@@ -221,7 +247,7 @@ def pairwise_row_argmin(boxes1, boxes2, cfg):
         raise ValueError('pairwise_row_argmin needs at least one column box')
     vmin = torch.empty((n,), dtype=torch.float32, device=b1.device)
     idx = torch.empty((n,), dtype=torch.int32, device=b1.device)
-    with torch.cuda.device(b1.device):
+    with _on_device(b1.device):
         code = _lib.load().gd_pairwise_row_argmin(ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m,
                                                   _ptr(vmin), _ptr(idx), _stream_ptr())
     _lib.check(code, 'gd_pairwise_row_argmin')
@@ -255,7 +281,7 @@ def _fold_grad_output(grad, grad_out):
     go = grad_out.detach()
     if go.dtype != torch.float32:
         go = go.float()
-    with torch.cuda.device(grad.device):
+    with _on_device(grad.device):
         code = _lib.load().gd_scale_buffer(_ptr(grad), grad.numel(), _ptr(go), _stream_ptr())
     _lib.check(code, 'gd_scale_buffer')
 
@@ -279,7 +305,7 @@ class _AnchorDecodedLossFunction(torch.autograd.Function):
         dw = None
         if bbox_weights is not None:
             dw = (ctypes.c_float * 7)(*[float(x) for x in decode_weight])
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             code = lib.gd_anchor_decoded_loss_fwd_bwd(
                 ctypes.byref(cfg), _ptr(anchors), anchors.shape[0], _ptr(bbox_pred),
                 _stride0(bbox_pred), _ptr(bbox_targets), _stride0(bbox_targets),
@@ -358,7 +384,7 @@ class _CenterDecodedLossFunction(torch.autograd.Function):
             wstride = weight.stride(0) if n > 1 else 1
         elif wmode == _lib.WEIGHT_ROW7:
             wstride = _stride0(weight)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             code = lib.gd_center_decoded_loss_fwd_bwd(
                 ctypes.byref(cfg), ctypes.byref(coder), _ptr(pred), _stride0(pred), _ptr(locs),
                 locs.stride(0) if n > 1 else 2, _ptr(target), _stride0(target), _ptr(weight),
@@ -410,3 +436,66 @@ def center_decoded_loss(pred, pos_ind, target_box, weight, coder, cfg, scale,
             raise ValueError('weight must be [P] or [P,7]')
     flags = _lib.FLAG_MASK_ZERO_WEIGHT if mask_zero_weight else 0
     return _CenterDecodedLossFunction.apply(p, locs, t, w2, wmode, coder, cfg, scale, flags)
+
+
+# ---------------------------------------------------------------------------
+# pairwise distances with the assigner reductions fused (f2)
+# ---------------------------------------------------------------------------
+_PAIR_WORKSPACES = {}
+
+
+def _pair_workspace(device, m):
+    key = (device.index, _raw_stream(device.index))
+    need = _lib.load().gd_pairwise_workspace_bytes(m)
+    ws = _PAIR_WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 256 + 8 * 1024), dtype=torch.uint8, device=device)
+        _PAIR_WORKSPACES[key] = ws
+    return ws
+
+
+def pairwise_assign(boxes1, boxes2, cfg, want_matrix=False, similarity=False):
+    """Row and column minima / arg-minima of the pairwise distance matrix in one launch
+    (``gd_pairwise_assign``); the matrix itself is written only when ``want_matrix``.
+    Returns ``(row_min [N], row_argmin [N] int64, col_min [M], col_argmin [M] int64,
+    matrix | None)``.  Indices are -1 / values +inf on an empty axis."""
+    b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
+    n, m = b1.shape[0], b2.shape[0]
+    dev = b1.device
+    row_min = torch.empty((n,), dtype=torch.float32, device=dev)
+    row_idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    col_min = torch.empty((m,), dtype=torch.float32, device=dev)
+    col_idx = torch.empty((m,), dtype=torch.int32, device=dev)
+    mat = torch.empty((n, m), dtype=torch.float32, device=dev) if want_matrix else None
+    if n == 0 or m == 0:
+        row_min.fill_(float('inf'))
+        col_min.fill_(float('inf'))
+        row_idx.fill_(-1)
+        col_idx.fill_(-1)
+        return row_min, row_idx.long(), col_min, col_idx.long(), mat
+    ws = _pair_workspace(dev, m)
+    with _on_device(dev):
+        code = _lib.load().gd_pairwise_assign(
+            ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m, _ptr(row_min), _ptr(row_idx),
+            _ptr(col_min), _ptr(col_idx), _ptr(mat), m,
+            _lib.PAIR_SIMILARITY if similarity else 0, _ptr(ws), ws.numel(), _stream_ptr())
+    _lib.check(code, 'gd_pairwise_assign')
+    return row_min, row_idx.long(), col_min, col_idx.long(), mat
+
+
+def assign_from_minima(row_min, row_argmin, col_min, col_argmin, pos_thr, neg_lo, neg_hi,
+                       min_pos, match_low_quality=True):
+    """``(assigned_gt_inds [N] int64, max_overlaps [N])`` -- ``gd_assign_from_minima``."""
+    n, m = row_min.shape[0], col_min.shape[0]
+    dev = row_min.device
+    assigned = torch.empty((n,), dtype=torch.int64, device=dev)
+    max_ov = torch.empty((n,), dtype=torch.float32, device=dev)
+    ri = row_argmin.to(torch.int32)
+    ci = col_argmin.to(torch.int32)
+    with _on_device(dev):
+        code = _lib.load().gd_assign_from_minima(
+            _ptr(row_min), _ptr(ri), n, _ptr(col_min), _ptr(ci), m, float(pos_thr),
+            float(neg_lo), float(neg_hi), float(min_pos), 1 if match_low_quality else 0,
+            _ptr(assigned), _ptr(max_ov), _stream_ptr())
+    _lib.check(code, 'gd_assign_from_minima')
+    return assigned, max_ov

@@ -358,6 +358,32 @@ def center_head_gd_loss(module, pred, pos_ind, target_box, coder, avg_factor=Non
 
 
 # --------------------------------------------------------------------------
+# f2: MaxIoUAssigner semantics on a similarity matrix (upstream mmdet
+# ``MaxIoUAssigner.assign_wrt_overlaps``, ``gt_max_assign_all=False``; mmdet is not in
+# the reference checkout: parity unpinned, the loop below is the written contract).
+# ``sim`` is [N, M] (anchors x GTs), i.e. the transpose of mmdet's ``overlaps``.
+# --------------------------------------------------------------------------
+def max_sim_assign(sim, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0,
+                   match_low_quality=True):
+    n, m = sim.shape
+    assigned = sim.new_full((n,), -1, dtype=torch.long)
+    if m == 0:
+        return assigned.zero_(), sim.new_zeros((n,))
+    max_overlaps, argmax_overlaps = sim.max(dim=1)
+    gt_max_overlaps, gt_argmax_overlaps = sim.max(dim=0)
+    lo, hi = (neg_iou_thr if isinstance(neg_iou_thr, (tuple, list))
+              else (0.0, neg_iou_thr))
+    assigned[(max_overlaps >= lo) & (max_overlaps < hi)] = 0
+    pos = max_overlaps >= pos_iou_thr
+    assigned[pos] = argmax_overlaps[pos] + 1
+    if match_low_quality:
+        for i in range(m):
+            if gt_max_overlaps[i] >= min_pos_iou:
+                assigned[gt_argmax_overlaps[i]] = i + 1
+    return assigned, max_overlaps
+
+
+# --------------------------------------------------------------------------
 # helper used by tests and bench: loss + d loss / d pred in one call
 # --------------------------------------------------------------------------
 def loss_and_grad(module, pred, target, weight=None, avg_factor=None,

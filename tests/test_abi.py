@@ -201,3 +201,39 @@ def test_head_modules_validate_on_the_host():
     assert center.coder.norm_bbox == 1 and center.coder.out_size_factor == 4
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         center(torch.zeros(4, 11), torch.zeros(4, 3, dtype=torch.long), torch.zeros(4, 11))
+
+
+def test_pairwise_assign_argument_validation_without_gpu(lib):
+    cfg = _lib.make_config('gwd3d', 'log1p', True, 1.0, 1.0, (0, 0, 0.5))
+    null, one = ctypes.c_void_p(0), ctypes.c_void_p(16)
+    call = lib.gd_pairwise_assign
+    need = lib.gd_pairwise_workspace_bytes(256)
+    assert need == 256 + 8 * 256 and lib.gd_pairwise_workspace_bytes(-3) == 256
+    ok = (one, 8, one, 256, one, one, one, one)
+    assert call(ctypes.byref(cfg), *ok, null, 256, 0, null, 0, null) == -2       # no workspace
+    assert call(ctypes.byref(cfg), *ok, null, 256, 0, one, need - 1, null) == -2
+    assert call(ctypes.byref(cfg), *ok, one, 255, 0, one, need, null) == -1      # stride < m
+    assert call(ctypes.byref(cfg), *ok, null, 256, 4, one, need, null) == -1     # unknown flag
+    assert call(ctypes.byref(cfg), one, 8, one, 0, one, one, one, one, null, 0, 0, one, need,
+                null) == -1                                                       # m == 0
+    assert call(ctypes.byref(cfg), one, 8, one, 256, one, one, null, one, null, 256, 0, one,
+                need, null) == -1                                                 # null output
+    assert call(ctypes.byref(cfg), one, 0, one, 256, one, one, one, one, null, 256, 0, one,
+                need, null) == 0                                                  # n == 0
+    lab = lib.gd_assign_from_minima
+    assert lab(one, one, -1, one, one, 4, 0.6, 0.0, 0.45, 0.45, 1, one, null, null) == -1
+    assert lab(null, one, 8, one, one, 4, 0.6, 0.0, 0.45, 0.45, 1, one, null, null) == -1
+    assert lab(one, one, 8, null, one, 4, 0.6, 0.0, 0.45, 0.45, 1, one, null, null) == -1
+    assert lab(one, one, 0, null, null, 0, 0.6, 0.0, 0.45, 0.45, 1, null, null, null) == 0
+
+
+def test_assigner_modules_validate_on_the_host():
+    from mmdet3d_gaussian_b200 import GDMaxSimAssigner, GDSimilarity3D
+    with pytest.raises(NotImplementedError):
+        GDMaxSimAssigner(0.6, 0.45, gt_max_assign_all=True)
+    a = GDMaxSimAssigner(0.6, (0.1, 0.45), min_pos_iou=0.3, loss_type='bd3d', sqrt=False)
+    assert (a.neg_lo, a.neg_hi, a.cfg.flag) == (0.1, 0.45, 0)
+    with pytest.raises(TypeError):
+        GDSimilarity3D('gwd3d', sqrt=True)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        GDSimilarity3D()(torch.zeros(4, 7), torch.zeros(2, 7))

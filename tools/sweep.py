@@ -83,12 +83,38 @@ def main():
         ms2 = time_launch(lambda: _lib.check(lib.gd_pairwise_row_argmin(
             ctypes.byref(cfg), anchors.data_ptr(), 200_000, gts.data_ptr(), 256,
             vmin.data_ptr(), idx.data_ptr(), stream), 'gd_pairwise_row_argmin'), 20)
+        cmin = torch.empty(256, device=dev)
+        cidx = torch.empty(256, dtype=torch.int32, device=dev)
+        pws = ops._pair_workspace(dev, 256)
+        ms3 = time_launch(lambda: _lib.check(lib.gd_pairwise_assign(
+            ctypes.byref(cfg), anchors.data_ptr(), 200_000, gts.data_ptr(), 256,
+            vmin.data_ptr(), idx.data_ptr(), cmin.data_ptr(), cidx.data_ptr(), None, 256, 0,
+            pws.data_ptr(), pws.numel(), stream), 'gd_pairwise_assign'), 20)
         pairs = 200_000 * 256
         out['pairwise'].append({'loss': lt, 'n': 200_000, 'm': 256, 'matrix_ms': round(ms, 4),
                                 'matrix_Gpairs_per_s': round(pairs / ms / 1e6, 2),
                                 'matrix_write_GBps': round(4 * pairs / ms / 1e6, 1),
                                 'argmin_ms': round(ms2, 4),
-                                'argmin_Gpairs_per_s': round(pairs / ms2 / 1e6, 2)})
+                                'argmin_Gpairs_per_s': round(pairs / ms2 / 1e6, 2),
+                                'assign_ms': round(ms3, 4),
+                                'assign_Gpairs_per_s': round(pairs / ms3 / 1e6, 2)})
+    # small-M shapes (a handful of GTs per sample, KITTI-like): fused assign only
+    for m in ([] if args.only == 'elementwise' else (8, 32, 64)):
+        cfg = _lib.make_config('gwd3d', 'log1p', True, 1.0, 1.0, (0, 0, 0.5))
+        g2 = synth.make_targets(m, 'kitti', seed=6, device=dev)
+        nn = 321_408
+        a2 = synth.make_anchor_grid(nn, 'kitti', device=dev)
+        v2 = torch.empty(nn, device=dev)
+        i2 = torch.empty(nn, dtype=torch.int32, device=dev)
+        cm = torch.empty(m, device=dev)
+        ci = torch.empty(m, dtype=torch.int32, device=dev)
+        pws = ops._pair_workspace(dev, m)
+        ms = time_launch(lambda: _lib.check(lib.gd_pairwise_assign(
+            ctypes.byref(cfg), a2.data_ptr(), nn, g2.data_ptr(), m, v2.data_ptr(), i2.data_ptr(),
+            cm.data_ptr(), ci.data_ptr(), None, m, 0, pws.data_ptr(), pws.numel(), stream),
+            'gd_pairwise_assign'), 20)
+        out['pairwise'].append({'loss': 'gwd3d', 'n': nn, 'm': m, 'assign_ms': round(ms, 4),
+                                'assign_Gpairs_per_s': round(nn * m / ms / 1e6, 2)})
     print(json.dumps(out))
 
 
