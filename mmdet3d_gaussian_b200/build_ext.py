@@ -25,13 +25,19 @@ SOURCES = ['gd_loss_api.cu', 'gd_loss_inst_gwd.cu', 'gd_loss_inst_kld.cu', 'gd_l
 HEADERS = ['gd_math.cuh', 'gd_common.cuh', 'gd_loss_kernels.cuh', 'gd_decode.cuh', 'gd_pairwise.cuh']
 LIB_NAME = 'libgdloss_b200.so'
 LIB_PRECISE_NAME = 'libgdloss_b200_precise.so'   # -DGD_PRECISE_MATH=1, tests only
+LIB_TUNE_NAME = 'libgdloss_b200_tune.so'         # -DGD_TUNE=1, tools/tune_sweep.py only
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
               '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3']
 
 
-def lib_path(precise=False):
-    return os.path.join(PKG_DIR, LIB_PRECISE_NAME if precise else LIB_NAME)
+def _kind(precise=False, tune=False):
+    return 'tune' if tune else ('precise' if precise else '')
+
+
+def lib_path(precise=False, tune=False):
+    name = LIB_TUNE_NAME if tune else (LIB_PRECISE_NAME if precise else LIB_NAME)
+    return os.path.join(PKG_DIR, name)
 
 
 def _nvcc():
@@ -54,24 +60,24 @@ def _source_hash(extra=''):
     return h.hexdigest()
 
 
-def is_current(precise=False):
-    lib = lib_path(precise)
+def is_current(precise=False, tune=False):
+    lib = lib_path(precise, tune)
     stamp = lib + '.hash'
     if not (os.path.exists(lib) and os.path.exists(stamp)):
         return False
     with open(stamp) as f:
-        return f.read().strip() == _source_hash('precise' if precise else '')
+        return f.read().strip() == _source_hash(_kind(precise, tune))
 
 
-def build(force=False, precise=False, verbose=False):
+def build(force=False, precise=False, verbose=False, tune=False):
     """Compile the library if missing or stale; returns its path."""
-    lib = lib_path(precise)
-    if not force and is_current(precise):
+    lib = lib_path(precise, tune)
+    if not force and is_current(precise, tune):
         return lib
     nvcc = _nvcc()
-    build_dir = os.path.join(PKG_DIR, 'build', 'precise' if precise else 'fast')
+    build_dir = os.path.join(PKG_DIR, 'build', _kind(precise, tune) or 'fast')
     os.makedirs(build_dir, exist_ok=True)
-    defs = ['-DGD_PRECISE_MATH=1'] if precise else []
+    defs = ['-DGD_TUNE=1'] if tune else (['-DGD_PRECISE_MATH=1'] if precise else [])
 
     def compile_one(src):
         obj = os.path.join(build_dir, src.replace('.cu', '.o'))
@@ -93,10 +99,10 @@ def build(force=False, precise=False, verbose=False):
     if res.returncode != 0:
         raise RuntimeError(f'link failed:\n{res.stdout}\n{res.stderr}')
     with open(lib + '.hash', 'w') as f:
-        f.write(_source_hash('precise' if precise else ''))
+        f.write(_source_hash(_kind(precise, tune)))
     return lib
 
 
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, precise='--precise' in sys.argv,
-                verbose='-v' in sys.argv))
+                verbose='-v' in sys.argv, tune='--tune' in sys.argv))

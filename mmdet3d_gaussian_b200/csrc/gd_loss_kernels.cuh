@@ -32,7 +32,27 @@
 #pragma once
 #include "gd_common.cuh"
 
+// Tuning knobs of gd_warp_kernel.  The production library bakes GD_TUNE_DEFAULT in
+// at compile time (dead branches vanish); `-DGD_TUNE=1` builds
+// libgdloss_b200_tune.so, where the same knobs are read per launch from the
+// environment (GD_TUNE_FLAGS, GD_TUNE_WARPS) so one GPU session can measure all of
+// them (tools/tune_sweep.py).
+#ifndef GD_TUNE
+#define GD_TUNE 0
+#endif
+#ifndef GD_TUNE_DEFAULT
+#define GD_TUNE_DEFAULT 0
+#endif
+
 namespace gdk {
+
+enum : int {
+  kTuneLateWait = 1,       // wait for the previous tile's bulk store after the math, not before
+  kTuneLoadNormal = 2,     // loads with L2 evict_normal instead of evict_first
+  kTuneStoreHint = 4,      // bulk stores carry an L2 evict_first hint
+  kTuneNoMath = 8,         // (measurement only) replace the math by p + t*w: pipeline ceiling
+  kTuneGenericStore = 16,  // all lanes write the gradient tile with st.global.cs.v4
+};
 
 struct LossArgs {
   const float* pred;
@@ -49,6 +69,7 @@ struct LossArgs {
   double* partials;                       // [grid]
   unsigned int* ticket;                   // zero on entry, zero again on exit
   gd::PairParams<float> pp;
+  int tune = GD_TUNE_DEFAULT;             // only read by -DGD_TUNE=1 builds
 };
 
 // ---------------------------------------------------------------------------
@@ -255,6 +276,18 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   const int my_n = ntiles > gwarp ? (int)((ntiles - 1 - gwarp) / nwarps) + 1 : 0;
   const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
   uint64_t policy = 0;
+#if GD_TUNE
+  const int tune = a.tune;
+#else
+  constexpr int tune = GD_TUNE_DEFAULT;
+#endif
+  const bool early_wait = !(tune & (kTuneLateWait | kTuneGenericStore));
+  auto late_wait = [&](int i) {           // out buffer must be free before it is rewritten
+    if ((tune & kTuneLateWait) && !(tune & kTuneGenericStore)) {
+      if (lane == 0 && L.out && i > 0) bulk_wait_read<0>();
+      __syncwarp();
+    }
+  };
 
   auto issue = [&](int i) {               // lane 0 only
     const long long row0 = (gwarp + (long long)i * nwarps) * kTileRows;
@@ -274,7 +307,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
 #pragma unroll
     for (int s = 0; s < kWarpStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
-    policy = policy_evict_first();
+    policy = (tune & kTuneLoadNormal) ? policy_evict_normal() : policy_evict_first();
     const int pre = my_n < kWarpStages ? my_n : kWarpStages;
     for (int i = 0; i < pre; ++i) issue(i);
   }
@@ -305,7 +338,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       w[k] = row_weight_smem(sw, wmode, r);
     }
     // the previous tile's store must have finished READING the output buffer
-    if (lane == 0 && L.out && i > 0) bulk_wait_read<0>();
+    if (early_wait && lane == 0 && L.out && i > 0) bulk_wait_read<0>();
     __syncwarp();                          // stage s consumed by every lane; out buffer free
     if (lane == 0 && i + kWarpStages < my_n) issue(i + kWarpStages);
 
@@ -320,7 +353,14 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       for (int k = 0; k < R; ++k) {
         rare[k] = mask_zero && w[k] == 0.0f;
         const float ws = w[k] * a.scale;
-        const float l = gd::pair_eval_fast<float, LOSS, GRAD>(p[k], t[k], pp, ws, g[k], &rare[k]);
+        float l;
+        if (GD_TUNE && (tune & kTuneNoMath)) {
+          l = p[k][0];
+#pragma unroll
+          for (int c = 0; c < 7; ++c) g[k][c] = p[k][c] + t[k][c] * ws;
+        } else {
+          l = gd::pair_eval_fast<float, LOSS, GRAD>(p[k], t[k], pp, ws, g[k], &rare[k]);
+        }
         rl[k] = l * ws;
         lw[k] = l * w[k];
       }
@@ -329,6 +369,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         if (rare[k])
           lw[k] = eval_row<LOSS, GRAD>(p[k], t[k], w[k], pp, a.scale, mask_zero, g[k], &rl[k]);
       }
+      late_wait(i);
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int r = lane + 32 * k;
@@ -340,6 +381,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         if (want_rows) orow[r] = rl[k];
       }
     } else {
+      late_wait(i);
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const int r = lane + 32 * k;
@@ -354,12 +396,28 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         }
       }
     }
-    if (L.out) {
+    if (L.out && (tune & kTuneGenericStore)) {
+      __syncwarp();                        // tile complete in shared memory
+      if (GRAD) {                          // tile base is 128-B aligned, rows*7 a multiple of 4
+        const float4* s4 = reinterpret_cast<const float4*>(og);
+        float4* g4 = reinterpret_cast<float4*>(a.grad + row0 * 7);
+        const int nv = (rows * 7) >> 2;
+        for (int j = lane; j < nv; j += 32) __stcs(g4 + j, s4[j]);
+      }
+      if (want_rows)
+        for (int j = lane; j < rows; j += 32) __stcs(a.row_loss + row0 + j, orow[j]);
+      __syncwarp();                        // reads done before the next tile rewrites og
+    } else if (L.out) {
       fence_proxy_async_smem();            // generic-proxy writes -> visible to the bulk engine
       __syncwarp();
       if (lane == 0) {
-        if (GRAD) bulk_store(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes);
-        if (want_rows) bulk_store(a.row_loss + row0, orow, (uint32_t)rows * 4u);
+        if (tune & kTuneStoreHint) {
+          if (GRAD) bulk_store_hint(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes, policy);
+          if (want_rows) bulk_store_hint(a.row_loss + row0, orow, (uint32_t)rows * 4u, policy);
+        } else {
+          if (GRAD) bulk_store(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes);
+          if (want_rows) bulk_store(a.row_loss + row0, orow, (uint32_t)rows * 4u);
+        }
         bulk_commit();
       }
     }
@@ -400,7 +458,13 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
 constexpr int kSmemBudget = 227 * 1024 - 1024;   // opt-in max per CTA minus static + slack
 
 template <int LOSS, bool GRAD, int R, int SPEC, int WM>
-int launch_warp_inst(const LossArgs& a, int max_grid, cudaStream_t stream) {
+int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
+#if GD_TUNE
+  LossArgs a = a_in;
+  if (const char* e = getenv("GD_TUNE_FLAGS")) a.tune = atoi(e);
+#else
+  const LossArgs& a = a_in;
+#endif
   auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -413,6 +477,12 @@ int launch_warp_inst(const LossArgs& a, int max_grid, cudaStream_t stream) {
   constexpr int kWarpCap = R >= 4 ? 12 : 24;
   int warps = kSmemBudget / L.per_warp;
   if (warps > kWarpCap) warps = kWarpCap;
+#if GD_TUNE
+  if (const char* e = getenv("GD_TUNE_WARPS")) {
+    const int w = atoi(e);
+    if (w >= 1 && w < warps) warps = w;
+  }
+#endif
   if (warps < 1) return GD_ERR_BAD_ARG;
   const long long ntiles = ((a.n & ~3LL) + 32 * R - 1) / (32 * R);
   long long grid = (ntiles + warps - 1) / warps;
