@@ -26,6 +26,15 @@
 #include <stdint.h>
 
 #ifdef __cplusplus
+/* Only the entry points below are exported: the library is built with
+ * -fvisibility=hidden -fno-gnu-unique so two builds of it (e.g. the fast-math and the
+ * IEEE-math variant) can live in one process without sharing any state. */
+#if defined(__GNUC__)
+#define GD_API __attribute__((visibility("default")))
+#else
+#define GD_API
+#endif
+
 extern "C" {
 #endif
 
@@ -89,12 +98,12 @@ typedef struct gd_loss_config {
   float center_offset[3];  /* ref:9-12 */
 } gd_loss_config;
 
-int gd_abi_version(void);
+GD_API int gd_abi_version(void);
 
 /* Bytes of device workspace gd_loss_* needs for `n` rows.  The workspace must
  * be zero-filled ONCE when allocated; the kernels leave it zeroed again, so it
  * can be reused by later calls on the same stream without clearing. */
-size_t gd_loss_workspace_bytes(int64_t n);
+GD_API size_t gd_loss_workspace_bytes(int64_t n);
 
 /* Fused forward + backward: replaces GDLoss.forward (ref:298-310: preprocess x2,
  * distance, postprocess, weighted reduction, x loss_weight) AND the autograd
@@ -113,7 +122,7 @@ size_t gd_loss_workspace_bytes(int64_t n);
  *                  (nullable: forward only, e.g. under torch.no_grad)
  * The sum is deterministic: per-CTA partials in fp64, combined in fixed order
  * by the last CTA to finish. */
-int gd_loss_fwd_bwd(const gd_loss_config* cfg,
+GD_API int gd_loss_fwd_bwd(const gd_loss_config* cfg,
                     const float* pred, int64_t pred_row_stride,
                     const float* target, int64_t target_row_stride,
                     const float* weight, int32_t weight_mode, int64_t weight_row_stride,
@@ -125,27 +134,27 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg,
 /* Autograd fold: grad[i,:] *= *grad_output (0-dim upstream gradient; replaces the
  * first step of the reference's autograd backward).  Reads the scalar on the
  * device -- no host sync. */
-int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void* stream);
+GD_API int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void* stream);
 
 /* Same fold for a gradient buffer of any shape: buf[0..count) *= *scalar (head front
  * ends, whose gradient rows are wider than 7). */
-int gd_scale_buffer(float* buf, int64_t count, const float* scalar, void* stream);
+GD_API int gd_scale_buffer(float* buf, int64_t count, const float* scalar, void* stream);
 
 /* Autograd fold for reduction='none': grad[i,:] *= grad_output[i]. */
-int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_rows,
+GD_API int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_rows,
                        int64_t grad_output_stride, void* stream);
 
 /* Early-return branch of GDLoss.forward (ref:290-292): when a weight is given
  * and no element is > 0 the reference returns (pred*weight).sum().  This writes
  * flag[0] = 1 if any weight element is > 0 else 0 (count elements, any layout
  * flattened by the caller) so the shim can take that branch. */
-int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* stream);
+GD_API int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* stream);
 
 /* Pairwise matrix (new surface):
  *   out[i, j] = postprocess(distance(boxes1[i], boxes2[j]))   i<n, j<m
  * equal to the element-wise path on the broadcast-expanded pairs.  boxes
  * contiguous [n,7] / [m,7]; out row stride in elements (>= m). */
-int gd_pairwise(const gd_loss_config* cfg,
+GD_API int gd_pairwise(const gd_loss_config* cfg,
                 const float* boxes1, int64_t n,
                 const float* boxes2, int64_t m,
                 float* out, int64_t out_row_stride, void* stream);
@@ -153,7 +162,7 @@ int gd_pairwise(const gd_loss_config* cfg,
 /* Pairwise with the consumer fused (assigner use): per row i the argmin/min
  * over j, per column j the argmin over i is left to the caller via the matrix.
  *   row_min [n] fp32, row_argmin [n] int32; the matrix itself is not written. */
-int gd_pairwise_row_argmin(const gd_loss_config* cfg,
+GD_API int gd_pairwise_row_argmin(const gd_loss_config* cfg,
                            const float* boxes1, int64_t n,
                            const float* boxes2, int64_t m,
                            float* row_min, int32_t* row_argmin, void* stream);
@@ -167,7 +176,7 @@ enum {
 
 /* Bytes of device workspace gd_pairwise_assign needs for m columns.  Zero-filled ONCE
  * when allocated; the kernel leaves it zeroed again. */
-size_t gd_pairwise_workspace_bytes(int64_t m);
+GD_API size_t gd_pairwise_workspace_bytes(int64_t m);
 
 /* Pairwise distances with BOTH assigner reductions fused (SURVEY.md section 8 row f2;
  * what a MaxIoUAssigner-style consumer takes from an N x M cost matrix, cf. the
@@ -177,7 +186,7 @@ size_t gd_pairwise_workspace_bytes(int64_t m);
  * NaN is the minimum (torch.min semantics); ties go to the lowest index.  `out` is
  * optional: when null the matrix is never written.  The reductions and the matrix come
  * from the same per-pair instruction sequence, so they are bit-consistent. */
-int gd_pairwise_assign(const gd_loss_config* cfg,
+GD_API int gd_pairwise_assign(const gd_loss_config* cfg,
                        const float* boxes1, int64_t n,
                        const float* boxes2, int64_t m,
                        float* row_min, int32_t* row_argmin,
@@ -193,7 +202,7 @@ int gd_pairwise_assign(const gd_loss_config* cfg,
  *   match_low_quality: for each GT j in order with (1 - col_min[j]) >= min_pos:
  *                      assigned[col_argmin[j]] = j + 1   (the last GT wins)
  * assigned_gt_inds [n] int64, max_overlaps [n] fp32 (nullable) = 1 - row_min. */
-int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin, int64_t n,
+GD_API int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin, int64_t n,
                           const float* col_min, const int32_t* col_argmin, int64_t m,
                           float pos_thr, float neg_lo, float neg_hi, float min_pos,
                           int32_t match_low_quality, int64_t* assigned_gt_inds,
@@ -232,7 +241,7 @@ enum {
  *   grad_deltas   : per grad_mode; = scale * w_i * d loss_i / d deltas_pred[i]
  * No positives => loss 0 and zero gradient (the reference's `pos_bbox_pred.sum()`
  * branch, :160-161). */
-int gd_anchor_decoded_loss_fwd_bwd(const gd_loss_config* cfg,
+GD_API int gd_anchor_decoded_loss_fwd_bwd(const gd_loss_config* cfg,
                                    const float* anchors, int64_t anchor_rows,
                                    const float* deltas_pred, int64_t deltas_pred_row_stride,
                                    const float* deltas_target, int64_t deltas_target_row_stride,
@@ -264,7 +273,7 @@ typedef struct gd_center_coder {
  *   target : [n, >=7] real-world boxes (anno_boxes / encode()[..., :7]), row stride
  *   weight : as gd_loss_fwd_bwd (the reference passes none)
  *   grad_preds : nullable [n, grad_cols >= 7] with row stride; columns >= 7 are zeroed */
-int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_center_coder* coder,
+GD_API int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_center_coder* coder,
                                    const float* preds, int64_t preds_row_stride,
                                    const int64_t* locs, int64_t locs_row_stride,
                                    const float* target, int64_t target_row_stride,
@@ -280,7 +289,7 @@ int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_center_co
  * H2D of chunk k+1 / kernel of chunk k / D2H of chunk k-1 on internal streams,
  * returns when loss_host and grad_host are complete.  Host buffers may be
  * pageable or pinned (pinned is what overlaps).  grad_host nullable. */
-int gd_loss_fwd_bwd_host(const gd_loss_config* cfg,
+GD_API int gd_loss_fwd_bwd_host(const gd_loss_config* cfg,
                          const float* pred_host, const float* target_host,
                          const float* weight_host, int32_t weight_mode,
                          int64_t n, float scale,
@@ -289,9 +298,9 @@ int gd_loss_fwd_bwd_host(const gd_loss_config* cfg,
 
 /* Number of kernel launches issued by this library in this process (bench
  * `gpu_launches`). */
-int64_t gd_launch_count(void);
+GD_API int64_t gd_launch_count(void);
 
-const char* gd_error_string(int code);
+GD_API const char* gd_error_string(int code);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,8 @@ LIB_PRECISE_NAME = 'libgdloss_b200_precise.so'   # -DGD_PRECISE_MATH=1, tests on
 LIB_TUNE_NAME = 'libgdloss_b200_tune.so'         # -DGD_TUNE=1, tools/tune_sweep.py only
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
-              '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3']
+              '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3',
+              '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-fno-gnu-unique']
 
 
 def _kind(precise=False, tune=False):

@@ -19,10 +19,16 @@ constexpr int kTileBytes = kTile * kRowBytes;   // 7168, a multiple of 16
 
 extern std::atomic<int64_t> g_launches;  // bench `gpu_launches`
 
+constexpr int kMaxDevices = 64;
 struct DeviceInfo {
   int sm_count;
 };
 const DeviceInfo& device_info();          // cached per current device
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= kMaxDevices) ? 0 : dev;
+}
 
 inline gd::PairParams<float> make_pair_params(const gd_loss_config& c) {
   gd::PairParams<float> p;
@@ -46,6 +52,17 @@ inline bool config_ok(const gd_loss_config* c) {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// one lane of the (converged) warp; the same lane every time for a full mask
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) --------------

@@ -52,7 +52,11 @@ enum : int {
   kTuneStoreHint = 4,      // bulk stores carry an L2 evict_first hint
   kTuneNoMath = 8,         // (measurement only) replace the math by p + t*w: pipeline ceiling
   kTuneGenericStore = 16,  // all lanes write the gradient tile with st.global.cs.v4
+  kTuneHalfMath = 32,      // (measurement only) math on half of each lane's rows
+  kTuneLane0 = 64,         // copy commands issued by `lane == 0` instead of elect.sync
 };
+struct FullTile { static constexpr bool value = true; };
+struct PartTile { static constexpr bool value = false; };
 
 struct LossArgs {
   const float* pred;
@@ -247,11 +251,54 @@ __host__ __device__ inline WarpLayout warp_layout(int rows_per_lane, int wmode, 
 // SPEC >= 0: bits [1:0] fun, [2] tau_on, [3] flag are compile-time constants (the
 // per-row branches and constant loads disappear).
 // WM < 0: weight mode at run time, else compile-time.
+// N consecutive floats shared <-> registers with the widest aligned vector access
+// (N = 7 R per lane: R = 4 -> 7 x 128-bit, lane stride 112 B; R = 2 -> 7 x 64-bit, lane
+// stride 56 B; both strides are bank-conflict free within a quarter / half warp).
+template <int N>
+__device__ __forceinline__ void smem_load(float* dst, const float* src) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) {
+      const float4 v = reinterpret_cast<const float4*>(src)[j];
+      dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w;
+    }
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      const float2 v = reinterpret_cast<const float2*>(src)[j];
+      dst[2 * j] = v.x; dst[2 * j + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = src[j];
+  }
+}
+template <int N>
+__device__ __forceinline__ void smem_store(float* dst, const float* src) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j)
+      reinterpret_cast<float4*>(dst)[j] =
+          make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j)
+      reinterpret_cast<float2*>(dst)[j] = make_float2(src[2 * j], src[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) dst[j] = src[j];
+  }
+}
+
 template <int LOSS, bool GRAD, int R, int SPEC, int WM>
 __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const LossArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kTileRows = 32 * R;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // The warp index goes through a shuffle so the compiler knows it is warp-uniform:
+  // every address of the copy engine commands below then lives in uniform registers
+  // and the one-lane issue needs no per-lane "waterfall" loop around UBLKCP.
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wmode = WM >= 0 ? WM : a.wmode;
   const bool want_rows = a.row_loss != nullptr;
   gd::PairParams<float> pp = a.pp;
@@ -270,28 +317,48 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
 
   // rows the bulk path can move: a multiple of 4 rows keeps every copy a multiple of 16 B
   const long long n_main = a.n & ~3LL;
-  const long long ntiles = (n_main + kTileRows - 1) / kTileRows;
-  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  const int my_n = ntiles > gwarp ? (int)((ntiles - 1 - gwarp) / nwarps) + 1 : 0;
+  const int cta_warps = (int)(blockDim.x >> 5);
+  const long long gwarp = (long long)blockIdx.x * cta_warps + warp;
+  const long long nwarps = (long long)gridDim.x * cta_warps;
+  // Tile schedule: `full_rounds` rounds in which every warp takes one full tile
+  // (tile index gwarp + round * nwarps: the grid sweeps a contiguous window of each
+  // array), then ONE balanced round in which the remaining rows are split evenly over
+  // all warps (a multiple of 4 rows each), so that every warp finishes together instead
+  // of a fraction of them running one more full tile while the rest idle.
+  const long long round_rows = nwarps * kTileRows;
+  const int full_rounds = (int)(n_main / round_rows);
+  const long long tail_base = (long long)full_rounds * round_rows;
+  const int last_rows = (int)((((n_main - tail_base) + nwarps - 1) / nwarps + 3) & ~3LL);  // <= kTileRows
+  const int my_n = full_rounds + ((tail_base + gwarp * last_rows < n_main) ? 1 : 0);
+  auto tile_of = [&](int i, long long* row0) -> int {     // rows of this warp's i-th tile
+    if (i < full_rounds) {
+      *row0 = (gwarp + (long long)i * nwarps) * kTileRows;
+      return kTileRows;
+    }
+    *row0 = tail_base + gwarp * last_rows;
+    return (int)min((long long)last_rows, n_main - *row0);
+  };
   const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
-  uint64_t policy = 0;
 #if GD_TUNE
   const int tune = a.tune;
 #else
   constexpr int tune = GD_TUNE_DEFAULT;
 #endif
+  const uint64_t policy = (tune & kTuneLoadNormal) ? policy_evict_normal() : policy_evict_first();
   const bool early_wait = !(tune & (kTuneLateWait | kTuneGenericStore));
+  // One elected lane (always the same one: elect.sync is deterministic for a full
+  // mask) issues, commits and waits for the warp's copy-engine commands.
+  const bool leader = (tune & kTuneLane0) ? (lane == 0) : elect_one();
   auto late_wait = [&](int i) {           // out buffer must be free before it is rewritten
     if ((tune & kTuneLateWait) && !(tune & kTuneGenericStore)) {
-      if (lane == 0 && L.out && i > 0) bulk_wait_read<0>();
+      if (leader && L.out && i > 0) bulk_wait_read<0>();
       __syncwarp();
     }
   };
 
-  auto issue = [&](int i) {               // lane 0 only
-    const long long row0 = (gwarp + (long long)i * nwarps) * kTileRows;
-    const uint32_t rows = (uint32_t)min((long long)kTileRows, n_main - row0);
+  auto issue = [&](int i) {               // leader only
+    long long row0;
+    const uint32_t rows = (uint32_t)tile_of(i, &row0);
     const int s = i & (kWarpStages - 1);
     unsigned char* st = base + s * L.stage;
     const uint32_t box_bytes = rows * kRowBytes;
@@ -303,11 +370,10 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       bulk_load(st + 2 * kTileRows * kRowBytes, a.weight + row0 * wcols, w_bytes, &bars[s], policy);
   };
 
-  if (lane == 0) {
+  if (leader) {
 #pragma unroll
     for (int s = 0; s < kWarpStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
-    policy = (tune & kTuneLoadNormal) ? policy_evict_normal() : policy_evict_first();
     const int pre = my_n < kWarpStages ? my_n : kWarpStages;
     for (int i = 0; i < pre; ++i) issue(i);
   }
@@ -316,37 +382,42 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   float acc = 0.0f;
   for (int i = 0; i < my_n; ++i) {
     const int s = i & (kWarpStages - 1);
-    const long long row0 = (gwarp + (long long)i * nwarps) * kTileRows;
-    const int rows = (int)min((long long)kTileRows, n_main - row0);
+    long long row0;
+    const int rows = tile_of(i, &row0);
     const unsigned char* st = base + s * L.stage;
     const float* sp = reinterpret_cast<const float*>(st);
     const float* stg = reinterpret_cast<const float*>(st + kTileRows * kRowBytes);
     const float* sw = reinterpret_cast<const float*>(st + 2 * kTileRows * kRowBytes);
 
     mbar_wait(&bars[s], (uint32_t)((i / kWarpStages) & 1));
+    // Lane l owns the R consecutive rows R*l .. R*l + R - 1 of the tile: 28 R contiguous
+    // bytes per array, moved with 128-bit (R = 4) shared-memory accesses.  Rows past a
+    // partial tile's end read stale shared memory; they are never redone or stored.
     float p[R][7], t[R][7], w[R];
+    smem_load<7 * R>(&p[0][0], sp + 7 * R * lane);
+    smem_load<7 * R>(&t[0][0], stg + 7 * R * lane);
+    if (wmode == GD_WEIGHT_ROW) {
+      smem_load<R>(w, sw + R * lane);
+    } else if (wmode == GD_WEIGHT_ROW7) {
+      float w7[R][7];
+      smem_load<7 * R>(&w7[0][0], sw + 7 * R * lane);
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      // word 7r+c -> bank (7 lane + c) mod 32: conflict free.  Rows past a partial
-      // tile's end read stale shared memory; they are never evaluated or stored.
-      const int r = lane + 32 * k;
+      for (int k = 0; k < R; ++k) w[k] = row_weight_smem(&w7[k][0], GD_WEIGHT_ROW7, 0);
+    } else {
 #pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        p[k][c] = sp[7 * r + c];
-        t[k][c] = stg[7 * r + c];
-      }
-      w[k] = row_weight_smem(sw, wmode, r);
+      for (int k = 0; k < R; ++k) w[k] = 1.0f;
     }
     // the previous tile's store must have finished READING the output buffer
-    if (early_wait && lane == 0 && L.out && i > 0) bulk_wait_read<0>();
+    if (early_wait && leader && L.out && i > 0) bulk_wait_read<0>();
     __syncwarp();                          // stage s consumed by every lane; out buffer free
-    if (lane == 0 && i + kWarpStages < my_n) issue(i + kWarpStages);
+    if (leader && i + kWarpStages < my_n) issue(i + kWarpStages);
 
-    if (rows == kTileRows) {
-      // Full tile (all but at most one tile per kernel): the R rows of this lane go
-      // through the branch-free FAST math as one straight-line block, so their
-      // instruction streams interleave; rows it flags (clamped / degenerate
-      // extents, huge yaw, masked weight, ...) are redone on the robust path.
+    // The R rows of this lane go through the branch-free FAST math as one
+    // straight-line block, so their instruction streams interleave; rows it flags
+    // (clamped / degenerate extents, huge yaw, masked weight, ...) are redone on the
+    // robust path.  FULL: every lane row is valid (all tiles but the warp's last one).
+    auto eval_tile = [&](auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       float g[R][7], rl[R], lw[R];
       bool rare[R];
 #pragma unroll
@@ -354,7 +425,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         rare[k] = mask_zero && w[k] == 0.0f;
         const float ws = w[k] * a.scale;
         float l;
-        if (GD_TUNE && (tune & kTuneNoMath)) {
+        if (GD_TUNE && ((tune & kTuneNoMath) || ((tune & kTuneHalfMath) && k >= R / 2))) {
           l = p[k][0];
 #pragma unroll
           for (int c = 0; c < 7; ++c) g[k][c] = p[k][c] + t[k][c] * ws;
@@ -363,6 +434,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         }
         rl[k] = l * ws;
         lw[k] = l * w[k];
+        if (!FULL) rare[k] = rare[k] && (R * lane + k < rows);   // stale rows: never redone
       }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
@@ -372,33 +444,19 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       late_wait(i);
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        const int r = lane + 32 * k;
-        acc += lw[k];
-        if (GRAD) {
-#pragma unroll
-          for (int c = 0; c < 7; ++c) og[7 * r + c] = g[k][c];
-        }
-        if (want_rows) orow[r] = rl[k];
+        if (FULL || R * lane + k < rows) acc += lw[k];
       }
-    } else {
-      late_wait(i);
-#pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const int r = lane + 32 * k;
-        if (r < rows) {
-          float g[7], rl;
-          acc += eval_row<LOSS, GRAD>(p[k], t[k], w[k], pp, a.scale, mask_zero, g, &rl);
-          if (GRAD) {
-#pragma unroll
-            for (int c = 0; c < 7; ++c) og[7 * r + c] = g[c];
-          }
-          if (want_rows) orow[r] = rl;
-        }
-      }
-    }
+      // rows past the end of a partial tile are written to the staging buffer too (it
+      // has room for a full tile); the bulk store below only moves `rows` rows
+      if (GRAD) smem_store<7 * R>(og + 7 * R * lane, &g[0][0]);
+      if (want_rows) smem_store<R>(orow + R * lane, rl);
+    };
+    if (rows == kTileRows) eval_tile(FullTile{});
+    else eval_tile(PartTile{});
+
     if (L.out && (tune & kTuneGenericStore)) {
       __syncwarp();                        // tile complete in shared memory
-      if (GRAD) {                          // tile base is 128-B aligned, rows*7 a multiple of 4
+      if (GRAD) {                          // tile base is 16-B aligned, rows*7 a multiple of 4
         const float4* s4 = reinterpret_cast<const float4*>(og);
         float4* g4 = reinterpret_cast<float4*>(a.grad + row0 * 7);
         const int nv = (rows * 7) >> 2;
@@ -410,7 +468,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     } else if (L.out) {
       fence_proxy_async_smem();            // generic-proxy writes -> visible to the bulk engine
       __syncwarp();
-      if (lane == 0) {
+      if (leader) {
         if (tune & kTuneStoreHint) {
           if (GRAD) bulk_store_hint(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes, policy);
           if (want_rows) bulk_store_hint(a.row_loss + row0, orow, (uint32_t)rows * 4u, policy);
@@ -441,7 +499,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     }
     if (want_rows) a.row_loss[r] = rl;
   }
-  if (lane == 0 && L.out) bulk_wait_all<0>();
+  if (leader && L.out) bulk_wait_all<0>();
   if (a.loss_sum) finish_sum(acc, a);
 }
 
@@ -466,12 +524,15 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
   const LossArgs& a = a_in;
 #endif
   auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // opt in to the large dynamic shared memory once per device (function attributes are
+  // per context); a racing second call sets the same value
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     const cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const WarpLayout L = warp_layout(R, a.wmode, GRAD, a.row_loss != nullptr);
   constexpr int kWarpCap = R >= 4 ? 12 : 24;
@@ -484,18 +545,19 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
   }
 #endif
   if (warps < 1) return GD_ERR_BAD_ARG;
-  const long long ntiles = ((a.n & ~3LL) + 32 * R - 1) / (32 * R);
-  long long grid = (ntiles + warps - 1) / warps;
+  // Persistent: at most one CTA per SM with `warps` warps.  A batch too small to give
+  // every such warp 32 rows uses fewer warps, spread over as many SMs as possible.
   const long long sms = device_info().sm_count;
-  if (grid > sms) grid = sms;               // persistent: one CTA per SM
-  if (grid > max_grid) grid = max_grid;
-  if (grid < 1) grid = 1;
-  if (grid < sms && warps > 4) {            // small batch: spread tiles over more SMs
-    warps = 4;
-    grid = (ntiles + warps - 1) / warps;
-    if (grid > sms) grid = sms;
-    if (grid < 1) grid = 1;
+  const long long n_main = a.n & ~3LL;
+  long long want = (n_main + 31) / 32;                    // warps that would get >= 32 rows
+  if (want < 1) want = 1;
+  long long grid = sms < max_grid ? sms : max_grid;
+  if (want < grid * warps) {
+    const long long per_cta = (want + grid - 1) / grid;   // <= warps
+    warps = (int)per_cta;
+    grid = (want + per_cta - 1) / per_cta;
   }
+  if (grid < 1) grid = 1;
   kern<<<(int)grid, warps * 32, (size_t)warps * L.per_warp, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();

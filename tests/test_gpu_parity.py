@@ -457,3 +457,41 @@ def test_host_pipeline_matches_device_path():
     out.backward()
     assert abs(loss.item() - out.item()) <= 1e-6 * abs(out.item())
     assert torch.equal(grad, p.grad.cpu())
+
+
+# ---------------------------------------------------------------------------
+# 7. two builds of the library in one process (no shared state between them)
+# ---------------------------------------------------------------------------
+def test_fast_and_ieee_builds_coexist_and_agree():
+    """The production (approx-math) and the IEEE-math build are loaded side by side;
+    each must opt in to its own kernels' shared memory (the libraries export only the C
+    ABI, -fvisibility=hidden -fno-gnu-unique), and they must agree within the parity
+    tolerance on nice rows."""
+    import ctypes
+    from mmdet3d_gaussian_b200 import build_ext
+    precise_path = build_ext.build(precise=True)
+    fast = _lib.load()
+    slow = ctypes.CDLL(precise_path)
+    restype, argtypes = _lib.SIGNATURES['gd_loss_fwd_bwd']
+    slow.gd_loss_fwd_bwd.restype, slow.gd_loss_fwd_bwd.argtypes = restype, argtypes
+    n = 300_001
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=77, device='cuda')
+    ws = ops._workspace(pred.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for lt in ('gwd3d', 'kld3d', 'bd3d'):
+        cfg = _lib.make_config(lt, 'log1p', True, 0.0, 1.0, (0, 0, 0.5))
+        outs = []
+        for lib in (slow, fast, slow):
+            grad = torch.empty(n, 7, device='cuda')
+            loss = torch.empty((), device='cuda')
+            code = lib.gd_loss_fwd_bwd(ctypes.byref(cfg), pred.data_ptr(), 7, target.data_ptr(), 7,
+                                       w.data_ptr(), 1, 1, n, 1.0 / n, loss.data_ptr(), None,
+                                       grad.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _lib.VARIANTS['bulk'], 0, stream)
+            assert code == 0, (lt, code)
+            torch.cuda.synchronize()
+            outs.append((loss.item(), grad))
+        assert outs[0][0] == outs[2][0] and torch.equal(outs[0][1], outs[2][1])
+        assert abs(outs[0][0] - outs[1][0]) <= RTOL * abs(outs[0][0])
+        gn = outs[0][1].norm(dim=1).clamp_min(1e-2 / n)
+        assert ((outs[0][1] - outs[1][1]).norm(dim=1) / gn).max().item() <= RTOL

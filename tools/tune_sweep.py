@@ -17,12 +17,13 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mmdet3d_gaussian_b200 import _lib, build_ext, synth  # noqa: E402
 
-FLAGS = {'late_wait': 1, 'load_normal': 2, 'store_hint': 4, 'no_math': 8, 'generic_store': 16}
+FLAGS = {'late_wait': 1, 'load_normal': 2, 'store_hint': 4, 'no_math': 8, 'generic_store': 16,
+         'half_math': 32, 'lane0': 64}
 SETTINGS = [
-    ('base', 0, None), ('late_wait', 1, None), ('load_normal', 2, None), ('store_hint', 4, None),
+    ('base', 0, None), ('lane0', 64, None), ('late_wait', 1, None), ('load_normal', 2, None), ('store_hint', 4, None),
     ('late_wait+store_hint', 5, None), ('late_wait+load_normal', 3, None),
     ('generic_store', 16, None), ('generic_store+load_normal', 18, None),
-    ('no_math', 8, None), ('no_math+late_wait', 9, None), ('no_math+generic_store', 24, None),
+    ('no_math', 8, None), ('half_math', 32, None), ('no_math+generic_store', 24, None),
     ('warps10', 0, 10), ('warps8', 0, 8), ('warps6', 0, 6),
     ('late_wait+warps10', 1, 10), ('late_wait+warps8', 1, 8),
 ]
