@@ -52,6 +52,9 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--detail', action='store_true', help='extra per-config lines on stderr')
+    ap.add_argument('--watchdog', type=float, default=900.0,
+                    help='seconds after which all thread stacks are dumped and the process exits')
+    ap.add_argument('--verbose', action='store_true', help='phase log with timestamps on stderr')
     return ap.parse_args()
 
 
@@ -153,6 +156,11 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is allowed all
+    # host cores (torch is imported only below, so the override takes effect, including
+    # in the autograd engine's thread)
+    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
+    os.environ.pop('MKL_NUM_THREADS', None)
     sample, chunk = 1 << 21, 1 << 17
     steps = max(args.steps, 1)
     for _ in range(min(args.warmup, 1)):
@@ -193,6 +201,12 @@ def run_ours(args):
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
+    t_start = time.time()
+
+    def log(msg):
+        if args.verbose:
+            sys.stderr.write(f'[bench rank {rank} +{time.time() - t_start:6.1f}s] {msg}\n')
+            sys.stderr.flush()
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
@@ -202,6 +216,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
     n = args.pairs
+    log('process group and library ready')
 
     pred, target, weight = synth.make_pairs(n, 'kitti', seed=rank, device=dev)
     pred.requires_grad_(True)
@@ -236,9 +251,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('inputs generated')
     for _ in range(max(args.warmup, 3)):
         step()
+    log('warm-up enqueued')
     sync_all()
+    log('warm-up done')
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -255,6 +273,7 @@ def run_ours(args):
     sync_all()
     t_wall1 = time.time()
     launches = lib.gd_launch_count() - launches0
+    log('timed region done')
     ms_total = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -274,6 +293,7 @@ def run_ours(args):
     evs1.record()
     sync_all()
     value_sync = len(COMBOS) * n * world / (evs0.elapsed_time(evs1) / k_sync * 1e-3)
+    log('default-module pass done')
 
     # ---- kernel-only durations per config (CUDA events around bare C-ABI launches)
     per_cfg = {}
@@ -310,6 +330,7 @@ def run_ours(args):
         if (lt, fun) in COMBOS:
             fused_ms.append(ms)
     kernel_ms = sum(fused_ms) / len(fused_ms)
+    log('kernel-only timings done')
 
     # keep the device busy ~1.5 s more so the clock sampler sees it under load (rank 0
     # only, so NO collective in here: the other ranks are already past this point)
@@ -321,6 +342,7 @@ def run_ours(args):
         torch.cuda.synchronize()
     t_wall_load = time.time()
     clocks = sampler.stop(t_wall0, t_wall_load) if rank == 0 else None
+    log('clock sampling done')
 
     # ---- end to end through the C ABI with host buffers
     e2e = None
@@ -336,7 +358,9 @@ def run_ours(args):
                     ctypes.byref(cfg), hp.data_ptr(), ht.data_ptr(), hw.data_ptr(), 1, n,
                     LOSS_WEIGHT / avg, hloss.data_ptr(), hgrad.data_ptr(), local_rank, 1 << 20)
                 _lib.check(code, 'gd_loss_fwd_bwd_host')
+        log('host buffers pinned')
         e2e_step()
+        log('first e2e step done')
         k = max(2, min(args.steps, 5))
         sync_all()
         t0 = time.perf_counter()
@@ -355,8 +379,11 @@ def run_ours(args):
                'api': 'gd_loss_fwd_bwd_host (C ABI, pinned host buffers, 2^20-row chunks, '
                       '3 streams)'}
 
+    log('e2e done')
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    # CPU baseline: rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 in its workers,
+    # which would serialise the autograd thread of the CPU port)
+    if rank == 0 and world == 1 and not args.no_cpu:
         cpu_pairs_per_s(1 << 17, 1 << 17, 1)                     # warm the thread pool
         v, cores, secs = cpu_pairs_per_s(1 << 23, 1 << 17, 2)
         cpu = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
@@ -391,13 +418,19 @@ def run_ours(args):
             'losses': [float(x) for x in losses],
         }
         print(json.dumps(out))
+    log('report printed')
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    log('exit')
 
 
 if __name__ == '__main__':
     a = parse()
+    import faulthandler
+    # a hung collective or device call must not hang the caller: dump every thread's stack
+    # to stderr and exit non-zero
+    faulthandler.dump_traceback_later(a.watchdog, exit=True)
     if a.impl == 'reference':
         run_reference(a)
     else:
