@@ -70,6 +70,32 @@ def is_current(precise=False, tune=False):
         return f.read().strip() == _source_hash(_kind(precise, tune))
 
 
+def build_variant(tune_default):
+    """Production-style build with the kernel knobs baked in at compile time
+    (``-DGD_TUNE_DEFAULT=<bits>``): ``libgdloss_b200_v<bits>.so``, A/B measurements only."""
+    lib = os.path.join(PKG_DIR, f'libgdloss_b200_v{int(tune_default)}.so')
+    nvcc = _nvcc()
+    build_dir = os.path.join(PKG_DIR, 'build', f'v{int(tune_default)}')
+    os.makedirs(build_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(build_dir, src.replace('.cu', '.o'))
+        res = subprocess.run([nvcc] + NVCC_FLAGS + [f'-DGD_TUNE_DEFAULT={int(tune_default)}', '-I',
+                                                    INCLUDE, '-c', os.path.join(CSRC, src), '-o', obj],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{res.stdout}\n{res.stderr}')
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    res = subprocess.run([nvcc, '-shared', '-o', lib] + objs + ['-cudart', 'static'],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f'link failed:\n{res.stdout}\n{res.stderr}')
+    return lib
+
+
 def build(force=False, precise=False, verbose=False, tune=False):
     """Compile the library if missing or stale; returns its path."""
     lib = lib_path(precise, tune)
@@ -105,5 +131,8 @@ def build(force=False, precise=False, verbose=False, tune=False):
 
 
 if __name__ == '__main__':
+    if '--variant' in sys.argv:
+        print(build_variant(int(sys.argv[sys.argv.index('--variant') + 1])))
+        sys.exit(0)
     print(build(force='--force' in sys.argv, precise='--precise' in sys.argv,
                 verbose='-v' in sys.argv, tune='--tune' in sys.argv))

@@ -54,6 +54,7 @@ enum : int {
   kTuneGenericStore = 16,  // all lanes write the gradient tile with st.global.cs.v4
   kTuneHalfMath = 32,      // (measurement only) math on half of each lane's rows
   kTuneLane0 = 64,         // copy commands issued by `lane == 0` instead of elect.sync
+  kTuneStrided = 128,      // lane owns rows lane + 32 k (32-bit shared-memory accesses)
 };
 struct FullTile { static constexpr bool value = true; };
 struct PartTile { static constexpr bool value = false; };
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   // The warp index goes through a shuffle so the compiler knows it is warp-uniform:
   // every address of the copy engine commands below then lives in uniform registers
   // and the one-lane issue needs no per-lane "waterfall" loop around UBLKCP.
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int warp = (GD_TUNE_DEFAULT & kTuneLane0) ? (tid >> 5) : __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wmode = WM >= 0 ? WM : a.wmode;
   const bool want_rows = a.row_loss != nullptr;
   gd::PairParams<float> pp = a.pp;
@@ -394,18 +395,31 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     // bytes per array, moved with 128-bit (R = 4) shared-memory accesses.  Rows past a
     // partial tile's end read stale shared memory; they are never redone or stored.
     float p[R][7], t[R][7], w[R];
-    smem_load<7 * R>(&p[0][0], sp + 7 * R * lane);
-    smem_load<7 * R>(&t[0][0], stg + 7 * R * lane);
-    if (wmode == GD_WEIGHT_ROW) {
-      smem_load<R>(w, sw + R * lane);
-    } else if (wmode == GD_WEIGHT_ROW7) {
-      float w7[R][7];
-      smem_load<7 * R>(&w7[0][0], sw + 7 * R * lane);
+    if (tune & kTuneStrided) {
 #pragma unroll
-      for (int k = 0; k < R; ++k) w[k] = row_weight_smem(&w7[k][0], GD_WEIGHT_ROW7, 0);
+      for (int k = 0; k < R; ++k) {
+        const int r = lane + 32 * k;       // word 7r+c -> bank (7 lane + c) mod 32: conflict free
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          p[k][c] = sp[7 * r + c];
+          t[k][c] = stg[7 * r + c];
+        }
+        w[k] = row_weight_smem(sw, wmode, r);
+      }
     } else {
+      smem_load<7 * R>(&p[0][0], sp + 7 * R * lane);
+      smem_load<7 * R>(&t[0][0], stg + 7 * R * lane);
+      if (wmode == GD_WEIGHT_ROW) {
+        smem_load<R>(w, sw + R * lane);
+      } else if (wmode == GD_WEIGHT_ROW7) {
+        float w7[R][7];
+        smem_load<7 * R>(&w7[0][0], sw + 7 * R * lane);
 #pragma unroll
-      for (int k = 0; k < R; ++k) w[k] = 1.0f;
+        for (int k = 0; k < R; ++k) w[k] = row_weight_smem(&w7[k][0], GD_WEIGHT_ROW7, 0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) w[k] = 1.0f;
+      }
     }
     // the previous tile's store must have finished READING the output buffer
     if (early_wait && leader && L.out && i > 0) bulk_wait_read<0>();
@@ -416,6 +430,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     // straight-line block, so their instruction streams interleave; rows it flags
     // (clamped / degenerate extents, huge yaw, masked weight, ...) are redone on the
     // robust path.  FULL: every lane row is valid (all tiles but the warp's last one).
+    auto row_of = [&](int k) { return (tune & kTuneStrided) ? lane + 32 * k : R * lane + k; };
     auto eval_tile = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
       float g[R][7], rl[R], lw[R];
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         }
         rl[k] = l * ws;
         lw[k] = l * w[k];
-        if (!FULL) rare[k] = rare[k] && (R * lane + k < rows);   // stale rows: never redone
+        if (!FULL) rare[k] = rare[k] && (row_of(k) < rows);   // stale rows: never redone
       }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
@@ -444,12 +459,24 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       late_wait(i);
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        if (FULL || R * lane + k < rows) acc += lw[k];
+        if (FULL || row_of(k) < rows) acc += lw[k];
       }
       // rows past the end of a partial tile are written to the staging buffer too (it
       // has room for a full tile); the bulk store below only moves `rows` rows
-      if (GRAD) smem_store<7 * R>(og + 7 * R * lane, &g[0][0]);
-      if (want_rows) smem_store<R>(orow + R * lane, rl);
+      if (tune & kTuneStrided) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int r = lane + 32 * k;
+          if (GRAD) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) og[7 * r + c] = g[k][c];
+          }
+          if (want_rows) orow[r] = rl[k];
+        }
+      } else {
+        if (GRAD) smem_store<7 * R>(og + 7 * R * lane, &g[0][0]);
+        if (want_rows) smem_store<R>(orow + R * lane, rl);
+      }
     };
     if (rows == kTileRows) eval_tile(FullTile{});
     else eval_tile(PartTile{});

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""A/B of production-style builds of the fused kernel in ONE process on ONE GPU
+(boxes differ by a few percent under the power cap, so variants must be compared inside
+one run): `python tools/ab_variants.py 0 64 128 192` times libgdloss_b200_v<bits>.so
+(build_ext.build_variant) on the five bench configurations at 2^24 pairs, interleaved
+over several rounds, and prints one JSON document."""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmdet3d_gaussian_b200 import _lib, build_ext, synth  # noqa: E402
+from tune_sweep import COMBOS, bind, timed  # noqa: E402
+
+
+def main():
+    names = sys.argv[1:] or ['0']
+    n = 1 << 24
+    torch.cuda.set_device(0)
+    libs = {}
+    for nm in names:
+        path = build_ext.lib_path() if nm == 'prod' else os.path.join(
+            build_ext.PKG_DIR, f'libgdloss_b200_v{nm}.so')
+        libs[nm] = bind(path)
+    pred, target, weight = synth.make_pairs(n, 'kitti', seed=0, device='cuda')
+    grad = torch.empty(n, 7, device='cuda')
+    ref = torch.empty(n, 7, device='cuda')
+    loss = torch.empty((), device='cuda')
+    ws = torch.zeros(next(iter(libs.values())).gd_loss_workspace_bytes(n), dtype=torch.uint8,
+                     device='cuda')
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cfgs = {c: _lib.make_config(c[0], c[1], True, 0.0, 1.0, (0, 0, 0.5)) for c in COMBOS}
+
+    def launcher(lib, cfg, g):
+        def launch():
+            code = lib.gd_loss_fwd_bwd(
+                ctypes.byref(cfg), pred.data_ptr(), 7, target.data_ptr(), 7, weight.data_ptr(),
+                1, 1, n, 5.0 / n, loss.data_ptr(), None, g.data_ptr(), ws.data_ptr(), ws.numel(),
+                _lib.VARIANTS['bulk'], 0, stream)
+            if code != 0:
+                raise RuntimeError(f'gd_loss_fwd_bwd -> {code}')
+        return launch
+
+    rounds = 4
+    ms = {nm: {c: [] for c in COMBOS} for nm in names}
+    same = {nm: True for nm in names}
+    for c in COMBOS:
+        launcher(libs[names[0]], cfgs[c], ref)()
+        for nm in names[1:]:
+            launcher(libs[nm], cfgs[c], grad)()
+            torch.cuda.synchronize()
+            same[nm] = same[nm] and bool(torch.equal(grad, ref))
+    for _ in range(rounds):
+        for c in COMBOS:
+            for nm in names:
+                ms[nm][c].append(timed(launcher(libs[nm], cfgs[c], grad), 25, 5))
+    out = {'n': n, 'rounds': rounds, 'variants': {}}
+    for nm in names:
+        per = {f'{c[0]}/{c[1]}': round(88 * n / (sum(v) / len(v)) / 1e6, 1) for c, v in ms[nm].items()}
+        bench = [per[f'{lt}/{fun}'] for lt, fun in COMBOS[:4]]
+        out['variants'][nm] = {'GBps': per, 'bench_mean_GBps': round(4 / sum(1 / x for x in bench), 1),
+                               'grad_bit_identical_to_first': same[nm]}
+        sys.stderr.write(f"{nm:>6s} bench-mean {out['variants'][nm]['bench_mean_GBps']:8.1f}  " +
+                         ' '.join(f'{v:.0f}' for v in per.values()) + '\n')
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()

@@ -29,6 +29,16 @@ METRICS = [
     ('launch__block_size', 'block'),
     ('sm__cycles_elapsed.avg.per_second', 'SM clock'),
     ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem bank conflicts'),
+    ('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'fma pipe %'),
+    ('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'xu pipe %'),
+    ('smsp__warps_eligible.avg.per_cycle_active', 'eligible warps/cycle'),
+    ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+     'stall long_scoreboard /issue'),
+    ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'stall wait /issue'),
+    ('smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+     'stall not_selected /issue'),
+    ('smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+     'stall no_instruction /issue'),
 ]
 
 
@@ -43,9 +53,14 @@ def main():
     out_dir = os.path.join(ROOT, 'profiles')
     os.makedirs(out_dir, exist_ok=True)
     rep = os.path.join(src, 'prof_bulk.ncu-rep')
-    if os.path.exists(rep):
-        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True,
-                             text=True).stdout
+    raw_csv = os.path.join(src, 'prof_bulk_raw.csv')     # exported on the GPU box (ncu -i)
+    if os.path.exists(rep) or os.path.exists(raw_csv):
+        if os.path.exists(rep):
+            raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True,
+                                 text=True).stdout
+        else:
+            with open(raw_csv) as f:
+                raw = f.read()
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units, data = rows[0], rows[1], rows[2:]
         name_i = hdr.index('Kernel Name')
