@@ -48,7 +48,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs', type=int, default=N_PAIRS)
-    ap.add_argument('--variant', default='auto', choices=['auto', 'bulk', 'bulk_r2', 'staged'])
+    ap.add_argument('--variant', default='auto', choices=['auto', 'bulk', 'bulk_packed', 'bulk_r2', 'staged'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--detail', action='store_true', help='extra per-config lines on stderr')

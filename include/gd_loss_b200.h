@@ -67,7 +67,10 @@ enum {
   GD_VARIANT_STAGED = 1, /* LDG/STG staged through shared memory; any stride       */
   GD_VARIANT_BULK = 2,   /* persistent per-warp cp.async.bulk (TMA 1-D) + mbarrier
                             rings, 4 rows per lane                                 */
-  GD_VARIANT_BULK_R2 = 3 /* same, 2 rows per lane / twice the warps (tuning aid)   */
+  GD_VARIANT_BULK_R2 = 3, /* same, 2 rows per lane / twice the warps (tuning aid)  */
+  GD_VARIANT_BULK_PACKED = 4 /* GD_VARIANT_BULK with the FP32 math of two rows packed into
+                                FFMA2/FMUL2/FADD2 (gwd3d / kld3d / bd3d with gradient; other
+                                cases run GD_VARIANT_BULK).  Opt-in: not selected by AUTO.  */
 };
 
 /* flags of gd_loss_fwd_bwd */

@@ -13,7 +13,7 @@ LOSS_TYPES = {'gwd3d': 0, 'kld3d': 1, 'jd3d': 2, 'kld3d_symmax': 3,
               'kld3d_symmin': 4, 'bd3d': 5, 'kfiou3d': 6}
 FUNS = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
 WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
-VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3}
+VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3, 'bulk_packed': 4}
 FLAG_MASK_ZERO_WEIGHT = 1
 PAIR_SIMILARITY = 1
 GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3

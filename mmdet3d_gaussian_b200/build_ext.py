@@ -22,7 +22,8 @@ SOURCES = ['gd_loss_api.cu', 'gd_loss_inst_gwd.cu', 'gd_loss_inst_kld.cu', 'gd_l
            'gd_pairwise_inst_gwd.cu', 'gd_pairwise_inst_kld.cu', 'gd_pairwise_inst_jd.cu',
            'gd_pairwise_inst_symmax.cu', 'gd_pairwise_inst_symmin.cu', 'gd_pairwise_inst_bd.cu',
            'gd_pairwise_inst_kfiou.cu']
-HEADERS = ['gd_math.cuh', 'gd_common.cuh', 'gd_loss_kernels.cuh', 'gd_decode.cuh', 'gd_pairwise.cuh']
+HEADERS = ['gd_math.cuh', 'gd_packed.cuh', 'gd_common.cuh', 'gd_loss_kernels.cuh', 'gd_decode.cuh',
+           'gd_pairwise.cuh']
 LIB_NAME = 'libgdloss_b200.so'
 LIB_PRECISE_NAME = 'libgdloss_b200_precise.so'   # -DGD_PRECISE_MATH=1, tests only
 LIB_TUNE_NAME = 'libgdloss_b200_tune.so'         # -DGD_TUNE=1, tools/tune_sweep.py only

@@ -95,7 +95,7 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg, const float* pred, int64_t pred_r
                     size_t workspace_bytes, int32_t variant, int32_t flags, void* stream) {
   using namespace gdk;
   if (!config_ok(cfg) || n < 0 || (flags & ~GD_FLAG_MASK_ZERO_WEIGHT) || weight_mode < GD_WEIGHT_NONE || weight_mode > GD_WEIGHT_ROW7 ||
-      variant < GD_VARIANT_AUTO || variant > GD_VARIANT_BULK_R2)
+      variant < GD_VARIANT_AUTO || variant > GD_VARIANT_BULK_PACKED)
     return GD_ERR_BAD_ARG;
   if (n > 0 && (!pred || !target || (weight_mode != GD_WEIGHT_NONE && !weight)))
     return GD_ERR_BAD_ARG;
@@ -112,7 +112,8 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg, const float* pred, int64_t pred_r
                        (!row_loss || aligned16(row_loss)) && n >= 4;
   // n == 0 with a loss_sum falls through to a 1-CTA staged launch that writes
   // scale * 0 (nan when scale is nan: torch's mean of an empty tensor).
-  const bool want_bulk = variant == GD_VARIANT_BULK || variant == GD_VARIANT_BULK_R2;
+  const bool want_bulk = variant == GD_VARIANT_BULK || variant == GD_VARIANT_BULK_R2 ||
+                         variant == GD_VARIANT_BULK_PACKED;
   if (want_bulk && !bulk_ok) return GD_ERR_LAYOUT;
   const int v = want_bulk ? variant
                           : (variant == GD_VARIANT_AUTO && bulk_ok ? GD_VARIANT_BULK

@@ -31,6 +31,7 @@
 // the result is deterministic for a given grid.
 #pragma once
 #include "gd_common.cuh"
+#include "gd_packed.cuh"
 
 // Tuning knobs of gd_warp_kernel.  The production library bakes GD_TUNE_DEFAULT in
 // at compile time (dead branches vanish); `-DGD_TUNE=1` builds
@@ -291,7 +292,9 @@ __device__ __forceinline__ void smem_store(float* dst, const float* src) {
   }
 }
 
-template <int LOSS, bool GRAD, int R, int SPEC, int WM>
+// PACK: the FAST math of two rows of a lane runs as one packed-FP32 (f32x2) stream
+// (gd_packed.cuh); needs an even R and one of the three headline losses.
+template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
 __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const LossArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kTileRows = 32 * R;
@@ -309,6 +312,8 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     pp.tau_on = (SPEC >> 2) & 1;
     pp.flag = (SPEC >> 3) & 1;
   }
+  [[maybe_unused]] gd::PairParams<gd::f2> pp2;
+  if constexpr (PACK) pp2 = gd::broadcast_params(pp);
   const WarpLayout L = warp_layout(R, wmode, GRAD, want_rows);
   unsigned char* base = smem + (size_t)warp * L.per_warp;
   unsigned char* out_base = base + kWarpStages * L.stage;
@@ -435,6 +440,26 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       constexpr bool FULL = decltype(full_tag)::value;
       float g[R][7], rl[R], lw[R];
       bool rare[R];
+      if constexpr (PACK) {
+        static_assert(R % 2 == 0, "packed math pairs the rows of a lane");
+#pragma unroll
+        for (int k = 0; k < R; k += 2) {
+          rare[k] = mask_zero && w[k] == 0.0f;
+          rare[k + 1] = mask_zero && w[k + 1] == 0.0f;
+          const float ws0 = w[k] * a.scale, ws1 = w[k + 1] * a.scale;
+          float l0, l1;
+          gd::pair_eval_fast2<LOSS, GRAD>(p[k], t[k], p[k + 1], t[k + 1], pp2, ws0, ws1, g[k],
+                                          g[k + 1], &rare[k], &rare[k + 1], &l0, &l1);
+          rl[k] = l0 * ws0;
+          lw[k] = l0 * w[k];
+          rl[k + 1] = l1 * ws1;
+          lw[k + 1] = l1 * w[k + 1];
+          if (!FULL) {                         // stale rows: never redone
+            rare[k] = rare[k] && (row_of(k) < rows);
+            rare[k + 1] = rare[k + 1] && (row_of(k + 1) < rows);
+          }
+        }
+      } else {
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         rare[k] = mask_zero && w[k] == 0.0f;
@@ -450,6 +475,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         rl[k] = l * ws;
         lw[k] = l * w[k];
         if (!FULL) rare[k] = rare[k] && (row_of(k) < rows);   // stale rows: never redone
+      }
       }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
@@ -542,7 +568,7 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
 
 constexpr int kSmemBudget = 227 * 1024 - 1024;   // opt-in max per CTA minus static + slack
 
-template <int LOSS, bool GRAD, int R, int SPEC, int WM>
+template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
 int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
 #if GD_TUNE
   LossArgs a = a_in;
@@ -550,7 +576,7 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
 #else
   const LossArgs& a = a_in;
 #endif
-  auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM>;
+  auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM, PACK>;
   // opt in to the large dynamic shared memory once per device (function attributes are
   // per context); a racing second call sets the same value
   static bool attr_set[kMaxDevices] = {};
@@ -593,9 +619,10 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
 // Specialised instantiations exist for the shipped configurations (fun in
 // {none, log1p}, flag = default true, weights None / [N]); anything else takes the
 // run-time-parameter instantiation of the same kernel.
-template <int LOSS, bool GRAD, int R>
+template <int LOSS, bool GRAD, int R, bool PACK = false>
 int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
   constexpr bool kHasSpec = GRAD && (LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd);
+  static_assert(!PACK || kHasSpec, "packed math exists for the specialised instantiations only");
   if constexpr (kHasSpec) {
     const gd::PairParams<float>& pp = a.pp;
     const bool spec_ok = pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p) &&
@@ -604,8 +631,9 @@ int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
       const int spec = pp.fun | (pp.tau_on << 2) | (1 << 3);
 #define GD_SPEC_CASE(S)                                                                 \
   case S:                                                                               \
-    return a.wmode == GD_WEIGHT_ROW ? launch_warp_inst<LOSS, GRAD, R, S, 1>(a, max_grid, stream) \
-                                    : launch_warp_inst<LOSS, GRAD, R, S, 0>(a, max_grid, stream);
+    return a.wmode == GD_WEIGHT_ROW                                                     \
+               ? launch_warp_inst<LOSS, GRAD, R, S, 1, PACK>(a, max_grid, stream)       \
+               : launch_warp_inst<LOSS, GRAD, R, S, 0, PACK>(a, max_grid, stream);
       switch (spec) {
         GD_SPEC_CASE(8) GD_SPEC_CASE(9) GD_SPEC_CASE(12) GD_SPEC_CASE(13)
         default: break;
@@ -620,6 +648,15 @@ template <int LOSS>
 int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t stream) {
   const bool grad = a.grad != nullptr;
   if (variant == GD_VARIANT_BULK) {
+    return grad ? launch_warp<LOSS, true, 4>(a, max_grid, stream)
+                : launch_warp<LOSS, false, 4>(a, max_grid, stream);
+  }
+  if (variant == GD_VARIANT_BULK_PACKED) {
+    // packed math: gradient + one of the three headline losses; anything else (and any
+    // configuration without a specialised instantiation) runs the scalar bulk kernel
+    if constexpr (LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd) {
+      if (grad) return launch_warp<LOSS, true, 4, true>(a, max_grid, stream);
+    }
     return grad ? launch_warp<LOSS, true, 4>(a, max_grid, stream)
                 : launch_warp<LOSS, false, 4>(a, max_grid, stream);
   }

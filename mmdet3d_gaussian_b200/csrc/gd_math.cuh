@@ -73,6 +73,8 @@ struct Mth;
 
 template <>
 struct Mth<double> {
+  typedef bool mask;                         // result type of a comparison (one bit per value)
+  static GD_HD double sel(bool c, double a, double b) { return c ? a : b; }
   static GD_HD double rcp(double x) { return 1.0 / x; }
   static GD_HD double sqrt(double x) { return ::sqrt(x); }
   static GD_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
@@ -103,6 +105,8 @@ struct Mth<double> {
 
 template <>
 struct Mth<float> {
+  typedef bool mask;
+  static GD_HD float sel(bool c, float a, float b) { return c ? a : b; }
   // Device arithmetic: MUFU approximations (rcp/sqrt/rsqrt.approx.ftz: <= 1-2 ulp)
   // instead of the IEEE-rounded sequences (each ~8 instructions + a slow-path
   // call).  The parity budget is 1e-5 relative; these cost ~1e-7 per operation
@@ -284,20 +288,20 @@ GD_HD T clamp_extent(T v, T* mask) {
 // torch autograd convention probed in SURVEY.md appendix A).
 template <typename T>
 GD_HD T sqrt_clamp0(T x, T* dfac) {
-  const bool neg = x < (T)0;                   // NaN falls through and propagates
-  const T xc = neg ? (T)0 : x;
+  const typename Mth<T>::mask neg = x < (T)0;  // NaN falls through and propagates
+  const T xc = Mth<T>::sel(neg, (T)0, x);
   const T k = (T)0.5 * Mth<T>::rsqrt(xc);      // +inf at x == 0
-  *dfac = neg ? (T)0 : k;
+  *dfac = Mth<T>::sel(neg, (T)0, k);
   return Mth<T>::sqrt(xc);
 }
 
 // post map ref:24-39: f = log1p | expm1 | nlog | identity, then tau >= 1 ->
 // 1 - tau/(tau+f) = f/(tau+f).  Returns value, multiplies *dfac by d out / d in.
 template <typename T, bool FAST>
-GD_HD T post_map(T d, const PairParams<T>& P, T* dfac, bool* rare) {
+GD_HD T post_map(T d, const PairParams<T>& P, T* dfac, typename Mth<T>::mask* rare) {
   T f = d, df = (T)1;
   if (P.fun == kFunLog1p) {
-    if (FAST) {
+    if constexpr (FAST) {
       *rare |= !(d < (T)1e30);                 // inf / nan distance: robust path
       f = Mth<T>::log1p_pos(d);
     } else {
@@ -373,14 +377,15 @@ GD_HD void geom_derive(PairGeom<T>* g) {
 // branch-free range reduction is exact); NaNs fail every test and land on the
 // robust path too.
 template <typename T, bool NEED_PRED_ROT, bool FAST>
-GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool* rare) {
+GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P,
+                            typename Mth<T>::mask* rare) {
   PairGeom<T> g;
   g.dx = (p[0] - t[0]) + P.off[0] * (p[3] - t[3]);
   g.dy = (p[1] - t[1]) + P.off[1] * (p[4] - t[4]);
   g.dz = (p[2] - t[2]) + P.off[2] * (p[5] - t[5]);
-  if (FAST) {
+  if constexpr (FAST) {
     const T lo = (T)1e-4, hi = (T)1e4;
-    bool ok = p[3] >= lo && p[4] >= lo && p[5] >= lo && t[3] >= lo && t[4] >= lo && t[5] >= lo;
+    typename Mth<T>::mask ok = p[3] >= lo && p[4] >= lo && p[5] >= lo && t[3] >= lo && t[4] >= lo && t[5] >= lo;
     ok = ok && p[3] <= hi && p[4] <= hi && p[5] <= hi && t[3] <= hi && t[4] <= hi && t[5] <= hi;
     const T ymax = (T)16;
     ok = ok && (p[6] >= -ymax && p[6] <= ymax && t[6] >= -ymax && t[6] <= ymax);
@@ -401,7 +406,7 @@ GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool
     }
     geom_derive(&g);
     return g;
-  }
+  } else {
   T dummy;
   g.ap = (T)0.5 * clamp_extent(p[3], &g.ma);
   g.bp = (T)0.5 * clamp_extent(p[4], &g.mb);
@@ -431,6 +436,7 @@ GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P, bool
   }
   geom_derive(&g);
   return g;
+  }
 }
 
 // Local gradient (before the outer chain factor): w.r.t. centre difference in
@@ -457,7 +463,7 @@ GD_HD void store_grad(const PairGeom<T>& g, const PairParams<T>& P,
 // a2: GWD                                                        ref:42-106
 // ---------------------------------------------------------------------------
 template <typename T, bool GRAD, bool FAST>
-GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
+GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, typename Mth<T>::mask* rare) {
   const T A = g.A, B = g.B, C = g.C, D = g.D;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd;
   const T K = g.abp * g.abt;                                       // ref:91-92
@@ -480,7 +486,7 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
     // 1 / (2 (K e_p e_t)^(1/6)), product split so it cannot overflow
     if (g.has_r6) {                            // pairwise: per-box factors
       inv_n = (T)0.5 * (g.r6p * g.r6t);
-    } else if (FAST) {
+    } else if constexpr (FAST) {
       inv_n = (T)0.5 * Mth<T>::rsixthroot((g.abp * g.ep) * (g.abt * g.et));
     } else {
       const T vp = Mth<T>::sqrt(g.ap * g.bp * g.ep);
@@ -534,7 +540,7 @@ struct KldCommon {
 
 template <typename T, bool FAST>
 GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
-                LocalGrad<T>* L, T* ul, T* vl, bool* rare) {
+                LocalGrad<T>* L, T* ul, T* vl, typename Mth<T>::mask* rare) {
   // value: 0.5 (u^2/A + v^2/B + dz^2/E)/alpha^2 + 0.5 tr(Sp^-1 St) + 0.5 F/E
   //        + ln(a_p b_p e_p / a_t b_t e_t) - 1.5                   ref:122-137
   const T u = g.cp * g.dx + g.sp * g.dy;
@@ -569,7 +575,7 @@ GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
 
 template <typename T, bool FAST>
 GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
-                LocalGrad<T>* L, T* ul, T* vl, bool* rare) {
+                LocalGrad<T>* L, T* ul, T* vl, typename Mth<T>::mask* rare) {
   // KL with Sigma_t inverted (kld3d_loss(target, pred)); gradient still w.r.t. pred.
   const T u = g.cp * g.dx + g.sp * g.dy;
   const T v = -g.sp * g.dx + g.cp * g.dy;
@@ -612,12 +618,12 @@ GD_HD void rotate_centre_grad(const PairGeom<T>& g, T ul, T vl, LocalGrad<T>* L)
 
 template <typename T, int LOSS, bool GRAD, bool FAST>
 GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
-                        bool* rare) {
+                        typename Mth<T>::mask* rare) {
   LocalGrad<T> L;
   T ul = (T)0, vl = (T)0;
   T fac = (T)1;
   T val;
-  if (LOSS == kKld) {
+  if constexpr (LOSS == kKld) {
     val = kld_fwd<T, FAST>(g, P, GRAD, &L, &ul, &vl, rare);
     if (P.flag) {                                                  // ref:138-139
       T k;
@@ -630,7 +636,7 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
     T f = kld_fwd<T, FAST>(g, P, GRAD, &L, &ul, &vl, rare);
     T r = kld_rev<T, FAST>(g, P, GRAD, &Lr, &ulr, &vlr, rare);
     T wf, wr;                                  // d val / d f, d val / d r
-    if (LOSS == kJd) {                                             // ref:191-197
+    if constexpr (LOSS == kJd) {                                   // ref:191-197
       val = (T)0.5 * (f + r);
       wf = wr = (T)0.5;
       if (P.flag) {
@@ -675,7 +681,7 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
 // a4: Bhattacharyya                                             ref:144-186
 // ---------------------------------------------------------------------------
 template <typename T, bool GRAD, bool FAST>
-GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
+GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, typename Mth<T>::mask* rare) {
   const T A = g.A, B = g.B, C = g.C, D = g.D;
   const T E = g.E, F = g.F;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd, sc = g.sd * g.cd;
@@ -691,10 +697,12 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
   const T eps = amb * cmd * s2;
   const T detN = (A + C) * (B + D) + eps;                          // det(Sp+St)
   const T det_raw = (T)0.25 * detN;                                // ref:155-157
-  bool clamped = !(det_raw >= (T)1e-7);                            // ref:158
-  if (FAST) {                              // clamp active (or nan): robust path redoes the row
-    *rare |= clamped;
-    clamped = false;
+  const typename Mth<T>::mask clamp_m = !(det_raw >= (T)1e-7);     // ref:158
+  bool clamped = false;
+  if constexpr (FAST) {                    // clamp active (or nan): robust path redoes the row
+    *rare |= clamp_m;
+  } else {
+    clamped = clamp_m;
   }
   const T det = clamped ? (T)1e-7 : det_raw;
   const T idet = Mth<T>::rcp(det);
@@ -712,7 +720,7 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
     const T xb = db * db * ((T)0.5 * g.ibp * g.ibt);
     const T q = xa + xb + xa * xb + (T)0.25 * eps * ((g.iap * g.ibp) * (g.iat * g.ibt));
     const T qq = q + xe + q * xe;              // (1+q)(1+xe) - 1
-    if (FAST) {
+    if constexpr (FAST) {
       *rare |= !(qq >= (T)0 && qq < (T)1e30);
       shape = (T)0.5 * Mth<T>::log1p_pos(qq);
     } else {
@@ -769,7 +777,7 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
 // ---------------------------------------------------------------------------
 template <typename T, bool GRAD, bool FAST>
 GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* grad,
-                   bool* rare) {
+                   typename Mth<T>::mask* rare) {
   PairParams<T> P = Pin;
   P.tau_on = 0;                                                    // ref:247
   const T A = g.ap * g.ap, B = g.bp * g.bp, C = g.at * g.at, D = g.bt * g.bt;
@@ -862,11 +870,11 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* 
 // dispatchers
 // ---------------------------------------------------------------------------
 template <typename T, int LOSS, bool GRAD, bool FAST>
-GD_HD T core_eval(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, bool* rare) {
-  if (LOSS == kGwd) return gwd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
-  if (LOSS == kBd) return bd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
-  if (LOSS == kKfiou) return kfiou_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
-  return kld_family_core<T, LOSS, GRAD, FAST>(g, P, gscale, grad, rare);
+GD_HD T core_eval(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, typename Mth<T>::mask* rare) {
+  if constexpr (LOSS == kGwd) return gwd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  else if constexpr (LOSS == kBd) return bd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  else if constexpr (LOSS == kKfiou) return kfiou_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  else return kld_family_core<T, LOSS, GRAD, FAST>(g, P, gscale, grad, rare);
 }
 
 // element-wise path, ROBUST version: one (pred row, target row) pair for ANY input
@@ -888,14 +896,15 @@ GD_HD T pair_eval(const T* p, const T* t, const PairParams<T>& P, T gscale, T* g
 // kfiou3d has no fast variant (it is not a headline loss): always rare = true.
 template <typename T, int LOSS, bool GRAD>
 GD_HD T pair_eval_fast(const T* p, const T* t, const PairParams<T>& P, T gscale, T* grad,
-                       bool* rare) {
+                       typename Mth<T>::mask* rare) {
   constexpr bool kNeedRot = !(LOSS == kGwd || LOSS == kKfiou);
-  if (LOSS == kKfiou) {
+  if constexpr (LOSS == kKfiou) {
     *rare = true;
     return (T)0;
+  } else {
+    const PairGeom<T> g = make_geom<T, kNeedRot, true>(p, t, P, rare);
+    return core_eval<T, LOSS, GRAD, true>(g, P, gscale, grad, rare);
   }
-  const PairGeom<T> g = make_geom<T, kNeedRot, true>(p, t, P, rare);
-  return core_eval<T, LOSS, GRAD, true>(g, P, gscale, grad, rare);
 }
 
 // ---------------------------------------------------------------------------

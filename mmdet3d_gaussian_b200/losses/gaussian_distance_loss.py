@@ -50,7 +50,8 @@ class GDLoss(nn.Module):
     distance: ``normalize`` for ``gwd3d``, ``sqrt`` for the others.  Two extra,
     backwards-compatible keys are consumed here and never reach the distance:
 
-    * ``variant`` ('auto' | 'staged' | 'bulk') selects the kernel variant;
+    * ``variant`` ('auto' | 'staged' | 'bulk' | 'bulk_packed') selects the kernel variant
+      ('bulk_packed' = packed-FP32 math, opt-in, never chosen by 'auto');
     * ``host_sync`` (default True).  True keeps the reference's early return
       (ref:290-292) exactly, including its device->host sync
       (``torch.any(weight > 0)``).  False never syncs: rows whose weight is exactly

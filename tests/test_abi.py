@@ -57,9 +57,15 @@ def test_sass_is_sm100a_with_bulk_copies():
                          text=True).stdout
     assert 'sm_100a' in elf
     sass = subprocess.run([cuobjdump, '-sass', '-fun',
-                           '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1EEEvNS_8LossArgsE',
+                           '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1ELb0EEEvNS_8LossArgsE',
                            build_ext.lib_path()], capture_output=True, text=True).stdout
     assert 'UBLKCP' in sass and 'SYNCS' in sass
+    assert 'LDS.128' in sass and 'STS.128' in sass and 'FFMA2' not in sass
+    # the opt-in packed variant of the same kernel uses the packed FP32 pipe instructions
+    packed = subprocess.run([cuobjdump, '-sass', '-fun',
+                             '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1ELb1EEEvNS_8LossArgsE',
+                             build_ext.lib_path()], capture_output=True, text=True).stdout
+    assert 'FFMA2' in packed and 'FMUL2' in packed and 'UBLKCP' in packed
 
 
 def test_argument_validation_without_gpu(lib):

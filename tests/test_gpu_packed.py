@@ -1,0 +1,61 @@
+"""GPU parity of the OPT-IN packed-FP32 variant of the fused kernel
+(``variant='bulk_packed'`` = GD_VARIANT_BULK_PACKED, csrc/gd_packed.cuh).
+
+The variant is not selected by ``variant='auto'`` and has not been timed or validated
+on a GPU yet (it was written after the round's GPU budget was spent), so these tests only
+run when ``GD_B200_TEST_EXPERIMENTAL=1`` is set; the default ``pytest -m gpu`` suite
+covers exactly the kernels the library uses by default."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mmdet3d_gaussian_b200 import GDLoss, synth
+from oracle import gd_oracle
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('GD_B200_TEST_EXPERIMENTAL') != '1',
+                                 reason='opt-in variant: set GD_B200_TEST_EXPERIMENTAL=1')]
+RTOL = 1e-5
+
+
+def _run(kw, variant, pred, target, w, **fw):
+    p = pred.clone().cuda().requires_grad_(True)
+    out = GDLoss(variant=variant, host_sync=False, **kw)(p, target.cuda(), w.cuda(), **fw)
+    out.backward()
+    return out.item(), p.grad.cpu().double().numpy()
+
+
+@pytest.mark.parametrize('loss_type', ['gwd3d', 'kld3d', 'bd3d'])
+@pytest.mark.parametrize('fun,tau', [('log1p', 0.0), ('none', 0.0), ('log1p', 1.0), ('none', 2.0)])
+@pytest.mark.parametrize('n', [100_003, 4, 131, 1 << 20])
+def test_packed_vs_oracle_and_scalar(loss_type, fun, tau, n):
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=11, weights='bernoulli')
+    # rows the FAST path must hand to the robust path, in both halves of a pair
+    if n > 64:
+        pred[5, 4] = 1e-9
+        pred[8, 6] = 1000.0
+        target[9, 3] = 2e4
+    kw = dict(loss_type=loss_type, fun=fun, tau=tau, loss_weight=5.0)
+    lp, gp = _run(kw, 'bulk_packed', pred, target, w, avg_factor=float(n))
+    ls, gs = _run(kw, 'bulk', pred, target, w, avg_factor=float(n))
+    ref_l, ref_g = gd_oracle.loss_and_grad(gd_oracle.GDLossOracle(**kw), pred.double(),
+                                           target.double(), w.double(), avg_factor=float(n))
+    ref_g = ref_g.numpy()
+    assert abs(lp - ref_l.item()) <= RTOL * abs(ref_l.item())
+    assert abs(lp - ls) <= 2e-6 * abs(ls)
+    fin = np.isfinite(ref_g).all(axis=1)
+    gn = np.maximum(np.linalg.norm(ref_g[fin], axis=1), 1e-2 * 5.0 / n)
+    assert (np.linalg.norm(gp[fin] - ref_g[fin], axis=1) / gn).max() <= RTOL
+    assert (np.linalg.norm(gp[fin] - gs[fin], axis=1) / gn).max() <= 2e-6
+
+
+def test_packed_falls_back_for_other_configurations():
+    """Losses / modes without a packed instantiation run the scalar bulk kernel."""
+    pred, target, w = synth.make_pairs(5000, 'kitti', seed=3)
+    for kw in (dict(loss_type='jd3d'), dict(loss_type='kfiou3d', fun='none'),
+               dict(loss_type='gwd3d', normalize=False), dict(loss_type='kld3d', reduction='none')):
+        a = GDLoss(variant='bulk_packed', **kw)(pred.cuda(), target.cuda(), w.cuda())
+        b = GDLoss(variant='bulk', **kw)(pred.cuda(), target.cuda(), w.cuda())
+        assert torch.equal(a, b)

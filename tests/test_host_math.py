@@ -210,3 +210,20 @@ def test_pairwise_value_path(hostlib, lt):
             ctypes.c_int(FUN[fun]), ctypes.c_int(1), out.ctypes.data_as(ctypes.c_void_p))
         err = np.abs(out - ref) / np.maximum(np.abs(ref), 1e-3)
         assert err.max() < tol, (dt, err.max())
+
+
+def test_packed_instantiation_is_bit_identical_on_host(tmp_path):
+    """csrc/gd_packed.cuh (T = f2, two rows per 64-bit register; the opt-in
+    GD_VARIANT_BULK_PACKED kernels): on the host both halves use plain float
+    arithmetic, so value, gradient and the robust-path flag must equal the float
+    instantiation bit for bit for gwd3d / kld3d / bd3d x fun x tau x flag, including
+    rows the FAST path has to flag (tests/host_math/packed_harness.cpp)."""
+    exe = str(tmp_path / 'packed_harness')
+    subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-x', 'c++',
+                    os.path.join(HERE, 'host_math', 'packed_harness.cpp'), '-o', exe],
+                   check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('fun')]
+    assert len(lines) == 8 and all('mismatches gwd 0 kld 0 bd 0' in ln for ln in lines), out.stdout
+    assert all(int(ln.rsplit('rare rows', 1)[1].strip(' )')) > 0 for ln in lines)

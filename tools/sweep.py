@@ -50,7 +50,7 @@ def main():
         for lt in types + (['jd3d', 'kld3d_symmax', 'kld3d_symmin', 'kfiou3d'] if e == 24 else []):
             fun = 'none' if lt == 'kfiou3d' else 'log1p'
             cfg = _lib.make_config(lt, fun, True, 0.0, 1.0, (0, 0, 0.5))
-            for variant in ('bulk', 'bulk_r2', 'staged'):
+            for variant in ('bulk', 'bulk_packed', 'bulk_r2', 'staged'):
                 for mode, g, r, bpp in (('fwd+bwd', grad, None, 88), ('fwd', None, None, 60),
                                         ('fwd+bwd+rows', grad, rows, 92)):
                     if mode != 'fwd+bwd' and (e != 24 or lt not in types):
