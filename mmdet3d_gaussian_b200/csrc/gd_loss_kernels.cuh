@@ -56,7 +56,14 @@ enum : int {
   kTuneHalfMath = 32,      // (measurement only) math on half of each lane's rows
   kTuneLane0 = 64,         // copy commands issued by `lane == 0` instead of elect.sync
   kTuneStrided = 128,      // lane owns rows lane + 32 k (32-bit shared-memory accesses)
+  // Compile-time only (GD_TUNE_DEFAULT; ignored in GD_TUNE_FLAGS): instruction diets of the
+  // FAST math (gd_math.cuh, gd::Diet) and the packed math as the default of 'bulk'.
+  kTuneGuardMinMax = 256,  // nice-row screen with FMNMX3.NAN instead of 16 compares
+  kTuneStd = 512,          // specialised kernels assume alpha == 1, center_offset == (0,0,.5);
+                           // any other value takes the run-time-parameter kernel
+  kTunePacked = 1024,      // GD_VARIANT_BULK (and 'auto') run the packed-FP32 math
 };
+constexpr int kDietGuards = (GD_TUNE_DEFAULT & kTuneGuardMinMax) ? gd::kDietGuards : 0;
 struct FullTile { static constexpr bool value = true; };
 struct PartTile { static constexpr bool value = false; };
 
@@ -298,6 +305,7 @@ template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
 __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const LossArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kTileRows = 32 * R;
+  constexpr int kDiet = kDietGuards | ((SPEC >= 0 && (GD_TUNE_DEFAULT & kTuneStd)) ? gd::kDietStd : 0);
   const int tid = threadIdx.x, lane = tid & 31;
   // The warp index goes through a shuffle so the compiler knows it is warp-uniform:
   // every address of the copy engine commands below then lives in uniform registers
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
           rare[k + 1] = mask_zero && w[k + 1] == 0.0f;
           const float ws0 = w[k] * a.scale, ws1 = w[k + 1] * a.scale;
           float l0, l1;
-          gd::pair_eval_fast2<LOSS, GRAD>(p[k], t[k], p[k + 1], t[k + 1], pp2, ws0, ws1, g[k],
+          gd::pair_eval_fast2<LOSS, GRAD, kDiet>(p[k], t[k], p[k + 1], t[k + 1], pp2, ws0, ws1, g[k],
                                           g[k + 1], &rare[k], &rare[k + 1], &l0, &l1);
           rl[k] = l0 * ws0;
           lw[k] = l0 * w[k];
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
 #pragma unroll
           for (int c = 0; c < 7; ++c) g[k][c] = p[k][c] + t[k][c] * ws;
         } else {
-          l = gd::pair_eval_fast<float, LOSS, GRAD>(p[k], t[k], pp, ws, g[k], &rare[k]);
+          l = gd::pair_eval_fast<float, LOSS, GRAD, kDiet>(p[k], t[k], pp, ws, g[k], &rare[k]);
         }
         rl[k] = l * ws;
         lw[k] = l * w[k];
@@ -625,8 +633,11 @@ int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
   static_assert(!PACK || kHasSpec, "packed math exists for the specialised instantiations only");
   if constexpr (kHasSpec) {
     const gd::PairParams<float>& pp = a.pp;
-    const bool spec_ok = pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p) &&
-                         a.wmode != GD_WEIGHT_ROW7 && !a.row_loss;
+    bool spec_ok = pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p) &&
+                   a.wmode != GD_WEIGHT_ROW7 && !a.row_loss;
+    if (GD_TUNE_DEFAULT & kTuneStd)       // the specialised kernels bake these values in
+      spec_ok = spec_ok && pp.alpha2 == 1.0f && pp.inv_alpha2 == 1.0f && pp.off[0] == 0.0f &&
+                pp.off[1] == 0.0f && pp.off[2] == 0.5f;
     if (spec_ok) {
       const int spec = pp.fun | (pp.tau_on << 2) | (1 << 3);
 #define GD_SPEC_CASE(S)                                                                 \
@@ -647,6 +658,7 @@ int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
 template <int LOSS>
 int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t stream) {
   const bool grad = a.grad != nullptr;
+  if ((GD_TUNE_DEFAULT & kTunePacked) && variant == GD_VARIANT_BULK) variant = GD_VARIANT_BULK_PACKED;
   if (variant == GD_VARIANT_BULK) {
     return grad ? launch_warp<LOSS, true, 4>(a, max_grid, stream)
                 : launch_warp<LOSS, false, 4>(a, max_grid, stream);

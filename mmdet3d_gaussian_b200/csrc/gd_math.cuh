@@ -65,6 +65,28 @@ struct PairParams {
   int flag;      // 'normalize' (gwd) or 'sqrt' (others)   ref:43,110,145
 };
 
+// Optional compile-time "diet" of the FAST cores (template parameter DIET, default 0 =
+// the validated code, unchanged).  Both bits remove instructions only; see DESIGN.md.
+//   kDietGuards: the "nice row" screen of make_geom uses 3-input NaN-propagating
+//                min/max (FMNMX3.NAN) instead of 16 compares -- same decision.
+//   kDietStd:    the caller promises alpha == 1 and center_offset == (0, 0, 0.5) (the
+//                reference's defaults, ref:261-262, and what every shipped config uses):
+//                the multiplications by alpha^2 / 1/alpha^2 and by the zero x/y offsets
+//                disappear.  Values differ from DIET = 0 by FMA contraction only (<= 1 ulp
+//                per operation).
+enum Diet : int { kDietGuards = 1, kDietStd = 2 };
+
+template <int DIET, typename T>
+GD_HD T a2_times(const PairParams<T>& P, T x) {      // alpha^2 * x
+  if constexpr ((DIET & kDietStd) != 0) return x;
+  else return P.alpha2 * x;
+}
+template <int DIET, typename T>
+GD_HD T times_ia2(T x, const PairParams<T>& P) {     // x / alpha^2
+  if constexpr ((DIET & kDietStd) != 0) return x;
+  else return x * P.inv_alpha2;
+}
+
 // ---------------------------------------------------------------------------
 // scalar helpers
 // ---------------------------------------------------------------------------
@@ -101,6 +123,13 @@ struct Mth<double> {
   static GD_HD void sincos_fast(double x, double* s, double* c) { sincos(x, s, c); }
   static GD_HD double log1p_pos(double x) { return ::log1p(x); }
   static GD_HD double rsixthroot(double x) { return ::pow(x, -1.0 / 6.0); }
+  static GD_HD bool nice_row_minmax(double p3, double p4, double p5, double t3, double t4,
+                                    double t5, double yp, double yt) {
+    const double lo = 1e-4, hi = 1e4, ymax = 16;
+    return p3 >= lo && p4 >= lo && p5 >= lo && t3 >= lo && t4 >= lo && t5 >= lo && p3 <= hi &&
+           p4 <= hi && p5 <= hi && t3 <= hi && t4 <= hi && t5 <= hi && yp >= -ymax &&
+           yp <= ymax && yt >= -ymax && yt <= ymax;
+  }
 };
 
 template <>
@@ -272,6 +301,26 @@ struct Mth<float> {
     return rcbrt(sqrt(x));
 #endif
   }
+  // The "nice row" screen of make_geom<FAST> (six extents in [1e-4, 1e4], both yaws in
+  // [-16, 16], NaN fails) with 3-input NaN-propagating min/max: 5 FMNMX + 5 FSETP instead
+  // of 16 FSETP.  Same decision for every input.
+  static GD_HD bool nice_row_minmax(float p3, float p4, float p5, float t3, float t4, float t5,
+                                    float yp, float yt) {
+    const float lo = 1e-4f, hi = 1e4f, ymax = 16.0f;
+#if defined(__CUDA_ARCH__)
+    float mn, mx, ya;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(mn) : "f"(p3), "f"(p4), "f"(p5));
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(mn) : "f"(mn), "f"(t3), "f"(t4));
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(p3), "f"(p4), "f"(p5));
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(t3), "f"(t4));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(ya) : "f"(fabsf(yp)), "f"(fabsf(yt)));
+    return mn >= lo && t5 >= lo && mx <= hi && t5 <= hi && ya <= ymax;
+#else
+    return p3 >= lo && p4 >= lo && p5 >= lo && t3 >= lo && t4 >= lo && t5 >= lo && p3 <= hi &&
+           p4 <= hi && p5 <= hi && t3 <= hi && t4 <= hi && t5 <= hi && yp >= -ymax &&
+           yp <= ymax && yt >= -ymax && yt <= ymax;
+#endif
+  }
 };
 
 // torch.clamp(min, max) semantics (NaN propagates); returns the gradient mask
@@ -376,20 +425,30 @@ GD_HD void geom_derive(PairGeom<T>* g) {
 // +-16 rad (so r_p - r_t is formed with an absolute error below 1e-6 rad and the
 // branch-free range reduction is exact); NaNs fail every test and land on the
 // robust path too.
-template <typename T, bool NEED_PRED_ROT, bool FAST>
+template <typename T, bool NEED_PRED_ROT, bool FAST, int DIET = 0>
 GD_HD PairGeom<T> make_geom(const T* p, const T* t, const PairParams<T>& P,
                             typename Mth<T>::mask* rare) {
   PairGeom<T> g;
+  if constexpr ((DIET & kDietStd) != 0) {      // center_offset == (0, 0, 0.5)
+    g.dx = p[0] - t[0];
+    g.dy = p[1] - t[1];
+    g.dz = (p[2] - t[2]) + (T)0.5 * (p[5] - t[5]);
+  } else {
   g.dx = (p[0] - t[0]) + P.off[0] * (p[3] - t[3]);
   g.dy = (p[1] - t[1]) + P.off[1] * (p[4] - t[4]);
   g.dz = (p[2] - t[2]) + P.off[2] * (p[5] - t[5]);
+  }
   if constexpr (FAST) {
+    if constexpr ((DIET & kDietGuards) != 0) {
+      *rare |= !Mth<T>::nice_row_minmax(p[3], p[4], p[5], t[3], t[4], t[5], p[6], t[6]);
+    } else {
     const T lo = (T)1e-4, hi = (T)1e4;
     typename Mth<T>::mask ok = p[3] >= lo && p[4] >= lo && p[5] >= lo && t[3] >= lo && t[4] >= lo && t[5] >= lo;
     ok = ok && p[3] <= hi && p[4] <= hi && p[5] <= hi && t[3] <= hi && t[4] <= hi && t[5] <= hi;
     const T ymax = (T)16;
     ok = ok && (p[6] >= -ymax && p[6] <= ymax && t[6] >= -ymax && t[6] <= ymax);
     *rare |= !ok;
+    }
     g.ap = (T)0.5 * p[3];
     g.bp = (T)0.5 * p[4];
     g.ep = (T)0.5 * p[5];
@@ -446,13 +505,20 @@ struct LocalGrad {
   T gdx, gdy, gdz, ga, gb, ge, gr;
 };
 
-template <typename T>
+template <typename T, int DIET = 0>
 GD_HD void store_grad(const PairGeom<T>& g, const PairParams<T>& P,
                       const LocalGrad<T>& L, T fac, T* out) {
   // d/dw = 0.5 * [1e-7 <= w <= 1e7] * d/da + off_x * d/dc_x   
   out[0] = fac * L.gdx;
   out[1] = fac * L.gdy;
   out[2] = fac * L.gdz;
+  if constexpr ((DIET & kDietStd) != 0) {      // center_offset == (0, 0, 0.5)
+    out[3] = fac * ((T)0.5 * g.ma * L.ga);
+    out[4] = fac * ((T)0.5 * g.mb * L.gb);
+    out[5] = fac * ((T)0.5 * g.me * L.ge + (T)0.5 * L.gdz);
+    out[6] = fac * L.gr;
+    return;
+  }
   out[3] = fac * ((T)0.5 * g.ma * L.ga + P.off[0] * L.gdx);
   out[4] = fac * ((T)0.5 * g.mb * L.gb + P.off[1] * L.gdy);
   out[5] = fac * ((T)0.5 * g.me * L.ge + P.off[2] * L.gdz);
@@ -462,7 +528,7 @@ GD_HD void store_grad(const PairGeom<T>& g, const PairParams<T>& P,
 // ---------------------------------------------------------------------------
 // a2: GWD                                                        ref:42-106
 // ---------------------------------------------------------------------------
-template <typename T, bool GRAD, bool FAST>
+template <typename T, bool GRAD, bool FAST, int DIET = 0>
 GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, typename Mth<T>::mask* rare) {
   const T A = g.A, B = g.B, C = g.C, D = g.D;
   const T s2 = g.sd * g.sd, c2 = g.cd * g.cd;
@@ -478,7 +544,7 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
   const T eta = eps * Mth<T>::rcp(V + rU);                         // V - sqrt U
   const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
   const T W = da * da + db * db + (T)2 * eta + de * de;            // ref:81-97
-  const T d2 = g.dx * g.dx + g.dy * g.dy + g.dz * g.dz + P.alpha2 * W;  // ref:79,99
+  const T d2 = g.dx * g.dx + g.dy * g.dy + g.dz * g.dz + a2_times<DIET>(P, W);  // ref:79,99
   T k;                                                             // 1/(2 d)
   T d = sqrt_clamp0(d2, &k);                                       // ref:99
   T inv_n = (T)1;
@@ -509,17 +575,17 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
     L.gdx = (T)2 * g.dx * kn;
     L.gdy = (T)2 * g.dy * kn;
     L.gdz = (T)2 * g.dz * kn;
-    L.ga = P.alpha2 * dWa * kn;
-    L.gb = P.alpha2 * dWb * kn;
-    L.ge = P.alpha2 * (T)2 * de * kn;
-    L.gr = P.alpha2 * dWr * kn;
+    L.ga = a2_times<DIET>(P, dWa) * kn;
+    L.gb = a2_times<DIET>(P, dWb) * kn;
+    L.ge = a2_times<DIET>(P, (T)2) * de * kn;
+    L.gr = a2_times<DIET>(P, dWr) * kn;
     if (P.flag) {                                                  // d ln n / da = 1/(6a)
       const T g6 = gval * (T)(1.0 / 6.0);
       L.ga -= g6 * g.iap;
       L.gb -= g6 * g.ibp;
       L.ge -= g6 * g.iep;
     }
-    store_grad(g, P, L, fac * gscale, grad);
+    store_grad<T, DIET>(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -538,7 +604,7 @@ struct KldCommon {
   T s2, s2x2;        // sin^2 dl, sin(2 dl)
 };
 
-template <typename T, bool FAST>
+template <typename T, bool FAST, int DIET = 0>
 GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
                 LocalGrad<T>* L, T* ul, T* vl, typename Mth<T>::mask* rare) {
   // value: 0.5 (u^2/A + v^2/B + dz^2/E)/alpha^2 + 0.5 tr(Sp^-1 St) + 0.5 F/E
@@ -552,7 +618,7 @@ GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   // delta_i = (t_i - p_i)/p_i ; C/A = (1+delta_a)^2 ...
   const T qa = (g.at - g.ap) * iap, qb = (g.bt - g.bp) * ibp, qe = (g.et - g.ep) * iep;
   const T ra = g.at * iap, rb = g.bt * ibp, re = g.et * iep;       // = 1 + q
-  const T maha = (T)0.5 * (u * u * iA + v * v * iB + g.dz * g.dz * iE) * P.inv_alpha2;
+  const T maha = times_ia2<DIET>((T)0.5 * (u * u * iA + v * v * iB + g.dz * g.dz * iE), P);
   // sum(delta + delta^2/2) - log((1+da)(1+db)(1+de)) with a single log:
   const T pair = qa * qb + qa * qe + qb * qe + qa * qb * qe;       // Pi(1+d) - 1 - sum d
   const T shape = (T)0.5 * (qa * qa + qb * qb + qe * qe)
@@ -561,19 +627,19 @@ GD_HD T kld_fwd(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   if (want_grad) {
     const T s2x2 = (T)2 * g.sd * g.cd;
     const T rot = cmd * s2;
-    const T lu = u * iA * P.inv_alpha2, lv = v * iB * P.inv_alpha2;
+    const T lu = times_ia2<DIET>(u * iA, P), lv = times_ia2<DIET>(v * iB, P);
     *ul = lu;                                  // gradient w.r.t. (u, v): pred frame
     *vl = lv;
-    L->gdz = g.dz * iE * P.inv_alpha2;
-    L->ga = iap * (-qa * ((T)2 + qa) + rot * iA - u * u * iA * P.inv_alpha2);
-    L->gb = ibp * (-qb * ((T)2 + qb) - rot * iB - v * v * iB * P.inv_alpha2);
-    L->ge = iep * (-qe * ((T)2 + qe) - g.dz * g.dz * iE * P.inv_alpha2);
-    L->gr = (iA - iB) * (u * v * P.inv_alpha2 - (T)0.5 * cmd * s2x2);
+    L->gdz = times_ia2<DIET>(g.dz * iE, P);
+    L->ga = iap * (-qa * ((T)2 + qa) + rot * iA - times_ia2<DIET>(u * u * iA, P));
+    L->gb = ibp * (-qb * ((T)2 + qb) - rot * iB - times_ia2<DIET>(v * v * iB, P));
+    L->ge = iep * (-qe * ((T)2 + qe) - times_ia2<DIET>(g.dz * g.dz * iE, P));
+    L->gr = (iA - iB) * (times_ia2<DIET>(u * v, P) - (T)0.5 * cmd * s2x2);
   }
   return maha + shape;
 }
 
-template <typename T, bool FAST>
+template <typename T, bool FAST, int DIET = 0>
 GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
                 LocalGrad<T>* L, T* ul, T* vl, typename Mth<T>::mask* rare) {
   // KL with Sigma_t inverted (kld3d_loss(target, pred)); gradient still w.r.t. pred.
@@ -588,7 +654,7 @@ GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
   const T amb = g.amb;
   const T qa = (g.ap - g.at) * iat, qb = (g.bp - g.bt) * ibt, qe = (g.ep - g.et) * iet;
   const T ra = g.ap * iat, rb = g.bp * ibt, re = g.ep * iet;       // = 1 + q
-  const T maha = (T)0.5 * (ut * ut * iC + vt * vt * iD + g.dz * g.dz * iF) * P.inv_alpha2;
+  const T maha = times_ia2<DIET>((T)0.5 * (ut * ut * iC + vt * vt * iD + g.dz * g.dz * iF), P);
   const T pair = qa * qb + qa * qe + qb * qe + qa * qb * qe;
   const T shape = (T)0.5 * (qa * qa + qb * qb + qe * qe)
       + Mth<T>::template sum_minus_log_ratios<FAST>(qa + qb + qe, pair, ra, rb, re, rare)
@@ -597,10 +663,10 @@ GD_HD T kld_rev(const PairGeom<T>& g, const PairParams<T>& P, bool want_grad,
     const T s2x2 = (T)2 * g.sd * g.cd;
     const T A = g.A, B = g.B;
     // gradient w.r.t. (u', v') rotated back into the pred frame: R(-dl)
-    const T lut = ut * iC * P.inv_alpha2, lvt = vt * iD * P.inv_alpha2;
+    const T lut = times_ia2<DIET>(ut * iC, P), lvt = times_ia2<DIET>(vt * iD, P);
     *ul = g.cd * lut + g.sd * lvt;
     *vl = -g.sd * lut + g.cd * lvt;
-    L->gdz = g.dz * iF * P.inv_alpha2;
+    L->gdz = times_ia2<DIET>(g.dz * iF, P);
     L->ga = g.iap * (qa * ((T)2 + qa) + A * s2 * (iD - iC));
     L->gb = g.ibp * (qb * ((T)2 + qb) + B * s2 * (iC - iD));
     L->ge = g.iep * (qe * ((T)2 + qe));
@@ -616,7 +682,7 @@ GD_HD void rotate_centre_grad(const PairGeom<T>& g, T ul, T vl, LocalGrad<T>* L)
   L->gdy = g.sp * ul + g.cp * vl;
 }
 
-template <typename T, int LOSS, bool GRAD, bool FAST>
+template <typename T, int LOSS, bool GRAD, bool FAST, int DIET = 0>
 GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
                         typename Mth<T>::mask* rare) {
   LocalGrad<T> L;
@@ -624,7 +690,7 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
   T fac = (T)1;
   T val;
   if constexpr (LOSS == kKld) {
-    val = kld_fwd<T, FAST>(g, P, GRAD, &L, &ul, &vl, rare);
+    val = kld_fwd<T, FAST, DIET>(g, P, GRAD, &L, &ul, &vl, rare);
     if (P.flag) {                                                  // ref:138-139
       T k;
       val = sqrt_clamp0(val, &k);
@@ -633,8 +699,8 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
   } else {
     LocalGrad<T> Lr;
     T ulr = (T)0, vlr = (T)0;
-    T f = kld_fwd<T, FAST>(g, P, GRAD, &L, &ul, &vl, rare);
-    T r = kld_rev<T, FAST>(g, P, GRAD, &Lr, &ulr, &vlr, rare);
+    T f = kld_fwd<T, FAST, DIET>(g, P, GRAD, &L, &ul, &vl, rare);
+    T r = kld_rev<T, FAST, DIET>(g, P, GRAD, &Lr, &ulr, &vlr, rare);
     T wf, wr;                                  // d val / d f, d val / d r
     if constexpr (LOSS == kJd) {                                   // ref:191-197
       val = (T)0.5 * (f + r);
@@ -672,7 +738,7 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
   const T out = post_map<T, FAST>(val, P, &fac, rare);
   if (GRAD) {
     rotate_centre_grad(g, ul, vl, &L);
-    store_grad(g, P, L, fac * gscale, grad);
+    store_grad<T, DIET>(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -680,7 +746,7 @@ GD_HD T kld_family_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, 
 // ---------------------------------------------------------------------------
 // a4: Bhattacharyya                                             ref:144-186
 // ---------------------------------------------------------------------------
-template <typename T, bool GRAD, bool FAST>
+template <typename T, bool GRAD, bool FAST, int DIET = 0>
 GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, typename Mth<T>::mask* rare) {
   const T A = g.A, B = g.B, C = g.C, D = g.D;
   const T E = g.E, F = g.F;
@@ -708,7 +774,7 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
   const T idet = Mth<T>::rcp(det);
   const T iMl = Mth<T>::rcp(Ml);
   const T Q2 = u * u * M11 - (T)2 * u * v * M01 + v * v * M00;     // d^T adj(M) d
-  const T maha = (T)0.125 * (Q2 * idet + g.dz * g.dz * iMl) * P.inv_alpha2;  // ref:170-172,182
+  const T maha = times_ia2<DIET>((T)0.125 * (Q2 * idet + g.dz * g.dz * iMl), P);  // ref:170-172,182
   // shape: 0.5 ln det + 0.5 ln Ml - 0.25 ln(ABE) - 0.25 ln(CDF)    ref:174-180
   const T K = g.abp * g.abt;
   const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
@@ -739,13 +805,13 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
   }
   const T out = post_map<T, FAST>(val, P, &fac, rare);
   if (GRAD) {
-    const T c8 = (T)0.125 * P.inv_alpha2 * idet;                   // 1/(8 alpha^2 det)
+    const T c8 = times_ia2<DIET>((T)0.125, P) * idet;              // 1/(8 alpha^2 det)
     LocalGrad<T> L;
     // centre: M^-1 d / (4 alpha^2) in the pred frame, then rotate
     const T ul = (T)2 * c8 * (M11 * u - M01 * v);
     const T vl = (T)2 * c8 * (M00 * v - M01 * u);
     rotate_centre_grad(g, ul, vl, &L);
-    L.gdz = (T)0.25 * g.dz * iMl * P.inv_alpha2;
+    L.gdz = times_ia2<DIET>((T)0.25 * g.dz * iMl, P);
     const T iap = g.iap, ibp = g.ibp, iep = g.iep;
     T sa, sb, gam;                             // shape parts and d/d det_raw factor
     if (!clamped) {
@@ -765,9 +831,9 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
     }
     L.ga = g.ap * (v * v * c8 + gam * M11) + sa;
     L.gb = g.bp * (u * u * c8 + gam * M00) + sb;
-    L.ge = -(T)0.125 * g.dz * g.dz * iMl * iMl * P.inv_alpha2 * g.ep
+    L.ge = times_ia2<DIET>(-(T)0.125 * g.dz * g.dz * iMl * iMl, P) * g.ep
         + (T)0.25 * de * (g.ep + g.et) * iep * iMl;
-    store_grad(g, P, L, fac * gscale, grad);
+    store_grad<T, DIET>(g, P, L, fac * gscale, grad);
   }
   return out;
 }
@@ -869,12 +935,12 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* 
 // ---------------------------------------------------------------------------
 // dispatchers
 // ---------------------------------------------------------------------------
-template <typename T, int LOSS, bool GRAD, bool FAST>
+template <typename T, int LOSS, bool GRAD, bool FAST, int DIET = 0>
 GD_HD T core_eval(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad, typename Mth<T>::mask* rare) {
-  if constexpr (LOSS == kGwd) return gwd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
-  else if constexpr (LOSS == kBd) return bd_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
+  if constexpr (LOSS == kGwd) return gwd_core<T, GRAD, FAST, DIET>(g, P, gscale, grad, rare);
+  else if constexpr (LOSS == kBd) return bd_core<T, GRAD, FAST, DIET>(g, P, gscale, grad, rare);
   else if constexpr (LOSS == kKfiou) return kfiou_core<T, GRAD, FAST>(g, P, gscale, grad, rare);
-  else return kld_family_core<T, LOSS, GRAD, FAST>(g, P, gscale, grad, rare);
+  else return kld_family_core<T, LOSS, GRAD, FAST, DIET>(g, P, gscale, grad, rare);
 }
 
 // element-wise path, ROBUST version: one (pred row, target row) pair for ANY input
@@ -894,7 +960,7 @@ GD_HD T pair_eval(const T* p, const T* t, const PairParams<T>& P, T gscale, T* g
 // Identical formulas; *rare is set when the row is not "nice" (see make_geom) or
 // hits a guard inside the distance -- the caller must then call pair_eval on it.
 // kfiou3d has no fast variant (it is not a headline loss): always rare = true.
-template <typename T, int LOSS, bool GRAD>
+template <typename T, int LOSS, bool GRAD, int DIET = 0>
 GD_HD T pair_eval_fast(const T* p, const T* t, const PairParams<T>& P, T gscale, T* grad,
                        typename Mth<T>::mask* rare) {
   constexpr bool kNeedRot = !(LOSS == kGwd || LOSS == kKfiou);
@@ -902,8 +968,8 @@ GD_HD T pair_eval_fast(const T* p, const T* t, const PairParams<T>& P, T gscale,
     *rare = true;
     return (T)0;
   } else {
-    const PairGeom<T> g = make_geom<T, kNeedRot, true>(p, t, P, rare);
-    return core_eval<T, LOSS, GRAD, true>(g, P, gscale, grad, rare);
+    const PairGeom<T> g = make_geom<T, kNeedRot, true, DIET>(p, t, P, rare);
+    return core_eval<T, LOSS, GRAD, true, DIET>(g, P, gscale, grad, rare);
   }
 }
 

@@ -176,6 +176,12 @@ struct Mth<f2> {
     *c = mk2(c0, c1);
   }
   static GD_HD f2 inf() { return f2(Mth<float>::inf()); }
+  static GD_HD m2 nice_row_minmax(f2 p3, f2 p4, f2 p5, f2 t3, f2 t4, f2 t5, f2 yp, f2 yt) {
+    return m2{Mth<float>::nice_row_minmax(lo2(p3), lo2(p4), lo2(p5), lo2(t3), lo2(t4), lo2(t5),
+                                          lo2(yp), lo2(yt)),
+              Mth<float>::nice_row_minmax(hi2(p3), hi2(p4), hi2(p5), hi2(t3), hi2(t4), hi2(t5),
+                                          hi2(yp), hi2(yt))};
+  }
 
   // Same algorithm and constants as Mth<float>::sincos_fast; the quadrant index is
   // taken per half, the Cody-Waite reduction and the two polynomials run packed.
@@ -282,7 +288,7 @@ GD_HD PairParams<f2> broadcast_params(const PairParams<float>& P) {
 // Two (pred, target) rows through the FAST cores at once.  pa/ta, pb/tb: the two rows;
 // wsa/wsb their weight*scale factors; ga/gb receive the gradients; rare_a/rare_b are
 // OR-ed with "this row must be redone on the robust path".  Returns the two values.
-template <int LOSS, bool GRAD>
+template <int LOSS, bool GRAD, int DIET = 0>
 GD_HD void pair_eval_fast2(const float* pa, const float* ta, const float* pb, const float* tb,
                            const PairParams<f2>& P, float wsa, float wsb, float* ga, float* gb,
                            bool* rare_a, bool* rare_b, float* la, float* lb) {
@@ -294,7 +300,7 @@ GD_HD void pair_eval_fast2(const float* pa, const float* ta, const float* pb, co
     t[c] = mk2(ta[c], tb[c]);
   }
   m2 rare = m2{*rare_a, *rare_b};
-  const f2 l = pair_eval_fast<f2, LOSS, GRAD>(p, t, P, mk2(wsa, wsb), g, &rare);
+  const f2 l = pair_eval_fast<f2, LOSS, GRAD, DIET>(p, t, P, mk2(wsa, wsb), g, &rare);
   *la = lo2(l);
   *lb = hi2(l);
   if (GRAD) {

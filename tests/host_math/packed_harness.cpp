@@ -43,6 +43,22 @@ long run(int fun, int tau_on, int flag, long n, unsigned seed, long* nrare) {
       if (memcmp(&l[h], &ls[h], 4)) ++bad;
       if (memcmp(g[h], gs[h], 28)) ++bad;
     }
+    // The instruction "diets" (gd::Diet: min/max row screen, alpha == 1 and
+    // center_offset == (0,0,.5) folded) change nothing on the host either: x * 1.0f and
+    // y + 0.0f * x are exact and -ffp-contract=off forbids the FMA contractions that
+    // make the device results differ by <= 1 ulp per operation.
+    constexpr int kAll = gd::kDietGuards | gd::kDietStd;
+    float gd_[2][7], ld[2], g2[2][7], l2[2];
+    bool rd[2] = {false, false}, r2[2] = {false, false};
+    ld[0] = gd::pair_eval_fast<float, LOSS, true, kAll>(p[0], t[0], P, 0.7f, gd_[0], &rd[0]);
+    ld[1] = gd::pair_eval_fast<float, LOSS, true, kAll>(p[1], t[1], P, 1.3f, gd_[1], &rd[1]);
+    gd::pair_eval_fast2<LOSS, true, kAll>(p[0], t[0], p[1], t[1], Q, 0.7f, 1.3f, g2[0], g2[1], &r2[0], &r2[1], &l2[0], &l2[1]);
+    for (int h = 0; h < 2; ++h) {
+      if (rd[h] != rs[h] || r2[h] != rs[h]) { ++bad; continue; }
+      if (rs[h]) continue;
+      if (memcmp(&ld[h], &ls[h], 4) || memcmp(&l2[h], &ls[h], 4)) ++bad;
+      if (memcmp(gd_[h], gs[h], 28) || memcmp(g2[h], gs[h], 28)) ++bad;
+    }
   }
   return bad;
 }

@@ -3,7 +3,13 @@
 (boxes differ by a few percent under the power cap, so variants must be compared inside
 one run): `python tools/ab_variants.py 0 64 128 192` times libgdloss_b200_v<bits>.so
 (build_ext.build_variant) on the five bench configurations at 2^24 pairs, interleaved
-over several rounds, and prints one JSON document."""
+over several rounds, and prints one JSON document.
+
+Bits of <bits> = GD_TUNE_DEFAULT (csrc/gd_loss_kernels.cuh): 1 late store wait, 2 loads
+evict_normal, 4 store hint, 16 generic stores, 64 lane-0 issue, 128 strided layout,
+256 min/max row screen, 512 alpha == 1 / center_offset == (0,0,.5) folded, 1024 packed-FP32
+math.  Variants with bit 512 or 1024 are not bit-identical to variant 0 on the device (FMA
+contraction, FFMA2): `grad_max_row_rel_diff_to_first` reports how far they are."""
 import ctypes
 import json
 import os
@@ -47,12 +53,17 @@ def main():
     rounds = 4
     ms = {nm: {c: [] for c in COMBOS} for nm in names}
     same = {nm: True for nm in names}
+    maxrel = {nm: 0.0 for nm in names}     # worst per-row |dgrad| / |grad| vs the first library
     for c in COMBOS:
         launcher(libs[names[0]], cfgs[c], ref)()
         for nm in names[1:]:
             launcher(libs[nm], cfgs[c], grad)()
             torch.cuda.synchronize()
             same[nm] = same[nm] and bool(torch.equal(grad, ref))
+            if not same[nm]:
+                num = (grad - ref).norm(dim=1)
+                den = ref.norm(dim=1).clamp_min(1e-30)
+                maxrel[nm] = max(maxrel[nm], float((num / den).max()))
     for _ in range(rounds):
         for c in COMBOS:
             for nm in names:
@@ -62,7 +73,8 @@ def main():
         per = {f'{c[0]}/{c[1]}': round(88 * n / (sum(v) / len(v)) / 1e6, 1) for c, v in ms[nm].items()}
         bench = [per[f'{lt}/{fun}'] for lt, fun in COMBOS[:4]]
         out['variants'][nm] = {'GBps': per, 'bench_mean_GBps': round(4 / sum(1 / x for x in bench), 1),
-                               'grad_bit_identical_to_first': same[nm]}
+                               'grad_bit_identical_to_first': same[nm],
+                               'grad_max_row_rel_diff_to_first': maxrel[nm]}
         sys.stderr.write(f"{nm:>6s} bench-mean {out['variants'][nm]['bench_mean_GBps']:8.1f}  " +
                          ' '.join(f'{v:.0f}' for v in per.values()) + '\n')
     print(json.dumps(out))
