@@ -411,6 +411,9 @@ def run_ours(args):
                          'peak_source': peak_src, 'kernel': 'gd_warp_kernel (fused fwd+bwd, bulk-copy warp pipelines)',
                          'bytes_per_pair': BYTES_PER_PAIR, 'pairs_per_launch': n,
                          'kernel_ms': kernel_ms, 'frac_of_8TBps_nominal': achieved / 8000.0,
+                         # the same figure from the timed region itself (module calls: the
+                         # fused launch + the grad_output fold that exits at once + Python)
+                         'achieved_timed_region': BYTES_PER_PAIR * len(COMBOS) * n / (ms_step * 1e-3) / 1e9,
                          'per_config': per_cfg},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
             'value_default_module': value_sync,

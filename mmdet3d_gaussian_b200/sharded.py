@@ -68,3 +68,96 @@ class ShardedGDLoss(torch.nn.Module):
         if dist.is_available() and dist.is_initialized():
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
         return total + (local - local.detach())
+
+
+# ---------------------------------------------------------------------------
+# pairwise path ("Pairwise"): anchors (rows) sharded, the M GT
+# boxes replicated.  Row minima are local; the per-GT minima over ALL anchors need one
+# all-reduce(MIN) of M packed (value, global anchor index) 64-bit keys.
+# ---------------------------------------------------------------------------
+_NO_INDEX = 0x7fffffff          # "no anchor" (empty shard); sorts after every real index
+
+
+def pack_min_keys(values, index):
+    """float32 ``values`` [M] + int64 ``index`` [M] (< 2^31 - 1, negative = none) ->
+    int64 keys whose signed order is (value, index) lexicographic with NaN FIRST and
+    ties -> lowest index, the order the kernel's own column reduction uses
+    (``csrc/gd_pairwise.cuh``) and ``torch.min`` follows."""
+    bits = values.detach().to(torch.float32).contiguous().view(torch.int32).to(torch.int64)
+    # order-preserving float -> signed int map: negatives have their low 31 bits flipped
+    ordered = torch.where(bits < 0, bits ^ 0x7fffffff, bits)
+    ordered = torch.where(torch.isnan(values), torch.full_like(ordered, -(1 << 31)), ordered)
+    idx = index.to(torch.int64)
+    idx = torch.where(idx < 0, torch.full_like(idx, _NO_INDEX), idx)
+    return (ordered << 32) | idx
+
+
+def unpack_min_keys(keys):
+    """Inverse of ``pack_min_keys``: ``(values float32 [M], index int64 [M])``; index -1
+    where no rank had an anchor; a NaN value comes back as the canonical NaN."""
+    ordered = keys >> 32                                     # arithmetic shift keeps the sign
+    idx = keys & 0xffffffff
+    nan = ordered == -(1 << 31)
+    bits = torch.where(ordered < 0, ordered ^ 0x7fffffff, ordered)
+    bits = torch.where(nan, torch.full_like(bits, 0x7fc00000), bits)
+    values = bits.to(torch.int32).view(torch.float32)
+    idx = torch.where(idx == _NO_INDEX, torch.full_like(idx, -1), idx)
+    return values, idx
+
+
+def merge_column_minima(col_min, col_argmin, row_offset, group=None):
+    """Per-GT ``(min, argmin)`` over all ranks' anchor shards from each rank's local
+    ``(col_min [M], col_argmin [M])`` (local row indices, -1 = empty shard): local
+    indices are shifted by ``row_offset`` and ONE ``all_reduce(MIN)`` of M int64 keys
+    merges them.  Returns ``(global_min float32 [M], global_argmin int64 [M])``, the same
+    on every rank and identical to the reduction of the unsharded matrix."""
+    idx = col_argmin.to(torch.int64)
+    idx = torch.where(idx >= 0, idx + int(row_offset), idx)
+    keys = pack_min_keys(col_min, idx)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+    return unpack_min_keys(keys)
+
+
+class ShardedGDMaxSimAssigner(torch.nn.Module):
+    """``GDMaxSimAssigner`` over row-sharded anchors: every rank passes ITS anchors and
+    the (replicated) GT boxes; labels come back for the local anchors only and equal
+    the unsharded assignment.  ``assigner`` needs the ``GDMaxSimAssigner`` attributes
+    (thresholds, ``cfg``); ``pairwise_fn`` / ``assign_fn`` default to the fused CUDA
+    operators and exist so the CPU tests can inject the oracle."""
+
+    def __init__(self, assigner, group=None, pairwise_fn=None, assign_fn=None):
+        super().__init__()
+        self.assigner = assigner
+        self.group = group
+        self._pairwise = pairwise_fn
+        self._assign = assign_fn
+
+    @torch.no_grad()
+    def assign(self, bboxes, gt_bboxes, row_offset):
+        a = self.assigner
+        if self._pairwise is None:
+            from . import ops
+            row_min, row_arg, col_min, col_arg, _ = ops.pairwise_assign(
+                bboxes[..., :7], gt_bboxes[..., :7], a.cfg)
+        else:
+            row_min, row_arg, col_min, col_arg = self._pairwise(bboxes, gt_bboxes)
+        n = bboxes.shape[0]
+        gmin, garg = merge_column_minima(col_min, col_arg, row_offset, self.group)
+        local = garg - int(row_offset)
+        local = torch.where((garg >= 0) & (local >= 0) & (local < n), local,
+                            torch.full_like(local, -1))
+        if self._assign is None:
+            from . import ops
+            assigned, max_ov = ops.assign_from_minima(
+                row_min, row_arg, gmin, local, a.pos_iou_thr, a.neg_lo, a.neg_hi,
+                a.min_pos_iou, a.match_low_quality)
+        else:
+            assigned, max_ov = self._assign(row_min, row_arg, gmin, local)
+        if gt_bboxes.shape[0] == 0:
+            assigned.zero_()
+            max_ov.zero_()
+        return dict(assigned_gt_inds=assigned, max_overlaps=max_ov,
+                    gt_max_overlaps=1.0 - gmin, gt_argmax_overlaps=garg)
+
+    forward = assign

@@ -144,3 +144,39 @@ def test_c4_shape_consistency():
         cv, ci = first_argmin(mat, 0)
         assert same_bits(rmin, rv) and torch.equal(ridx, ri)
         assert same_bits(cmin, cv) and torch.equal(cidx, ci)
+
+
+def test_sharded_assigner_emulated_shards():
+    """Row-sharded assignment (pairwise): per-shard fused minima, the
+    64-bit (value, anchor) keys of ``sharded.pack_min_keys`` merged with an element-wise MIN
+    (what the all-reduce does across ranks) and ``gd_assign_from_minima`` fed with shard-local
+    arg-minima (-1 = the winner lives in another shard) reproduce the single-GPU labels."""
+    from mmdet3d_gaussian_b200 import sharded
+    n, m, world = 5003, 40, 3
+    b1 = synth.make_anchor_grid(n, 'waymo', device='cuda')
+    b2 = synth.make_targets(m, 'waymo', seed=2, device='cuda')
+    b2[:, 0] = b2[:, 0] * 2.0 - 70.0
+    b1[n - 1] = b1[3]                              # the same anchor in two shards: a cross-shard tie
+    kw = dict(loss_type='gwd3d', fun='log1p', tau=1.0)
+    base = GDMaxSimAssigner(0.6, 0.45, 0.45, True, **kw)
+    full = base.assign(b1, b2)
+    keys, parts = None, []
+    for r in range(world):
+        lo, hi = sharded.shard_bounds(n, r, world)
+        rmin, rarg, cmin, carg, _ = ops.pairwise_assign(b1[lo:hi], b2, base.cfg)
+        k = sharded.pack_min_keys(cmin, torch.where(carg >= 0, carg + lo, carg))
+        keys = k if keys is None else torch.minimum(keys, k)
+        parts.append((rmin, rarg, lo, hi))
+    gmin, garg = sharded.unpack_min_keys(keys)
+    assert torch.equal(garg, full['gt_argmax_overlaps'])
+    assert same_bits(1.0 - gmin, full['gt_max_overlaps'])
+    labels = []
+    for rmin, rarg, lo, hi in parts:
+        local = torch.where((garg >= lo) & (garg < hi), garg - lo, torch.full_like(garg, -1))
+        assigned, _ = ops.assign_from_minima(rmin, rarg, gmin, local, 0.6, 0.0, 0.45, 0.45, True)
+        labels.append(assigned)
+    assert torch.equal(torch.cat(labels), full['assigned_gt_inds'])
+    # the module wrapper without a process group is the single-GPU assigner
+    res = sharded.ShardedGDMaxSimAssigner(base).assign(b1, b2, 0)
+    assert torch.equal(res['assigned_gt_inds'], full['assigned_gt_inds'])
+    assert torch.equal(res['gt_argmax_overlaps'], full['gt_argmax_overlaps'])

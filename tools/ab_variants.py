@@ -22,8 +22,33 @@ from mmdet3d_gaussian_b200 import _lib, build_ext, synth  # noqa: E402
 from tune_sweep import COMBOS, bind, timed  # noqa: E402
 
 
+def sustained(launch, sampler, seconds=2.0):
+    """~2 s of back-to-back launches of ONE variant: ms per launch + clocks / power."""
+    import time
+    for _ in range(5):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    calls = 0
+    while time.time() - t0 < seconds:
+        for _ in range(200):
+            launch()
+        calls += 200
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    row = {'ms': round(e0.elapsed_time(e1) / calls, 5)}
+    row.update(sampler.window(t0, t1))
+    time.sleep(0.5)
+    return row
+
+
 def main():
-    names = sys.argv[1:] or ['0']
+    power = '--power' in sys.argv
+    names = [a for a in sys.argv[1:] if not a.startswith('--')] or ['0']
     n = 1 << 24
     torch.cuda.set_device(0)
     libs = {}
@@ -77,6 +102,20 @@ def main():
                                'grad_max_row_rel_diff_to_first': maxrel[nm]}
         sys.stderr.write(f"{nm:>6s} bench-mean {out['variants'][nm]['bench_mean_GBps']:8.1f}  " +
                          ' '.join(f'{v:.0f}' for v in per.values()) + '\n')
+    if power:
+        # each variant alone, long enough for the power cap to settle: GB/s next to the
+        # SM clock and board power it was achieved at
+        from power_probe import Sampler
+        sampler = Sampler()
+        for nm in names:
+            sus = {}
+            for c in (COMBOS[0], COMBOS[3]):
+                row = sustained(launcher(libs[nm], cfgs[c], grad), sampler)
+                row['GBps'] = round(88 * n / row['ms'] / 1e6, 1)
+                sus[f'{c[0]}/{c[1]}'] = row
+                sys.stderr.write(f'{nm:>6s} sustained {c[0]}/{c[1]} {json.dumps(row)}\n')
+            out['variants'][nm]['sustained'] = sus
+        sampler.proc.terminate()
     print(json.dumps(out))
 
 

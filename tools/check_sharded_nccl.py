@@ -17,7 +17,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mmdet3d_gaussian_b200 import GDLoss, sharded, synth  # noqa: E402
+from mmdet3d_gaussian_b200 import GDLoss, GDMaxSimAssigner, sharded, synth  # noqa: E402
 from oracle import gd_oracle  # noqa: E402
 
 N = 786_432
@@ -73,6 +73,42 @@ def main():
                                     'loss_rel_err': rel, 'grad_max_row_rel_err': gerr,
                                     'ms_per_call_max_over_ranks': round(float(ms.item()), 4),
                                     'ok': good})
+    # pairwise path (C4-like): anchors sharded, GTs replicated, per-GT minima merged with
+    # one all-reduce(MIN) of 64-bit (value, anchor) keys; labels must equal the
+    # single-GPU assigner's bit for bit
+    na, m = 200_000, 256
+    anchors = synth.make_anchor_grid(na, 'waymo')
+    gts = synth.make_targets(m, 'waymo', seed=5)
+    gts[:, 0] = gts[:, 0] * 2.0 - 70.0
+    base = GDMaxSimAssigner(0.6, 0.45, 0.45, True, loss_type='gwd3d', fun='log1p', tau=1.0)
+    alo, ahi = sharded.shard_bounds(na, rank, world)
+    smod = sharded.ShardedGDMaxSimAssigner(base)
+    a_loc, g_dev = anchors[alo:ahi].to(dev), gts.to(dev)
+    res = smod.assign(a_loc, g_dev, alo)
+    labels = [None] * world
+    dist.all_gather_object(labels, res['assigned_gt_inds'].cpu())
+    for _ in range(5):
+        smod.assign(a_loc, g_dev, alo)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        smod.assign(a_loc, g_dev, alo)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 50], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        full = base.assign(anchors.to(dev), g_dev)
+        same = bool(torch.equal(torch.cat(labels), full['assigned_gt_inds'].cpu())) and \
+            bool(torch.equal(res['gt_argmax_overlaps'].cpu(), full['gt_argmax_overlaps'].cpu())) and \
+            bool(torch.equal(res['gt_max_overlaps'].cpu().view(torch.int32),
+                             full['gt_max_overlaps'].cpu().view(torch.int32)))
+        ok = ok and same
+        report['pairwise_assign'] = {'anchors': na, 'gts': m, 'equal_to_single_gpu': same,
+                                     'positives': int((full['assigned_gt_inds'] > 0).sum()),
+                                     'ms_per_call_max_over_ranks': round(float(ms.item()), 4)}
     if rank == 0:
         report['ok'] = ok
         print(json.dumps(report))
