@@ -16,6 +16,7 @@ WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
 VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3, 'bulk_packed': 4}
 FLAG_MASK_ZERO_WEIGHT = 1
 PAIR_SIMILARITY = 1
+PAIR_PACKED = 2            # opt-in packed-FP32 pairwise kernel (not GPU-validated yet)
 GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3
 
 

@@ -27,6 +27,7 @@
 // instruction sequence per pair, so indices derived from either are bit-identical.
 #pragma once
 #include "gd_common.cuh"
+#include "gd_packed.cuh"
 
 namespace gdk {
 
@@ -209,6 +210,221 @@ template <int LOSS>
 int launch_pairwise(const PairwiseArgs& a, cudaStream_t st) {
   return a.row_min ? launch_pairwise_spec<LOSS, true>(a, st)
                    : launch_pairwise_spec<LOSS, false>(a, st);
+}
+
+// ---------------------------------------------------------------------------
+// Packed-FP32 variant (OPT-IN: GD_PAIR_PACKED / GD_B200_PAIRWISE_PACKED=1).  The scalar
+// kernel above is issue bound (profiles/r01d_pairwise_ncu.md: 89 % of the issue slots, 48 %
+// of the FMA pipe, ~111 instructions per pair).  Here one lane evaluates TWO rows against
+// its column box per pass: the row tile lives in shared memory as float2 {row 2k, row 2k+1}
+// per BoxGauss field, so ONE 64-bit broadcast load yields a packed operand and the FAST
+// cores run as FFMA2 / FMUL2 / FADD2 (gd_packed.cuh) -- half the issue slots for the FP32
+// part and half the shared-memory loads.  Same mapping, reductions, tie rules and
+// workspace protocol as gd_pairwise_kernel; rows ascend within a lane (pair p = rows
+// 2p, 2p+1; a warp takes pairs ry, ry + wy, ...).  Values may differ from the scalar kernel
+// in the last bit (FMA contraction); matrix and reductions of THIS kernel still come from
+// one instruction sequence, so its indices are bit-consistent with its own matrix.
+// Only gwd3d / kld3d / bd3d with a compile-time SPEC; anything else runs the scalar kernel.
+// ---------------------------------------------------------------------------
+constexpr int kPairsPerCta = kRowsPerCta / 2;
+constexpr int kPairStride = (gd::kGaussFields + 1) & ~1;   // float2 per pair, padded: 16-B rows
+
+template <int LOSS, int SPEC, bool REDUCE>
+__global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const PairwiseArgs a) {
+  static_assert(SPEC >= 0, "packed pairwise kernels are compile-time specialised");
+  __shared__ __align__(16) float2 s_pair[kPairsPerCta][kPairStride];
+  __shared__ unsigned char s_nice[kRowsPerCta];
+  __shared__ unsigned long long s_best[REDUCE ? kRowsPerCta : 1][kWarps];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  gd::PairParams<float> pp = a.pp;
+  pp.fun = SPEC & 3;
+  pp.tau_on = (SPEC >> 2) & 1;
+  pp.flag = (SPEC >> 3) & 1;
+  const gd::PairParams<gd::f2> pp2 = gd::broadcast_params(pp);
+  const int wx = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
+  const int wy = kWarps / wx;
+  const int cgrp = warp % wx, ry = warp / wx;
+  const long long chunk = 32LL * wx;
+  const bool want_col = REDUCE && a.col_keys != nullptr;
+  const bool one_chunk = a.m <= chunk;
+  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  unsigned int cbest = 0xffffffffu, crow = 0u;
+
+  // scalar BoxGauss of one row of the tile, rebuilt from the packed tile (cold path only)
+  auto row_gauss = [&](int r) {
+    float f[gd::kGaussFields];
+    const float* src = reinterpret_cast<const float*>(&s_pair[r >> 1][0]) + (r & 1);
+#pragma unroll
+    for (int k = 0; k < gd::kGaussFields; ++k) f[k] = src[2 * k];
+    gd::BoxGauss<float> b = gd::gauss_from_fields<float>(f);
+    b.nice = s_nice[r];
+    return b;
+  };
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kRowsPerCta;
+    const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
+    const int npairs = (rows + 1) >> 1;
+    __syncthreads();                           // previous tile fully consumed
+    if (tid < rows) {
+      const gd::BoxGauss<float> b = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
+      float f[gd::kGaussFields];
+      gd::gauss_to_fields(b, f);
+      float* dst = reinterpret_cast<float*>(&s_pair[tid >> 1][0]) + (tid & 1);
+#pragma unroll
+      for (int k = 0; k < gd::kGaussFields; ++k) dst[2 * k] = f[k];
+      s_nice[tid] = (unsigned char)b.nice;
+      if (tid == rows - 1 && (rows & 1)) {     // odd tile: the last pair's upper half is a copy
+#pragma unroll
+        for (int k = 0; k < gd::kGaussFields; ++k) dst[2 * k + 1] = f[k];
+        s_nice[rows] = (unsigned char)b.nice;
+      }
+    }
+    if (REDUCE) {
+      for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads) (&s_best[0][0])[i] = ~0ull;
+    }
+    __syncthreads();
+    for (long long c0 = (long long)blockIdx.y * chunk; c0 < a.m; c0 += (long long)gridDim.y * chunk) {
+      if (c0 + 32LL * cgrp >= a.m) continue;   // this warp's 32 columns are all past the end
+      const long long j = c0 + 32LL * cgrp + lane;
+      const bool live = j < a.m;
+      gd::BoxGauss<float> t;
+      if (live) t = gd::box_gauss(a.b2 + j * 7, pp);
+      else t = row_gauss(0);                   // any valid box: the result is discarded
+      gd::BoxGauss<gd::f2> t2;
+      {
+        float f[gd::kGaussFields];
+        gd::f2 f2v[gd::kGaussFields];
+        gd::gauss_to_fields(t, f);
+#pragma unroll
+        for (int k = 0; k < gd::kGaussFields; ++k) f2v[k] = gd::mk2(f[k], f[k]);
+        t2 = gd::gauss_from_fields<gd::f2>(f2v);
+      }
+      if (want_col && !one_chunk) cbest = 0xffffffffu;
+
+      // one row of the pair: matrix store and reductions, exactly as the scalar kernel
+      // (the store address is carried as a pointer instead of being re-derived per row)
+      float* optr = (a.out != nullptr && live) ? a.out + (row0 + 2 * ry) * a.out_stride + j : nullptr;
+      const long long pair_step = 2LL * wy * a.out_stride;
+      auto emit = [&](int r, float v, float* dst) {
+        if (dst != nullptr) __stcs(dst, a.similarity ? 1.0f - v : v);
+        if (REDUCE) {
+          const unsigned int key = live ? order_key(v) : 0xffffffffu;
+          const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
+          const unsigned int who = __ballot_sync(0xffffffffu, key == mn);
+          if (lane == 0 && mn != 0xffffffffu) {
+            const unsigned long long k64 =
+                ((unsigned long long)mn << 32) |
+                (unsigned int)(c0 + 32LL * cgrp + (__ffs(who) - 1));
+            if (k64 < s_best[r][warp]) s_best[r][warp] = k64;
+          }
+          if (want_col && key < cbest) {       // rows ascend within a lane: first minimum kept
+            cbest = key;
+            crow = (unsigned int)(row0 + r);
+          }
+        }
+      };
+
+      for (int pr = ry; pr < npairs; pr += wy) {
+        gd::f2 f2v[kPairStride];
+        const float4* src4 = reinterpret_cast<const float4*>(&s_pair[pr][0]);
+#pragma unroll
+        for (int k = 0; k < kPairStride / 2; ++k) {
+          const float4 v = src4[k];            // 128-bit broadcast load: two fields x {row 2 pr, 2 pr + 1}
+          f2v[2 * k] = gd::mk2(v.x, v.y);
+          f2v[2 * k + 1] = gd::mk2(v.z, v.w);
+        }
+        const gd::BoxGauss<gd::f2> p2 = gd::gauss_from_fields<gd::f2>(f2v);
+        gd::m2 rare{!(s_nice[2 * pr] && t.nice), !(s_nice[2 * pr + 1] && t.nice)};
+        const gd::f2 v2 = gd::pair_value_fast2<LOSS>(p2, t2, pp2, &rare);
+        float v0 = gd::lo2(v2), v1 = gd::hi2(v2);
+        if (rare.lo) v0 = gd::pair_value<float, LOSS>(row_gauss(2 * pr), t, pp);
+        if (rare.hi) v1 = gd::pair_value<float, LOSS>(row_gauss(2 * pr + 1), t, pp);
+        emit(2 * pr, v0, optr);
+        if (2 * pr + 1 < rows)                          // warp-uniform condition
+          emit(2 * pr + 1, v1, optr != nullptr ? optr + a.out_stride : nullptr);
+        if (optr != nullptr) optr += pair_step;
+      }
+      if (want_col && !one_chunk && live && cbest != 0xffffffffu)
+        atomicMax(a.col_keys + j, ~(((unsigned long long)cbest << 32) | crow));
+    }
+    if (REDUCE) {
+      __syncthreads();
+      if (tid < rows) {
+        unsigned long long k = s_best[tid][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
+        a.row_min[row0 + tid] = key_value((unsigned int)(k >> 32));
+        a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
+      }
+    }
+  }
+  if (want_col) {
+    if (one_chunk) {
+      const long long j = 32LL * cgrp + lane;
+      if (j < a.m && cbest != 0xffffffffu)
+        atomicMax(a.col_keys + j, ~(((unsigned long long)cbest << 32) | crow));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (long long j = tid; j < a.m; j += kThreads) {
+        const unsigned long long k = ~__ldcg(a.col_keys + j);
+        a.col_min[j] = key_value((unsigned int)(k >> 32));
+        a.col_argmin[j] = (int)(unsigned int)(k & 0xffffffffu);
+        a.col_keys[j] = 0ull;
+      }
+      if (tid == 0) *a.ticket = 0u;
+    }
+  }
+}
+
+template <int LOSS, int SPEC, bool REDUCE>
+int launch_pairwise_packed_inst(const PairwiseArgs& a, cudaStream_t st) {
+  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  if (ntiles > 2147483647LL || a.m > 0x7fffffffLL || a.n > 0xffffffffLL) return GD_ERR_BAD_ARG;
+  const int wx = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
+  dim3 grid;
+  if (REDUCE) {
+    long long gx = ntiles;
+    if (a.col_keys) {
+      const long long cap = (long long)device_info().sm_count * 6;
+      if (gx > cap) gx = cap;
+    }
+    grid = dim3((unsigned)gx, 1);
+  } else {
+    long long gy = (a.m + 32LL * wx - 1) / (32LL * wx);
+    if (gy > 65535) gy = 65535;
+    grid = dim3((unsigned)ntiles, (unsigned)gy);
+  }
+  gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE><<<grid, kThreads, 0, st>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+// returns kNoPackedKernel when the configuration has no packed instantiation; the caller
+// then launches the scalar kernel
+constexpr int kNoPackedKernel = -1000;
+
+template <int LOSS>
+int launch_pairwise_packed(const PairwiseArgs& a, cudaStream_t st) {
+  static_assert(LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd, "gwd3d, kld3d, bd3d");
+  const gd::PairParams<float>& pp = a.pp;
+  if (!(pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p))) return kNoPackedKernel;
+#define GD_PACKED_CASE(S)                                                         \
+  case S:                                                                         \
+    return a.row_min ? launch_pairwise_packed_inst<LOSS, S, true>(a, st)          \
+                     : launch_pairwise_packed_inst<LOSS, S, false>(a, st);
+  switch (pp.fun | (pp.tau_on << 2) | (1 << 3)) {
+    GD_PACKED_CASE(8) GD_PACKED_CASE(9) GD_PACKED_CASE(12) GD_PACKED_CASE(13)
+    default: break;
+  }
+#undef GD_PACKED_CASE
+  return kNoPackedKernel;
 }
 
 }  // namespace gdk

@@ -59,3 +59,45 @@ def test_packed_falls_back_for_other_configurations():
         a = GDLoss(variant='bulk_packed', **kw)(pred.cuda(), target.cuda(), w.cuda())
         b = GDLoss(variant='bulk', **kw)(pred.cuda(), target.cuda(), w.cuda())
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('loss_type', ['gwd3d', 'kld3d', 'bd3d'])
+@pytest.mark.parametrize('fun,tau', [('log1p', 1.0), ('none', 0.0)])
+@pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (700, 64), (1001, 129), (2050, 256), (400, 700)])
+def test_packed_pairwise(loss_type, fun, tau, n, m):
+    """Opt-in packed pairwise kernel (GD_PAIR_PACKED): its matrix vs the fp64 oracle (1e-5)
+    and vs the scalar kernel (last-bit differences only); its fused minima equal the minima
+    of ITS OWN matrix bit for bit (ties -> lowest index, NaN first), odd row counts and
+    ragged column counts included; degenerate boxes take the robust path."""
+    from mmdet3d_gaussian_b200 import GDPairwiseDistance
+    b1 = synth.make_anchor_grid(n, 'waymo', device='cuda')
+    b2 = synth.make_targets(m, 'waymo', seed=n + m, device='cuda')
+    b2[:, 0] = b2[:, 0] * 2.0 - 70.0
+    if m > 4:
+        b2[m - 1] = b2[1]                       # exact ties between columns
+    if n > 70:
+        b1[n - 1] = b1[3]                       # exact ties between rows (odd and even)
+        b1[68] = b1[3]
+        b1[10, 4] = 1e-9                        # rows the FAST cores must hand over
+        b1[11, 6] = 1000.0
+    mod = GDPairwiseDistance(loss_type, fun=fun, tau=tau)
+    scalar = mod(b1, b2)
+    rmin, ridx, cmin, cidx, mat = mod.assign(b1, b2, want_matrix=True, packed=True)
+    ref = gd_oracle.pairwise_distance(b1.cpu().double(), b2.cpu().double(), loss_type, fun=fun,
+                                      tau=tau)
+    err = (mat.cpu().double() - ref).abs() / ref.abs().clamp_min(1e-3)
+    assert err.max() < RTOL
+    assert ((mat - scalar).abs() / scalar.abs().clamp_min(1e-3)).max() < 2e-6
+
+    def first_argmin(x, dim):
+        key = torch.where(torch.isnan(x), torch.full_like(x, -float('inf')), x)
+        mn = key.min(dim=dim, keepdim=True).values
+        idx = (key == mn).to(torch.uint8).argmax(dim=dim)
+        return torch.gather(x, dim, idx.unsqueeze(dim)).squeeze(dim), idx
+    for _ in range(2):                          # the workspace must come back clean
+        rv, ri = first_argmin(mat, 1)
+        cv, ci = first_argmin(mat, 0)
+        assert torch.equal(rmin.view(torch.int32), rv.view(torch.int32)) and torch.equal(ridx, ri)
+        assert torch.equal(cmin.view(torch.int32), cv.view(torch.int32)) and torch.equal(cidx, ci)
+        rmin, ridx, cmin, cidx, none = mod.assign(b1, b2, packed=True)
+        assert none is None

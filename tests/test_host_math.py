@@ -227,3 +227,6 @@ def test_packed_instantiation_is_bit_identical_on_host(tmp_path):
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith('fun')]
     assert len(lines) == 8 and all('mismatches gwd 0 kld 0 bd 0' in ln for ln in lines), out.stdout
     assert all(int(ln.rsplit('rare rows', 1)[1].strip(' )')) > 0 for ln in lines)
+    # pairwise path (gd_pairwise_packed_kernel): two rows x one column per packed evaluation
+    plines = [ln for ln in out.stdout.splitlines() if ln.startswith('pairwise')]
+    assert len(plines) == 4 and all('mismatches gwd 0 kld 0 bd 0' in ln for ln in plines), out.stdout

@@ -39,4 +39,14 @@ timeout -s KILL 200 python tools/pipe_probe.py 2 24 > $OUT/pipe_probe.json 2> $O
 stamp "pipe_probe exit $?"; cat $OUT/pipe_probe.err | tail -8
 timeout -s KILL 200 python tools/power_probe.py > $OUT/power_probe.json 2> $OUT/power_probe.err
 stamp "power_probe exit $?"
+# opt-in packed pairwise kernel: its own gated tests, the whole pairwise surface routed
+# through it (environment switch), then timing next to the scalar kernel
+GD_B200_TEST_EXPERIMENTAL=1 timeout -s KILL 400 python -m pytest tests/test_gpu_packed.py -m gpu -q \
+  -k pairwise --timeout=300 -p no:cacheprovider > $OUT/pytest_pairwise_packed.log 2>&1
+stamp "pytest (packed pairwise) exit $?"; tail -2 $OUT/pytest_pairwise_packed.log
+GD_B200_PAIRWISE_PACKED=1 timeout -s KILL 400 python -m pytest tests/test_gpu_assign.py \
+  tests/test_eval_affinity.py -m gpu -q --timeout=300 -p no:cacheprovider > $OUT/pytest_pairwise_forced.log 2>&1
+stamp "pytest (pairwise surface, packed forced) exit $?"; tail -2 $OUT/pytest_pairwise_forced.log
+timeout -s KILL 300 python tools/sweep.py --only pairwise --packed > $OUT/sweep_pairwise.json 2> $OUT/sweep_pairwise.err
+stamp "sweep pairwise exit $?"
 du -sh $OUT
