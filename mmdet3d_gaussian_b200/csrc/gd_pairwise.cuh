@@ -215,26 +215,32 @@ int launch_pairwise(const PairwiseArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // Packed-FP32 variant (OPT-IN: GD_PAIR_PACKED / GD_B200_PAIRWISE_PACKED=1).  The scalar
 // kernel above is issue bound (profiles/r01d_pairwise_ncu.md: 89 % of the issue slots, 48 %
-// of the FMA pipe, ~111 instructions per pair).  Here one lane evaluates TWO rows against
-// its column box per pass: the row tile lives in shared memory as float2 {row 2k, row 2k+1}
-// per BoxGauss field, so ONE 64-bit broadcast load yields a packed operand and the FAST
-// cores run as FFMA2 / FMUL2 / FADD2 (gd_packed.cuh) -- half the issue slots for the FP32
-// part and half the shared-memory loads.  Same mapping, reductions, tie rules and
-// workspace protocol as gd_pairwise_kernel; rows ascend within a lane (pair p = rows
-// 2p, 2p+1; a warp takes pairs ry, ry + wy, ...).  Values may differ from the scalar kernel
-// in the last bit (FMA contraction); matrix and reductions of THIS kernel still come from
-// one instruction sequence, so its indices are bit-consistent with its own matrix.
+// of the FMA pipe, ~105 instructions per pair in the matrix loop and ~50 more per pair for
+// the fused reductions).  Three changes, same results contract:
+//   * TWO rows per pass.  The row tile lives in shared memory as float2 {row 2k, row 2k+1}
+//     per BoxGauss field; one 128-bit broadcast load yields two packed operands and the
+//     FAST cores run as FFMA2 / FMUL2 / FADD2 (gd_packed.cuh) with the column box as the
+//     scalar-broadcast operand: half the issue slots for the FP32 part.
+//   * CPL columns per lane (1, 2, 4 or 8; column q of a lane is base + 32 q + lane, so the
+//     stores of one q stay coalesced).  A warp covers 32 CPL columns of a row pair, every
+//     shared-memory load serves 2 CPL pairs, and the row reduction is done in the lane first:
+//     ONE pair of REDUX.MIN per row and warp instead of one REDUX + ballot per 32 pairs.
+//   * All 8 warps of the CTA take different row pairs (pair p -> warp p mod 8): a row is
+//     owned by one warp, so its running minimum needs no cross-warp merge.
+// Reductions keep the contract of the scalar kernel: order-preserving keys, NaN lowest,
+// ties -> lowest column / lowest row, matrix and minima from one instruction sequence.
+// Values may differ from the scalar kernel in the last bit (FMA contraction).
 // Only gwd3d / kld3d / bd3d with a compile-time SPEC; anything else runs the scalar kernel.
 // ---------------------------------------------------------------------------
 constexpr int kPairsPerCta = kRowsPerCta / 2;
 constexpr int kPairStride = (gd::kGaussFields + 1) & ~1;   // float2 per pair, padded: 16-B rows
 
-template <int LOSS, int SPEC, bool REDUCE>
+template <int LOSS, int SPEC, bool REDUCE, int CPL>
 __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const PairwiseArgs a) {
   static_assert(SPEC >= 0, "packed pairwise kernels are compile-time specialised");
   __shared__ __align__(16) float2 s_pair[kPairsPerCta][kPairStride];
   __shared__ unsigned char s_nice[kRowsPerCta];
-  __shared__ unsigned long long s_best[REDUCE ? kRowsPerCta : 1][kWarps];
+  __shared__ unsigned long long s_best[REDUCE ? kRowsPerCta : 1];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   gd::PairParams<float> pp = a.pp;
@@ -242,14 +248,16 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
   pp.tau_on = (SPEC >> 2) & 1;
   pp.flag = (SPEC >> 3) & 1;
   const gd::PairParams<gd::f2> pp2 = gd::broadcast_params(pp);
-  const int wx = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
-  const int wy = kWarps / wx;
-  const int cgrp = warp % wx, ry = warp / wx;
-  const long long chunk = 32LL * wx;
+  constexpr long long kChunk = 32LL * CPL;     // columns one warp covers per pass
   const bool want_col = REDUCE && a.col_keys != nullptr;
-  const bool one_chunk = a.m <= chunk;
+  const bool one_chunk = a.m <= kChunk;        // column minima can stay in registers across tiles
   const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
-  unsigned int cbest = 0xffffffffu, crow = 0u;
+  unsigned int cbest[CPL], crow[CPL];
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    cbest[q] = 0xffffffffu;
+    crow[q] = 0u;
+  }
 
   // scalar BoxGauss of one row of the tile, rebuilt from the packed tile (cold path only)
   auto row_gauss = [&](int r) {
@@ -260,6 +268,14 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
     gd::BoxGauss<float> b = gd::gauss_from_fields<float>(f);
     b.nice = s_nice[r];
     return b;
+  };
+  auto flush_cols = [&](long long c0) {        // this lane's column minima -> global keys
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const long long j = c0 + 32LL * q + lane;
+      if (j < a.m && cbest[q] != 0xffffffffu)
+        atomicMax(a.col_keys + j, ~(((unsigned long long)cbest[q] << 32) | crow[q]));
+    }
   };
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -281,52 +297,27 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
         s_nice[rows] = (unsigned char)b.nice;
       }
     }
-    if (REDUCE) {
-      for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads) (&s_best[0][0])[i] = ~0ull;
-    }
+    if (REDUCE && tid < kRowsPerCta) s_best[tid] = ~0ull;
     __syncthreads();
-    for (long long c0 = (long long)blockIdx.y * chunk; c0 < a.m; c0 += (long long)gridDim.y * chunk) {
-      if (c0 + 32LL * cgrp >= a.m) continue;   // this warp's 32 columns are all past the end
-      const long long j = c0 + 32LL * cgrp + lane;
-      const bool live = j < a.m;
-      gd::BoxGauss<float> t;
-      if (live) t = gd::box_gauss(a.b2 + j * 7, pp);
-      else t = row_gauss(0);                   // any valid box: the result is discarded
-      gd::BoxGauss<gd::f2> t2;
-      {
-        float f[gd::kGaussFields];
-        gd::f2 f2v[gd::kGaussFields];
-        gd::gauss_to_fields(t, f);
+    for (long long c0 = (long long)blockIdx.y * kChunk; c0 < a.m; c0 += (long long)gridDim.y * kChunk) {
+      // this lane's CPL column boxes (scalar: they enter the packed math as broadcast operands)
+      gd::BoxGauss<float> t[CPL];
+      bool live[CPL];
 #pragma unroll
-        for (int k = 0; k < gd::kGaussFields; ++k) f2v[k] = gd::mk2(f[k], f[k]);
-        t2 = gd::gauss_from_fields<gd::f2>(f2v);
+      for (int q = 0; q < CPL; ++q) {
+        const long long j = c0 + 32LL * q + lane;
+        live[q] = j < a.m;
+        if (live[q]) t[q] = gd::box_gauss(a.b2 + j * 7, pp);
+        else t[q] = row_gauss(0);              // any valid box: the result is discarded
       }
-      if (want_col && !one_chunk) cbest = 0xffffffffu;
+      if (want_col && !one_chunk) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) cbest[q] = 0xffffffffu;
+      }
+      float* optr = a.out != nullptr ? a.out + (row0 + 2 * warp) * a.out_stride + c0 + lane : nullptr;
+      const long long pair_step = 2LL * kWarps * a.out_stride;
 
-      // one row of the pair: matrix store and reductions, exactly as the scalar kernel
-      // (the store address is carried as a pointer instead of being re-derived per row)
-      float* optr = (a.out != nullptr && live) ? a.out + (row0 + 2 * ry) * a.out_stride + j : nullptr;
-      const long long pair_step = 2LL * wy * a.out_stride;
-      auto emit = [&](int r, float v, float* dst) {
-        if (dst != nullptr) __stcs(dst, a.similarity ? 1.0f - v : v);
-        if (REDUCE) {
-          const unsigned int key = live ? order_key(v) : 0xffffffffu;
-          const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
-          const unsigned int who = __ballot_sync(0xffffffffu, key == mn);
-          if (lane == 0 && mn != 0xffffffffu) {
-            const unsigned long long k64 =
-                ((unsigned long long)mn << 32) |
-                (unsigned int)(c0 + 32LL * cgrp + (__ffs(who) - 1));
-            if (k64 < s_best[r][warp]) s_best[r][warp] = k64;
-          }
-          if (want_col && key < cbest) {       // rows ascend within a lane: first minimum kept
-            cbest = key;
-            crow = (unsigned int)(row0 + r);
-          }
-        }
-      };
-
-      for (int pr = ry; pr < npairs; pr += wy) {
+      for (int pr = warp; pr < npairs; pr += kWarps) {
         gd::f2 f2v[kPairStride];
         const float4* src4 = reinterpret_cast<const float4*>(&s_pair[pr][0]);
 #pragma unroll
@@ -336,36 +327,86 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
           f2v[2 * k + 1] = gd::mk2(v.z, v.w);
         }
         const gd::BoxGauss<gd::f2> p2 = gd::gauss_from_fields<gd::f2>(f2v);
-        gd::m2 rare{!(s_nice[2 * pr] && t.nice), !(s_nice[2 * pr + 1] && t.nice)};
-        const gd::f2 v2 = gd::pair_value_fast2<LOSS>(p2, t2, pp2, &rare);
-        float v0 = gd::lo2(v2), v1 = gd::hi2(v2);
-        if (rare.lo) v0 = gd::pair_value<float, LOSS>(row_gauss(2 * pr), t, pp);
-        if (rare.hi) v1 = gd::pair_value<float, LOSS>(row_gauss(2 * pr + 1), t, pp);
-        emit(2 * pr, v0, optr);
-        if (2 * pr + 1 < rows)                          // warp-uniform condition
-          emit(2 * pr + 1, v1, optr != nullptr ? optr + a.out_stride : nullptr);
+        const bool nice0 = s_nice[2 * pr] != 0, nice1 = s_nice[2 * pr + 1] != 0;
+        const bool has_hi = 2 * pr + 1 < rows;  // warp-uniform
+        // in-lane minima over this lane's columns, per row of the pair: (key, q)
+        unsigned int k0 = 0xffffffffu, k1 = 0xffffffffu, q0 = 0u, q1 = 0u;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          gd::BoxGauss<gd::f2> t2;
+          {
+            float f[gd::kGaussFields];
+            gd::f2 fq[gd::kGaussFields];
+            gd::gauss_to_fields(t[q], f);
+#pragma unroll
+            for (int k = 0; k < gd::kGaussFields; ++k) fq[k] = gd::mk2(f[k], f[k]);
+            t2 = gd::gauss_from_fields<gd::f2>(fq);
+          }
+          gd::m2 rare{!(nice0 && t[q].nice), !(nice1 && t[q].nice)};
+          const gd::f2 v2 = gd::pair_value_fast2<LOSS>(p2, t2, pp2, &rare);
+          float v0 = gd::lo2(v2), v1 = gd::hi2(v2);
+          if (rare.lo || rare.hi) {             // cold: one branch on the common path
+            if (rare.lo) v0 = gd::pair_value<float, LOSS>(row_gauss(2 * pr), t[q], pp);
+            if (rare.hi) v1 = gd::pair_value<float, LOSS>(row_gauss(2 * pr + 1), t[q], pp);
+          }
+          if (optr != nullptr && live[q]) {
+            __stcs(optr + 32 * q, a.similarity ? 1.0f - v0 : v0);
+            if (has_hi) __stcs(optr + a.out_stride + 32 * q, a.similarity ? 1.0f - v1 : v1);
+          }
+          if (REDUCE) {
+            const unsigned int key0 = live[q] ? order_key(v0) : 0xffffffffu;
+            const unsigned int key1 = (live[q] && has_hi) ? order_key(v1) : 0xffffffffu;
+            if (key0 < k0) {                   // strict: the lowest q (lowest column) keeps ties
+              k0 = key0;
+              q0 = (unsigned int)q;
+            }
+            if (key1 < k1) {
+              k1 = key1;
+              q1 = (unsigned int)q;
+            }
+            if (want_col) {                    // rows ascend within a lane: first minimum kept
+              if (key0 < cbest[q]) {
+                cbest[q] = key0;
+                crow[q] = (unsigned int)(row0 + 2 * pr);
+              }
+              if (key1 < cbest[q]) {
+                cbest[q] = key1;
+                crow[q] = (unsigned int)(row0 + 2 * pr + 1);
+              }
+            }
+          }
+        }
         if (optr != nullptr) optr += pair_step;
+        if (REDUCE) {
+          // row minimum over the warp's 32 CPL columns: min key, then min column among the
+          // lanes that hold it; this warp owns the row, so the running best needs no atomics
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const unsigned int key = h ? k1 : k0;
+            const unsigned int col = (unsigned int)(c0 + 32LL * (h ? q1 : q0) + lane);
+            const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
+            const unsigned int cmin = __reduce_min_sync(0xffffffffu, key == mn ? col : 0xffffffffu);
+            if (lane == 0 && mn != 0xffffffffu) {
+              const unsigned long long k64 = ((unsigned long long)mn << 32) | cmin;
+              if (k64 < s_best[2 * pr + h]) s_best[2 * pr + h] = k64;
+            }
+          }
+        }
       }
-      if (want_col && !one_chunk && live && cbest != 0xffffffffu)
-        atomicMax(a.col_keys + j, ~(((unsigned long long)cbest << 32) | crow));
+      if (want_col && !one_chunk) flush_cols(c0);
     }
     if (REDUCE) {
       __syncthreads();
       if (tid < rows) {
-        unsigned long long k = s_best[tid][0];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
+        const unsigned long long k = s_best[tid];
         a.row_min[row0 + tid] = key_value((unsigned int)(k >> 32));
         a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
       }
     }
   }
   if (want_col) {
-    if (one_chunk) {
-      const long long j = 32LL * cgrp + lane;
-      if (j < a.m && cbest != 0xffffffffu)
-        atomicMax(a.col_keys + j, ~(((unsigned long long)cbest << 32) | crow));
-    }
+    if (one_chunk) flush_cols(0);
+    // last CTA to finish unpacks the column keys and restores the workspace
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
@@ -383,27 +424,35 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
   }
 }
 
-template <int LOSS, int SPEC, bool REDUCE>
-int launch_pairwise_packed_inst(const PairwiseArgs& a, cudaStream_t st) {
+template <int LOSS, int SPEC, bool REDUCE, int CPL>
+int launch_pairwise_packed_cpl(const PairwiseArgs& a, cudaStream_t st) {
   const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
-  if (ntiles > 2147483647LL || a.m > 0x7fffffffLL || a.n > 0xffffffffLL) return GD_ERR_BAD_ARG;
-  const int wx = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
   dim3 grid;
-  if (REDUCE) {
+  if (REDUCE) {                              // every CTA walks all columns of its rows
     long long gx = ntiles;
-    if (a.col_keys) {
+    if (a.col_keys) {                        // persistent: bounds the column atomics
       const long long cap = (long long)device_info().sm_count * 6;
       if (gx > cap) gx = cap;
     }
     grid = dim3((unsigned)gx, 1);
   } else {
-    long long gy = (a.m + 32LL * wx - 1) / (32LL * wx);
+    long long gy = (a.m + 32LL * CPL - 1) / (32LL * CPL);
     if (gy > 65535) gy = 65535;
     grid = dim3((unsigned)ntiles, (unsigned)gy);
   }
-  gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE><<<grid, kThreads, 0, st>>>(a);
+  gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE, CPL><<<grid, kThreads, 0, st>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
+}
+
+template <int LOSS, int SPEC, bool REDUCE>
+int launch_pairwise_packed_inst(const PairwiseArgs& a, cudaStream_t st) {
+  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  if (ntiles > 2147483647LL || a.m > 0x7fffffffLL || a.n > 0xffffffffLL) return GD_ERR_BAD_ARG;
+  if (a.m <= 32) return launch_pairwise_packed_cpl<LOSS, SPEC, REDUCE, 1>(a, st);
+  if (a.m <= 64) return launch_pairwise_packed_cpl<LOSS, SPEC, REDUCE, 2>(a, st);
+  if (a.m <= 128) return launch_pairwise_packed_cpl<LOSS, SPEC, REDUCE, 4>(a, st);
+  return launch_pairwise_packed_cpl<LOSS, SPEC, REDUCE, 8>(a, st);
 }
 
 // returns kNoPackedKernel when the configuration has no packed instantiation; the caller

@@ -63,7 +63,8 @@ def test_packed_falls_back_for_other_configurations():
 
 @pytest.mark.parametrize('loss_type', ['gwd3d', 'kld3d', 'bd3d'])
 @pytest.mark.parametrize('fun,tau', [('log1p', 1.0), ('none', 0.0)])
-@pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (700, 64), (1001, 129), (2050, 256), (400, 700)])
+@pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (700, 64), (1001, 129), (2050, 256), (400, 700),
+                                 (60001, 40)])
 def test_packed_pairwise(loss_type, fun, tau, n, m):
     """Opt-in packed pairwise kernel (GD_PAIR_PACKED): its matrix vs the fp64 oracle (1e-5)
     and vs the scalar kernel (last-bit differences only); its fused minima equal the minima
