@@ -50,6 +50,8 @@ def parse():
     ap.add_argument('--pairs', type=int, default=N_PAIRS)
     ap.add_argument('--variant', default='auto', choices=['auto', 'bulk', 'bulk_packed', 'bulk_r2', 'staged'])
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-chunk-log2', type=int, default=20,
+                    help='rows per chunk of the host-buffer pipeline (e2e), as a power of two')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--detail', action='store_true', help='extra per-config lines on stderr')
     ap.add_argument('--watchdog', type=float, default=900.0,
@@ -356,7 +358,8 @@ def run_ours(args):
             for cfg in cfgs:
                 code = lib.gd_loss_fwd_bwd_host(
                     ctypes.byref(cfg), hp.data_ptr(), ht.data_ptr(), hw.data_ptr(), 1, n,
-                    LOSS_WEIGHT / avg, hloss.data_ptr(), hgrad.data_ptr(), local_rank, 1 << 20)
+                    LOSS_WEIGHT / avg, hloss.data_ptr(), hgrad.data_ptr(), local_rank,
+                    1 << args.e2e_chunk_log2)
                 _lib.check(code, 'gd_loss_fwd_bwd_host')
         log('host buffers pinned')
         e2e_step()
@@ -376,8 +379,8 @@ def run_ours(args):
                'h2d_bytes_per_step': len(COMBOS) * n * 60,
                'd2h_bytes_per_step': len(COMBOS) * (n * 28 + 4),
                'steps': k, 'ms_per_step': dt / k * 1e3,
-               'api': 'gd_loss_fwd_bwd_host (C ABI, pinned host buffers, 2^20-row chunks, '
-                      '3 streams)'}
+               'api': f'gd_loss_fwd_bwd_host (C ABI, pinned host buffers, 2^{args.e2e_chunk_log2}-row '
+                      f'chunks, 3 streams)'}
 
     log('e2e done')
     cpu = None

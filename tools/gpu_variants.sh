@@ -50,3 +50,17 @@ stamp "pytest (pairwise surface, packed forced) exit $?"; tail -2 $OUT/pytest_pa
 timeout -s KILL 300 python tools/sweep.py --only pairwise --packed > $OUT/sweep_pairwise.json 2> $OUT/sweep_pairwise.err
 stamp "sweep pairwise exit $?"
 du -sh $OUT
+# host-buffer pipeline: chunk size of the e2e path (tail of the last D2H vs per-chunk overhead)
+for L in 17 18 19 20 21; do
+  timeout -s KILL 200 python bench.py --steps 5 --warmup 3 --no-cpu --e2e-chunk-log2 $L \
+    > $OUT/bench_e2e_chunk$L.json 2> $OUT/bench_e2e_chunk$L.err
+  python - <<PY
+import json
+try:
+    d = json.load(open('$OUT/bench_e2e_chunk$L.json'))
+    print('e2e chunk 2^$L:', round(d['e2e']['value'] / 1e9, 4), 'G pairs/s')
+except Exception as e:
+    print('e2e chunk 2^$L: failed', e)
+PY
+done
+stamp "e2e chunk sweep done"
