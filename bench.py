@@ -53,6 +53,9 @@ def parse():
     ap.add_argument('--e2e-chunk-log2', type=int, default=20,
                     help='rows per chunk of the host-buffer pipeline (e2e), as a power of two')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--eager-gpu', action='store_true',
+                    help='also time the reference algorithm (oracle port, eager torch + autograd) '
+                         'on THIS GPU: the incumbent a user of the reference runs today')
     ap.add_argument('--detail', action='store_true', help='extra per-config lines on stderr')
     ap.add_argument('--watchdog', type=float, default=900.0,
                     help='seconds after which all thread stacks are dumped and the process exits')
@@ -403,6 +406,32 @@ def run_ours(args):
                          f'configs x 2^23 pairs (half the batch) in 2^17-row chunks, best of 2 '
                          f'passes ({secs:.2f} s per pass)'}
 
+    eager = None
+    if rank == 0 and world == 1 and args.eager_gpu:
+        # baseline leg only: the reference's own op sequence (oracle port) on CUDA tensors
+        from oracle import gd_oracle
+        rows, chunk = min(n, 1 << 22), 1 << 20
+        emods = [gd_oracle.GDLossOracle(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT)
+                 for lt, fun in COMBOS]
+
+        def eager_pass():
+            for mod in emods:
+                for lo in range(0, rows, chunk):
+                    p = pred.detach()[lo:lo + chunk].clone().requires_grad_(True)
+                    mod(p, target[lo:lo + chunk], weight[lo:lo + chunk],
+                        avg_factor=float(rows)).backward()
+        eager_pass()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        eager_pass()
+        g1.record()
+        torch.cuda.synchronize()
+        eager = {'value': len(COMBOS) * rows / (g0.elapsed_time(g1) * 1e-3), 'unit': 'pairs/s',
+                 'kind': 'port on cuda (eager torch + autograd, fp32)',
+                 'sample': f'4 configs x 2^{rows.bit_length() - 1} pairs in 2^20-row chunks'}
+        log('eager-gpu baseline done')
+
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
@@ -429,7 +458,7 @@ def run_ours(args):
                          'achieved_timed_region': BYTES_PER_PAIR * len(COMBOS) * n / (ms_step * 1e-3) / 1e9,
                          'per_config': per_cfg},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
-            'value_default_module': value_sync,
+            'value_default_module': value_sync, 'gpu_eager_baseline': eager,
             'lib': os.path.relpath(_lib.loaded_path(), ROOT),
             'losses': [float(x) for x in losses],
         }

@@ -12,7 +12,7 @@ timeout -s KILL 200 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/sm
 stamp "smoke exit $?"; tail -5 $OUT/smoke.log
 timeout -s KILL 600 python -m pytest tests -m gpu -q --timeout=300 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1
 stamp "pytest exit $?"; tail -3 $OUT/pytest_gpu.log
-timeout -s KILL 300 python bench.py --steps 100 --warmup 5 > $OUT/bench_auto.json 2> $OUT/bench_auto.err
+timeout -s KILL 300 python bench.py --steps 100 --warmup 5 --eager-gpu > $OUT/bench_auto.json 2> $OUT/bench_auto.err
 stamp "bench exit $?"; head -c 900 $OUT/bench_auto.json; echo
 timeout -s KILL 200 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
 stamp "bench reference exit $?"
