@@ -619,6 +619,14 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
     grid = (want + per_cta - 1) / per_cta;
   }
   if (grid < 1) grid = 1;
+#if GD_TUNE
+  // measurement only: fewer active SMs (the board is power capped: does a smaller grid at a
+  // higher SM clock move more bytes?)
+  if (const char* e = getenv("GD_TUNE_GRID")) {
+    const int g = atoi(e);
+    if (g >= 1 && g < grid) grid = g;
+  }
+#endif
   kern<<<(int)grid, warps * 32, (size_t)warps * L.per_warp, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();

@@ -90,14 +90,20 @@ def main():
                                         grad.data_ptr(), ws.data_ptr(), ws.numel(),
                                         _lib.VARIANTS['bulk'], 0, stream)
             assert code == 0, code
-        for name, flags, warps in (('base', 0, None), ('half_math', 32, None), ('no_math', 8, None),
-                                   ('warps8', 0, 8)):
+        for name, flags, warps, grid in (('base', 0, None, None), ('half_math', 32, None, None),
+                                         ('no_math', 8, None, None), ('warps8', 0, 8, None),
+                                         # fewer active SMs under the power cap (GD_TUNE_GRID)
+                                         ('grid140', 0, None, 140), ('grid132', 0, None, 132),
+                                         ('grid120', 0, None, 120), ('grid104', 0, None, 104),
+                                         ('no_math grid132', 8, None, 132)):
             os.environ['GD_TUNE_FLAGS'] = str(flags)
-            if warps is None:
-                os.environ.pop('GD_TUNE_WARPS', None)
-            else:
-                os.environ['GD_TUNE_WARPS'] = str(warps)
+            for key, val in (('GD_TUNE_WARPS', warps), ('GD_TUNE_GRID', grid)):
+                if val is None:
+                    os.environ.pop(key, None)
+                else:
+                    os.environ[key] = str(val)
             run(f'{lt}/{fun} {name}', launch, 88 * n)
+        os.environ.pop('GD_TUNE_GRID', None)
     sampler.proc.terminate()
     print(json.dumps(out))
 
