@@ -278,10 +278,24 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
     }
   };
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * kRowsPerCta;
-    const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
-    const int npairs = (rows + 1) >> 1;
+  // this lane's CPL column boxes (scalar: they enter the packed math as broadcast operands)
+  gd::BoxGauss<float> t[CPL];
+  bool live[CPL];
+  auto load_cols = [&](long long c0) {
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) {
+      const long long j = c0 + 32LL * q + lane;
+      live[q] = j < a.m;
+      // a dead lane evaluates the last column again; its results are never used
+      t[q] = gd::box_gauss(a.b2 + (live[q] ? j : a.m - 1) * 7, pp);
+    }
+    if (want_col && !one_chunk) {
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) cbest[q] = 0xffffffffu;
+    }
+  };
+  // rows of one tile -> packed shared-memory tile (+ the tile's running row minima)
+  auto convert_rows = [&](long long row0, int rows) {
     __syncthreads();                           // previous tile fully consumed
     if (tid < rows) {
       const gd::BoxGauss<float> b = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
@@ -299,102 +313,8 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
     }
     if (REDUCE && tid < kRowsPerCta) s_best[tid] = ~0ull;
     __syncthreads();
-    for (long long c0 = (long long)blockIdx.y * kChunk; c0 < a.m; c0 += (long long)gridDim.y * kChunk) {
-      // this lane's CPL column boxes (scalar: they enter the packed math as broadcast operands)
-      gd::BoxGauss<float> t[CPL];
-      bool live[CPL];
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        const long long j = c0 + 32LL * q + lane;
-        live[q] = j < a.m;
-        if (live[q]) t[q] = gd::box_gauss(a.b2 + j * 7, pp);
-        else t[q] = row_gauss(0);              // any valid box: the result is discarded
-      }
-      if (want_col && !one_chunk) {
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) cbest[q] = 0xffffffffu;
-      }
-      float* optr = a.out != nullptr ? a.out + (row0 + 2 * warp) * a.out_stride + c0 + lane : nullptr;
-      const long long pair_step = 2LL * kWarps * a.out_stride;
-
-      for (int pr = warp; pr < npairs; pr += kWarps) {
-        gd::f2 f2v[kPairStride];
-        const float4* src4 = reinterpret_cast<const float4*>(&s_pair[pr][0]);
-#pragma unroll
-        for (int k = 0; k < kPairStride / 2; ++k) {
-          const float4 v = src4[k];            // 128-bit broadcast load: two fields x {row 2 pr, 2 pr + 1}
-          f2v[2 * k] = gd::mk2(v.x, v.y);
-          f2v[2 * k + 1] = gd::mk2(v.z, v.w);
-        }
-        const gd::BoxGauss<gd::f2> p2 = gd::gauss_from_fields<gd::f2>(f2v);
-        const bool nice0 = s_nice[2 * pr] != 0, nice1 = s_nice[2 * pr + 1] != 0;
-        const bool has_hi = 2 * pr + 1 < rows;  // warp-uniform
-        // in-lane minima over this lane's columns, per row of the pair: (key, q)
-        unsigned int k0 = 0xffffffffu, k1 = 0xffffffffu, q0 = 0u, q1 = 0u;
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-          gd::BoxGauss<gd::f2> t2;
-          {
-            float f[gd::kGaussFields];
-            gd::f2 fq[gd::kGaussFields];
-            gd::gauss_to_fields(t[q], f);
-#pragma unroll
-            for (int k = 0; k < gd::kGaussFields; ++k) fq[k] = gd::mk2(f[k], f[k]);
-            t2 = gd::gauss_from_fields<gd::f2>(fq);
-          }
-          gd::m2 rare{!(nice0 && t[q].nice), !(nice1 && t[q].nice)};
-          const gd::f2 v2 = gd::pair_value_fast2<LOSS>(p2, t2, pp2, &rare);
-          float v0 = gd::lo2(v2), v1 = gd::hi2(v2);
-          if (rare.lo || rare.hi) {             // cold: one branch on the common path
-            if (rare.lo) v0 = gd::pair_value<float, LOSS>(row_gauss(2 * pr), t[q], pp);
-            if (rare.hi) v1 = gd::pair_value<float, LOSS>(row_gauss(2 * pr + 1), t[q], pp);
-          }
-          if (optr != nullptr && live[q]) {
-            __stcs(optr + 32 * q, a.similarity ? 1.0f - v0 : v0);
-            if (has_hi) __stcs(optr + a.out_stride + 32 * q, a.similarity ? 1.0f - v1 : v1);
-          }
-          if (REDUCE) {
-            const unsigned int key0 = live[q] ? order_key(v0) : 0xffffffffu;
-            const unsigned int key1 = (live[q] && has_hi) ? order_key(v1) : 0xffffffffu;
-            if (key0 < k0) {                   // strict: the lowest q (lowest column) keeps ties
-              k0 = key0;
-              q0 = (unsigned int)q;
-            }
-            if (key1 < k1) {
-              k1 = key1;
-              q1 = (unsigned int)q;
-            }
-            if (want_col) {                    // rows ascend within a lane: first minimum kept
-              if (key0 < cbest[q]) {
-                cbest[q] = key0;
-                crow[q] = (unsigned int)(row0 + 2 * pr);
-              }
-              if (key1 < cbest[q]) {
-                cbest[q] = key1;
-                crow[q] = (unsigned int)(row0 + 2 * pr + 1);
-              }
-            }
-          }
-        }
-        if (optr != nullptr) optr += pair_step;
-        if (REDUCE) {
-          // row minimum over the warp's 32 CPL columns: min key, then min column among the
-          // lanes that hold it; this warp owns the row, so the running best needs no atomics
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const unsigned int key = h ? k1 : k0;
-            const unsigned int col = (unsigned int)(c0 + 32LL * (h ? q1 : q0) + lane);
-            const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
-            const unsigned int cmin = __reduce_min_sync(0xffffffffu, key == mn ? col : 0xffffffffu);
-            if (lane == 0 && mn != 0xffffffffu) {
-              const unsigned long long k64 = ((unsigned long long)mn << 32) | cmin;
-              if (k64 < s_best[2 * pr + h]) s_best[2 * pr + h] = k64;
-            }
-          }
-        }
-      }
-      if (want_col && !one_chunk) flush_cols(c0);
-    }
+  };
+  auto finish_rows = [&](long long row0, int rows) {
     if (REDUCE) {
       __syncthreads();
       if (tid < rows) {
@@ -402,6 +322,118 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
         a.row_min[row0 + tid] = key_value((unsigned int)(k >> 32));
         a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
       }
+    }
+  };
+  // all row pairs of the tile against this lane's columns of the chunk at c0
+  auto process = [&](long long row0, int rows, long long c0) {
+    const int npairs = (rows + 1) >> 1;
+    float* optr = a.out != nullptr ? a.out + (row0 + 2 * warp) * a.out_stride + c0 + lane : nullptr;
+    const long long pair_step = 2LL * kWarps * a.out_stride;
+    for (int pr = warp; pr < npairs; pr += kWarps) {
+      gd::f2 f2v[kPairStride];
+      const float4* src4 = reinterpret_cast<const float4*>(&s_pair[pr][0]);
+#pragma unroll
+      for (int k = 0; k < kPairStride / 2; ++k) {
+        const float4 v = src4[k];              // 128-bit broadcast load: two fields x {row 2 pr, 2 pr + 1}
+        f2v[2 * k] = gd::mk2(v.x, v.y);
+        f2v[2 * k + 1] = gd::mk2(v.z, v.w);
+      }
+      const gd::BoxGauss<gd::f2> p2 = gd::gauss_from_fields<gd::f2>(f2v);
+      const bool nice0 = s_nice[2 * pr] != 0, nice1 = s_nice[2 * pr + 1] != 0;
+      const bool has_hi = 2 * pr + 1 < rows;    // warp-uniform
+      // in-lane minima over this lane's columns, per row of the pair: (key, q)
+      unsigned int k0 = 0xffffffffu, k1 = 0xffffffffu, q0 = 0u, q1 = 0u;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        gd::BoxGauss<gd::f2> t2;
+        {
+          float f[gd::kGaussFields];
+          gd::f2 fq[gd::kGaussFields];
+          gd::gauss_to_fields(t[q], f);
+#pragma unroll
+          for (int k = 0; k < gd::kGaussFields; ++k) fq[k] = gd::mk2(f[k], f[k]);
+          t2 = gd::gauss_from_fields<gd::f2>(fq);
+        }
+        gd::m2 rare{!(nice0 && t[q].nice), !(nice1 && t[q].nice)};
+        const gd::f2 v2 = gd::pair_value_fast2<LOSS>(p2, t2, pp2, &rare);
+        float v0 = gd::lo2(v2), v1 = gd::hi2(v2);
+        if (rare.lo || rare.hi) {               // cold: one branch on the common path
+          if (rare.lo) v0 = gd::pair_value<float, LOSS>(row_gauss(2 * pr), t[q], pp);
+          if (rare.hi) v1 = gd::pair_value<float, LOSS>(row_gauss(2 * pr + 1), t[q], pp);
+        }
+        if (optr != nullptr && live[q]) {
+          __stcs(optr + 32 * q, a.similarity ? 1.0f - v0 : v0);
+          if (has_hi) __stcs(optr + a.out_stride + 32 * q, a.similarity ? 1.0f - v1 : v1);
+        }
+        if (REDUCE) {
+          const unsigned int key0 = live[q] ? order_key(v0) : 0xffffffffu;
+          const unsigned int key1 = (live[q] && has_hi) ? order_key(v1) : 0xffffffffu;
+          if (key0 < k0) {                     // strict: the lowest q (lowest column) keeps ties
+            k0 = key0;
+            q0 = (unsigned int)q;
+          }
+          if (key1 < k1) {
+            k1 = key1;
+            q1 = (unsigned int)q;
+          }
+          if (want_col) {                      // rows ascend within a lane: first minimum kept
+            if (key0 < cbest[q]) {
+              cbest[q] = key0;
+              crow[q] = (unsigned int)(row0 + 2 * pr);
+            }
+            if (key1 < cbest[q]) {
+              cbest[q] = key1;
+              crow[q] = (unsigned int)(row0 + 2 * pr + 1);
+            }
+          }
+        }
+      }
+      if (optr != nullptr) optr += pair_step;
+      if (REDUCE) {
+        // row minimum over the warp's 32 CPL columns: min key, then min column among the
+        // lanes that hold it; this warp owns the row, so the running best needs no atomics
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const unsigned int key = h ? k1 : k0;
+          const unsigned int col = (unsigned int)(c0 + 32LL * (h ? q1 : q0) + lane);
+          const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
+          const unsigned int cmin = __reduce_min_sync(0xffffffffu, key == mn ? col : 0xffffffffu);
+          if (lane == 0 && mn != 0xffffffffu) {
+            const unsigned long long k64 = ((unsigned long long)mn << 32) | cmin;
+            if (k64 < s_best[2 * pr + h]) s_best[2 * pr + h] = k64;
+          }
+        }
+      }
+    }
+  };
+
+  // Loop order.  Column boxes are converted (sincos, reciprocals, ...) once per chunk and
+  // CTA and reused for every tile the CTA walks -- possible whenever a row's minimum does not
+  // have to be carried across chunks: matrix-only launches (each CTA owns one chunk column,
+  // blockIdx.y) and reductions whose columns fit one chunk (m <= 32 CPL; up to 256 GT boxes).
+  // Reductions over several chunks keep the tile-outer order so that s_best stays per tile.
+  if (!REDUCE || one_chunk) {
+    for (long long c0 = (long long)blockIdx.y * kChunk; c0 < a.m; c0 += (long long)gridDim.y * kChunk) {
+      load_cols(c0);
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * kRowsPerCta;
+        const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
+        convert_rows(row0, rows);
+        process(row0, rows, c0);
+        finish_rows(row0, rows);
+      }
+    }
+  } else {
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = tile * kRowsPerCta;
+      const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
+      convert_rows(row0, rows);
+      for (long long c0 = 0; c0 < a.m; c0 += kChunk) {
+        load_cols(c0);
+        process(row0, rows, c0);
+        if (want_col) flush_cols(c0);
+      }
+      finish_rows(row0, rows);
     }
   }
   if (want_col) {
@@ -435,10 +467,13 @@ int launch_pairwise_packed_cpl(const PairwiseArgs& a, cudaStream_t st) {
       if (gx > cap) gx = cap;
     }
     grid = dim3((unsigned)gx, 1);
-  } else {
+  } else {                                   // one chunk column per blockIdx.y, persistent in x
     long long gy = (a.m + 32LL * CPL - 1) / (32LL * CPL);
     if (gy > 65535) gy = 65535;
-    grid = dim3((unsigned)ntiles, (unsigned)gy);
+    long long gx = ((long long)device_info().sm_count * 8 + gy - 1) / gy;
+    if (gx > ntiles) gx = ntiles;
+    if (gx < 1) gx = 1;
+    grid = dim3((unsigned)gx, (unsigned)gy);
   }
   gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE, CPL><<<grid, kThreads, 0, st>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
