@@ -163,6 +163,11 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
   }
 }
 
+// Host-side launchers.  tests/host_math/pairwise_emul.cpp compiles THIS header with g++
+// (GD_HOST_EMULATION: one OS thread per CUDA thread, barriers for __syncthreads and the
+// warp collectives) to run the kernels' index / reduction logic on a machine without a GPU;
+// it supplies its own launch loop, so the <<< >>> code is left out there.
+#if !defined(GD_HOST_EMULATION)
 template <int LOSS, int SPEC, bool REDUCE>
 int launch_pairwise_inst(const PairwiseArgs& a, cudaStream_t st) {
   const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
@@ -211,6 +216,7 @@ int launch_pairwise(const PairwiseArgs& a, cudaStream_t st) {
   return a.row_min ? launch_pairwise_spec<LOSS, true>(a, st)
                    : launch_pairwise_spec<LOSS, false>(a, st);
 }
+#endif  // !GD_HOST_EMULATION
 
 // ---------------------------------------------------------------------------
 // Packed-FP32 variant (OPT-IN: GD_PAIR_PACKED / GD_B200_PAIRWISE_PACKED=1).  The scalar
@@ -456,6 +462,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_packed_kernel(const Pair
   }
 }
 
+#if !defined(GD_HOST_EMULATION)
 template <int LOSS, int SPEC, bool REDUCE, int CPL>
 int launch_pairwise_packed_cpl(const PairwiseArgs& a, cudaStream_t st) {
   const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
@@ -510,5 +517,6 @@ int launch_pairwise_packed(const PairwiseArgs& a, cudaStream_t st) {
 #undef GD_PACKED_CASE
   return kNoPackedKernel;
 }
+#endif  // !GD_HOST_EMULATION
 
 }  // namespace gdk

@@ -1,0 +1,248 @@
+// TEST-ONLY: runs the pairwise CUDA kernels' SOURCE (csrc/gd_pairwise.cuh: the scalar
+// gd_pairwise_kernel and the opt-in gd_pairwise_packed_kernel) on the host, so their index,
+// tiling, tie-breaking and reduction logic can be checked on a machine without a GPU.
+//
+// How: the header is compiled by g++ with GD_HOST_EMULATION.  One OS thread stands for one
+// CUDA thread of a CTA (256 of them), `__shared__` becomes function-static storage,
+// `__syncthreads` a CTA-wide barrier, the warp collectives (`__reduce_min_sync`,
+// `__ballot_sync`) a 32-thread barrier around a scratch line, global atomics the GCC
+// builtins.  CTAs of the grid run one after the other.  The arithmetic is the host
+// instantiation of gd_math.cuh / gd_packed.cuh (plain float, no MUFU, no FFMA2), so VALUES
+// are not what the device computes to the last bit; what is exercised is everything around
+// the arithmetic: which (row, column) lands where, partial tiles, odd row counts, dead
+// lanes, chunked columns, the workspace protocol, NaN-first / lowest-index tie rules.
+// It is never linked into the shipped library and is not a CPU fallback.
+//
+// Output: a small binary protocol on stdout is avoided; the harness is a shared library
+// driven by tests/test_pairwise_emulation.py through ctypes.
+#include <cuda_runtime.h>
+
+#include <string.h>
+
+#include <atomic>
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define GD_HOST_EMULATION 1
+
+// ---- the CUDA execution model, emulated ---------------------------------------------------
+struct EmuDim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+static thread_local EmuDim3 threadIdx, blockIdx;
+static EmuDim3 gridDim, blockDim;
+
+struct EmuCta {
+  explicit EmuCta(int nthreads) : all(nthreads) {
+    for (int w = 0; w < (nthreads + 31) / 32; ++w) warps.emplace_back(new Warp());
+  }
+  struct Warp {
+    std::barrier<> bar{32};
+    unsigned scratch[32];
+  };
+  std::barrier<> all;
+  std::vector<std::unique_ptr<Warp>> warps;
+};
+static EmuCta* g_cta = nullptr;
+
+static inline void __syncthreads() { g_cta->all.arrive_and_wait(); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  EmuCta::Warp& w = *g_cta->warps[threadIdx.x >> 5];
+  w.scratch[threadIdx.x & 31] = v;
+  w.bar.arrive_and_wait();
+  unsigned m = w.scratch[0];
+  for (int i = 1; i < 32; ++i) m = w.scratch[i] < m ? w.scratch[i] : m;
+  w.bar.arrive_and_wait();
+  return m;
+}
+static inline unsigned __ballot_sync(unsigned, bool p) {
+  EmuCta::Warp& w = *g_cta->warps[threadIdx.x >> 5];
+  w.scratch[threadIdx.x & 31] = p ? 1u : 0u;
+  w.bar.arrive_and_wait();
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) m |= w.scratch[i] << i;
+  w.bar.arrive_and_wait();
+  return m;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline float __uint_as_float(unsigned u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+template <typename T>
+static inline void __stcs(T* p, T v) { *p = v; }
+template <typename T>
+static inline T __ldcg(const T* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+}
+using std::min;
+
+#undef __shared__
+#define __shared__ static
+#undef __global__
+#define __global__
+#undef __launch_bounds__
+#define __launch_bounds__(...)
+#undef __device__
+#define __device__
+#undef __forceinline__
+#define __forceinline__ inline
+
+#include "../../mmdet3d_gaussian_b200/csrc/gd_pairwise.cuh"
+
+namespace gdk {
+std::atomic<int64_t> g_launches{0};
+}
+
+// run `kernel(args)` over a grid, one CTA at a time, kThreads OS threads per CTA
+template <typename K>
+static void emu_launch(K kernel, unsigned gx, unsigned gy, const gdk::PairwiseArgs& args) {
+  gridDim.x = gx;
+  gridDim.y = gy;
+  blockDim.x = gdk::kThreads;
+  for (unsigned by = 0; by < gy; ++by) {
+    for (unsigned bx = 0; bx < gx; ++bx) {
+      EmuCta cta(gdk::kThreads);
+      g_cta = &cta;
+      std::vector<std::thread> ts;
+      ts.reserve(gdk::kThreads);
+      for (int t = 0; t < gdk::kThreads; ++t) {
+        ts.emplace_back([=, &args]() {
+          threadIdx.x = (unsigned)t;
+          blockIdx.x = bx;
+          blockIdx.y = by;
+          kernel(args);
+        });
+      }
+      for (auto& th : ts) th.join();
+      g_cta = nullptr;
+    }
+  }
+}
+
+static gdk::PairwiseArgs make_args(const gd_loss_config* cfg, const float* b1, long long n,
+                                   const float* b2, long long m, float* out, float* row_min,
+                                   int* row_argmin, float* col_min, int* col_argmin,
+                                   unsigned long long* col_keys, unsigned* ticket, int similarity) {
+  gdk::PairwiseArgs a{};
+  a.b1 = b1;
+  a.n = n;
+  a.b2 = b2;
+  a.m = m;
+  a.out = out;
+  a.out_stride = m;
+  a.similarity = similarity;
+  a.row_min = row_min;
+  a.row_argmin = row_argmin;
+  a.col_keys = col_keys;
+  a.col_min = col_min;
+  a.col_argmin = col_argmin;
+  a.ticket = ticket;
+  a.pp = gdk::make_pair_params(*cfg);
+  return a;
+}
+
+template <int LOSS, int SPEC, bool REDUCE>
+static void run_scalar(const gdk::PairwiseArgs& a, unsigned cap) {
+  // the grid rules of launch_pairwise_inst (csrc/gd_pairwise.cuh), with the SM count as input
+  const long long ntiles = (a.n + gdk::kRowsPerCta - 1) / gdk::kRowsPerCta;
+  const int wx = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
+  unsigned gx, gy = 1;
+  if (REDUCE) {
+    long long g = ntiles;
+    if (a.col_keys && g > cap) g = cap;
+    gx = (unsigned)g;
+  } else {
+    gx = (unsigned)ntiles;
+    gy = (unsigned)((a.m + 32LL * wx - 1) / (32LL * wx));
+  }
+  emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE>, gx, gy, a);
+}
+
+template <int LOSS, int SPEC, bool REDUCE, int CPL>
+static void run_packed_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
+  // the grid rules of launch_pairwise_packed_cpl
+  const long long ntiles = (a.n + gdk::kRowsPerCta - 1) / gdk::kRowsPerCta;
+  unsigned gx, gy = 1;
+  if (REDUCE) {
+    long long g = ntiles;
+    if (a.col_keys && g > cap) g = cap;
+    gx = (unsigned)g;
+  } else {
+    long long y = (a.m + 32LL * CPL - 1) / (32LL * CPL);
+    long long g = (cap + y - 1) / y;
+    if (g > ntiles) g = ntiles;
+    if (g < 1) g = 1;
+    gx = (unsigned)g;
+    gy = (unsigned)y;
+  }
+  emu_launch(gdk::gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, a);
+}
+
+template <int LOSS, int SPEC, bool REDUCE>
+static void run_packed(const gdk::PairwiseArgs& a, unsigned cap, int force_cpl) {
+  int cpl = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
+  if (force_cpl) cpl = force_cpl;              // smaller CPL than needed = several chunks
+  switch (cpl) {
+    case 1: run_packed_cpl<LOSS, SPEC, REDUCE, 1>(a, cap); break;
+    case 2: run_packed_cpl<LOSS, SPEC, REDUCE, 2>(a, cap); break;
+    case 4: run_packed_cpl<LOSS, SPEC, REDUCE, 4>(a, cap); break;
+    default: run_packed_cpl<LOSS, SPEC, REDUCE, 8>(a, cap); break;
+  }
+}
+
+// loss: 0 gwd3d, 1 kld3d, 5 bd3d; fun log1p, tau >= 1 (SPEC 13), flag on -- the C4 configuration.
+// packed: 0 = scalar kernel, 1 = packed kernel.  reduce: fused minima (+ the matrix when `out`).
+// cap: CTA cap of the persistent reductions (the library uses 6 x SM count).
+extern "C" int gd_emul_pairwise(int loss, int packed, int reduce, int force_cpl, unsigned cap,
+                                const float* b1, long long n, const float* b2, long long m,
+                                float* out, float* row_min, int* row_argmin, float* col_min,
+                                int* col_argmin, int similarity) {
+  gd_loss_config cfg{};
+  cfg.loss_type = loss;
+  cfg.fun = GD_FUN_LOG1P;
+  cfg.flag = 1;
+  cfg.tau = 1.0f;
+  cfg.alpha = 1.0f;
+  cfg.center_offset[0] = 0.0f;
+  cfg.center_offset[1] = 0.0f;
+  cfg.center_offset[2] = 0.5f;
+  std::vector<unsigned long long> keys((size_t)m + 1, 0ull);
+  unsigned ticket = 0;
+  const gdk::PairwiseArgs a =
+      make_args(&cfg, b1, n, b2, m, out, reduce ? row_min : nullptr, reduce ? row_argmin : nullptr,
+                col_min, col_argmin, reduce ? keys.data() : nullptr, &ticket, similarity);
+  constexpr int S = 13;
+#define GD_EMU_CASE(L)                                                          \
+  if (loss == L) {                                                              \
+    if (packed) {                                                               \
+      if (reduce) run_packed<L, S, true>(a, cap, force_cpl);                    \
+      else run_packed<L, S, false>(a, cap, force_cpl);                          \
+    } else {                                                                    \
+      if (reduce) run_scalar<L, S, true>(a, cap);                               \
+      else run_scalar<L, S, false>(a, cap);                                     \
+    }                                                                           \
+  }
+  GD_EMU_CASE(0) GD_EMU_CASE(1) GD_EMU_CASE(5)
+#undef GD_EMU_CASE
+  // workspace protocol: the kernels must leave keys and ticket zeroed again
+  int dirty = ticket != 0;
+  for (auto k : keys) dirty |= (k != 0ull);
+  return dirty;
+}
