@@ -150,6 +150,65 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-#endif  // __CUDACC__
+#elif defined(GD_HOST_EMULATION)
+// Host stand-ins for the copy-engine / mbarrier primitives (tests/host_math/loss_emul.cpp
+// runs the kernels' SOURCE with one OS thread per CUDA thread).  A bulk copy is a memcpy
+// done by the issuing thread; the mbarrier keeps its phase bit and pending byte count in the
+// same 8 bytes of "shared memory".  The harness provides threadIdx, __shfl_*_sync,
+// __syncwarp, ... before including this header.
+struct EmuMbar {
+  volatile uint32_t phase;
+  volatile int32_t pending;
+};
+inline bool elect_one() { return (threadIdx.x & 31u) == 0u; }
+inline void mbar_init(uint64_t* bar, uint32_t) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->phase = 0;
+  b->pending = 0;
+}
+inline void fence_mbar_init() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void fence_proxy_async_smem() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  reinterpret_cast<EmuMbar*>(bar)->pending = (int32_t)bytes;
+}
+inline void emu_complete_tx(uint64_t* bar, uint32_t bytes) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  b->pending = b->pending - (int32_t)bytes;
+  if (b->pending == 0) {
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    b->phase = b->phase ^ 1u;                  // phase complete
+  }
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+  while (__atomic_load_n(&b->phase, __ATOMIC_SEQ_CST) == parity) emu_yield();
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t) {
+  memcpy(smem_dst, gsrc, bytes);
+  emu_complete_tx(bar, bytes);
+}
+inline void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  memcpy(gdst, smem_src, bytes);
+}
+inline void bulk_store_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t) {
+  memcpy(gdst, smem_src, bytes);
+}
+inline void bulk_commit() {}
+template <int N>
+inline void bulk_wait_read() {}
+template <int N>
+inline void bulk_wait_all() {}
+inline uint64_t policy_evict_first() { return 0; }
+inline uint64_t policy_evict_normal() { return 0; }
+inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+inline double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif  // __CUDACC__ / GD_HOST_EMULATION
 
 }  // namespace gdk

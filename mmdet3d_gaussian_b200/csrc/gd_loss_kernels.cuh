@@ -303,7 +303,11 @@ __device__ __forceinline__ void smem_store(float* dst, const float* src) {
 // (gd_packed.cuh); needs an even R and one of the three headline losses.
 template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
 __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const LossArgs a) {
+#if defined(GD_HOST_EMULATION)
+  unsigned char* smem = emu_dynamic_smem();   // tests/host_math/loss_emul.cpp
+#else
   extern __shared__ __align__(128) unsigned char smem[];
+#endif
   constexpr int kTileRows = 32 * R;
   constexpr int kDiet = kDietGuards | ((SPEC >= 0 && (GD_TUNE_DEFAULT & kTuneStd)) ? gd::kDietStd : 0);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -565,16 +569,16 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
 }
 
 // ---------------------------------------------------------------------------
-// host-side dispatch
+// host-side dispatch (left out of the CPU emulation build, which has its own launch loop)
 // ---------------------------------------------------------------------------
+constexpr int kSmemBudget = 227 * 1024 - 1024;   // opt-in max per CTA minus static + slack
+#if !defined(GD_HOST_EMULATION)
 template <int LOSS, bool GRAD>
 int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
   gd_staged_kernel<LOSS, GRAD><<<grid, kThreads, 0, stream>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
-
-constexpr int kSmemBudget = 227 * 1024 - 1024;   // opt-in max per CTA minus static + slack
 
 template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
 int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
@@ -690,6 +694,8 @@ int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t strea
   return grad ? launch_staged<LOSS, true>(a, (int)grid, stream)
               : launch_staged<LOSS, false>(a, (int)grid, stream);
 }
+
+#endif  // !GD_HOST_EMULATION
 
 constexpr int kMaxGrid = 65536;           // partials capacity of the workspace
 

@@ -2,11 +2,9 @@
 // gd_pairwise_kernel and the opt-in gd_pairwise_packed_kernel) on the host, so their index,
 // tiling, tie-breaking and reduction logic can be checked on a machine without a GPU.
 //
-// How: the header is compiled by g++ with GD_HOST_EMULATION.  One OS thread stands for one
-// CUDA thread of a CTA (256 of them), `__shared__` becomes function-static storage,
-// `__syncthreads` a CTA-wide barrier, the warp collectives (`__reduce_min_sync`,
-// `__ballot_sync`) a 32-thread barrier around a scratch line, global atomics the GCC
-// builtins.  CTAs of the grid run one after the other.  The arithmetic is the host
+// How: the header is compiled by g++ under the execution-model emulation of cuda_emul.h (one
+// OS thread per CUDA thread, barriers for __syncthreads and the warp collectives, CTAs of the
+// grid one after the other).  The arithmetic is the host
 // instantiation of gd_math.cuh / gd_packed.cuh (plain float, no MUFU, no FFMA2), so VALUES
 // are not what the device computes to the last bit; what is exercised is everything around
 // the arithmetic: which (row, column) lands where, partial tiles, odd row counts, dead
@@ -15,125 +13,12 @@
 //
 // Output: a small binary protocol on stdout is avoided; the harness is a shared library
 // driven by tests/test_pairwise_emulation.py through ctypes.
-#include <cuda_runtime.h>
-
-#include <string.h>
-
-#include <atomic>
-#include <barrier>
-#include <memory>
-#include <thread>
-#include <vector>
-
-#define GD_HOST_EMULATION 1
-
-// ---- the CUDA execution model, emulated ---------------------------------------------------
-struct EmuDim3 {
-  unsigned x = 1, y = 1, z = 1;
-};
-static thread_local EmuDim3 threadIdx, blockIdx;
-static EmuDim3 gridDim, blockDim;
-
-struct EmuCta {
-  explicit EmuCta(int nthreads) : all(nthreads) {
-    for (int w = 0; w < (nthreads + 31) / 32; ++w) warps.emplace_back(new Warp());
-  }
-  struct Warp {
-    std::barrier<> bar{32};
-    unsigned scratch[32];
-  };
-  std::barrier<> all;
-  std::vector<std::unique_ptr<Warp>> warps;
-};
-static EmuCta* g_cta = nullptr;
-
-static inline void __syncthreads() { g_cta->all.arrive_and_wait(); }
-static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
-  EmuCta::Warp& w = *g_cta->warps[threadIdx.x >> 5];
-  w.scratch[threadIdx.x & 31] = v;
-  w.bar.arrive_and_wait();
-  unsigned m = w.scratch[0];
-  for (int i = 1; i < 32; ++i) m = w.scratch[i] < m ? w.scratch[i] : m;
-  w.bar.arrive_and_wait();
-  return m;
-}
-static inline unsigned __ballot_sync(unsigned, bool p) {
-  EmuCta::Warp& w = *g_cta->warps[threadIdx.x >> 5];
-  w.scratch[threadIdx.x & 31] = p ? 1u : 0u;
-  w.bar.arrive_and_wait();
-  unsigned m = 0;
-  for (int i = 0; i < 32; ++i) m |= w.scratch[i] << i;
-  w.bar.arrive_and_wait();
-  return m;
-}
-static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-static inline unsigned __float_as_uint(float f) {
-  unsigned u;
-  memcpy(&u, &f, 4);
-  return u;
-}
-static inline float __uint_as_float(unsigned u) {
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-template <typename T>
-static inline void __stcs(T* p, T v) { *p = v; }
-template <typename T>
-static inline T __ldcg(const T* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
-static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
-  unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
-  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
-  }
-  return old;
-}
-static inline unsigned atomicAdd(unsigned* p, unsigned v) {
-  return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
-}
-using std::min;
-
-#undef __shared__
-#define __shared__ static
-#undef __global__
-#define __global__
-#undef __launch_bounds__
-#define __launch_bounds__(...)
-#undef __device__
-#define __device__
-#undef __forceinline__
-#define __forceinline__ inline
+#include "cuda_emul.h"
 
 #include "../../mmdet3d_gaussian_b200/csrc/gd_pairwise.cuh"
 
 namespace gdk {
 std::atomic<int64_t> g_launches{0};
-}
-
-// run `kernel(args)` over a grid, one CTA at a time, kThreads OS threads per CTA
-template <typename K>
-static void emu_launch(K kernel, unsigned gx, unsigned gy, const gdk::PairwiseArgs& args) {
-  gridDim.x = gx;
-  gridDim.y = gy;
-  blockDim.x = gdk::kThreads;
-  for (unsigned by = 0; by < gy; ++by) {
-    for (unsigned bx = 0; bx < gx; ++bx) {
-      EmuCta cta(gdk::kThreads);
-      g_cta = &cta;
-      std::vector<std::thread> ts;
-      ts.reserve(gdk::kThreads);
-      for (int t = 0; t < gdk::kThreads; ++t) {
-        ts.emplace_back([=, &args]() {
-          threadIdx.x = (unsigned)t;
-          blockIdx.x = bx;
-          blockIdx.y = by;
-          kernel(args);
-        });
-      }
-      for (auto& th : ts) th.join();
-      g_cta = nullptr;
-    }
-  }
 }
 
 static gdk::PairwiseArgs make_args(const gd_loss_config* cfg, const float* b1, long long n,
@@ -172,7 +57,7 @@ static void run_scalar(const gdk::PairwiseArgs& a, unsigned cap) {
     gx = (unsigned)ntiles;
     gy = (unsigned)((a.m + 32LL * wx - 1) / (32LL * wx));
   }
-  emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE>, gx, gy, a);
+  emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE>, gx, gy, gdk::kThreads, a);
 }
 
 template <int LOSS, int SPEC, bool REDUCE, int CPL>
@@ -192,7 +77,7 @@ static void run_packed_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
     gx = (unsigned)g;
     gy = (unsigned)y;
   }
-  emu_launch(gdk::gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, a);
+  emu_launch(gdk::gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, gdk::kThreads, a);
 }
 
 template <int LOSS, int SPEC, bool REDUCE>

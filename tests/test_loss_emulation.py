@@ -1,0 +1,191 @@
+"""CPU run of the fused loss kernels' SOURCE (csrc/gd_loss_kernels.cuh) under the
+thread-per-CUDA-thread emulation of tests/host_math/cuda_emul.h + loss_emul.cpp.
+
+Covers what no other CPU test can reach: the warp pipeline's tile schedule (full rounds + one
+balanced round for any n, grid and warp count), the 128-bit and strided shared-memory
+layouts, n mod 4 leftovers, weight modes, zero-weight masking, per-row loss output, the FAST /
+robust hand-over inside a tile, the packed-math pairing of a lane's rows, and the
+deterministic grid-wide sum -- for the production build AND for the build variants prepared
+for the next GPU session (GD_TUNE_DEFAULT bits: 256 min/max screen, 512 default alpha/offset
+folded, 1024 packed math, 128 strided layout).  Arithmetic is the host instantiation (plain
+float): variants must agree with the production kernel BIT FOR BIT here; on the device they may
+differ in the last place (FMA contraction), which the GPU parity suite bounds."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from mmdet3d_gaussian_b200 import synth
+from oracle import gd_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CUDA_INC = '/usr/local/cuda/include'
+LOSS = {'gwd3d': 0, 'kld3d': 1, 'bd3d': 5}
+SPEC = {('none', 0.0): 8, ('log1p', 0.0): 9, ('log1p', 1.0): 13}
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, 'cuda_runtime.h')),
+                                reason='needs the CUDA headers (no GPU needed)')
+_LIBS = {}
+
+
+def emul(bits):
+    if bits not in _LIBS:
+        out = os.path.join(tempfile.mkdtemp(prefix=f'gd_loss_emul_{bits}_'), 'loss_emul.so')
+        subprocess.run(['g++', '-O1', '-std=c++20', '-ffp-contract=off', '-shared', '-fPIC',
+                        '-pthread', '-w', f'-DGD_TUNE_DEFAULT={bits}', '-I', CUDA_INC, '-I',
+                        os.path.join(ROOT, 'include'), '-x', 'c++',
+                        os.path.join(HERE, 'host_math', 'loss_emul.cpp'), '-o', out], check=True)
+        lib = ctypes.CDLL(out)
+        lib.gd_emul_loss.restype = ctypes.c_int
+        lib.gd_emul_loss.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p] * 3 + [
+            ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int] + [
+            ctypes.c_void_p] * 3
+        assert lib.gd_emul_tune_default() == bits
+        _LIBS[bits] = lib
+    return _LIBS[bits]
+
+
+def run(bits, loss, kind, spec, pack, grid, warps, pred, target, weight, tau=0.0, scale=1.0,
+        mask_zero=0, want_rows=False, want_grad=True):
+    n = pred.shape[0]
+    p = np.ascontiguousarray(pred.numpy().astype(np.float32))
+    t = np.ascontiguousarray(target.numpy().astype(np.float32))
+    wmode, w = 0, None
+    if weight is not None:
+        w = np.ascontiguousarray(weight.numpy().astype(np.float32))
+        wmode = 2 if w.ndim == 2 else 1
+    total = np.full(1, -7.0, np.float32)
+    rows = np.full(n, -7.0, np.float32) if want_rows else None
+    grad = np.full((n, 7), -7.0, np.float32) if want_grad else None
+    ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None   # noqa: E731
+    rc = emul(bits).gd_emul_loss(LOSS[loss], kind, spec, pack, grid, warps, ptr(p), ptr(t), ptr(w),
+                                 wmode, n, scale, tau, mask_zero, ptr(total), ptr(rows), ptr(grad))
+    assert rc == 0, rc
+    return float(total[0]), rows, grad
+
+
+def oracle_rows(loss, fun, tau, pred, target):
+    mod = gd_oracle.GDLossOracle(loss, fun=fun, tau=tau, reduction='none')
+    l, g = gd_oracle.loss_and_grad(mod, pred.double(), target.double())
+    return l.numpy(), g.numpy()
+
+
+def make(n, seed=0, extreme=True):
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=seed, weights='bernoulli')
+    if n > 200:                                   # rows the FAST math must hand to the robust path:
+        pred[5, 4] = 1e-9                         # first tile, last tile, the n mod 4 leftovers
+        pred[130, 6] = 1000.0
+        # a 2e4 m target against a 4 m prediction: also robust-path, but in float32 the bd3d
+        # shape gradient loses digits there (terms of size C^2 cancel to size C; the
+        # reference's own float32 is off by 10x on such a row) -- kept out of the bd3d
+        # oracle comparison, see DESIGN.md "known limits"
+        target[n - 2, 3] = 2e4 if extreme else 3.0
+        target[n - 2, 6] = 1.0 if extreme else -40.0
+        pred[n // 2, 3] = 5e-5
+    return pred, target, w
+
+
+def check_against_oracle(loss, fun, tau, pred, target, w, scale, total, grad, rows=None):
+    rl, rg = oracle_rows(loss, fun, tau, pred, target)
+    wd = np.ones(len(rl)) if w is None else (w.double().numpy() if w.dim() == 1
+                                             else w.double().mean(-1).numpy())
+    fin = np.isfinite(rg).all(1)
+    want = scale * float((wd * rl).sum())
+    assert abs(total - want) <= 2e-5 * abs(want), (total, want)
+    gw = rg * (scale * wd)[:, None]
+    floor = 1e-2 * scale * max(float(np.abs(wd).max()), 1e-30)
+    err = np.linalg.norm(grad[fin] - gw[fin], axis=1) / np.maximum(np.linalg.norm(gw[fin], axis=1),
+                                                                   floor)
+    assert err.max() <= 2e-5, err.max()
+    if rows is not None:
+        assert np.abs(rows - scale * wd * rl).max() <= 2e-5 * max(np.abs(scale * wd * rl).max(), 1e-30)
+
+
+@pytest.mark.parametrize('n,grid,warps', [(4, 1, 12), (131, 1, 2), (1000, 3, 5), (5003, 3, 12),
+                                          (2049, 2, 7)])
+def test_warp_kernel_schedule_and_values(n, grid, warps):
+    """Production build: every row processed exactly once whatever n / grid / warps, values and
+    gradients against the fp64 oracle, specialised == run-time-parameter instantiation."""
+    pred, target, w = make(n)
+    for (fun, tau), spec in SPEC.items():
+        total, _, grad = run(0, 'kld3d', 1, spec, 0, grid, warps, pred, target, w, tau=tau,
+                             scale=5.0 / n)
+        assert not (grad == -7.0).all(axis=1).any()                  # no row left unwritten
+        check_against_oracle('kld3d', fun, tau, pred, target, w, 5.0 / n, total, grad)
+        if fun == 'log1p':
+            total2, _, grad2 = run(0, 'kld3d', 1, -1, 0, grid, warps, pred, target, w, tau=tau,
+                                   scale=5.0 / n)
+            assert total2 == total and np.array_equal(grad2.view(np.int32), grad.view(np.int32))
+
+
+@pytest.mark.parametrize('loss', ['gwd3d', 'kld3d', 'bd3d'])
+@pytest.mark.parametrize('bits', [1024, 1792, 1920, 768])
+def test_variants_equal_production_bit_for_bit(loss, bits):
+    """Build variants (diets, packed math, strided layout) == production kernel, bit for bit in
+    the host arithmetic: loss sum, every gradient row, robust-path rows included."""
+    n = 1003
+    pred, target, w = make(n, seed=3)
+    for (fun, tau), spec in SPEC.items():
+        base = run(0, loss, 1, spec, 0, 2, 5, pred, target, w, tau=tau, scale=5.0 / n)
+        pack = 1 if bits & 1024 else 0
+        # bit 1024 routes 'bulk' to the packed kernels in the library; here it is explicit
+        var = run(bits, loss, 1, spec, pack, 2, 5, pred, target, w, tau=tau, scale=5.0 / n)
+        if bits & 128:      # strided layout: a lane sums different rows -> another summation order
+            assert abs(var[0] - base[0]) <= 1e-6 * abs(base[0]), (loss, bits, fun, tau)
+        else:
+            assert var[0] == base[0], (loss, bits, fun, tau)
+        assert np.array_equal(var[2].view(np.int32), base[2].view(np.int32)), (loss, bits, fun, tau)
+    # the production library's own opt-in packed variant (GD_VARIANT_BULK_PACKED)
+    p0 = run(0, loss, 1, 9, 1, 2, 5, pred, target, w, scale=5.0 / n)
+    b9 = run(0, loss, 1, 9, 0, 2, 5, pred, target, w, scale=5.0 / n)
+    assert p0[0] == b9[0] and np.array_equal(p0[2].view(np.int32), b9[2].view(np.int32))
+
+
+def test_weight_modes_masking_rows_and_forward_only():
+    n = 777
+    pred, target, w = make(n, seed=5)
+    w7 = torch.rand(n, 7)
+    for weight in (None, w, w7):
+        total, rows, grad = run(0, 'gwd3d', 1, -1, 0, 2, 3, pred, target, weight, scale=2.0,
+                                want_rows=True)
+        check_against_oracle('gwd3d', 'log1p', 0.0, pred, target, weight, 2.0, total, grad, rows)
+        # forward only (torch.no_grad): same sum, no gradient buffer
+        total_f, rows_f, _ = run(0, 'gwd3d', 1, -1, 0, 2, 3, pred, target, weight, scale=2.0,
+                                 want_rows=True, want_grad=False)
+        assert total_f == total and np.array_equal(rows_f, rows)
+    # zero-weight masking: NaN rows with weight 0 must not leak into the sum or the gradient
+    p2 = pred.clone()
+    dead = (w == 0).nonzero().flatten()[:5]
+    p2[dead, 0] = float('nan')
+    total, _, grad = run(0, 'kld3d', 1, 9, 0, 2, 3, p2, target, w, scale=1.0, mask_zero=1)
+    assert np.isfinite(total) and (grad[dead.numpy()] == 0).all()
+    ref_total, _, ref_grad = run(0, 'kld3d', 1, 9, 0, 2, 3, pred, target, w, scale=1.0, mask_zero=1)
+    assert total == ref_total
+    keep = np.ones(n, bool)
+    keep[dead.numpy()] = False
+    assert np.array_equal(grad[keep].view(np.int32), ref_grad[keep].view(np.int32))
+
+
+def test_staged_kernel_matches_warp_kernel_rows():
+    """gd_staged_kernel (any stride / alignment; robust math on every row) against the oracle;
+    different grids give the same per-row results."""
+    n = 700
+    pred, target, w = make(n, seed=7, extreme=False)
+    t1, r1, g1 = run(0, 'bd3d', 0, -1, 0, 1, 8, pred, target, w, scale=3.0, want_rows=True)
+    t2, r2, g2 = run(0, 'bd3d', 0, -1, 0, 3, 8, pred, target, w, scale=3.0, want_rows=True)
+    check_against_oracle('bd3d', 'log1p', 0.0, pred, target, w, 3.0, t1, g1, r1)
+    assert np.array_equal(g1.view(np.int32), g2.view(np.int32)) and np.array_equal(r1, r2)
+    assert abs(t1 - t2) <= 1e-6 * abs(t1)
+
+
+def test_sum_is_deterministic_and_grid_dependent_only():
+    n = 3000
+    pred, target, w = make(n, seed=9)
+    a = run(0, 'kld3d', 1, 9, 0, 3, 6, pred, target, w, scale=1.0 / n)
+    b = run(0, 'kld3d', 1, 9, 0, 3, 6, pred, target, w, scale=1.0 / n)
+    assert a[0] == b[0] and np.array_equal(a[2], b[2])
