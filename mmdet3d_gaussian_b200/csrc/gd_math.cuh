@@ -816,11 +816,16 @@ GD_HD T bd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad,
     T sa, sb, gam;                             // shape parts and d/d det_raw factor
     if (!clamped) {
       const T idN = Mth<T>::rcp(detN);
-      // a_p M11/det/2... - 1/(2 a_p) = [(A - t00)(B + t11) + t01^2] / (2 a_p detN)
-      const T Amt = da * (g.ap + g.at) + cmd * s2;                 // A - t00
-      const T Bmt = db * (g.bp + g.bt) - cmd * s2;                 // B - t11
-      sa = (T)0.5 * (Amt * (B + t11) + t01 * t01) * idN * iap;
-      sb = (T)0.5 * (Bmt * (A + t00) + t01 * t01) * idN * ibp;
+      // a_p M11/det/2... - 1/(2 a_p) = [(A - t00)(B + t11) + t01^2] / (2 a_p detN).  Expanding
+      // with t00 t11 - t01^2 = C D, t00 = C - (C-D) s2, t11 = D + (C-D) s2 gives
+      //   (A - t00)(B + t11) + t01^2 = (A - C)(B + D) + (A + B)(C - D) s2
+      //   (B - t11)(A + t00) + t01^2 = (B - D)(A + C) - (A + B)(C - D) s2
+      // -- the same shape as detN.  No term of size C^2 appears (the product form cancels two
+      // of them, which costs float32 every digit once the extents differ by ~10^3), and both
+      // terms vanish separately as the boxes coincide.
+      const T rot2 = (A + B) * (cmd * s2);
+      sa = (T)0.5 * (da * (g.ap + g.at) * (B + D) + rot2) * idN * iap;
+      sb = (T)0.5 * (db * (g.bp + g.bt) * (A + C) - rot2) * idN * ibp;
       gam = -Q2 * c8 * idet;                   // Mahalanobis part of d/d det
       L.gr = -amb * (u * v * c8 + (gam + (T)0.5 * idet) * M01);
     } else {

@@ -230,3 +230,44 @@ def test_packed_instantiation_is_bit_identical_on_host(tmp_path):
     # pairwise path (gd_pairwise_packed_kernel): two rows x one column per packed evaluation
     plines = [ln for ln in out.stdout.splitlines() if ln.startswith('pairwise')]
     assert len(plines) == 4 and all('mismatches gwd 0 kld 0 bd 0' in ln for ln in plines), out.stdout
+
+
+@pytest.mark.parametrize('lt', ['gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'bd3d'])
+def test_strongly_mismatched_boxes_fp32(hostlib, lt):
+    """Float32 accuracy when prediction and target differ by orders of magnitude (early
+    training, bad initialisation): per-row gradient and loss against the float64 instantiation
+    for extents scaled by 10 ... 10^4 (one, two opposite, all three) and centres shifted by up
+    to 10^4 m, on the robust path and, where the row is "nice", on the FAST path.  Regression
+    test for the bd3d shape gradient, whose product form lost every digit beyond a 10^3 ratio
+    (1.5e-5 at 10, 27 % at 10^3) until it was rewritten as (A-C)(B+D) + (A+B)(C-D) sin^2."""
+    pred, target, _ = synth.make_pairs(1500, 'kitti', seed=7)
+    worst = 0.0
+    for what in ('w', 'h', 'l', 'wh', 'shift', 'all'):
+        for ratio in (10.0, 100.0, 1e3, 1e4):
+            t2 = target.clone()
+            if what == 'w':
+                t2[:, 3] *= ratio
+            elif what == 'h':
+                t2[:, 4] *= ratio
+            elif what == 'l':
+                t2[:, 5] *= ratio
+            elif what == 'wh':
+                t2[:, 3] *= ratio
+                t2[:, 4] /= ratio
+            elif what == 'shift':
+                t2[:, 0] += ratio
+            else:
+                t2[:, 3:6] *= ratio
+            a = (lt, pred, t2, (0, 0, 0.5), 1.0, 0.0, 'log1p', True)
+            l32, g32 = host_eval(hostlib, *a, 'f32')
+            l64, g64 = host_eval(hostlib, *a, 'f64')
+            fl, fg, rr = host_eval_fast(hostlib, *a, 'f32')
+            gn = np.linalg.norm(g64, axis=1)
+            ok = np.isfinite(g64).all(1) & (gn > 0)
+            e = (np.linalg.norm(g32 - g64, axis=1) / np.maximum(gn, 1e-300))[ok].max()
+            el = (np.abs(l32 - l64) / np.maximum(np.abs(l64), 1e-30))[ok].max()
+            fast = ok & (rr == 0)
+            ef = (np.linalg.norm(fg - g64, axis=1) / np.maximum(gn, 1e-300))[fast].max() if fast.any() else 0.0
+            worst = max(worst, e, el, ef)
+            assert e < 3e-6 and el < 1e-6 and ef < 3e-6, (lt, what, ratio, e, el, ef)
+    assert worst > 0.0
