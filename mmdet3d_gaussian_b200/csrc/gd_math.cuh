@@ -879,7 +879,14 @@ GD_HD T kfiou_core(const PairGeom<T>& g, const PairParams<T>& Pin, T gscale, T* 
     const T K = (g.ap * g.bp) * (g.at * g.bt);
     const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
     const T i4K = (T)0.25 * Mth<T>::rcp(K);
-    const T dv = da * g.bp * g.ep + g.at * (db * g.ep + g.bt * de);   // vol_p - vol_t, no cancellation
+    // vol_p - vol_t.  The telescoped form is exact-ish when the boxes nearly coincide (each
+    // term is small), but its terms grow without bound when two extents move in opposite
+    // directions at constant volume (w x 1000, h / 1000) and then cancel; the plain
+    // difference has an error of ~ulp(vol) whatever the shapes.  Take whichever is bounded
+    // better.
+    const T tv1 = da * g.bp * g.ep, tv2 = g.at * (db * g.ep), tv3 = g.at * (g.bt * de);
+    const T tmag = (tv1 < (T)0 ? -tv1 : tv1) + (tv2 < (T)0 ? -tv2 : tv2) + (tv3 < (T)0 ? -tv3 : tv3);
+    const T dv = (tmag > (T)2 * (volp + volt)) ? (volp - volt) : (tv1 + (tv2 + tv3));
     const T i4vv = (T)0.25 * Mth<T>::rcp(volp * volt);
     const T x1 = dv * dv * i4vv;
     const T xa = da * da * Mth<T>::rcp((T)2 * g.ap * g.at);

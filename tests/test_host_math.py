@@ -232,14 +232,15 @@ def test_packed_instantiation_is_bit_identical_on_host(tmp_path):
     assert len(plines) == 4 and all('mismatches gwd 0 kld 0 bd 0' in ln for ln in plines), out.stdout
 
 
-@pytest.mark.parametrize('lt', ['gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'bd3d'])
+@pytest.mark.parametrize('lt', ['gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'bd3d', 'kfiou3d'])
 def test_strongly_mismatched_boxes_fp32(hostlib, lt):
     """Float32 accuracy when prediction and target differ by orders of magnitude (early
     training, bad initialisation): per-row gradient and loss against the float64 instantiation
     for extents scaled by 10 ... 10^4 (one, two opposite, all three) and centres shifted by up
     to 10^4 m, on the robust path and, where the row is "nice", on the FAST path.  Regression
     test for the bd3d shape gradient, whose product form lost every digit beyond a 10^3 ratio
-    (1.5e-5 at 10, 27 % at 10^3) until it was rewritten as (A-C)(B+D) + (A+B)(C-D) sin^2."""
+    (1.5e-5 at 10, 27 % at 10^3) until it was rewritten as (A-C)(B+D) + (A+B)(C-D) sin^2, and
+    for the kfiou3d volume difference (telescoped form: 2.5e-4 at w x 1000, h / 1000)."""
     pred, target, _ = synth.make_pairs(1500, 'kitti', seed=7)
     worst = 0.0
     for what in ('w', 'h', 'l', 'wh', 'shift', 'all'):
@@ -258,7 +259,7 @@ def test_strongly_mismatched_boxes_fp32(hostlib, lt):
                 t2[:, 0] += ratio
             else:
                 t2[:, 3:6] *= ratio
-            a = (lt, pred, t2, (0, 0, 0.5), 1.0, 0.0, 'log1p', True)
+            a = (lt, pred, t2, (0, 0, 0.5), 1.0, 0.0, 'none' if lt == 'kfiou3d' else 'log1p', True)
             l32, g32 = host_eval(hostlib, *a, 'f32')
             l64, g64 = host_eval(hostlib, *a, 'f64')
             fl, fg, rr = host_eval_fast(hostlib, *a, 'f32')
