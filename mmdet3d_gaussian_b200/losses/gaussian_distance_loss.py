@@ -58,6 +58,10 @@ class GDLoss(nn.Module):
       0 are masked inside the kernel (0 loss, 0 gradient).  For non-negative
       weights the two agree on every finite row; the all-zero batch returns 0
       with zero gradients either way.
+      ``'overlap'`` (opt-in, not GPU-validated yet) has the semantics of True but queues
+      the fused kernel speculatively BEFORE the host waits for the probe, so the GPU
+      does not idle during the sync; the speculative result is dropped in the (rare)
+      early-return case.
     """
 
     BAG_GD_LOSS = tuple(_lib.LOSS_TYPES)          # ref:253-259
@@ -79,7 +83,8 @@ class GDLoss(nn.Module):
         self.reduction = reduction
         self.loss_weight = loss_weight
         self.variant = kwargs.pop('variant', 'auto')
-        self.host_sync = bool(kwargs.pop('host_sync', True))
+        hs = kwargs.pop('host_sync', True)
+        self.host_sync = hs if hs == 'overlap' else bool(hs)
         self.kwargs = kwargs                                      # ref:278
         self._cfg_cache = {}
 
@@ -103,6 +108,8 @@ class GDLoss(nn.Module):
         assert reduction_override in (None, 'none', 'mean', 'sum')   # ref:287
         reduction = (
             reduction_override if reduction_override else self.reduction)  # ref:288-289
+        if self.host_sync == 'overlap' and (weight is not None) and (reduction != 'none'):
+            return self._forward_overlapped(pred, target, weight, avg_factor, reduction, kwargs)
         if self.host_sync and (weight is not None) and (reduction != 'none') and (
                 not ops.any_positive(weight)):                    # ref:290-291
             return (pred * weight).sum()                          # ref:292
@@ -114,6 +121,27 @@ class GDLoss(nn.Module):
         return ops.gd_loss(pred, target, weight, cfg, scale, rows_out=rows_out,
                            variant=self.variant,
                            mask_zero_weight=not self.host_sync)
+
+    def _forward_overlapped(self, pred, target, weight, avg_factor, reduction, kwargs):
+        """``host_sync='overlap'``: same decision as ref:290-292, but the fused launch is
+        queued before the host blocks on the probe."""
+        probe = ops.any_positive_begin(weight)
+        out, err = None, None
+        try:
+            _kwargs = deepcopy(self.kwargs) if (self.kwargs or kwargs) else {}
+            _kwargs.update(kwargs)
+            cfg = self._config(_kwargs)
+            scale, rows_out = _scale_and_mode(reduction, avg_factor, pred.numel() // 7,
+                                              self.loss_weight)
+            out = ops.gd_loss(pred, target, weight, cfg, scale, rows_out=rows_out,
+                              variant=self.variant, mask_zero_weight=False)
+        except Exception as e:                # raised only if the early return does not apply
+            err = e
+        if not probe.result():                                    # ref:290-291
+            return (pred * weight).sum()                          # ref:292
+        if err is not None:
+            raise err
+        return out
 
     def extra_repr(self):
         return (f'loss_type={self.loss_type!r}, fun={self.fun!r}, tau={self.tau}, '

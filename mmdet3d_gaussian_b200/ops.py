@@ -215,6 +215,51 @@ def any_positive(weight):
     return bool(flag.item())
 
 
+class _PositiveProbe:
+    """``any(weight > 0)`` in flight: the probe kernel and a copy of its flag into pinned
+    host memory are queued, an event marks the copy.  ``result()`` blocks the HOST until that
+    event only -- work queued on the stream after the probe (the speculative fused launch)
+    keeps the GPU busy meanwhile."""
+    __slots__ = ('host', 'event')
+
+    def __init__(self, host, event):
+        self.host, self.event = host, event
+
+    def result(self):
+        self.event.synchronize()
+        return bool(int(self.host[0]))
+
+
+_PROBE_SLOTS = {}
+
+
+def any_positive_begin(weight):
+    """Start the early-return probe of ``GDLoss.forward`` (reference
+    ``gaussian_distance_loss.py:290``) without waiting for it; see ``_PositiveProbe``.
+    One pinned slot per (device, stream): the caller must consume the result before it
+    starts the next probe on that stream (``GDLoss.forward`` does)."""
+    _require_cuda(weight, 'weight')
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    dev = w.device
+    key = (dev.index, _raw_stream(dev.index))
+    slot = _PROBE_SLOTS.get(key)
+    if slot is None:
+        slot = (torch.empty((1,), dtype=torch.int32, device=dev),
+                torch.zeros((1,), dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        _PROBE_SLOTS[key] = slot
+    flag, host, event = slot
+    with _on_device(dev):
+        code = _lib.load().gd_any_positive(_ptr(w), w.numel(), _ptr(flag), _stream_ptr())
+        _lib.check(code, 'gd_any_positive')
+        host.copy_(flag, non_blocking=True)
+        event.record()
+    return _PositiveProbe(host, event)
+
+
 def _boxes(t, name):
     _require_cuda(t, name)
     if t.dim() != 2 or t.shape[1] != 7:

@@ -102,3 +102,28 @@ def test_packed_pairwise(loss_type, fun, tau, n, m):
         assert torch.equal(cmin.view(torch.int32), cv.view(torch.int32)) and torch.equal(cidx, ci)
         rmin, ridx, cmin, cidx, none = mod.assign(b1, b2, packed=True)
         assert none is None
+
+
+def test_overlapped_host_sync_mode():
+    """``host_sync='overlap'`` (opt-in): the decisions and results of the default module
+    (reference gaussian_distance_loss.py:290-292), with the fused launch queued before the
+    host waits for the probe."""
+    pred, target, w = synth.make_pairs(20_000, 'kitti', seed=4, weights='bernoulli')
+    for kw in (dict(loss_type='kld3d', fun='log1p', tau=0.0), dict(loss_type='gwd3d')):
+        outs = []
+        for hs in (True, 'overlap'):
+            p = pred.clone().cuda().requires_grad_(True)
+            loss = GDLoss(host_sync=hs, **kw)(p, target.cuda(), w.cuda(), avg_factor=123.0)
+            loss.backward()
+            outs.append((loss.item(), p.grad.clone()))
+        assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    # early return: no positive weight -> (pred * weight).sum(), gradient = weight
+    w7 = -torch.rand(64, 7)
+    p = pred[:64].clone().cuda().requires_grad_(True)
+    out = GDLoss('kld3d', host_sync='overlap')(p, target[:64].cuda(), w7.cuda())
+    out.backward()
+    assert torch.allclose(out.cpu(), (pred[:64] * w7).sum()) and torch.equal(p.grad.cpu(), w7)
+    # reduction='none' and weight=None never probe
+    rows = GDLoss('bd3d', host_sync='overlap', reduction='none')(pred[:50].cuda(), target[:50].cuda(),
+                                                                  w[:50].cuda())
+    assert rows.shape == (50,)
