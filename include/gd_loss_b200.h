@@ -296,6 +296,16 @@ GD_API int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_ce
                                    void* workspace, size_t workspace_bytes,
                                    int32_t flags, void* stream);
 
+/* How gd_loss_fwd_bwd_host cuts n rows into chunks (pure host arithmetic, callable without
+ * a GPU).  Chunks are `chunk_rows` rows (rounded up to a multiple of 256; <= 0 selects the
+ * default 2^20), except that the LAST chunk of a multi-chunk input is tapered -- halved
+ * repeatedly down to chunk_rows / 8 -- so that the device->host copy of the final piece,
+ * which nothing can overlap, is short (n <= chunk_rows stays a single chunk).  Every chunk start is a multiple of 256 rows (16-byte aligned rows).
+ * Writes up to `capacity` (start, rows) pairs and returns the number of chunks, or a negative
+ * GD_ERR_* (more chunks than capacity / than the pipeline supports). */
+GD_API int64_t gd_host_chunk_plan(int64_t n, int64_t chunk_rows, int64_t* starts, int64_t* rows,
+                                  int64_t capacity);
+
 /* End-to-end entry with HOST buffers (bench `e2e`): chunks rows, overlaps
  * H2D of chunk k+1 / kernel of chunk k / D2H of chunk k-1 on internal streams,
  * returns when loss_host and grad_host are complete.  Host buffers may be

@@ -62,6 +62,7 @@ SIGNATURES = {
         _i64, _i64, _f32, _vp, _vp, _i64, _i32, _vp, ctypes.c_size_t, _i32, _vp]),
     'gd_loss_fwd_bwd_host': (ctypes.c_int, [_cfgp, _vp, _vp, _vp, _i32, _i64, _f32,
                                             _vp, _vp, _i32, _i64]),
+    'gd_host_chunk_plan': (_i64, [_i64, _i64, _vp, _vp, _i64]),
     'gd_launch_count': (_i64, []),
     'gd_error_string': (ctypes.c_char_p, [ctypes.c_int]),
 }

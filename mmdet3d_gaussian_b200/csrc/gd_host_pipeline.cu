@@ -8,6 +8,7 @@
 // on the host in chunk order in fp64 => deterministic.  This is the one entry
 // point that owns device memory (a per-device cache that only grows).
 #include <mutex>
+#include <vector>
 
 #include "gd_common.cuh"
 
@@ -82,6 +83,40 @@ static int ensure(Pipe& p, long long chunk_rows, long long w_floats) {
 
 }  // namespace gdk
 
+extern "C" int64_t gd_host_chunk_plan(int64_t n, int64_t chunk_rows, int64_t* starts, int64_t* rows,
+                                      int64_t capacity) {
+  using namespace gdk;
+  if (n < 0 || capacity < 0 || (capacity > 0 && (!starts || !rows))) return GD_ERR_BAD_ARG;
+  if (chunk_rows <= 0) chunk_rows = 1 << 20;
+  chunk_rows = (chunk_rows + 255) & ~255LL;            // whole tiles; keeps chunks 16 B aligned
+  long long piece_min = (chunk_rows / 8 + 255) & ~255LL;
+  if (piece_min < 256) piece_min = 256;
+  const bool taper = n > chunk_rows;                   // single-chunk inputs stay one launch
+  int64_t count = 0;
+  long long r = 0;
+  while (r < n) {
+    long long take = n - r;
+    if (take > chunk_rows) {
+      take = chunk_rows;                               // a full chunk, more rows follow
+    } else if (taper && take > piece_min) {
+      // inside the last chunk: halve (rounded up to 256 rows) until piece_min is reached
+      long long half = ((take + 1) / 2 + 255) & ~255LL;
+      if (half < piece_min) half = piece_min;
+      if (half < take) take = half;
+    }
+    if (count >= kMaxChunks) return GD_ERR_BAD_ARG;
+    if (count < capacity) {
+      starts[count] = r;
+      rows[count] = take;
+    } else if (capacity > 0) {
+      return GD_ERR_BAD_ARG;
+    }
+    ++count;
+    r += take;
+  }
+  return count;
+}
+
 extern "C" int gd_loss_fwd_bwd_host(const gd_loss_config* cfg, const float* pred_host,
                                     const float* target_host, const float* weight_host,
                                     int32_t weight_mode, int64_t n, float scale,
@@ -100,8 +135,13 @@ extern "C" int gd_loss_fwd_bwd_host(const gd_loss_config* cfg, const float* pred
   if (chunk_rows <= 0) chunk_rows = 1 << 20;
   chunk_rows = (chunk_rows + 255) & ~255LL;            // whole tiles; keeps chunks 16 B aligned
   if (chunk_rows > n) chunk_rows = (n + 255) & ~255LL;
-  const long long nchunks = (n + chunk_rows - 1) / chunk_rows;
-  if (nchunks > kMaxChunks) return GD_ERR_BAD_ARG;
+  // chunk boundaries: full chunks, the last one tapered (see gd_host_chunk_plan)
+  const int64_t nplan = gd_host_chunk_plan(n, chunk_rows, nullptr, nullptr, 0);
+  if (nplan < 0) return (int)nplan;
+  std::vector<int64_t> c_start((size_t)nplan), c_rows((size_t)nplan);
+  if (gd_host_chunk_plan(n, chunk_rows, c_start.data(), c_rows.data(), nplan) != nplan)
+    return GD_ERR_BAD_ARG;
+  const long long nchunks = nplan;
   const int wcols = weight_mode == GD_WEIGHT_ROW7 ? 7 : (weight_mode == GD_WEIGHT_ROW ? 1 : 0);
 
   std::lock_guard<std::mutex> lock(g_mu);
@@ -116,8 +156,8 @@ extern "C" int gd_loss_fwd_bwd_host(const gd_loss_config* cfg, const float* pred
   }
   for (long long c = 0; c < nchunks && rc == 0; ++c) {
     Slot& sl = p.slot[c % kSlots];
-    const long long r0 = c * chunk_rows;
-    const long long rows = (n - r0 < chunk_rows) ? (n - r0) : chunk_rows;
+    const long long r0 = c_start[(size_t)c];
+    const long long rows = c_rows[(size_t)c];
     cudaError_t e = cudaMemcpyAsync(sl.pred, pred_host + r0 * 7, (size_t)rows * kRowBytes,
                                     cudaMemcpyHostToDevice, sl.stream);
     if (e == cudaSuccess)

@@ -243,3 +243,35 @@ def test_assigner_modules_validate_on_the_host():
         GDSimilarity3D('gwd3d', sqrt=True)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         GDSimilarity3D()(torch.zeros(4, 7), torch.zeros(2, 7))
+
+
+def test_host_chunk_plan(lib):
+    """gd_host_chunk_plan (how gd_loss_fwd_bwd_host cuts rows; pure host arithmetic): the
+    chunks tile [0, n) exactly, every start is a multiple of 256 rows, no chunk exceeds
+    chunk_rows, a multi-chunk input ends in a tapered tail of at most chunk_rows / 8 rows and
+    a single-chunk input stays one launch."""
+    import ctypes
+    for n, chunk in ((0, 0), (1, 0), (1000, 0), (1 << 20, 0), ((1 << 20) + 1, 0), (1 << 24, 0),
+                     ((1 << 24) + 12345, 1 << 20), (5_000_000, 1 << 18), (777, 256), (70_000, 1000)):
+        cnt = lib.gd_host_chunk_plan(n, chunk, None, None, 0)
+        assert cnt >= 0
+        starts = (ctypes.c_int64 * max(cnt, 1))()
+        rows = (ctypes.c_int64 * max(cnt, 1))()
+        assert lib.gd_host_chunk_plan(n, chunk, ctypes.cast(starts, ctypes.c_void_p),
+                                      ctypes.cast(rows, ctypes.c_void_p), cnt) == cnt
+        eff = ((chunk if chunk > 0 else 1 << 20) + 255) // 256 * 256
+        pos = 0
+        for i in range(cnt):
+            assert starts[i] == pos and starts[i] % 256 == 0 and 0 < rows[i] <= eff
+            pos += rows[i]
+        assert pos == n
+        if n <= eff:
+            assert cnt == (1 if n else 0)
+        else:
+            assert rows[cnt - 1] <= (eff // 8 + 255) // 256 * 256
+            assert cnt <= n // eff + 1 + 4                      # a handful of extra launches
+    # capacity too small / bad arguments
+    buf = (ctypes.c_int64 * 2)()
+    assert lib.gd_host_chunk_plan(1 << 24, 1 << 20, ctypes.cast(buf, ctypes.c_void_p),
+                                  ctypes.cast(buf, ctypes.c_void_p), 2) < 0
+    assert lib.gd_host_chunk_plan(-1, 0, None, None, 0) < 0
