@@ -59,13 +59,24 @@ def run(bits, loss, kind, spec, pack, grid, warps, pred, target, weight, tau=0.0
     if weight is not None:
         w = np.ascontiguousarray(weight.numpy().astype(np.float32))
         wmode = 2 if w.ndim == 2 else 1
-    total = np.full(1, -7.0, np.float32)
-    rows = np.full(n, -7.0, np.float32) if want_rows else None
-    grad = np.full((n, 7), -7.0, np.float32) if want_grad else None
+    # every output sits between two guard bands: a write outside its array is caught
+    G = 64
+    bufs = {}
+
+    def guarded(name, count):
+        full = np.full(count + 2 * G, -7.0, np.float32)
+        full[:G] = full[-G:] = 91.0
+        bufs[name] = full
+        return full[G:G + count]
+    total = guarded('loss', 1)
+    rows = guarded('rows', n) if want_rows else None
+    grad = guarded('grad', n * 7).reshape(n, 7) if want_grad else None
     ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None   # noqa: E731
     rc = emul(bits).gd_emul_loss(LOSS[loss], kind, spec, pack, grid, warps, ptr(p), ptr(t), ptr(w),
                                  wmode, n, scale, tau, mask_zero, ptr(total), ptr(rows), ptr(grad))
     assert rc == 0, rc
+    for name, full in bufs.items():
+        assert (full[:G] == 91.0).all() and (full[-G:] == 91.0).all(), f'write outside {name}'
     return float(total[0]), rows, grad
 
 

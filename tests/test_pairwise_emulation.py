@@ -48,13 +48,24 @@ def run(lib, loss, packed, reduce, b1, b2, want_matrix=True, force_cpl=0, cap=3,
     n, m = b1.shape[0], b2.shape[0]
     a1 = np.ascontiguousarray(b1.numpy().astype(np.float32))
     a2 = np.ascontiguousarray(b2.numpy().astype(np.float32))
-    out = np.full((n, m), -7.0, np.float32) if want_matrix else None
-    rmin, ridx = np.full(n, -7.0, np.float32), np.full(n, -7, np.int32)
-    cmin, cidx = np.full(m, -7.0, np.float32), np.full(m, -7, np.int32)
+    # every output sits between two guard bands: a write outside its array is caught
+    G = 64
+    bufs = {}
+
+    def guarded(name, count, dtype, fill):
+        full = np.full(count + 2 * G, fill, dtype)
+        full[:G] = full[-G:] = 91
+        bufs[name] = full
+        return full[G:G + count]
+    out = guarded('out', n * m, np.float32, -7.0).reshape(n, m) if want_matrix else None
+    rmin, ridx = guarded('rmin', n, np.float32, -7.0), guarded('ridx', n, np.int32, -7)
+    cmin, cidx = guarded('cmin', m, np.float32, -7.0), guarded('cidx', m, np.int32, -7)
     p = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None   # noqa: E731
     dirty = lib.gd_emul_pairwise(LOSS[loss], packed, reduce, force_cpl, cap, p(a1), n, p(a2), m,
                                  p(out), p(rmin), p(ridx), p(cmin), p(cidx), similarity)
     assert dirty == 0, 'column-key workspace / ticket not restored'
+    for name, full in bufs.items():
+        assert (full[:G] == 91).all() and (full[-G:] == 91).all(), f'write outside {name}'
     return out, rmin, ridx, cmin, cidx
 
 
