@@ -236,3 +236,27 @@ def test_anchor_decode_known_answers():
     out = gd_oracle.decode_delta_xyzwlhr(a, d)
     assert torch.allclose(out[:, 5], 2 * a[:, 5])
     assert torch.allclose(out[:, 2] + out[:, 5] / 2, a[:, 2] + a[:, 5] / 2)
+
+
+def _mismatch_golden():
+    import json as _json
+    import os as _os
+    here = _os.path.dirname(_os.path.abspath(__file__))
+    z = np.load(_os.path.join(here, 'golden', 'gd_mismatch_golden.npz'))
+    return z, _json.loads(bytes(z['manifest']).decode())
+
+
+def test_oracle_matches_reference_on_mismatched_boxes():
+    """Oracle (fp64) == the unmodified reference's fp64 output on strongly mismatched pairs
+    (extent ratios 10 ... 1000, shifts to 1000 m, elongated boxes):
+    tests/golden/gd_mismatch_golden.npz, written by oracle/make_mismatch_golden.py."""
+    z, man = _mismatch_golden()
+    pred = torch.from_numpy(z['pred']).double()
+    target = torch.from_numpy(z['target']).double()
+    assert len(man['cases']) == 20 and pred.shape[0] == len(man['tags']) == 120
+    for c in man['cases']:
+        loss, grad = gd_oracle.loss_and_grad(gd_oracle.GDLossOracle(**c['kwargs']), pred, target)
+        rl, rg = z[f"case/{c['id']}/loss"], z[f"case/{c['id']}/grad"]
+        assert np.allclose(loss.numpy(), rl, rtol=1e-11, atol=1e-300), c
+        gn = np.abs(rg).max(1, keepdims=True)
+        assert (np.abs(grad.numpy() - rg) <= 1e-10 * gn + 1e-300).all(), c
