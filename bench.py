@@ -135,11 +135,11 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port (reference algorithm, eager torch, fp32, all host threads)
 # ---------------------------------------------------------------------------
-def cpu_pairs_per_s(sample_rows, chunk_rows, repeats):
+def cpu_pairs_per_s(sample_rows, chunk_rows, repeats, threads=None):
     import torch
     from oracle import gd_oracle
     from mmdet3d_gaussian_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     pred, target, w = synth.make_pairs(sample_rows, 'kitti', seed=0)
     mods = [gd_oracle.GDLossOracle(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT)
@@ -431,6 +431,11 @@ def run_ours(args):
                'sample': 'oracle port (reference algorithm, eager torch fp32 + autograd), 4 '
                          f'configs x 2^23 pairs (half the batch) in 2^17-row chunks, best of 2 '
                          f'passes ({secs:.2f} s per pass)'}
+        # the single-thread row of SURVEY.md section 8d (bounded: 4 x 2^20 pairs, one pass)
+        v1, _, secs1 = cpu_pairs_per_s(1 << 20, 1 << 17, 1, threads=1)
+        cpu['value_1thread'] = v1
+        cpu['sample_1thread'] = f'4 configs x 2^20 pairs, one pass ({secs1:.2f} s)'
+        torch.set_num_threads(os.cpu_count() or 1)
 
     eager = None
     if rank == 0 and world == 1 and args.eager_gpu:
