@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GD_ABI_VERSION 1
+#define GD_ABI_VERSION 2
 
 /* loss_type: keys of GDLoss.BAG_GD_LOSS                                ref:253-259 */
 enum {
@@ -68,9 +68,13 @@ enum {
   GD_VARIANT_BULK = 2,   /* persistent per-warp cp.async.bulk (TMA 1-D) + mbarrier
                             rings, 4 rows per lane                                 */
   GD_VARIANT_BULK_R2 = 3, /* same, 2 rows per lane / twice the warps (tuning aid)  */
-  GD_VARIANT_BULK_PACKED = 4 /* GD_VARIANT_BULK with the FP32 math of two rows packed into
+  GD_VARIANT_BULK_PACKED = 4, /* GD_VARIANT_BULK with the FP32 math of two rows packed into
                                 FFMA2/FMUL2/FADD2 (gwd3d / kld3d / bd3d with gradient; other
                                 cases run GD_VARIANT_BULK).  Opt-in: not selected by AUTO.  */
+  GD_VARIANT_BULK_ANY = 5    /* the bulk pipeline for ROW-STRIDED and/or 16-byte-unaligned
+                                inputs (4-byte aligned): whole wide rows are copied, columns
+                                0..6 picked in shared memory.  AUTO takes it whenever
+                                GD_VARIANT_BULK cannot run and the rows fit shared memory.   */
 };
 
 /* flags of gd_loss_fwd_bwd */
@@ -134,6 +138,46 @@ GD_API int gd_loss_fwd_bwd(const gd_loss_config* cfg,
                     void* workspace, size_t workspace_bytes,
                     int32_t variant, int32_t flags, void* stream);
 
+/* The same launch with every argument in one struct, plus what the positional entry point
+ * cannot express (ABI >= 2).  Zero-initialise the struct, then fill what applies. */
+typedef struct gd_loss_io {
+  const float* pred;   int64_t pred_row_stride;     /* as gd_loss_fwd_bwd */
+  const float* target; int64_t target_row_stride;
+  const float* weight; int32_t weight_mode; int64_t weight_row_stride;
+  int64_t n;
+  float scale;
+  /* nullable, 1 fp32 on the DEVICE: the effective scale is scale / *scale_div.  Lets
+   * avg_factor stay a device scalar (gd_centerpoint_head.py:407 computes it with .item(),
+   * gd_anchor3d_head.py:102-105 with nonzero + len: both host syncs) -- pass
+   * scale = loss_weight, scale_div = avg_factor. */
+  const float* scale_div;
+  float* loss_sum; float* row_loss; float* grad_pred;
+  /* nullable, 1 fp32 := 1 if ANY element of `weight` is > 0 else 0 -- the reference's
+   * early-return condition `torch.any(weight > 0)` (ref:290) evaluated inside the same
+   * launch (needs loss_sum).  Feed it to gd_early_return_fix. */
+  float* status;
+  void* workspace; size_t workspace_bytes;
+  int32_t variant; int32_t flags;
+} gd_loss_io;
+
+GD_API int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream);
+
+/* Early-return branch of GDLoss.forward WITHOUT a host sync (ref:290-292): launched right
+ * after gd_loss_launch on the same stream.  Reads *status on the device; when it is non-zero
+ * (some weight element > 0: the normal case) the kernel exits at once.  Otherwise it
+ * overwrites the outputs with what the reference returns:
+ *   loss_sum := sum_{i,c} pred[i,c] * weight(i,c)          (pred * weight).sum(), ref:292
+ *   grad_pred[i,c] := weight(i,c)                          its autograd gradient
+ * with weight(i,c) = weight[i * weight_row_stride + c * weight_col_stride]: ([n,7]: (s,1);
+ * a [7] weight against [7,7] rows broadcasts over columns: (0,1); [1]: (0,0)).  No
+ * loss_weight / avg_factor (the reference applies none on this branch).  grad_pred nullable. */
+GD_API int gd_early_return_fix(const float* status,
+                               const float* pred, int64_t pred_row_stride,
+                               const float* weight, int64_t weight_row_stride,
+                               int64_t weight_col_stride, int64_t n,
+                               float* loss_sum, float* grad_pred,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* Autograd fold: grad[i,:] *= *grad_output (0-dim upstream gradient; replaces the
  * first step of the reference's autograd backward).  Reads the scalar on the
  * device -- no host sync. */
@@ -152,6 +196,26 @@ GD_API int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_r
  * flag[0] = 1 if any weight element is > 0 else 0 (count elements, any layout
  * flattened by the caller) so the shim can take that branch. */
 GD_API int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* stream);
+
+/* The same probe without stalling the GPU (the host-visible form of ref:290 for weight
+ * shapes where the reference's early return RAISES, so the host has to know): queues the
+ * probe kernel (it stops at the first positive element it sees), a 4-byte copy of the flag
+ * into `flag_host` (PINNED host memory) and records `event` behind it.  The caller then
+ * queues the fused launch and only afterwards waits with gd_probe_event_wait -- the GPU
+ * stays busy during the wait.  `event` comes from gd_probe_event_create (a cudaEvent_t
+ * without timing; one per stream, reusable, lives as long as the process). */
+GD_API int gd_probe_event_create(void** event);
+GD_API int gd_probe_begin(const float* weight, int64_t count, int32_t* flag, int32_t* flag_host,
+                          void* event, void* stream);
+GD_API int gd_probe_event_wait(void* event);
+
+/* out[0] := max(#{i : 0 <= labels[i] < num_classes}, 1) as fp32 -- the avg_factor of the
+ * anchor head's labels mode when the caller passes none (reduction='mean' over the positives,
+ * gd_anchor3d_head.py:102-105 without nonzero / len), for gd_loss_io.scale_div.
+ * Workspace as gd_loss_workspace_bytes. */
+GD_API int gd_count_positive_labels(const int64_t* labels, int64_t total, int64_t num_classes,
+                                    float* out, void* workspace, size_t workspace_bytes,
+                                    void* stream);
 
 /* Pairwise matrix (new surface):
  *   out[i, j] = postprocess(distance(boxes1[i], boxes2[j]))   i<n, j<m
@@ -248,6 +312,8 @@ enum {
  *                   OR labels[T] (int64) + num_classes: positive <=> 0 <= label < num_classes
  *                   (:102-104) decided in-kernel -- no nonzero, no host sync.
  *   scale         : loss_weight / avg_factor (as gd_loss_fwd_bwd)
+ *   scale_div     : nullable DEVICE scalar; effective scale = scale / *scale_div (as
+ *                   gd_loss_io.scale_div: avg_factor without the host sync of :102-105)
  *   loss_sum      : nullable, 1 fp32 := scale * sum_pos w_i loss_i
  *   grad_deltas   : per grad_mode; = scale * w_i * d loss_i / d deltas_pred[i]
  * No positives => loss 0 and zero gradient (the reference's `pos_bbox_pred.sum()`
@@ -260,7 +326,7 @@ GD_API int gd_anchor_decoded_loss_fwd_bwd(const gd_loss_config* cfg,
                                    const float* decode_weight_host,
                                    const int64_t* pos_inds, int64_t num_pos,
                                    const int64_t* labels, int64_t num_classes,
-                                   int64_t total_rows, float scale,
+                                   int64_t total_rows, float scale, const float* scale_div,
                                    float* loss_sum, float* grad_deltas, int32_t grad_mode,
                                    void* workspace, size_t workspace_bytes,
                                    int32_t flags, void* stream);
@@ -290,7 +356,7 @@ GD_API int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_ce
                                    const float* target, int64_t target_row_stride,
                                    const float* weight, int32_t weight_mode,
                                    int64_t weight_row_stride,
-                                   int64_t n, float scale,
+                                   int64_t n, float scale, const float* scale_div,
                                    float* loss_sum, float* grad_preds,
                                    int64_t grad_row_stride, int32_t grad_cols,
                                    void* workspace, size_t workspace_bytes,

@@ -55,7 +55,7 @@ __device__ __forceinline__ float anchor_row_weight(const AnchorArgs& a, long lon
 }
 
 template <int LOSS, bool GRAD>
-__device__ __forceinline__ float anchor_row(const AnchorArgs& a, long long i, float* g) {
+__device__ __forceinline__ float anchor_row(const AnchorArgs& a, long long i, float scale, float* g) {
   float an[7], dp[7], dt[7];
   const float* ar = a.anchors + (i % a.anchor_rows) * 7;
   const float* pr = a.dpred + i * a.dp_stride;
@@ -67,7 +67,7 @@ __device__ __forceinline__ float anchor_row(const AnchorArgs& a, long long i, fl
     dt[c] = __ldg(tr + c);
   }
   const float w = anchor_row_weight(a, i);
-  const float ws = w * a.sum.scale;
+  const float ws = w * scale;
   float l = gd::anchor_pair_eval<float, LOSS, GRAD>(an, dp, dt, a.sum.pp, ws, g);
   if (a.sum.mask_zero_w && w == 0.0f) {
     l = 0.0f;
@@ -81,24 +81,26 @@ __device__ __forceinline__ float anchor_row(const AnchorArgs& a, long long i, fl
 
 template <int LOSS, bool GRAD>
 __global__ void __launch_bounds__(kThreads) gd_anchor_index_kernel(const AnchorArgs a) {
+  const float scale = effective_scale(a.sum);
   float acc = 0.0f;
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long k = (long long)blockIdx.x * kThreads + threadIdx.x; k < a.num_pos; k += stride) {
     const long long i = a.pos_inds[k];
     if (i < 0 || i >= a.total_rows) continue;      // never dereference a bad index
     float g[7];
-    acc += anchor_row<LOSS, GRAD>(a, i, g);
+    acc += anchor_row<LOSS, GRAD>(a, i, scale, g);
     if (GRAD) {
       float* o = a.grad_mode == GD_GRAD_SCATTER ? a.grad + i * 7 : a.grad + k * 7;
 #pragma unroll
       for (int c = 0; c < 7; ++c) o[c] = g[c];
     }
   }
-  if (a.sum.loss_sum) finish_sum(acc, a.sum);
+  if (a.sum.loss_sum) finish_sum(acc, a.sum, scale);
 }
 
 template <int LOSS, bool GRAD>
 __global__ void __launch_bounds__(kThreads) gd_anchor_mask_kernel(const AnchorArgs a) {
+  const float scale = effective_scale(a.sum);
   __shared__ __align__(16) float s_g[kTile * 7];
   const int tid = threadIdx.x;
   const long long ntiles = (a.total_rows + kTile - 1) / kTile;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) gd_anchor_mask_kernel(const AnchorAr
     for (int c = 0; c < 7; ++c) g[c] = 0.0f;
     if (tid < rows) {
       const long long lab = __ldcs(a.labels + i);
-      if (lab >= 0 && lab < a.num_classes) acc += anchor_row<LOSS, GRAD>(a, i, g);
+      if (lab >= 0 && lab < a.num_classes) acc += anchor_row<LOSS, GRAD>(a, i, scale, g);
     }
     if (GRAD) {
 #pragma unroll
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) gd_anchor_mask_kernel(const AnchorAr
       __syncthreads();
     }
   }
-  if (a.sum.loss_sum) finish_sum(acc, a.sum);
+  if (a.sum.loss_sum) finish_sum(acc, a.sum, scale);
 }
 
 struct CenterArgs {
@@ -142,6 +144,7 @@ struct CenterArgs {
 
 template <int LOSS, bool GRAD>
 __global__ void __launch_bounds__(kThreads) gd_center_kernel(const CenterArgs a) {
+  const float scale = effective_scale(a.sum);
   float acc = 0.0f;
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long k = (long long)blockIdx.x * kThreads + threadIdx.x; k < a.n; k += stride) {
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) gd_center_kernel(const CenterArgs a)
     float w = 1.0f;
     if (a.wmode == GD_WEIGHT_ROW) w = __ldg(a.weight + k * a.w_stride);
     if (a.wmode == GD_WEIGHT_ROW7) w = row_weight_smem(a.weight + k * a.w_stride, GD_WEIGHT_ROW7, 0);
-    const float ws = w * a.sum.scale;
+    const float ws = w * scale;
     float l = gd::center_pair_eval<float, LOSS, GRAD>(pr, lx, ly, t, a.dec, a.sum.pp, ws, g);
     if (a.sum.mask_zero_w && w == 0.0f) {
       l = 0.0f;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) gd_center_kernel(const CenterArgs a)
       for (int c = 7; c < a.g_cols; ++c) o[c] = 0.0f;   // dir / vel columns take no GD gradient
     }
   }
-  if (a.sum.loss_sum) finish_sum(acc, a.sum);
+  if (a.sum.loss_sum) finish_sum(acc, a.sum, scale);
 }
 
 template <int LOSS>
@@ -210,11 +213,12 @@ int launch_center(const CenterArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-static bool fill_sum(LossArgs* s, const gd_loss_config* cfg, float scale, float* loss_sum,
-                     void* workspace, size_t workspace_bytes, int32_t flags) {
+static bool fill_sum(LossArgs* s, const gd_loss_config* cfg, float scale, const float* scale_div,
+                     float* loss_sum, void* workspace, size_t workspace_bytes, int32_t flags) {
   if (loss_sum && (!workspace || workspace_bytes < gd_loss_workspace_bytes(0))) return false;
   *s = LossArgs{};
   s->scale = scale;
+  s->scale_div = scale_div;
   s->loss_sum = loss_sum;
   s->mask_zero_w = (flags & GD_FLAG_MASK_ZERO_WEIGHT) ? 1 : 0;
   s->ticket = reinterpret_cast<unsigned int*>(workspace);
@@ -246,8 +250,8 @@ int gd_anchor_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const float* ancho
                                    int64_t bbox_weights_row_stride,
                                    const float* decode_weight_host, const int64_t* pos_inds,
                                    int64_t num_pos, const int64_t* labels, int64_t num_classes,
-                                   int64_t total_rows, float scale, float* loss_sum,
-                                   float* grad_deltas, int32_t grad_mode, void* workspace,
+                                   int64_t total_rows, float scale, const float* scale_div,
+                                   float* loss_sum, float* grad_deltas, int32_t grad_mode, void* workspace,
                                    size_t workspace_bytes, int32_t flags, void* stream) {
   using namespace gdk;
   if (!config_ok(cfg) || total_rows < 0 || num_pos < 0 || anchor_rows <= 0 ||
@@ -266,7 +270,7 @@ int gd_anchor_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const float* ancho
   if (work > 0 && (!anchors || !deltas_pred || !deltas_target)) return GD_ERR_BAD_ARG;
   if (bbox_weights && !decode_weight_host) return GD_ERR_BAD_ARG;
   AnchorArgs a{};
-  if (!fill_sum(&a.sum, cfg, scale, loss_sum, workspace, workspace_bytes, flags))
+  if (!fill_sum(&a.sum, cfg, scale, scale_div, loss_sum, workspace, workspace_bytes, flags))
     return GD_ERR_WORKSPACE;
   if (work == 0 && !loss_sum) return 0;
   a.anchors = anchors;
@@ -295,7 +299,8 @@ int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_center_co
                                    const float* target, int64_t target_row_stride,
                                    const float* weight, int32_t weight_mode,
                                    int64_t weight_row_stride, int64_t n, float scale,
-                                   float* loss_sum, float* grad_preds, int64_t grad_row_stride,
+                                   const float* scale_div, float* loss_sum, float* grad_preds,
+                                   int64_t grad_row_stride,
                                    int32_t grad_cols, void* workspace, size_t workspace_bytes,
                                    int32_t flags, void* stream) {
   using namespace gdk;
@@ -306,7 +311,7 @@ int gd_center_decoded_loss_fwd_bwd(const gd_loss_config* cfg, const gd_center_co
     return GD_ERR_BAD_ARG;
   if (grad_preds && (grad_cols < 7 || grad_row_stride < grad_cols)) return GD_ERR_BAD_ARG;
   CenterArgs a{};
-  if (!fill_sum(&a.sum, cfg, scale, loss_sum, workspace, workspace_bytes, flags))
+  if (!fill_sum(&a.sum, cfg, scale, scale_div, loss_sum, workspace, workspace_bytes, flags))
     return GD_ERR_WORKSPACE;
   if (n == 0 && !loss_sum) return 0;
   a.preds = preds;

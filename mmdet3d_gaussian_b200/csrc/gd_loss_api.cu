@@ -58,12 +58,94 @@ __global__ void __launch_bounds__(kThreads) gd_scale_grad_rows_kernel(
 __global__ void __launch_bounds__(kThreads) gd_any_positive_kernel(const float* __restrict__ w,
                                                                    long long count,
                                                                    int* __restrict__ flag) {
+  // The answer is almost always "yes" after the first few elements: every CTA re-reads the
+  // flag (L2) before each grid-stride step and stops as soon as any CTA has set it, so the
+  // probe costs a few microseconds instead of a pass over the weights.
   const long long stride = (long long)gridDim.x * kThreads;
   bool any = false;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < count; i += stride) {
-    any |= (w[i] > 0.0f);
+  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < count; i0 += stride) {
+    if (*reinterpret_cast<volatile int*>(flag) != 0) return;      // CTA-uniform
+    const long long i = i0 + threadIdx.x;
+    if (i < count) any = w[i] > 0.0f;
+    if (__syncthreads_or(any)) {
+      if (threadIdx.x == 0) atomicOr(flag, 1);
+      return;
+    }
   }
-  if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// ref:290-292 decided on the device: *status == 0 (no weight element > 0) -> the outputs of
+// the fused launch are replaced by (pred * weight).sum() and its gradient `weight`.
+struct EarlyArgs {
+  const float* status;
+  const float* pred;
+  long long pstride;
+  const float* weight;
+  long long wrow, wcol;
+  long long nel;
+  float* loss_sum;
+  float* grad;
+  double* partials;
+  unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(kThreads) gd_early_return_kernel(const EarlyArgs e) {
+  if (__ldg(e.status) != 0.0f) return;     // the normal case: one launch, no traffic
+  __shared__ double s_part[kThreads / 32];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long stride = (long long)gridDim.x * kThreads;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * kThreads + tid; i < e.nel; i += stride) {
+    const long long r = i / 7;
+    const int c = (int)(i - r * 7);
+    const float w = e.weight[r * e.wrow + c * e.wcol];
+    acc += (double)(e.pred[r * e.pstride + c] * w);
+    if (e.grad) e.grad[i] = w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += s_part[w];
+    e.partials[blockIdx.x] = s;
+    __threadfence();
+    s_last = atomicAdd(e.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(e.partials + b);
+    *e.loss_sum = (float)tot;
+    *e.ticket = 0u;
+  }
+}
+
+// positives of the anchor head's labels mode; ticket[0] = CTA ticket, ticket[2] = count
+__global__ void __launch_bounds__(kThreads) gd_count_labels_kernel(
+    const long long* __restrict__ labels, long long total, long long num_classes,
+    float* __restrict__ out, unsigned int* ticket) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  unsigned int c = 0;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+    const long long lab = labels[i];
+    c += (lab >= 0 && lab < num_classes) ? 1u : 0u;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(ticket + 2, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned int tot = __ldcg(ticket + 2);
+      *out = (float)(tot > 0u ? tot : 1u);
+      ticket[2] = 0u;
+      ticket[0] = 0u;
+    }
+  }
 }
 
 extern template int launch_loss<gd::kGwd>(const LossArgs&, int, int, cudaStream_t);
@@ -93,49 +175,109 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg, const float* pred, int64_t pred_r
                     int32_t weight_mode, int64_t weight_row_stride, int64_t n, float scale,
                     float* loss_sum, float* row_loss, float* grad_pred, void* workspace,
                     size_t workspace_bytes, int32_t variant, int32_t flags, void* stream) {
+  gd_loss_io io{};
+  io.pred = pred;
+  io.pred_row_stride = pred_row_stride;
+  io.target = target;
+  io.target_row_stride = target_row_stride;
+  io.weight = weight;
+  io.weight_mode = weight_mode;
+  io.weight_row_stride = weight_row_stride;
+  io.n = n;
+  io.scale = scale;
+  io.loss_sum = loss_sum;
+  io.row_loss = row_loss;
+  io.grad_pred = grad_pred;
+  io.workspace = workspace;
+  io.workspace_bytes = workspace_bytes;
+  io.variant = variant;
+  io.flags = flags;
+  return gd_loss_launch(cfg, &io, stream);
+}
+
+int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream) {
   using namespace gdk;
-  if (!config_ok(cfg) || n < 0 || (flags & ~GD_FLAG_MASK_ZERO_WEIGHT) || weight_mode < GD_WEIGHT_NONE || weight_mode > GD_WEIGHT_ROW7 ||
-      variant < GD_VARIANT_AUTO || variant > GD_VARIANT_BULK_PACKED)
+  if (!io) return GD_ERR_BAD_ARG;
+  const int64_t n = io->n;
+  const int32_t weight_mode = io->weight_mode, variant = io->variant, flags = io->flags;
+  if (!config_ok(cfg) || n < 0 || (flags & ~GD_FLAG_MASK_ZERO_WEIGHT) ||
+      weight_mode < GD_WEIGHT_NONE || weight_mode > GD_WEIGHT_ROW7 || variant < GD_VARIANT_AUTO ||
+      variant > GD_VARIANT_BULK_ANY)
     return GD_ERR_BAD_ARG;
-  if (n > 0 && (!pred || !target || (weight_mode != GD_WEIGHT_NONE && !weight)))
+  if (n > 0 && (!io->pred || !io->target || (weight_mode != GD_WEIGHT_NONE && !io->weight)))
     return GD_ERR_BAD_ARG;
-  if (loss_sum && (!workspace || workspace_bytes < gd_loss_workspace_bytes(n)))
+  if (io->status && !io->loss_sum) return GD_ERR_BAD_ARG;
+  if (io->loss_sum && (!io->workspace || io->workspace_bytes < gd_loss_workspace_bytes(n)))
     return GD_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (n == 0 && !loss_sum) return 0;       // empty batch, nothing to write
+  if (n == 0 && !io->loss_sum) return 0;       // empty batch, nothing to write
   const int wcols = weight_mode == GD_WEIGHT_ROW7 ? 7 : 1;
-  const bool bulk_ok = pred_row_stride == 7 && target_row_stride == 7 && aligned16(pred) &&
-                       aligned16(target) &&
+  const bool out_ok = (!io->grad_pred || aligned16(io->grad_pred)) &&
+                      (!io->row_loss || aligned16(io->row_loss));
+  const bool bulk_ok = io->pred_row_stride == 7 && io->target_row_stride == 7 &&
+                       aligned16(io->pred) && aligned16(io->target) &&
                        (weight_mode == GD_WEIGHT_NONE ||
-                        (weight_row_stride == wcols && aligned16(weight))) &&
-                       (!grad_pred || aligned16(grad_pred)) &&
-                       (!row_loss || aligned16(row_loss)) && n >= 4;
+                        (io->weight_row_stride == wcols && aligned16(io->weight))) &&
+                       out_ok && n >= 4;
+
+  LossArgs a;
+  a.pred = io->pred;
+  a.target = io->target;
+  a.weight = io->weight;
+  a.pstride = io->pred_row_stride;
+  a.tstride = io->target_row_stride;
+  a.wstride = weight_mode == GD_WEIGHT_NONE ? 0 : io->weight_row_stride;
+  a.n = n;
+  a.wmode = weight_mode;
+  a.mask_zero_w = (flags & GD_FLAG_MASK_ZERO_WEIGHT) ? 1 : 0;
+  a.scale = io->scale;
+  a.scale_div = io->scale_div;
+  a.status = io->status;
+  a.loss_sum = io->loss_sum;
+  a.row_loss = io->row_loss;
+  a.grad = io->grad_pred;
+  a.ticket = reinterpret_cast<unsigned int*>(io->workspace);
+  a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(io->workspace) + 256);
+  a.pp = make_pair_params(*cfg);
+
+  // Row-strided / unaligned inputs: bulk copies of whole wide rows (GD_VARIANT_BULK_ANY) when
+  // the strides are sane and a useful number of warps fits the shared memory.
+  bool any_ok = false;
+  if (!bulk_ok && out_ok && n >= 16) {
+    const bool strides_ok =
+        a.pstride >= 7 && a.tstride >= 7 && a.pstride <= 64 && a.tstride <= 64 &&
+        (weight_mode == GD_WEIGHT_NONE || (a.wstride >= wcols && a.wstride <= 64)) &&
+        (reinterpret_cast<uintptr_t>(a.pred) & 3u) == 0 &&
+        (reinterpret_cast<uintptr_t>(a.target) & 3u) == 0 &&
+        (reinterpret_cast<uintptr_t>(a.weight) & 3u) == 0;
+    if (strides_ok) {
+      const WarpLayout L = warp_layout(4, weight_mode, a.grad != nullptr, a.row_loss != nullptr,
+                                       true, a.pstride, a.tstride, a.wstride);
+      any_ok = kSmemBudget / L.per_warp >= 6;
+    }
+  }
   // n == 0 with a loss_sum falls through to a 1-CTA staged launch that writes
   // scale * 0 (nan when scale is nan: torch's mean of an empty tensor).
   const bool want_bulk = variant == GD_VARIANT_BULK || variant == GD_VARIANT_BULK_R2 ||
                          variant == GD_VARIANT_BULK_PACKED;
   if (want_bulk && !bulk_ok) return GD_ERR_LAYOUT;
-  const int v = want_bulk ? variant
-                          : (variant == GD_VARIANT_AUTO && bulk_ok ? GD_VARIANT_BULK
-                                                                   : GD_VARIANT_STAGED);
-
-  LossArgs a;
-  a.pred = pred;
-  a.target = target;
-  a.weight = weight;
-  a.pstride = pred_row_stride;
-  a.tstride = target_row_stride;
-  a.wstride = weight_row_stride;
-  a.n = n;
-  a.wmode = weight_mode;
-  a.mask_zero_w = (flags & GD_FLAG_MASK_ZERO_WEIGHT) ? 1 : 0;
-  a.scale = scale;
-  a.loss_sum = loss_sum;
-  a.row_loss = row_loss;
-  a.grad = grad_pred;
-  a.ticket = reinterpret_cast<unsigned int*>(workspace);
-  a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + 256);
-  a.pp = make_pair_params(*cfg);
+  if (variant == GD_VARIANT_BULK_ANY && !(any_ok || (bulk_ok && n >= 16))) return GD_ERR_LAYOUT;
+  int v = variant;
+  if (variant == GD_VARIANT_AUTO)
+    v = bulk_ok ? ((GD_TUNE_DEFAULT & kTunePacked) ? GD_VARIANT_BULK_PACKED : GD_VARIANT_BULK)
+                : (any_ok ? GD_VARIANT_BULK_ANY : GD_VARIANT_STAGED);
+  if (v == GD_VARIANT_BULK_ANY) {
+    // rows [4, 4 + n_bulk) in tiles (>= 1 row stays behind them: the aligned copy window of
+    // the last tile may reach 12 bytes into the next row), the rest from global memory
+    a.row_lo = 4;
+    a.n_bulk = (n - 1 - a.row_lo) & ~3LL;
+    auto shift = [&](const float* base, long long stride) {
+      return (int)((reinterpret_cast<uintptr_t>(base + a.row_lo * stride) & 15u) >> 2);
+    };
+    a.pshift = shift(a.pred, a.pstride);
+    a.tshift = shift(a.target, a.tstride);
+    a.wshift = weight_mode == GD_WEIGHT_NONE ? 0 : shift(a.weight, a.wstride);
+  }
 
   switch (cfg->loss_type) {
     case GD_LOSS_GWD3D: return launch_loss<gd::kGwd>(a, v, kMaxGrid, st);
@@ -147,6 +289,36 @@ int gd_loss_fwd_bwd(const gd_loss_config* cfg, const float* pred, int64_t pred_r
     case GD_LOSS_KFIOU3D: return launch_loss<gd::kKfiou>(a, v, kMaxGrid, st);
   }
   return GD_ERR_BAD_ARG;
+}
+
+int gd_early_return_fix(const float* status, const float* pred, int64_t pred_row_stride,
+                        const float* weight, int64_t weight_row_stride, int64_t weight_col_stride,
+                        int64_t n, float* loss_sum, float* grad_pred, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  using namespace gdk;
+  if (!status || n < 0 || !loss_sum || (n > 0 && (!pred || !weight)) || weight_row_stride < 0 ||
+      weight_col_stride < 0)
+    return GD_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < gd_loss_workspace_bytes(n)) return GD_ERR_WORKSPACE;
+  EarlyArgs e;
+  e.status = status;
+  e.pred = pred;
+  e.pstride = pred_row_stride;
+  e.weight = weight;
+  e.wrow = weight_row_stride;
+  e.wcol = weight_col_stride;
+  e.nel = n * 7;
+  e.loss_sum = loss_sum;
+  e.grad = grad_pred;
+  e.ticket = reinterpret_cast<unsigned int*>(workspace);
+  e.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  long long grid = (e.nel + kThreads * 8 - 1) / (kThreads * 8);
+  const long long cap = (long long)device_info().sm_count * 4;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  gd_early_return_kernel<<<(int)grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
 }
 
 int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void* stream) {
@@ -204,6 +376,47 @@ int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* str
   const long long cap = (long long)device_info().sm_count * 8;
   if (grid > cap) grid = cap;
   gd_any_positive_kernel<<<(int)grid, kThreads, 0, st>>>(weight, count, flag);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gd_probe_event_create(void** event) {
+  if (!event) return GD_ERR_BAD_ARG;
+  cudaEvent_t ev;
+  const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) return (int)e;
+  *event = ev;
+  return 0;
+}
+
+int gd_probe_begin(const float* weight, int64_t count, int32_t* flag, int32_t* flag_host,
+                   void* event, void* stream) {
+  if (!flag_host || !event) return GD_ERR_BAD_ARG;
+  const int rc = gd_any_positive(weight, count, flag, stream);
+  if (rc != 0) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(flag_host, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), st);
+}
+
+int gd_probe_event_wait(void* event) {
+  if (!event) return GD_ERR_BAD_ARG;
+  return (int)cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event));
+}
+
+int gd_count_positive_labels(const int64_t* labels, int64_t total, int64_t num_classes, float* out,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace gdk;
+  if (total < 0 || !out || (total > 0 && !labels)) return GD_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < gd_loss_workspace_bytes(total)) return GD_ERR_WORKSPACE;
+  long long grid = (total + kThreads * 4 - 1) / (kThreads * 4);
+  const long long cap = (long long)device_info().sm_count * 4;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  gd_count_labels_kernel<<<(int)grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(labels), total, num_classes, out,
+      reinterpret_cast<unsigned int*>(workspace));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }

@@ -61,7 +61,7 @@ enum : int {
   kTuneGuardMinMax = 256,  // nice-row screen with FMNMX3.NAN instead of 16 compares
   kTuneStd = 512,          // specialised kernels assume alpha == 1, center_offset == (0,0,.5);
                            // any other value takes the run-time-parameter kernel
-  kTunePacked = 1024,      // GD_VARIANT_BULK (and 'auto') run the packed-FP32 math
+  kTunePacked = 1024,      // GD_VARIANT_AUTO runs the packed-FP32 math where it exists
 };
 constexpr int kDietGuards = (GD_TUNE_DEFAULT & kTuneGuardMinMax) ? gd::kDietGuards : 0;
 struct FullTile { static constexpr bool value = true; };
@@ -80,17 +80,34 @@ struct LossArgs {
   float* row_loss;
   float* grad;
   double* partials;                       // [grid]
-  unsigned int* ticket;                   // zero on entry, zero again on exit
+  unsigned int* ticket;                   // zero on entry, zero again on exit; ticket[1] = any-positive word
   gd::PairParams<float> pp;
   int tune = GD_TUNE_DEFAULT;             // only read by -DGD_TUNE=1 builds
+  // effective scale = scale / *scale_div when scale_div is given (avg_factor living on the
+  // device: gd_centerpoint_head.py:407 without its .item())
+  const float* scale_div = nullptr;
+  // nullable, 1 fp32 := any(weight > 0) ? 1 : 0 over every weight ELEMENT (ref:290), written by
+  // the last CTA together with loss_sum; consumed by gd_early_return_fix
+  float* status = nullptr;
+  // gd_warp_kernel<..., ANY = true> (row-strided and/or 16-byte-unaligned inputs): rows
+  // [row_lo, row_lo + n_bulk) go through the bulk-copy tiles, the <= 8 rows around them are
+  // read straight from global memory; *shift = words between the 16-byte aligned copy
+  // window and the first element of a tile (constant: tiles are multiples of 4 rows)
+  long long row_lo = 0, n_bulk = 0;
+  int pshift = 0, tshift = 0, wshift = 0;
 };
+
+__device__ __forceinline__ float effective_scale(const LossArgs& a) {
+  return a.scale_div ? a.scale / __ldg(a.scale_div) : a.scale;
+}
 
 // ---------------------------------------------------------------------------
 // deterministic grid-wide sum
 // ---------------------------------------------------------------------------
 constexpr int kMaxWarps = 32;
 
-__device__ __forceinline__ void finish_sum(float acc, const LossArgs& a) {
+__device__ __forceinline__ void finish_sum(float acc, const LossArgs& a, float scale,
+                                           bool any_pos = false) {
   __shared__ float s_warp[kMaxWarps];
   __shared__ double s_dwarp[kMaxWarps];
   __shared__ bool s_last;
@@ -98,11 +115,12 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a) {
   const int nwarps = (int)(blockDim.x >> 5), nthreads = (int)blockDim.x;
   acc = warp_sum(acc);
   if (lane == 0) s_warp[warp] = acc;
-  __syncthreads();
+  const int cta_any = __syncthreads_or(any_pos ? 1 : 0);     // also orders s_warp
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += (double)s_warp[w];
     a.partials[blockIdx.x] = s;
+    if (a.status && cta_any) atomicOr(a.ticket + 1, 1u);
     __threadfence();
     const unsigned int t = atomicAdd(a.ticket, 1u);
     s_last = (t == gridDim.x - 1);
@@ -118,7 +136,11 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a) {
     if (tid == 0) {
       double tot = 0.0;
       for (int w = 0; w < nwarps; ++w) tot += s_dwarp[w];
-      *a.loss_sum = (float)(tot * (double)a.scale);
+      *a.loss_sum = (float)(tot * (double)scale);
+      if (a.status) {
+        *a.status = __ldcg(a.ticket + 1) ? 1.0f : 0.0f;
+        a.ticket[1] = 0u;
+      }
       *a.ticket = 0u;                     // leave the workspace reusable
     }
   }
@@ -201,6 +223,9 @@ __global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
   __shared__ __align__(16) float s_w[kTile * 7];       // [N,7] weights only
   const int tid = threadIdx.x;
   const long long ntiles = (a.n + kTile - 1) / kTile;
+  const float scale = effective_scale(a);
+  const bool probe = a.status != nullptr;   // any(weight > 0) over every weight element, ref:290
+  bool anyp = false;
   float acc = 0.0f;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * kTile;
@@ -219,7 +244,15 @@ __global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
         t[c] = s_tgt[7 * tid + c];
       }
       const float w = (a.wmode == GD_WEIGHT_ROW7) ? row_weight_smem(s_w, a.wmode, tid) : w1;
-      acc += eval_row<LOSS, GRAD>(p, t, w, a.pp, a.scale, a.mask_zero_w != 0, g, &rl);
+      if (probe) {
+        if (a.wmode == GD_WEIGHT_ROW7) {
+#pragma unroll
+          for (int c = 0; c < 7; ++c) anyp |= s_w[7 * tid + c] > 0.0f;
+        } else if (a.wmode == GD_WEIGHT_ROW) {
+          anyp |= w > 0.0f;
+        }
+      }
+      acc += eval_row<LOSS, GRAD>(p, t, w, a.pp, scale, a.mask_zero_w != 0, g, &rl);
       if (a.row_loss) __stcs(a.row_loss + row0 + tid, rl);
       if (GRAD) {
 #pragma unroll
@@ -230,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
     if (GRAD) store_rows(a.grad, s_pred, 7, row0, rows, tid);
     __syncthreads();
   }
-  if (a.loss_sum) finish_sum(acc, a);
+  if (a.loss_sum) finish_sum(acc, a, scale, anyp);
 }
 
 // ---------------------------------------------------------------------------
@@ -239,20 +272,36 @@ __global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
 constexpr int kWarpStages = 2;
 
 struct WarpLayout {
+  int ptile;      // bytes of one pred tile
+  int ttile;      // bytes of one target tile
   int wtile;      // bytes of one weight tile
   int stage;      // bytes of one input stage (pred | target | weight)
   int out;        // bytes of the output buffer (grad | row loss)
-  int per_warp;   // shared memory bytes one warp needs
+  long long per_warp;   // shared memory bytes one warp needs
 };
 
+// Contiguous 16-byte aligned inputs (ANY = false): a tile of an array is `trows` packed
+// rows.  ANY = true: a tile is the 16-byte aligned window around `trows` rows of `stride`
+// floats each, up to 12 bytes of lead-in and 12 of round-up included.
+__host__ __device__ inline int any_tile_bytes(int trows, long long stride) {
+  return (int)(((long long)trows * stride * 4 + 16 + 15) & ~15LL);
+}
 __host__ __device__ inline WarpLayout warp_layout(int rows_per_lane, int wmode, bool grad,
-                                                  bool rows) {
+                                                  bool rows, bool any = false, long long ps = 7,
+                                                  long long ts = 7, long long wsd = 0) {
   const int trows = 32 * rows_per_lane;
   WarpLayout L;
-  L.wtile = wmode == GD_WEIGHT_ROW7 ? trows * kRowBytes : (wmode == GD_WEIGHT_ROW ? trows * 4 : 0);
-  L.stage = 2 * trows * kRowBytes + L.wtile;
+  if (any) {
+    L.ptile = any_tile_bytes(trows, ps);
+    L.ttile = any_tile_bytes(trows, ts);
+    L.wtile = wmode != GD_WEIGHT_NONE ? any_tile_bytes(trows, wsd) : 0;
+  } else {
+    L.ptile = L.ttile = trows * kRowBytes;
+    L.wtile = wmode == GD_WEIGHT_ROW7 ? trows * kRowBytes : (wmode == GD_WEIGHT_ROW ? trows * 4 : 0);
+  }
+  L.stage = L.ptile + L.ttile + L.wtile;
   L.out = (grad ? trows * kRowBytes : 0) + (rows ? trows * 4 : 0);
-  L.per_warp = kWarpStages * L.stage + L.out + 16;      // + two mbarriers
+  L.per_warp = (long long)kWarpStages * L.stage + L.out + 16;      // + two mbarriers
   return L;
 }
 
@@ -301,7 +350,13 @@ __device__ __forceinline__ void smem_store(float* dst, const float* src) {
 
 // PACK: the FAST math of two rows of a lane runs as one packed-FP32 (f32x2) stream
 // (gd_packed.cuh); needs an even R and one of the three headline losses.
-template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
+// ANY: inputs with any row stride (the CenterGDHead call site passes `[..., :7]` views of
+// 9- / 11-wide rows, gd_centerpoint_head.py:413-423) and any 4-byte alignment.  4 rows of
+// `stride` floats are 16 * stride bytes, so every tile of whole WIDE rows is still one
+// 1-D bulk copy once its start is rounded down to 16 bytes; the lanes pick columns 0..6 out
+// of shared memory (row lane + 32 k: bank = lane * stride mod 32, conflict free for odd
+// strides).  The gradient is contiguous [n,7] as always.
+template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false, bool ANY = false>
 __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const LossArgs a) {
 #if defined(GD_HOST_EMULATION)
   unsigned char* smem = emu_dynamic_smem();   // tests/host_math/loss_emul.cpp
@@ -319,6 +374,15 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   const bool want_rows = a.row_loss != nullptr;
   gd::PairParams<float> pp = a.pp;
   const bool mask_zero = a.mask_zero_w != 0;
+  const float scale = effective_scale(a);
+  const bool probe = a.status != nullptr;     // any(weight > 0), ref:290
+  bool anyp = false;
+  const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
+  // row strides in floats / lead-in words of a tile in shared memory
+  const int ps = ANY ? (int)a.pstride : 7, ts = ANY ? (int)a.tstride : 7;
+  const int wsd = ANY ? (int)a.wstride : wcols;
+  const int psh = ANY ? a.pshift : 0, tsh = ANY ? a.tshift : 0, wsh = ANY ? a.wshift : 0;
+  const long long row_lo = ANY ? a.row_lo : 0;
   if (SPEC >= 0) {
     pp.fun = SPEC & 3;
     pp.tau_on = (SPEC >> 2) & 1;
@@ -326,7 +390,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   }
   [[maybe_unused]] gd::PairParams<gd::f2> pp2;
   if constexpr (PACK) pp2 = gd::broadcast_params(pp);
-  const WarpLayout L = warp_layout(R, wmode, GRAD, want_rows);
+  const WarpLayout L = warp_layout(R, wmode, GRAD, want_rows, ANY, ps, ts, wsd);
   unsigned char* base = smem + (size_t)warp * L.per_warp;
   unsigned char* out_base = base + kWarpStages * L.stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_base + L.out);
@@ -334,7 +398,8 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   float* orow = reinterpret_cast<float*>(out_base + (GRAD ? kTileRows * kRowBytes : 0));
 
   // rows the bulk path can move: a multiple of 4 rows keeps every copy a multiple of 16 B
-  const long long n_main = a.n & ~3LL;
+  // (ANY: rows [row_lo, row_lo + n_main); tile row indices below are relative to row_lo)
+  const long long n_main = ANY ? a.n_bulk : (a.n & ~3LL);
   const int cta_warps = (int)(blockDim.x >> 5);
   const long long gwarp = (long long)blockIdx.x * cta_warps + warp;
   const long long nwarps = (long long)gridDim.x * cta_warps;
@@ -356,7 +421,6 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     *row0 = tail_base + gwarp * last_rows;
     return (int)min((long long)last_rows, n_main - *row0);
   };
-  const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
 #if GD_TUNE
   const int tune = a.tune;
 #else
@@ -379,13 +443,27 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     const uint32_t rows = (uint32_t)tile_of(i, &row0);
     const int s = i & (kWarpStages - 1);
     unsigned char* st = base + s * L.stage;
-    const uint32_t box_bytes = rows * kRowBytes;
-    const uint32_t w_bytes = wmode ? rows * wcols * 4u : 0u;
-    mbar_arrive_expect_tx(&bars[s], 2 * box_bytes + w_bytes);
-    bulk_load(st, a.pred + row0 * 7, box_bytes, &bars[s], policy);
-    bulk_load(st + kTileRows * kRowBytes, a.target + row0 * 7, box_bytes, &bars[s], policy);
-    if (wmode)
-      bulk_load(st + 2 * kTileRows * kRowBytes, a.weight + row0 * wcols, w_bytes, &bars[s], policy);
+    if constexpr (ANY) {
+      // 16-byte aligned window around the tile's wide rows: starts `shift` words before the
+      // first element and is rounded up; the bytes past the last row of the tile belong to
+      // the next row of the array, which exists (the host keeps >= 1 row behind n_bulk)
+      const long long g0 = row_lo + row0;
+      const uint32_t pb = (uint32_t)(((psh + rows * ps) * 4 + 15) & ~15);
+      const uint32_t tb = (uint32_t)(((tsh + rows * ts) * 4 + 15) & ~15);
+      const uint32_t wb = wmode ? (uint32_t)(((wsh + rows * wsd) * 4 + 15) & ~15) : 0u;
+      mbar_arrive_expect_tx(&bars[s], pb + tb + wb);
+      bulk_load(st, a.pred + g0 * ps - psh, pb, &bars[s], policy);
+      bulk_load(st + L.ptile, a.target + g0 * ts - tsh, tb, &bars[s], policy);
+      if (wmode) bulk_load(st + L.ptile + L.ttile, a.weight + g0 * wsd - wsh, wb, &bars[s], policy);
+    } else {
+      const uint32_t box_bytes = rows * kRowBytes;
+      const uint32_t w_bytes = wmode ? rows * wcols * 4u : 0u;
+      mbar_arrive_expect_tx(&bars[s], 2 * box_bytes + w_bytes);
+      bulk_load(st, a.pred + row0 * 7, box_bytes, &bars[s], policy);
+      bulk_load(st + kTileRows * kRowBytes, a.target + row0 * 7, box_bytes, &bars[s], policy);
+      if (wmode)
+        bulk_load(st + 2 * kTileRows * kRowBytes, a.weight + row0 * wcols, w_bytes, &bars[s], policy);
+    }
   };
 
   if (leader) {
@@ -403,25 +481,40 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     long long row0;
     const int rows = tile_of(i, &row0);
     const unsigned char* st = base + s * L.stage;
-    const float* sp = reinterpret_cast<const float*>(st);
-    const float* stg = reinterpret_cast<const float*>(st + kTileRows * kRowBytes);
-    const float* sw = reinterpret_cast<const float*>(st + 2 * kTileRows * kRowBytes);
+    const float* sp = reinterpret_cast<const float*>(st) + psh;
+    const float* stg = reinterpret_cast<const float*>(st + L.ptile) + tsh;
+    const float* sw = reinterpret_cast<const float*>(st + L.ptile + L.ttile) + wsh;
 
     mbar_wait(&bars[s], (uint32_t)((i / kWarpStages) & 1));
     // Lane l owns the R consecutive rows R*l .. R*l + R - 1 of the tile: 28 R contiguous
     // bytes per array, moved with 128-bit (R = 4) shared-memory accesses.  Rows past a
     // partial tile's end read stale shared memory; they are never redone or stored.
     float p[R][7], t[R][7], w[R];
-    if (tune & kTuneStrided) {
+    bool wpos[R];                          // any element of the row's weight > 0 (probe only)
+    const bool strided = ANY || (tune & kTuneStrided);
+    if (strided) {
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        const int r = lane + 32 * k;       // word 7r+c -> bank (7 lane + c) mod 32: conflict free
+        const int r = lane + 32 * k;       // word s*r+c -> bank (s lane + c) mod 32: conflict free, s odd
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
-          p[k][c] = sp[7 * r + c];
-          t[k][c] = stg[7 * r + c];
+          p[k][c] = sp[ps * r + c];
+          t[k][c] = stg[ts * r + c];
         }
-        w[k] = row_weight_smem(sw, wmode, r);
+        if (wmode == GD_WEIGHT_ROW7) {
+          float w7[7];
+#pragma unroll
+          for (int c = 0; c < 7; ++c) w7[c] = sw[wsd * r + c];
+          w[k] = row_weight_smem(w7, GD_WEIGHT_ROW7, 0);
+          wpos[k] = false;
+          if (probe) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) wpos[k] |= w7[c] > 0.0f;
+          }
+        } else {
+          w[k] = wmode == GD_WEIGHT_ROW ? sw[wsd * r] : 1.0f;
+          wpos[k] = w[k] > 0.0f;
+        }
       }
     } else {
       smem_load<7 * R>(&p[0][0], sp + 7 * R * lane);
@@ -432,10 +525,21 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         float w7[R][7];
         smem_load<7 * R>(&w7[0][0], sw + 7 * R * lane);
 #pragma unroll
-        for (int k = 0; k < R; ++k) w[k] = row_weight_smem(&w7[k][0], GD_WEIGHT_ROW7, 0);
+        for (int k = 0; k < R; ++k) {
+          w[k] = row_weight_smem(&w7[k][0], GD_WEIGHT_ROW7, 0);
+          wpos[k] = false;
+          if (probe) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) wpos[k] |= w7[k][c] > 0.0f;
+          }
+        }
       } else {
 #pragma unroll
         for (int k = 0; k < R; ++k) w[k] = 1.0f;
+      }
+      if (wmode != GD_WEIGHT_ROW7) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) wpos[k] = w[k] > 0.0f;
       }
     }
     // the previous tile's store must have finished READING the output buffer
@@ -447,7 +551,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     // straight-line block, so their instruction streams interleave; rows it flags
     // (clamped / degenerate extents, huge yaw, masked weight, ...) are redone on the
     // robust path.  FULL: every lane row is valid (all tiles but the warp's last one).
-    auto row_of = [&](int k) { return (tune & kTuneStrided) ? lane + 32 * k : R * lane + k; };
+    auto row_of = [&](int k) { return strided ? lane + 32 * k : R * lane + k; };
     auto eval_tile = [&](auto full_tag) {
       constexpr bool FULL = decltype(full_tag)::value;
       float g[R][7], rl[R], lw[R];
@@ -458,7 +562,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
         for (int k = 0; k < R; k += 2) {
           rare[k] = mask_zero && w[k] == 0.0f;
           rare[k + 1] = mask_zero && w[k + 1] == 0.0f;
-          const float ws0 = w[k] * a.scale, ws1 = w[k + 1] * a.scale;
+          const float ws0 = w[k] * scale, ws1 = w[k + 1] * scale;
           float l0, l1;
           gd::pair_eval_fast2<LOSS, GRAD, kDiet>(p[k], t[k], p[k + 1], t[k + 1], pp2, ws0, ws1, g[k],
                                           g[k + 1], &rare[k], &rare[k + 1], &l0, &l1);
@@ -475,7 +579,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         rare[k] = mask_zero && w[k] == 0.0f;
-        const float ws = w[k] * a.scale;
+        const float ws = w[k] * scale;
         float l;
         if (GD_TUNE && ((tune & kTuneNoMath) || ((tune & kTuneHalfMath) && k >= R / 2))) {
           l = p[k][0];
@@ -492,16 +596,19 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         if (rare[k])
-          lw[k] = eval_row<LOSS, GRAD>(p[k], t[k], w[k], pp, a.scale, mask_zero, g[k], &rl[k]);
+          lw[k] = eval_row<LOSS, GRAD>(p[k], t[k], w[k], pp, scale, mask_zero, g[k], &rl[k]);
       }
       late_wait(i);
 #pragma unroll
       for (int k = 0; k < R; ++k) {
-        if (FULL || row_of(k) < rows) acc += lw[k];
+        if (FULL || row_of(k) < rows) {
+          acc += lw[k];
+          anyp |= wpos[k];
+        }
       }
       // rows past the end of a partial tile are written to the staging buffer too (it
       // has room for a full tile); the bulk store below only moves `rows` rows
-      if (tune & kTuneStrided) {
+      if (strided) {
 #pragma unroll
         for (int k = 0; k < R; ++k) {
           const int r = lane + 32 * k;
@@ -523,41 +630,51 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       __syncwarp();                        // tile complete in shared memory
       if (GRAD) {                          // tile base is 16-B aligned, rows*7 a multiple of 4
         const float4* s4 = reinterpret_cast<const float4*>(og);
-        float4* g4 = reinterpret_cast<float4*>(a.grad + row0 * 7);
+        float4* g4 = reinterpret_cast<float4*>(a.grad + (row_lo + row0) * 7);
         const int nv = (rows * 7) >> 2;
         for (int j = lane; j < nv; j += 32) __stcs(g4 + j, s4[j]);
       }
       if (want_rows)
-        for (int j = lane; j < rows; j += 32) __stcs(a.row_loss + row0 + j, orow[j]);
+        for (int j = lane; j < rows; j += 32) __stcs(a.row_loss + row_lo + row0 + j, orow[j]);
       __syncwarp();                        // reads done before the next tile rewrites og
     } else if (L.out) {
       fence_proxy_async_smem();            // generic-proxy writes -> visible to the bulk engine
       __syncwarp();
       if (leader) {
         if (tune & kTuneStoreHint) {
-          if (GRAD) bulk_store_hint(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes, policy);
-          if (want_rows) bulk_store_hint(a.row_loss + row0, orow, (uint32_t)rows * 4u, policy);
+          if (GRAD) bulk_store_hint(a.grad + (row_lo + row0) * 7, og, (uint32_t)rows * kRowBytes, policy);
+          if (want_rows) bulk_store_hint(a.row_loss + row_lo + row0, orow, (uint32_t)rows * 4u, policy);
         } else {
-          if (GRAD) bulk_store(a.grad + row0 * 7, og, (uint32_t)rows * kRowBytes);
-          if (want_rows) bulk_store(a.row_loss + row0, orow, (uint32_t)rows * 4u);
+          if (GRAD) bulk_store(a.grad + (row_lo + row0) * 7, og, (uint32_t)rows * kRowBytes);
+          if (want_rows) bulk_store(a.row_loss + row_lo + row0, orow, (uint32_t)rows * 4u);
         }
         bulk_commit();
       }
     }
   }
 
-  // <= 3 leftover rows (n % 4): block 0 warp 0, straight from global memory
+  // leftover rows -- n % 4 <= 3 of them, or (ANY) the <= 4 rows in front of row_lo and the
+  // <= 4 behind row_lo + n_main: block 0 warp 0, straight from global memory
   if (blockIdx.x == 0 && tid < (int)(a.n - n_main)) {
-    const long long r = n_main + tid;
+    const long long r = tid < row_lo ? tid : n_main + tid;
     float p[7], t[7], g[7], rl, w = 1.0f;
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
-      p[c] = a.pred[r * 7 + c];
-      t[c] = a.target[r * 7 + c];
+      p[c] = a.pred[r * ps + c];
+      t[c] = a.target[r * ts + c];
     }
-    if (wmode == GD_WEIGHT_ROW) w = a.weight[r];
-    if (wmode == GD_WEIGHT_ROW7) w = row_weight_smem(a.weight + r * 7, GD_WEIGHT_ROW7, 0);
-    acc += eval_row<LOSS, GRAD>(p, t, w, pp, a.scale, mask_zero, g, &rl);
+    if (wmode == GD_WEIGHT_ROW) {
+      w = a.weight[r * wsd];
+      anyp |= w > 0.0f;
+    }
+    if (wmode == GD_WEIGHT_ROW7) {
+      w = row_weight_smem(a.weight + r * wsd, GD_WEIGHT_ROW7, 0);
+      if (probe) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) anyp |= a.weight[r * wsd + c] > 0.0f;
+      }
+    }
+    acc += eval_row<LOSS, GRAD>(p, t, w, pp, scale, mask_zero, g, &rl);
     if (GRAD) {
 #pragma unroll
       for (int c = 0; c < 7; ++c) a.grad[r * 7 + c] = g[c];
@@ -565,7 +682,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
     if (want_rows) a.row_loss[r] = rl;
   }
   if (leader && L.out) bulk_wait_all<0>();
-  if (a.loss_sum) finish_sum(acc, a);
+  if (a.loss_sum) finish_sum(acc, a, scale, anyp);
 }
 
 // ---------------------------------------------------------------------------
@@ -580,7 +697,7 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false>
+template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false, bool ANY = false>
 int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
 #if GD_TUNE
   LossArgs a = a_in;
@@ -588,7 +705,7 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
 #else
   const LossArgs& a = a_in;
 #endif
-  auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM, PACK>;
+  auto kern = gd_warp_kernel<LOSS, GRAD, R, SPEC, WM, PACK, ANY>;
   // opt in to the large dynamic shared memory once per device (function attributes are
   // per context); a racing second call sets the same value
   static bool attr_set[kMaxDevices] = {};
@@ -599,9 +716,10 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
-  const WarpLayout L = warp_layout(R, a.wmode, GRAD, a.row_loss != nullptr);
+  const WarpLayout L = warp_layout(R, a.wmode, GRAD, a.row_loss != nullptr, ANY, a.pstride,
+                                   a.tstride, a.wstride);
   constexpr int kWarpCap = R >= 4 ? 12 : 24;
-  int warps = kSmemBudget / L.per_warp;
+  int warps = (int)(kSmemBudget / L.per_warp);
   if (warps > kWarpCap) warps = kWarpCap;
 #if GD_TUNE
   if (const char* e = getenv("GD_TUNE_WARPS")) {
@@ -613,7 +731,7 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
   // Persistent: at most one CTA per SM with `warps` warps.  A batch too small to give
   // every such warp 32 rows uses fewer warps, spread over as many SMs as possible.
   const long long sms = device_info().sm_count;
-  const long long n_main = a.n & ~3LL;
+  const long long n_main = ANY ? a.n_bulk : (a.n & ~3LL);
   long long want = (n_main + 31) / 32;                    // warps that would get >= 32 rows
   if (want < 1) want = 1;
   long long grid = sms < max_grid ? sms : max_grid;
@@ -645,8 +763,7 @@ int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
   static_assert(!PACK || kHasSpec, "packed math exists for the specialised instantiations only");
   if constexpr (kHasSpec) {
     const gd::PairParams<float>& pp = a.pp;
-    bool spec_ok = pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p) &&
-                   a.wmode != GD_WEIGHT_ROW7 && !a.row_loss;
+    bool spec_ok = pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p);
     if (GD_TUNE_DEFAULT & kTuneStd)       // the specialised kernels bake these values in
       spec_ok = spec_ok && pp.alpha2 == 1.0f && pp.inv_alpha2 == 1.0f && pp.off[0] == 0.0f &&
                 pp.off[1] == 0.0f && pp.off[2] == 0.5f;
@@ -654,6 +771,10 @@ int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
       const int spec = pp.fun | (pp.tau_on << 2) | (1 << 3);
 #define GD_SPEC_CASE(S)                                                                 \
   case S:                                                                               \
+    if constexpr (!PACK) {                                                              \
+      if (a.wmode == GD_WEIGHT_ROW7)                                                    \
+        return launch_warp_inst<LOSS, GRAD, R, S, 2, PACK>(a, max_grid, stream);        \
+    }                                                                                   \
     return a.wmode == GD_WEIGHT_ROW                                                     \
                ? launch_warp_inst<LOSS, GRAD, R, S, 1, PACK>(a, max_grid, stream)       \
                : launch_warp_inst<LOSS, GRAD, R, S, 0, PACK>(a, max_grid, stream);
@@ -670,7 +791,6 @@ int launch_warp(const LossArgs& a, int max_grid, cudaStream_t stream) {
 template <int LOSS>
 int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t stream) {
   const bool grad = a.grad != nullptr;
-  if ((GD_TUNE_DEFAULT & kTunePacked) && variant == GD_VARIANT_BULK) variant = GD_VARIANT_BULK_PACKED;
   if (variant == GD_VARIANT_BULK) {
     return grad ? launch_warp<LOSS, true, 4>(a, max_grid, stream)
                 : launch_warp<LOSS, false, 4>(a, max_grid, stream);
@@ -679,7 +799,8 @@ int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t strea
     // packed math: gradient + one of the three headline losses; anything else (and any
     // configuration without a specialised instantiation) runs the scalar bulk kernel
     if constexpr (LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd) {
-      if (grad) return launch_warp<LOSS, true, 4, true>(a, max_grid, stream);
+      if (grad && a.wmode != GD_WEIGHT_ROW7 && !a.row_loss)
+        return launch_warp<LOSS, true, 4, true>(a, max_grid, stream);
     }
     return grad ? launch_warp<LOSS, true, 4>(a, max_grid, stream)
                 : launch_warp<LOSS, false, 4>(a, max_grid, stream);
@@ -687,6 +808,10 @@ int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t strea
   if (variant == GD_VARIANT_BULK_R2) {
     return grad ? launch_warp<LOSS, true, 2>(a, max_grid, stream)
                 : launch_warp<LOSS, false, 2>(a, max_grid, stream);
+  }
+  if (variant == GD_VARIANT_BULK_ANY) {
+    return grad ? launch_warp_inst<LOSS, true, 4, -1, -1, false, true>(a, max_grid, stream)
+                : launch_warp_inst<LOSS, false, 4, -1, -1, false, true>(a, max_grid, stream);
   }
   long long grid = (a.n + kTile - 1) / kTile;
   if (grid > max_grid) grid = max_grid;

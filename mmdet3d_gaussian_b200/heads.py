@@ -28,7 +28,8 @@ def _as_loss(cfg_or_module):
 
 
 def _scale(loss, avg_factor, count):
-    """mmdet ``weight_reduce_loss`` folded into one scalar."""
+    """mmdet ``weight_reduce_loss`` folded into one scalar for a
+    HOST ``avg_factor`` (the rule the shim applies; kept in Python for the CPU tests)."""
     if loss.reduction == 'none':
         raise NotImplementedError('the fused head losses return the reduced scalar only')
     if avg_factor is not None:
@@ -43,6 +44,22 @@ def _scale(loss, avg_factor, count):
     return loss.loss_weight / count if count > 0 else float('nan')
 
 
+def _scale_args(loss, avg_factor, count):
+    """(loss_weight, scale_mode, avg_factor) for the shim: mode 0 = final scale, 1 = divide by
+    ``avg_factor`` (number or device tensor), 2 = divide by the device-side count."""
+    if loss.reduction == 'none':
+        raise NotImplementedError('the fused head losses return the reduced scalar only')
+    if avg_factor is not None:
+        if loss.reduction == 'sum':
+            raise ValueError('avg_factor can not be used with reduction="sum"')
+        return loss.loss_weight, 1, avg_factor
+    if loss.reduction == 'sum':
+        return loss.loss_weight, 0, None
+    if count is None:
+        return loss.loss_weight, 2, None
+    return (loss.loss_weight / count if count > 0 else float('nan')), 0, None
+
+
 class GDAnchorHeadLoss(nn.Module):
     """``loss_bbox`` contribution of the decoded-box GD loss in
     ``GDAnchor3DHead.loss_single`` (gd_anchor3d_head.py:102-141).
@@ -53,6 +70,11 @@ class GDAnchorHeadLoss(nn.Module):
     * ``pos_inds`` (int64 ``[P]``): the reference's ``nonzero`` result (:102-105);
     * ``labels`` (int64 ``[T]``) + ``num_classes``: positives are decided inside the
       kernel -- no ``nonzero``, no device->host sync, CUDA-graph capturable (f4).
+
+    ``avg_factor``: a number, a one-element CUDA tensor (read by the kernel, no sync) or None.
+    None with ``reduction='mean'`` averages over the positives like the reference's
+    ``loss.mean()``: their number is ``len(pos_inds)``, or in ``labels`` mode counted ON THE
+    DEVICE (``gd_count_positive_labels``; at least 1, so no positives give 0, :160-161).
 
     ``decode_weight`` is ``train_cfg['decode_weight']`` (:128-131): falsy -> no
     weights; a scalar or 7 values -> row weight
@@ -71,15 +93,15 @@ class GDAnchorHeadLoss(nn.Module):
         loss = self.loss_decoded_bbox
         extra = dict(loss.kwargs)
         extra.update(kwargs)
-        cfg = loss._config(extra)
+        cfg = loss._shim_config(extra)
         count = int(pos_inds.numel()) if pos_inds is not None else None
-        scale = _scale(loss, avg_factor, count)
+        lw, mode, avg = _scale_args(loss, avg_factor, count)
         dw = self.decode_weight if self.decode_weight else None
         return ops.anchor_decoded_loss(
             anchors, bbox_pred.reshape(-1, bbox_pred.shape[-1]),
             bbox_targets.reshape(-1, bbox_targets.shape[-1]),
             None if bbox_weights is None else bbox_weights.reshape(-1, bbox_weights.shape[-1]),
-            dw, cfg, scale, pos_inds=pos_inds, labels=labels, num_classes=num_classes)
+            dw, cfg, lw, mode, avg, pos_inds=pos_inds, labels=labels, num_classes=num_classes)
 
 
 class GDCenterHeadLoss(nn.Module):
@@ -92,19 +114,29 @@ class GDCenterHeadLoss(nn.Module):
     ``type`` / ``code_size`` are ignored).
     ``forward(pred [P,C], pos_ind [P,3] int64, target_box [P,>=7], weight=None,
     avg_factor=None)``; the gradient w.r.t. ``pred`` has zeros in columns >= 7.
+    ``avg_factor`` may be a one-element CUDA tensor -- e.g.
+    ``heatmap.eq(1).float().sum().clamp(min=1)`` WITHOUT the reference's ``.item()`` (:407):
+    the kernel divides by it, the call never syncs and captures into a CUDA graph.
     """
 
     def __init__(self, loss_gd, bbox_coder):
         super().__init__()
         self.loss_gd = _as_loss(loss_gd)
-        self.coder = _lib.make_center_coder(bbox_coder['pc_range'], bbox_coder['out_size_factor'],
-                                            bbox_coder['voxel_size'],
-                                            bbox_coder.get('norm_bbox', True))
+        self._coder_args = (tuple(bbox_coder['pc_range']), bbox_coder['out_size_factor'],
+                            tuple(bbox_coder['voxel_size']), bbox_coder.get('norm_bbox', True))
+        self._coder = None
+
+    @property
+    def coder(self):
+        if self._coder is None:
+            self._coder = _lib.make_shim_center_coder(*self._coder_args)
+        return self._coder
 
     def forward(self, pred, pos_ind, target_box, weight=None, avg_factor=None, **kwargs):
         loss = self.loss_gd
         extra = dict(loss.kwargs)
         extra.update(kwargs)
-        cfg = loss._config(extra)
-        scale = _scale(loss, avg_factor, int(pred.shape[0]))
-        return ops.center_decoded_loss(pred, pos_ind, target_box, weight, self.coder, cfg, scale)
+        cfg = loss._shim_config(extra)
+        lw, mode, avg = _scale_args(loss, avg_factor, int(pred.shape[0]))
+        return ops.center_decoded_loss(pred, pos_ind, target_box, weight, self.coder, cfg, lw,
+                                       mode, avg)

@@ -26,8 +26,9 @@ _FLAG = {'gwd3d': ('normalize', True),        # ref:43
 
 
 def _scale_and_mode(reduction, avg_factor, n, loss_weight):
-    """mmdet ``weight_reduce_loss`` folded into one scalar.
-    Returns (scale, rows_out)."""
+    """mmdet ``weight_reduce_loss`` folded into one scalar, as the
+    C++ shim applies it (``csrc/torch_shim.cpp``; this Python statement of the rule is what
+    the CPU tests check).  Returns (scale, rows_out)."""
     if avg_factor is None:
         if reduction == 'mean':
             # loss.mean(): divides by N (not by sum of weights); mean of empty is nan
@@ -50,18 +51,26 @@ class GDLoss(nn.Module):
     distance: ``normalize`` for ``gwd3d``, ``sqrt`` for the others.  Two extra,
     backwards-compatible keys are consumed here and never reach the distance:
 
-    * ``variant`` ('auto' | 'staged' | 'bulk' | 'bulk_packed') selects the kernel variant
-      ('bulk_packed' = packed-FP32 math, opt-in, never chosen by 'auto');
-    * ``host_sync`` (default True).  True keeps the reference's early return
-      (ref:290-292) exactly, including its device->host sync
-      (``torch.any(weight > 0)``).  False never syncs: rows whose weight is exactly
-      0 are masked inside the kernel (0 loss, 0 gradient).  For non-negative
-      weights the two agree on every finite row; the all-zero batch returns 0
-      with zero gradients either way.
-      ``'overlap'`` (opt-in, not GPU-validated yet) has the semantics of True but queues
-      the fused kernel speculatively BEFORE the host waits for the probe, so the GPU
-      does not idle during the sync; the speculative result is dropped in the (rare)
-      early-return case.
+    * ``variant`` ('auto' | 'staged' | 'bulk' | 'bulk_packed' | 'bulk_any') pins the kernel
+      variant (tests / measurements; 'auto' picks the fastest one the layout allows);
+    * ``host_sync`` (default True).  True = the reference's semantics exactly, early return
+      (ref:290-292) included, WITHOUT stalling the GPU: for ``[N,7]`` weights (the KITTI head's
+      call, ``gd_anchor3d_head.py:128-141``) and wherever else ``pred * weight`` has the shape
+      of ``pred``, ``any(weight > 0)`` is evaluated inside the fused launch and a second, tiny
+      launch swaps in ``(pred * weight).sum()`` / ``grad = weight`` when it is false -- no
+      host involvement at all, CUDA-graph capturable.  For other ``[N]`` weights the
+      reference RAISES a broadcasting error when the branch is taken, so the host must learn
+      the answer: a probe kernel and a 4-byte copy are queued, the fused launch is queued
+      right behind them, and only then does the host wait for the probe -- the GPU never
+      idles.  ``weight=None`` and ``reduction='none'`` never probe (as the reference).
+      False never waits and never raises: rows whose weight is exactly 0 are masked inside
+      the kernel (0 loss, 0 gradient, even where the distance is inf/nan); for non-negative
+      weights the value and gradient equal the reference's on every finite row.
+      ``'overlap'`` is accepted as an alias of True (round-1 name of this behaviour).
+
+    ``avg_factor`` may be a Python number or a one-element CUDA tensor; the tensor is read by
+    the kernel (no ``.item()``), which is what lets the heads drop their host syncs
+    (``gd_centerpoint_head.py:407``).
     """
 
     BAG_GD_LOSS = tuple(_lib.LOSS_TYPES)          # ref:253-259
@@ -84,23 +93,37 @@ class GDLoss(nn.Module):
         self.loss_weight = loss_weight
         self.variant = kwargs.pop('variant', 'auto')
         hs = kwargs.pop('host_sync', True)
-        self.host_sync = hs if hs == 'overlap' else bool(hs)
+        self.host_sync = True if hs == 'overlap' else bool(hs)
         self.kwargs = kwargs                                      # ref:278
         self._cfg_cache = {}
 
-    def _config(self, extra):
+    def _key(self, extra):
         name, default = _FLAG[self.loss_type]
-        unknown = set(extra) - {name}
-        if unknown:
-            # the reference forwards **kwargs into the distance function, which
-            # raises TypeError on names it does not accept (ref:301-310)
-            raise TypeError(f'{self.loss_type}_loss() got an unexpected keyword '
-                            f'argument {sorted(unknown)[0]!r}')
-        key = (self.loss_type, self.fun, bool(extra.get(name, default)), float(self.tau),
-               float(self.alpha), tuple(float(x) for x in self.center_offset))
+        if extra:
+            unknown = set(extra) - {name}
+            if unknown:
+                # the reference forwards **kwargs into the distance function, which
+                # raises TypeError on names it does not accept (ref:301-310)
+                raise TypeError(f'{self.loss_type}_loss() got an unexpected keyword '
+                                f'argument {sorted(unknown)[0]!r}')
+            default = bool(extra.get(name, default))
+        return (self.loss_type, self.fun, default, float(self.tau), float(self.alpha),
+                tuple(self.center_offset))
+
+    def _config(self, extra):
+        """ctypes ``gd_loss_config`` (pairwise / direct C-ABI callers)."""
+        key = ('c',) + self._key(extra)
         cfg = self._cfg_cache.get(key)
         if cfg is None:
-            cfg = self._cfg_cache[key] = _lib.make_config(*key)
+            cfg = self._cfg_cache[key] = _lib.make_config(*key[1:])
+        return cfg
+
+    def _shim_config(self, extra):
+        """``gd_loss_config`` held by the C++ shim."""
+        key = self._key(extra)
+        cfg = self._cfg_cache.get(key)
+        if cfg is None:
+            cfg = self._cfg_cache[key] = _lib.make_shim_config(*key)
         return cfg
 
     def forward(self, pred, target, weight=None, avg_factor=None,
@@ -108,40 +131,15 @@ class GDLoss(nn.Module):
         assert reduction_override in (None, 'none', 'mean', 'sum')   # ref:287
         reduction = (
             reduction_override if reduction_override else self.reduction)  # ref:288-289
-        if self.host_sync == 'overlap' and (weight is not None) and (reduction != 'none'):
-            return self._forward_overlapped(pred, target, weight, avg_factor, reduction, kwargs)
-        if self.host_sync and (weight is not None) and (reduction != 'none') and (
-                not ops.any_positive(weight)):                    # ref:290-291
-            return (pred * weight).sum()                          # ref:292
-        _kwargs = deepcopy(self.kwargs) if (self.kwargs or kwargs) else {}   # ref:293
-        _kwargs.update(kwargs)                                    # ref:294
-        cfg = self._config(_kwargs)
-        n = pred.numel() // 7
-        scale, rows_out = _scale_and_mode(reduction, avg_factor, n, self.loss_weight)
-        return ops.gd_loss(pred, target, weight, cfg, scale, rows_out=rows_out,
-                           variant=self.variant,
+        if self.kwargs or kwargs:
+            _kwargs = deepcopy(self.kwargs)                       # ref:293
+            _kwargs.update(kwargs)                                # ref:294
+        else:
+            _kwargs = None
+        # ref:290-292 (early return), ref:295-310 and mmdet's weighted_loss: in the shim
+        return ops.gd_loss(pred, target, weight, self._shim_config(_kwargs), self.loss_weight,
+                           reduction, avg_factor, self.variant,
                            mask_zero_weight=not self.host_sync)
-
-    def _forward_overlapped(self, pred, target, weight, avg_factor, reduction, kwargs):
-        """``host_sync='overlap'``: same decision as ref:290-292, but the fused launch is
-        queued before the host blocks on the probe."""
-        probe = ops.any_positive_begin(weight)
-        out, err = None, None
-        try:
-            _kwargs = deepcopy(self.kwargs) if (self.kwargs or kwargs) else {}
-            _kwargs.update(kwargs)
-            cfg = self._config(_kwargs)
-            scale, rows_out = _scale_and_mode(reduction, avg_factor, pred.numel() // 7,
-                                              self.loss_weight)
-            out = ops.gd_loss(pred, target, weight, cfg, scale, rows_out=rows_out,
-                              variant=self.variant, mask_zero_weight=False)
-        except Exception as e:                # raised only if the early return does not apply
-            err = e
-        if not probe.result():                                    # ref:290-291
-            return (pred * weight).sum()                          # ref:292
-        if err is not None:
-            raise err
-        return out
 
     def extra_repr(self):
         return (f'loss_type={self.loss_type!r}, fun={self.fun!r}, tau={self.tau}, '

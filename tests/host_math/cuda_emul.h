@@ -39,6 +39,7 @@ struct EmuCta {
   };
   std::barrier<> all;
   std::vector<std::unique_ptr<Warp>> warps;
+  int vote = 0;
 };
 static EmuCta* g_cta = nullptr;
 alignas(128) static unsigned char g_emu_smem[228 * 1024];
@@ -46,6 +47,15 @@ alignas(128) static unsigned char g_emu_smem[228 * 1024];
 static inline unsigned char* emu_dynamic_smem() { return g_emu_smem; }
 static inline void emu_yield() { std::this_thread::yield(); }
 static inline void __syncthreads() { g_cta->all.arrive_and_wait(); }
+static inline int __syncthreads_or(int p) {
+  if (p) __atomic_fetch_or(&g_cta->vote, 1, __ATOMIC_SEQ_CST);
+  g_cta->all.arrive_and_wait();
+  const int r = __atomic_load_n(&g_cta->vote, __ATOMIC_SEQ_CST);
+  g_cta->all.arrive_and_wait();
+  if (threadIdx.x == 0) g_cta->vote = 0;
+  g_cta->all.arrive_and_wait();
+  return r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline EmuCta::Warp& emu_warp() { return *g_cta->warps[threadIdx.x >> 5]; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp().bar.arrive_and_wait(); }
@@ -118,6 +128,11 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
   }
   return old;
 }
+static inline unsigned atomicOr(unsigned* p, unsigned v) {
+  return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST);
+}
+static inline unsigned __ldcg(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline float __ldg(const float* p) { return *p; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) {
   return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
 }

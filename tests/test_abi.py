@@ -25,7 +25,7 @@ def test_library_is_in_tree_and_current(lib):
     assert _lib.loaded_path() == build_ext.lib_path()
     assert os.path.dirname(_lib.loaded_path()).endswith('mmdet3d_gaussian_b200')
     assert build_ext.is_current()
-    assert lib.gd_abi_version() == 1
+    assert lib.gd_abi_version() == 2
 
 
 def test_every_declared_symbol_is_exported(lib):
@@ -57,13 +57,13 @@ def test_sass_is_sm100a_with_bulk_copies():
                          text=True).stdout
     assert 'sm_100a' in elf
     sass = subprocess.run([cuobjdump, '-sass', '-fun',
-                           '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1ELb0EEEvNS_8LossArgsE',
+                           '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1ELb0ELb0EEEvNS_8LossArgsE',
                            build_ext.lib_path()], capture_output=True, text=True).stdout
     assert 'UBLKCP' in sass and 'SYNCS' in sass
     assert 'LDS.128' in sass and 'STS.128' in sass and 'FFMA2' not in sass
     # the opt-in packed variant of the same kernel uses the packed FP32 pipe instructions
     packed = subprocess.run([cuobjdump, '-sass', '-fun',
-                             '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1ELb1EEEvNS_8LossArgsE',
+                             '_ZN3gdk14gd_warp_kernelILi1ELb1ELi4ELi9ELi1ELb1ELb0EEEvNS_8LossArgsE',
                              build_ext.lib_path()], capture_output=True, text=True).stdout
     assert 'FFMA2' in packed and 'FMUL2' in packed and 'UBLKCP' in packed
 
@@ -147,7 +147,7 @@ def test_head_front_end_argument_validation_without_gpu(lib):
     def call_anchor(pos=one, npos=4, labels=null, grad=one, mode=_lib.GRAD_SCATTER, bw=null,
                     dwp=None, arows=4, loss=null, ws=null, wsb=0, total=16):
         return anchor(ctypes.byref(cfg), one, arows, one, 7, one, 7, bw, 7, dwp, pos, npos,
-                      labels, 3, total, 1.0, loss, grad, mode, ws, wsb, 0, null)
+                      labels, 3, total, 1.0, null, loss, grad, mode, ws, wsb, 0, null)
     # well-formed empty calls are accepted in every mode (nothing is launched)
     assert call_anchor(pos=null, npos=0, labels=one, mode=_lib.GRAD_DENSE, total=0) == 0
     assert call_anchor(npos=0, mode=_lib.GRAD_SCATTER) == 0
@@ -170,7 +170,7 @@ def test_head_front_end_argument_validation_without_gpu(lib):
     def call_center(c=ctypes.byref(coder), preds=one, n=4, wmode=0, w=null, grad=one, gstride=11,
                     gcols=11, loss=null):
         return center(ctypes.byref(cfg), c, preds, 11, one, 3, one, 11, w, wmode, 1, n, 1.0,
-                      loss, grad, gstride, gcols, null, 0, 0, null)
+                      null, loss, grad, gstride, gcols, null, 0, 0, null)
     assert call_center(c=None) == -1
     assert call_center(preds=null) == -1
     assert call_center(n=-1) == -1
