@@ -266,18 +266,7 @@ int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream
   if (variant == GD_VARIANT_AUTO)
     v = bulk_ok ? ((GD_TUNE_DEFAULT & kTunePacked) ? GD_VARIANT_BULK_PACKED : GD_VARIANT_BULK)
                 : (any_ok ? GD_VARIANT_BULK_ANY : GD_VARIANT_STAGED);
-  if (v == GD_VARIANT_BULK_ANY) {
-    // rows [4, 4 + n_bulk) in tiles (>= 1 row stays behind them: the aligned copy window of
-    // the last tile may reach 12 bytes into the next row), the rest from global memory
-    a.row_lo = 4;
-    a.n_bulk = (n - 1 - a.row_lo) & ~3LL;
-    auto shift = [&](const float* base, long long stride) {
-      return (int)((reinterpret_cast<uintptr_t>(base + a.row_lo * stride) & 15u) >> 2);
-    };
-    a.pshift = shift(a.pred, a.pstride);
-    a.tshift = shift(a.target, a.tstride);
-    a.wshift = weight_mode == GD_WEIGHT_NONE ? 0 : shift(a.weight, a.wstride);
-  }
+  if (v == GD_VARIANT_BULK_ANY) plan_any(&a);
 
   switch (cfg->loss_type) {
     case GD_LOSS_GWD3D: return launch_loss<gd::kGwd>(a, v, kMaxGrid, st);

@@ -822,6 +822,22 @@ int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t strea
 
 #endif  // !GD_HOST_EMULATION
 
+// Tile plan of gd_warp_kernel<..., ANY = true>: rows [4, 4 + n_bulk) in tiles (>= 1 row stays
+// behind them: the 16-byte aligned copy window of the last tile may reach 12 bytes into the
+// next row, and the window of the first tile up to 12 bytes into row 3), the <= 8 rows around
+// them straight from global memory; the lead-in words of each array are constant because
+// tiles start at multiples of 4 rows (16 * stride bytes).  Needs n >= 16.
+inline void plan_any(LossArgs* a) {
+  a->row_lo = 4;
+  a->n_bulk = (a->n - 1 - a->row_lo) & ~3LL;
+  auto shift = [&](const float* base, long long stride) {
+    return (int)((reinterpret_cast<uintptr_t>(base + a->row_lo * stride) & 15u) >> 2);
+  };
+  a->pshift = shift(a->pred, a->pstride);
+  a->tshift = shift(a->target, a->tstride);
+  a->wshift = a->wmode == GD_WEIGHT_NONE ? 0 : shift(a->weight, a->wstride);
+}
+
 constexpr int kMaxGrid = 65536;           // partials capacity of the workspace
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

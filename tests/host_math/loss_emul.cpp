@@ -103,3 +103,66 @@ extern "C" int gd_emul_loss(int loss, int kind, int spec, int pack, int grid, in
 }
 
 extern "C" int gd_emul_tune_default() { return GD_TUNE_DEFAULT; }
+
+// gd_warp_kernel<LOSS, GRAD, 4, -1, -1, false, ANY = true>: row-strided / unaligned inputs,
+// plus the device-side scale divisor and the any-positive status word.  The plan (row_lo,
+// n_bulk, shifts) is the library's own (gdk::plan_any).  ws = {ticket, any word}.
+template <int LOSS>
+static void run_any(const gdk::LossArgs& a, int grid, int warps) {
+  const gdk::WarpLayout L = gdk::warp_layout(4, a.wmode, a.grad != nullptr, a.row_loss != nullptr,
+                                             true, a.pstride, a.tstride, a.wstride);
+  const int fit = (int)((long long)gdk::kSmemBudget / L.per_warp);   // as launch_warp_inst
+  if (warps > fit) warps = fit;
+  if (warps < 1) return;
+  if (a.grad) emu_launch(gdk::gd_warp_kernel<LOSS, true, 4, -1, -1, false, true>, (unsigned)grid, 1, warps * 32, a);
+  else emu_launch(gdk::gd_warp_kernel<LOSS, false, 4, -1, -1, false, true>, (unsigned)grid, 1, warps * 32, a);
+}
+
+extern "C" int gd_emul_loss_any(int loss, int kind, int grid, int warps, const float* pred,
+                                long long pstride, const float* target, long long tstride,
+                                const float* weight, int wmode, long long wstride, long long n,
+                                float scale, const float* scale_div, float tau, float* status,
+                                float* loss_sum, float* row_loss, float* grad) {
+  gd_loss_config cfg{};
+  cfg.loss_type = loss;
+  cfg.fun = GD_FUN_LOG1P;
+  cfg.flag = 1;
+  cfg.tau = tau;
+  cfg.alpha = 1.0f;
+  cfg.center_offset[2] = 0.5f;
+  std::vector<double> partials((size_t)grid + 1, 0.0);
+  unsigned ws[4] = {0, 0, 0, 0};
+  gdk::LossArgs a{};
+  a.pred = pred;
+  a.target = target;
+  a.weight = weight;
+  a.pstride = pstride;
+  a.tstride = tstride;
+  a.wstride = wmode == GD_WEIGHT_NONE ? 0 : wstride;
+  a.n = n;
+  a.wmode = wmode;
+  a.scale = scale;
+  a.scale_div = scale_div;
+  a.status = status;
+  a.loss_sum = loss_sum;
+  a.row_loss = row_loss;
+  a.grad = grad;
+  a.partials = partials.data();
+  a.ticket = ws;
+  a.pp = gdk::make_pair_params(cfg);
+  a.tune = GD_TUNE_DEFAULT;
+  if (kind == 1) {
+    if (n < 16) return 1;
+    gdk::plan_any(&a);
+    if (loss == 0) run_any<0>(a, grid, warps);
+    else if (loss == 1) run_any<1>(a, grid, warps);
+    else if (loss == 5) run_any<5>(a, grid, warps);
+    else return 1;
+  } else {
+    if (loss == 0) run_loss<0>(a, 0, -1, 0, grid, warps);
+    else if (loss == 1) run_loss<1>(a, 0, -1, 0, grid, warps);
+    else if (loss == 5) run_loss<5>(a, 0, -1, 0, grid, warps);
+    else return 1;
+  }
+  return (ws[0] != 0 || ws[1] != 0) ? 2 : 0;
+}

@@ -175,6 +175,106 @@ def test_anchor_head_mask_mode_is_graph_capturable():
     assert torch.equal(cap_grad, eager_grad)
 
 
+def test_anchor_head_labels_mode_counts_positives_on_the_device():
+    """labels mode, reduction='mean', no avg_factor: the mean runs over the positives like the
+    reference's loss.mean() over the gathered rows (gd_anchor3d_head.py:102-141), their number
+    counted on the device -- equal to the index mode, where the host knows len(pos_inds); no
+    positives give 0; a device-tensor avg_factor equals the same number passed from the host.
+    All of it captures into one CUDA graph."""
+    kw = CONFIGS[0]
+    b = synth.make_anchor_head_batch(50_000, 20_000, pos_frac=0.01, seed=13)
+    g = cuda(b)
+    head = GDAnchorHeadLoss(dict(type='GDLoss', **kw), 1)
+    ref_loss, ref_grad = oracle_anchor(kw, b, 1, None)           # mean over the P positives
+    bp = g['bbox_pred'].clone().requires_grad_(True)
+    loss = head(g['anchors'], bp, g['bbox_targets'], g['bbox_weights'], labels=g['labels'],
+                num_classes=3)
+    loss.backward()
+    check(loss.item(), bp.grad.cpu().double().numpy(), ref_loss, ref_grad, 'device count')
+    bp2 = g['bbox_pred'].clone().requires_grad_(True)
+    loss2 = head(g['anchors'], bp2, g['bbox_targets'], g['bbox_weights'], pos_inds=g['pos_inds'])
+    loss2.backward()
+    assert abs(loss.item() - loss2.item()) <= 2e-6 * abs(loss2.item())
+    assert torch.allclose(bp.grad, bp2.grad, rtol=2e-6, atol=0)
+    # device avg_factor == host avg_factor
+    af = torch.tensor([123.0], device='cuda')
+    l_dev = head(g['anchors'], g['bbox_pred'], g['bbox_targets'], g['bbox_weights'],
+                 labels=g['labels'], num_classes=3, avg_factor=af)
+    l_host = head(g['anchors'], g['bbox_pred'], g['bbox_targets'], g['bbox_weights'],
+                  labels=g['labels'], num_classes=3, avg_factor=123.0)
+    assert abs(l_dev.item() - l_host.item()) <= 2e-7 * abs(l_host.item())
+    # no positives
+    bp3 = g['bbox_pred'].clone().requires_grad_(True)
+    l0 = head(g['anchors'], bp3, g['bbox_targets'], g['bbox_weights'],
+              labels=torch.full((50_000,), 3, device='cuda'), num_classes=3)
+    l0.backward()
+    assert l0.item() == 0.0 and float(bp3.grad.abs().sum()) == 0.0
+    # graph capture with the device-side count; replay after the labels changed
+    labels = g['labels'].clone()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        bps = g['bbox_pred'].clone().requires_grad_(True)
+        torch.autograd.grad(head(g['anchors'], bps, g['bbox_targets'], g['bbox_weights'],
+                                 labels=labels, num_classes=3), bps)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            cl = head(g['anchors'], bps, g['bbox_targets'], g['bbox_weights'], labels=labels,
+                      num_classes=3)
+            cg, = torch.autograd.grad(cl, bps)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert cl.item() == loss.item() and torch.equal(cg, bp.grad)
+    labels[b['pos_inds'][::2].cuda()] = 3                         # drop every other positive
+    graph.replay()
+    torch.cuda.synchronize()
+    bp4 = g['bbox_pred'].clone().requires_grad_(True)
+    l4 = head(g['anchors'], bp4, g['bbox_targets'], g['bbox_weights'], labels=labels, num_classes=3)
+    l4.backward()
+    assert cl.item() == l4.item() and torch.equal(cg, bp4.grad)
+    assert abs(l4.item() - loss.item()) > 1e-4 * abs(loss.item())
+
+
+def test_center_head_is_graph_capturable_with_device_avg_factor():
+    """CenterGDHead.loss computes avg_factor as heatmap.eq(1).float().sum().item()
+    (gd_centerpoint_head.py:407): with the count kept on the device the whole GD branch -- the
+    count, the decode, the loss and its gradient -- captures into one CUDA graph (f4)."""
+    kw = dict(CONFIGS[0], tau=0.0)
+    c = synth.make_center_head_batch(20_000, seed=16)
+    g = cuda(c)
+    head = GDCenterHeadLoss(dict(type='GDLoss', **kw), c['coder'])
+    heat = (torch.rand(2, 128, 128, device='cuda') < 0.01).float()
+
+    def run(p):
+        num_pos = heat.eq(1).float().sum().clamp(min=1)            # :407 without .item()
+        loss = head(p, g['pos_ind'], g['target_box'], avg_factor=num_pos)
+        grad, = torch.autograd.grad(loss, p)
+        return loss, grad
+    ref_loss, ref_grad = oracle_center(kw, c, float(heat.sum().clamp(min=1)))
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ps = g['pred'].clone().requires_grad_(True)
+        run(ps)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            cl, cg = run(ps)
+    graph.replay()
+    torch.cuda.synchronize()
+    check(cl.item(), cg.cpu().double().numpy()[:, :7], ref_loss, ref_grad[:, :7], 'center graph')
+    heat.zero_()                                                   # no positives -> avg_factor 1
+    graph.replay()
+    torch.cuda.synchronize()
+    ref1, _ = oracle_center(kw, c, 1.0)
+    assert abs(cl.item() - ref1) <= RTOL * abs(ref1)
+    # and GDLoss itself on the head's strided views with the device scalar
+    dec = gd_oracle.decode_centerpoint_yaw(c['pos_ind'][..., 1:], c['pred'], **c['coder']).cuda()
+    p7 = dec.detach().requires_grad_(True)
+    out = GDLoss(**kw)(p7[..., :7], g['target_box'][..., :7], avg_factor=torch.ones((), device='cuda'))
+    out.backward()
+    assert abs(out.item() - ref1) <= 2e-5 * abs(ref1)
+
+
 def oracle_center(kw, c, avg, weight=None):
     p = c['pred'].double().requires_grad_(True)
     mod = gd_oracle.GDLossOracle(**kw)

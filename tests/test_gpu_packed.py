@@ -1,12 +1,7 @@
-"""GPU parity of the OPT-IN packed-FP32 variant of the fused kernel
-(``variant='bulk_packed'`` = GD_VARIANT_BULK_PACKED, csrc/gd_packed.cuh).
-
-The variant is not selected by ``variant='auto'`` and has not been timed or validated
-on a GPU yet (it was written after the round's GPU budget was spent), so these tests only
-run when ``GD_B200_TEST_EXPERIMENTAL=1`` is set; the default ``pytest -m gpu`` suite
-covers exactly the kernels the library uses by default."""
-import os
-
+"""GPU parity of the packed-FP32 variant of the fused kernel (``variant='bulk_packed'`` =
+GD_VARIANT_BULK_PACKED, csrc/gd_packed.cuh -- what ``variant='auto'`` runs for gwd3d / kld3d /
+bd3d since round 2, build_ext.TUNE_DEFAULT) against the fp64 oracle and the scalar kernel
+(``variant='bulk'``), of the opt-in packed pairwise kernel, and of the ``host_sync`` aliases."""
 import numpy as np
 import pytest
 import torch
@@ -14,9 +9,7 @@ import torch
 from mmdet3d_gaussian_b200 import GDLoss, synth
 from oracle import gd_oracle
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('GD_B200_TEST_EXPERIMENTAL') != '1',
-                                 reason='opt-in variant: set GD_B200_TEST_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 

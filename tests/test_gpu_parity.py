@@ -1,7 +1,7 @@
 """GPU parity tests (run on the B200 box: ``pytest -m gpu``).
 
-Everything goes through the public ``GDLoss`` module -> ctypes -> C ABI
-(``libgdloss_b200.so``) -> CUDA kernels; the oracle (``oracle/gd_oracle.py``,
+Everything goes through the public ``GDLoss`` module -> torch C++ shim (``_C.so``) -> C ABI
+(``libgdloss_b200.so``) -> CUDA kernels (a few tests call the C ABI directly with ctypes); the oracle (``oracle/gd_oracle.py``,
 fp64 on CPU) and the golden vectors written from the unmodified reference
 (``tests/golden/gd_golden.npz``) are only the checkers.
 
@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
 ALL_TYPES = ('gwd3d', 'kld3d', 'jd3d', 'kld3d_symmax', 'kld3d_symmin', 'bd3d', 'kfiou3d')
-VARIANTS = ('bulk', 'bulk_r2', 'staged')
+VARIANTS = ('bulk', 'bulk_packed', 'bulk_any', 'bulk_r2', 'staged')
 
 
 @pytest.fixture(scope='module', autouse=True)
@@ -42,6 +42,8 @@ def dev(t):
 
 def run_ours(kwargs, pred, target, weight=None, avg_factor=None, override=None,
              variant='auto', grad_output=None, **fw):
+    if variant == 'bulk_any' and pred.shape[0] < 16:
+        variant = 'staged'                # the strided bulk pipeline needs >= 16 rows
     mod = GDLoss(variant=variant, **kwargs)
     p = pred.detach().clone().cuda().requires_grad_(True)
     out = mod(p, dev(target), dev(weight), avg_factor=avg_factor,
@@ -216,6 +218,62 @@ def test_strided_and_unaligned_views():
     assert abs(out3.item() - ref_l) <= RTOL * abs(ref_l)
 
 
+@pytest.mark.parametrize('loss_type', ('gwd3d', 'kld3d', 'bd3d'))
+def test_strided_views_at_size(loss_type):
+    """The CenterGDHead layout at 2^22 rows: `[..., :7]` views of 9-wide predictions and
+    11-wide targets (gd_centerpoint_head.py:413-423), a [N] weight that is a column of a wider
+    tensor, and 28-byte-offset slices.  'auto' must take the strided bulk pipeline
+    (GD_VARIANT_BULK_ANY); results equal the staged kernel's (robust math on every row) to
+    rounding, a 20k-row sample is checked against the fp64 oracle, and the contiguous kernel on
+    a packed copy of the same rows gives the same gradient bit for bit on the tile rows."""
+    n = 1 << 22
+    pred, target, w = synth.make_pairs(n, 'nuscenes', seed=6, device='cuda', weights='bernoulli')
+    wide_p = torch.full((n, 9), float('nan'), device='cuda')
+    wide_p[:, :7] = pred
+    wide_t = torch.full((n, 11), float('nan'), device='cuda')
+    wide_t[:, :7] = target
+    wide_w = torch.full((n, 3), float('nan'), device='cuda')
+    wide_w[:, 1] = w
+    kw = dict(loss_type=loss_type, fun='log1p', tau=0.0, loss_weight=5.0)
+    outs = {}
+    for variant in ('auto', 'bulk_any', 'staged'):
+        p = wide_p.clone().requires_grad_(True)
+        out = GDLoss(variant=variant, **kw)(p[:, :7], wide_t[:, :7], wide_w[:, 1], avg_factor=1234.0)
+        out.backward()
+        g = p.grad
+        assert bool(torch.isfinite(out)) and float(g[:, 7:].abs().max()) == 0.0
+        outs[variant] = (out.item(), g[:, :7].clone())
+    assert outs['auto'][0] == outs['bulk_any'][0] and torch.equal(outs['auto'][1], outs['bulk_any'][1])
+    assert abs(outs['auto'][0] - outs['staged'][0]) <= 2e-6 * abs(outs['staged'][0])
+    gn = outs['staged'][1].norm(dim=1).clamp_min(1e-3 * 5.0 / 1234.0)
+    assert ((outs['auto'][1] - outs['staged'][1]).norm(dim=1) / gn).max().item() <= 5e-6
+    # the same rows packed: contiguous kernel == strided kernel on the tile rows
+    pc = pred.clone().requires_grad_(True)
+    oc = GDLoss(variant='bulk', **kw)(pc, target, w, avg_factor=1234.0)
+    oc.backward()
+    lo, hi = 4, 4 + ((n - 1 - 4) & ~3)
+    assert torch.equal(pc.grad[lo:hi], outs['auto'][1][lo:hi])
+    assert abs(oc.item() - outs['auto'][0]) <= 2e-6 * abs(oc.item())
+    # sampled rows vs the fp64 oracle
+    idx = torch.randint(0, n, (20000,), device='cuda')
+    rows = GDLoss(**dict(kw, reduction='none'))(wide_p[:, :7], wide_t[:, :7], wide_w[:, 1])
+    rl, rg = run_oracle(dict(kw, reduction='none'), pred[idx].cpu(), target[idx].cpu(), w[idx].cpu())
+    row_check(rows[idx].cpu().double().numpy(),
+              (outs['auto'][1][idx] * 1234.0).cpu().double().numpy(), rl, rg, RTOL, 1e-6, 1e-6,
+              what=f'{loss_type} strided sample')
+    # 28-byte offset slices (4-byte aligned only), odd row count
+    p2 = pred.clone().requires_grad_(True)
+    o2 = GDLoss(**kw)(p2[1:-2], target[1:-2], w[1:-2], avg_factor=1234.0)
+    o2.backward()
+    p3 = pred[1:-2].clone().requires_grad_(True)
+    o3 = GDLoss(variant='staged', **kw)(p3, target[1:-2].clone(), w[1:-2].clone(), avg_factor=1234.0)
+    o3.backward()
+    assert abs(o2.item() - o3.item()) <= 2e-6 * abs(o3.item())
+    gn = p3.grad.norm(dim=1).clamp_min(1e-3 * 5.0 / 1234.0)
+    assert ((p2.grad[1:-2] - p3.grad).norm(dim=1) / gn).max().item() <= 5e-6
+    assert float(p2.grad[0].abs().max()) == 0.0 and float(p2.grad[-2:].abs().max()) == 0.0
+
+
 def test_early_return_and_weight_shapes():
     pred, target, _ = synth.make_pairs(500, 'kitti', seed=8)
     p = pred.cuda().requires_grad_(True)
@@ -241,6 +299,108 @@ def test_early_return_and_weight_shapes():
         GDLoss('gwd3d')(p, target.cuda().requires_grad_(True))
     with pytest.raises(RuntimeError):
         GDLoss('gwd3d')(pred, target)                 # CPU tensors: no fallback
+
+
+def test_early_return_decided_on_the_device():
+    """The default module (reference ctor keys only) takes the early return of ref:290-292
+    without any host involvement wherever `pred * weight` has the shape of pred: value
+    (pred * weight).sum(), gradient = weight, no loss_weight / avg_factor -- for every kernel
+    variant, with grad and under no_grad, and inside a CUDA graph whose replays see weights
+    that flip between 'some positive' and 'none positive'."""
+    n = 5000
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=8, weights='bernoulli')
+    pc, tc = pred.cuda(), target.cuda()
+    kw = dict(loss_type='kld3d', fun='log1p', tau=0.0, loss_weight=5.0)
+    wneg = -torch.rand(n, 7)
+    want = float((pred.double() * wneg.double()).sum())
+    for variant in ('auto', 'bulk', 'bulk_any', 'staged'):
+        p = pc.clone().requires_grad_(True)
+        out = GDLoss(variant=variant, **kw)(p, tc, wneg.cuda(), avg_factor=3.0)
+        out.backward()
+        assert abs(out.item() - want) <= 1e-5 * abs(want)
+        assert torch.equal(p.grad.cpu(), wneg)
+        with torch.no_grad():
+            o2 = GDLoss(variant=variant, **kw)(pc, tc, wneg.cuda(), avg_factor=3.0)
+        assert o2.item() == out.item()
+    # one positive ELEMENT in a row whose mean is negative: ref:290 looks at elements -> no
+    # early return, and the (negative) row means weigh the loss as in the reference
+    wmix = wneg.clone()
+    wmix[n - 1, 2] = 1e-3
+    ref_l, ref_g = run_oracle(kw, pred, target, wmix, 3.0)
+    l, g = run_ours(kw, pred, target, wmix, 3.0)
+    assert abs(l - ref_l) <= RTOL * abs(ref_l)
+    assert np.abs(g - ref_g).max() <= RTOL * np.abs(ref_g).max()
+    # strided [N,7] weights (a view of a wider tensor)
+    wide = torch.zeros(n, 9).cuda()
+    wide[:, :7] = wneg.cuda()
+    p = pc.clone().requires_grad_(True)
+    out = GDLoss(**kw)(p, tc, wide[:, :7])
+    out.backward()
+    assert abs(out.item() - want) <= 1e-5 * abs(want) and torch.equal(p.grad.cpu(), wneg)
+    # a [7] weight against [7,7] rows broadcasts over COLUMNS in (pred * weight)
+    w7 = -torch.rand(7)
+    p = pc[:7].clone().requires_grad_(True)
+    out = GDLoss(**kw)(p, tc[:7], w7.cuda())
+    out.backward()
+    ref = (pred[:7].double() * w7.double()).sum()
+    assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert torch.equal(p.grad.cpu(), w7.expand(7, 7))
+    # CUDA graph: the decision is data dependent and lives in the graph
+    mod = GDLoss(**kw)
+    ws = wneg.cuda().clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ps = pc.clone().requires_grad_(True)
+        torch.autograd.grad(mod(ps, tc, ws, avg_factor=3.0), ps)
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            gl = mod(ps, tc, ws, avg_factor=3.0)
+            gg, = torch.autograd.grad(gl, ps)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert abs(gl.item() - want) <= 1e-5 * abs(want) and torch.equal(gg.cpu(), wneg)
+    ws.copy_(wmix.cuda())
+    graph.replay()
+    torch.cuda.synchronize()
+    assert abs(gl.item() - ref_l) <= RTOL * abs(ref_l)
+    assert np.abs(gg.cpu().double().numpy() - ref_g).max() <= RTOL * np.abs(ref_g).max()
+    ws.copy_(wneg.cuda())
+    graph.replay()
+    torch.cuda.synchronize()
+    assert abs(gl.item() - want) <= 1e-5 * abs(want) and torch.equal(gg.cpu(), wneg)
+    # [N] weights: the reference raises when the branch is taken -> the host must know; that
+    # cannot be captured, and the module says so instead of silently changing semantics
+    w1 = w.cuda()
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g2, stream=s):
+                mod(ps, tc, w1, avg_factor=3.0)
+    torch.cuda.synchronize()
+    # ... and the same call outside a capture works (and host_sync=False captures)
+    assert bool(torch.isfinite(mod(ps, tc, w1, avg_factor=3.0)))
+
+
+def test_device_avg_factor():
+    """avg_factor as a one-element CUDA tensor is divided in-kernel (no .item()): same result
+    as the Python number, graph capturable (gd_centerpoint_head.py:407 without its sync)."""
+    n = 30_000
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=18, weights='bernoulli')
+    w7 = w[:, None].expand(n, 7).contiguous()
+    for kw, wt in ((dict(loss_type='gwd3d', fun='log1p', tau=0.0, loss_weight=5.0), w7),
+                   (dict(loss_type='bd3d', fun='none', tau=1.0, loss_weight=2.0), None),
+                   (dict(loss_type='jd3d', loss_weight=1.5), w7)):
+        num_pos = torch.tensor(float(int((w > 0).sum())), device='cuda')
+        ref_l, ref_g = run_oracle(kw, pred, target, wt, float(num_pos))
+        for variant in ('auto', 'staged', 'bulk_any'):
+            l, g = run_ours(kw, pred, target, wt, num_pos, variant=variant)
+            assert abs(l - ref_l) <= RTOL * abs(ref_l)
+            assert np.abs(g - ref_g).max() <= RTOL * np.abs(ref_g).max()
+    # int64 0-dim and [1] tensors are accepted as well
+    l2, _ = run_ours(kw, pred, target, wt, num_pos.long().reshape(1))
+    assert abs(l2 - ref_l) <= RTOL * abs(ref_l)
 
 
 @pytest.mark.parametrize('loss_type', ('gwd3d', 'kld3d', 'bd3d', 'jd3d', 'kld3d_symmin'))
@@ -348,11 +508,92 @@ def test_autograd_contract():
 # ---------------------------------------------------------------------------
 # 4. size-independent properties at BASELINE.json's full size (C2: 2^24 pairs)
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize('weights', ('rows', 'rows7'))
+def test_c3_nuscenes_weighted_at_size(weights):
+    """BASELINE config C3 at size: 786,432 nuScenes-prior rows (8 samples x 6 tasks x 128 x 128),
+    Bernoulli(0.5) x U(0,1) weights as [N] and as [N,7], avg_factor = #positive, gwd3d: reduced
+    loss and a 20k-row sample of the gradient against the fp64 oracle, every kernel variant,
+    plus shard additivity over 2 / 4 / 8 row shards (the multi-GPU partition)."""
+    n = 786_432
+    pred, target, w = synth.make_pairs(n, 'nuscenes', seed=5, weights='bernoulli')
+    wt = w if weights == 'rows' else w[:, None].expand(n, 7).contiguous()
+    af = float(max(int((w > 0).sum()), 1))
+    kw = dict(loss_type='gwd3d', fun='log1p', tau=0.0, loss_weight=5.0)
+    idx = torch.randperm(n)[:20000]
+    mod = gd_oracle.GDLossOracle(**kw)
+    # fp64 oracle of the whole batch in chunks (its intermediates are ~3 KB per pair)
+    tot = 0.0
+    for lo in range(0, n, 1 << 17):
+        sl = slice(lo, lo + (1 << 17))
+        tot += float(mod(pred[sl].double(), target[sl].double(), wt[sl].double(), avg_factor=af))
+    _, sg = run_oracle(kw, pred[idx], target[idx], wt[idx], af)
+    pc, tc, wc = pred.cuda(), target.cuda(), wt.cuda()
+    for variant in ('auto', 'bulk', 'bulk_any', 'staged'):
+        p = pc.clone().requires_grad_(True)
+        out = GDLoss(variant=variant, **kw)(p, tc, wc, avg_factor=af)
+        out.backward()
+        assert abs(out.item() - tot) <= RTOL * abs(tot), (variant, out.item(), tot)
+        g = p.grad[idx.cuda()].cpu().double().numpy()
+        gn = np.maximum(np.linalg.norm(sg, axis=1), 1e-3 * np.linalg.norm(sg, axis=1).max())
+        assert (np.linalg.norm(g - sg, axis=1) / gn).max() <= RTOL, variant
+    whole = GDLoss(**kw)(pc, tc, wc, avg_factor=af).double().item()
+    for shards in (2, 4, 8):
+        k = n // shards
+        parts = sum(GDLoss(**kw)(pc[i * k:(i + 1) * k], tc[i * k:(i + 1) * k], wc[i * k:(i + 1) * k],
+                                 avg_factor=af).double().item() for i in range(shards))
+        assert abs(parts - whole) <= 2e-6 * abs(whole)
+
+
+@pytest.mark.parametrize('layout', ('contiguous', 'strided'))
+def test_largest_sweep_size_2_28(layout):
+    """BASELINE config C5's largest size, 2^28 pairs (7.5 GB per [N,7] array; element offsets
+    pass 2^31): finite, the sum equals the sum of 16 row shards, the two halves of a batch made
+    of two identical halves give identical gradients, sampled rows (the very last ones included)
+    agree with the fp64 oracle."""
+    n = 1 << 28
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * (1 << 30):
+        pytest.skip('needs 40 GB of free device memory')
+    half = n // 2
+    cols = 7 if layout == 'contiguous' else 9
+    ph, th, wh = synth.make_pairs(half, 'kitti', seed=1, device='cuda', weights='bernoulli')
+    pred = torch.empty(n, cols, device='cuda')
+    pred[:half, :7] = ph
+    pred[half:, :7] = ph
+    target = torch.cat([th, th])
+    w = torch.cat([wh, wh])
+    del th
+    pv = pred[:, :7]
+    kw = dict(loss_type='kld3d', fun='log1p', tau=0.0, reduction='sum')
+    p = pred.requires_grad_(True)
+    total = GDLoss(**kw)(p[:, :7], target, w)
+    total.backward()
+    g = p.grad
+    assert bool(torch.isfinite(total)) and bool(torch.isfinite(g[:, :7]).all())
+    k = n // 16
+    with torch.no_grad():
+        parts = sum(GDLoss(**kw)(pv[i * k:(i + 1) * k], target[i * k:(i + 1) * k],
+                                 w[i * k:(i + 1) * k]).double().item() for i in range(16))
+    assert abs(parts - total.double().item()) <= 2e-6 * abs(total.item())
+    lo, hi = 8, half - 8                       # the rows around the tiles take the robust path
+    assert torch.equal(g[lo:hi, :7], g[half + lo:half + hi, :7])
+    idx = torch.cat([torch.randint(0, n, (4000,), device='cuda'),
+                     torch.arange(n - 9, n, device='cuda'), torch.arange(0, 9, device='cuda')])
+    rl, rg = run_oracle(dict(kw, reduction='none'), pv.detach()[idx].cpu(), target[idx].cpu(),
+                        w[idx].cpu())
+    with torch.no_grad():
+        rows = GDLoss(**dict(kw, reduction='none'))(pv.detach()[idx].contiguous(),
+                                                    target[idx].contiguous(), w[idx].contiguous())
+    row_check(rows.cpu().double().numpy(), g[idx][:, :7].cpu().double().numpy(), rl, rg, RTOL,
+              1e-6, 1e-6, what='2^28 sample')
+
+
+@pytest.mark.parametrize('fun', ('log1p', 'none'))
 @pytest.mark.parametrize('loss_type', ('kld3d', 'bd3d', 'gwd3d'))
-def test_full_size_properties(loss_type):
+def test_full_size_properties(loss_type, fun):
     n = 1 << 24
     pred, target, w = synth.make_pairs(n, 'kitti', seed=0, device='cuda')
-    kw = dict(loss_type=loss_type, fun='log1p', tau=0.0, reduction='sum')
+    kw = dict(loss_type=loss_type, fun=fun, tau=0.0, reduction='sum')
     mod = GDLoss(**kw)
     p = pred.requires_grad_(True)
     total = mod(p, target, w)

@@ -46,6 +46,11 @@ def emul(bits):
             ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_int] + [
             ctypes.c_void_p] * 3
         assert lib.gd_emul_tune_default() == bits
+        lib.gd_emul_loss_any.restype = ctypes.c_int
+        lib.gd_emul_loss_any.argtypes = [ctypes.c_int] * 4 + [
+            ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
+            ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p,
+            ctypes.c_float] + [ctypes.c_void_p] * 4
         _LIBS[bits] = lib
     return _LIBS[bits]
 
@@ -198,3 +203,107 @@ def test_sum_is_deterministic_and_grid_dependent_only():
     a = run(0, 'kld3d', 1, 9, 0, 3, 6, pred, target, w, scale=1.0 / n)
     b = run(0, 'kld3d', 1, 9, 0, 3, 6, pred, target, w, scale=1.0 / n)
     assert a[0] == b[0] and np.array_equal(a[2], b[2])
+
+
+def run_any(loss, kind, grid, warps, pred, target, weight, pstride=7, tstride=7, wstride=None,
+            offsets=(0, 0, 0), scale=1.0, scale_div=None, want_status=False, want_rows=False,
+            want_grad=True, tau=0.0):
+    """gd_warp_kernel<..., ANY> (kind 1) or gd_staged_kernel (kind 0) on row-strided inputs that
+    start `offsets` floats into 16-byte aligned buffers; the gaps between the rows and around
+    the arrays are NaN, so any read of a byte that is not a box element shows."""
+    n = pred.shape[0]
+
+    def place(x, stride, off):
+        cols = x.shape[1] if x.ndim == 2 else 1
+        raw = np.full(n * stride + off + 64, np.nan, np.float32)
+        base = (-raw.ctypes.data // 4) % 4            # floats to the next 16-byte boundary
+        view = raw[base + off:base + off + n * stride].reshape(n, stride)
+        view[:, :cols] = x.reshape(n, cols)
+        assert (view.ctypes.data - 4 * off) % 16 == 0
+        return raw, view
+    praw, pv = place(pred.numpy().astype(np.float32), pstride, offsets[0])
+    traw, tv = place(target.numpy().astype(np.float32), tstride, offsets[1])
+    wmode, wv, wraw = 0, None, None
+    if weight is not None:
+        wnp = weight.numpy().astype(np.float32)
+        wmode = 2 if wnp.ndim == 2 else 1
+        wstride = wstride or (7 if wmode == 2 else 1)
+        wraw, wv = place(wnp, wstride, offsets[2])
+    G = 64
+    bufs = {}
+
+    def guarded(name, count):
+        raw = np.full(count + 2 * G + 4, -7.0, np.float32)
+        base = (-raw.ctypes.data // 4) % 4
+        full = raw[base:base + count + 2 * G]
+        full[:G] = full[G + count:] = 91.0
+        bufs[name] = (full, count)
+        return full[G:G + count]
+    total = guarded('loss', 1)
+    rows = guarded('rows', n) if want_rows else None
+    grad = guarded('grad', n * 7).reshape(n, 7) if want_grad else None
+    status = np.full(1, -1.0, np.float32) if want_status else None
+    sdiv = np.array([scale_div], np.float32) if scale_div is not None else None
+    ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None   # noqa: E731
+    rc = emul(0).gd_emul_loss_any(LOSS[loss], kind, grid, warps, ptr(pv), pstride, ptr(tv), tstride,
+                                  ptr(wv), wmode, wstride or 0, n, scale, ptr(sdiv), tau,
+                                  ptr(status), ptr(total), ptr(rows), ptr(grad))
+    assert rc == 0, rc
+    for name, (full, count) in bufs.items():
+        assert (full[:G] == 91.0).all() and (full[G + count:] == 91.0).all(), f'write outside {name}'
+    return float(total[0]), rows, grad, (None if status is None else float(status[0]))
+
+
+@pytest.mark.parametrize('n,grid,warps', [(16, 1, 2), (137, 1, 3), (1030, 2, 5), (2051, 3, 7)])
+@pytest.mark.parametrize('pstride,tstride,offsets', [(9, 11, (0, 0, 0)), (7, 7, (7, 0, 1)),
+                                                     (9, 10, (1, 2, 3)), (8, 7, (3, 3, 2)),
+                                                     (11, 9, (2, 1, 0))])
+def test_any_stride_kernel_schedule_and_values(n, grid, warps, pstride, tstride, offsets):
+    """Bulk pipeline on row-strided / 4-byte-aligned inputs: every row processed exactly once,
+    no byte outside the box columns influences the result (the padding is NaN), values equal the
+    contiguous warp kernel bit for bit (same FAST / robust math), weights of both layouts."""
+    pred, target, w = make(n, seed=n)
+    w7 = torch.rand(n, 7)
+    for weight, wstride in ((None, None), (w, 1), (w, 3), (w7, 7), (w7, 9)):
+        total, rows, grad, _ = run_any('kld3d', 1, grid, warps, pred, target, weight, pstride,
+                                       tstride, wstride, offsets, scale=5.0 / n, want_rows=True)
+        assert np.isfinite(grad).any() and not (grad == -7.0).all(axis=1).any()
+        ref_total, ref_rows, ref_grad = run(0, 'kld3d', 1, -1, 0, grid, warps, pred, target, weight,
+                                            scale=5.0 / n, want_rows=True)
+        # tile rows run the same FAST math as the contiguous kernel: bit for bit; the <= 8
+        # rows around the tiles take the robust path (last-place differences)
+        lo, hi = 4, 4 + ((n - 1 - 4) & ~3)
+        assert np.array_equal(grad[lo:hi].view(np.int32), ref_grad[lo:hi].view(np.int32))
+        assert np.array_equal(rows[lo:hi].view(np.int32), ref_rows[lo:hi].view(np.int32))
+        assert np.allclose(grad, ref_grad, rtol=2e-5, atol=1e-9)
+        assert np.allclose(rows, ref_rows, rtol=2e-6, atol=0)
+        assert abs(total - ref_total) <= 1e-6 * abs(ref_total)
+    # forward only
+    t2, r2, _, _ = run_any('kld3d', 1, grid, warps, pred, target, w, pstride, tstride, 1, offsets,
+                           scale=5.0 / n, want_rows=True, want_grad=False)
+    assert t2 == run_any('kld3d', 1, grid, warps, pred, target, w, pstride, tstride, 1, offsets,
+                         scale=5.0 / n, want_rows=True)[0]
+
+
+@pytest.mark.parametrize('kind', [0, 1])
+def test_status_word_and_device_scale(kind):
+    """any(weight > 0) over every weight ELEMENT (ref:290) from inside the fused launch, and the
+    scale divisor read from (device) memory: staged kernel and ANY warp kernel."""
+    n = 517
+    pred, target, w = make(n, seed=2)
+    base = run_any('gwd3d', kind, 2, 3, pred, target, w, scale=5.0, want_status=True)
+    assert base[3] == 1.0
+    div = run_any('gwd3d', kind, 2, 3, pred, target, w, scale=5.0, scale_div=40.0, want_status=True)
+    assert abs(div[0] - base[0] / 40.0) <= 2e-7 * abs(base[0] / 40.0)
+    assert np.allclose(div[2], base[2] / 40.0, rtol=3e-7, atol=0)
+    for wz in (torch.zeros(n), -torch.rand(n), torch.zeros(n, 7), -torch.rand(n, 7)):
+        assert run_any('gwd3d', kind, 2, 3, pred, target, wz, want_status=True)[3] == 0.0
+    # [N,7]: one positive ELEMENT in a row whose mean is negative still counts (ref:290 tests
+    # the elements, ref:295 averages afterwards); first row, last row, a middle row
+    for r in (0, n - 1, 300):
+        w7 = -torch.rand(n, 7)
+        w7[r, 3] = 1e-3
+        assert run_any('gwd3d', kind, 2, 3, pred, target, w7, want_status=True)[3] == 1.0
+        w1 = -torch.rand(n)
+        w1[r] = 1e-3
+        assert run_any('gwd3d', kind, 2, 3, pred, target, w1, want_status=True)[3] == 1.0

@@ -13,7 +13,7 @@ CS=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck synccheck initcheck; do
   extra=""
   [ $tool = racecheck ] && extra="--racecheck-report all"
-  [ $tool = initcheck ] && extra="--track-unused-memory no"
+  [ $tool = initcheck ] && extra=""
   timeout -s KILL 900 $CS --tool $tool $extra --kernel-name kns=3gdk --print-limit 30 \
     --log-file $OUT/sanitizer_$tool.log python tools/sanitize_target.py $WHAT \
     > $OUT/sanitizer_$tool.out 2>&1

@@ -44,9 +44,10 @@ def main():
         pred.requires_grad_(True)
         w7 = w[:, None].expand(n, 7).contiguous()
         res = dict(pairs=n)
-        for name, mod, wt in (('module_sync', GDLoss(**KW), w7),
-                              ('module_nosync', GDLoss(host_sync=False, **KW), w7),
-                              ('module_nosync_noweight', GDLoss(host_sync=False, **KW), None)):
+        for name, mod, wt in (('module_default_w7', GDLoss(**KW), w7),
+                              ('module_default_w1', GDLoss(**KW), w),
+                              ('module_default_noweight', GDLoss(**KW), None),
+                              ('module_nosync_w7', GDLoss(host_sync=False, **KW), w7)):
             def call():
                 pred.grad = None
                 mod(pred, target, wt, avg_factor=float(n)).backward()
@@ -69,16 +70,24 @@ def main():
                                 w.data_ptr(), 1, 1, n, 5.0 / n, loss.data_ptr(), None,
                                 grad.data_ptr(), ws.data_ptr(), ws.numel(), 0, 0, stream)
         res['c_abi_us'] = round(wall_us(abi, 2000), 2)
+        # the module's forward alone from C++ (no Python module call): shim.gd_loss
+        sh = _lib.shim()
+        scfg = _lib.make_shim_config('gwd3d', 'log1p', True, 0.0, 1.0, (0, 0, 0.5))
+
+        def shim_call():
+            pred.grad = None
+            sh.gd_loss(pred, target, w7, scfg, 5.0, 1, float(n), 0, 1).backward()
+        res['shim_fwd_bwd_w7_us'] = round(wall_us(shim_call, 1000), 2)
         # CUDA graph of the module call (host_sync=False): replay cost
-        mod = GDLoss(host_sync=False, **KW)
+        mod = GDLoss(**KW)
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
             p_static = pred.detach().clone().requires_grad_(True)
-            g0, = torch.autograd.grad(mod(p_static, target, w, avg_factor=float(n)), p_static)
+            g0, = torch.autograd.grad(mod(p_static, target, w7, avg_factor=float(n)), p_static)
             s.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=s):
-                gl = mod(p_static, target, w, avg_factor=float(n))
+                gl = mod(p_static, target, w7, avg_factor=float(n))
                 gg, = torch.autograd.grad(gl, p_static)
         torch.cuda.synchronize()
         res['graph_replay_us'] = round(wall_us(graph.replay, 2000), 2)
@@ -96,7 +105,7 @@ def main():
         res['cpu_cores'] = os.cpu_count()
         out.append(res)
         if args.profile and n == 1000:
-            mod = GDLoss(host_sync=False, **KW)
+            mod = GDLoss(**KW)
             pr = cProfile.Profile()
             pr.enable()
             for _ in range(500):
