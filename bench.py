@@ -3,23 +3,35 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload at N=1 = BASELINE.json configs[1] ("C2"): KLD and BCD
-loss, tau=0, f(x)=x and f=log(1+x), fused forward+backward over 2^24 synthetic
-KITTI-prior box pairs with [N] weights, loss_weight=5, reduction='mean'.  One
-STEP = those four loss evaluations over the batch (4 x 2^24 pairs, 4 launches).
-Inputs (1.0 GB) are far larger than the 126 MB L2, so every launch streams from
-HBM (no flush needed; stated in `config.l2`).  N>1: one process per GPU
-(torchrun), every rank owns 2^24 rows (weak scaling), one NCCL all-reduce of the
-scalar loss after each evaluation, timing = max over ranks of CUDA-event time.
+Headline workload = BASELINE.json configs[1] ("C2"): KLD and BCD loss,
+tau=0, f(x)=x and f=log(1+x), fused forward+backward over 2^24 synthetic KITTI-prior box
+pairs with [N] weights, loss_weight=5, reduction='mean' with avg_factor.  One STEP = those
+four loss evaluations over the batch (4 x 2^24 pairs).  Inputs (1.0 GB per evaluation) are
+far larger than the 126 MB L2, so every launch streams from HBM (no flush needed;
+`config.l2`).
 
-`value`   : device-resident throughput (inputs in HBM before the timed region).
-`e2e`     : same four evaluations through the C ABI with HOST (pinned) buffers:
-            H2D of pred/target/weight, kernels, D2H of grad and loss inside the
-            timed region (gd_loss_fwd_bwd_host).
-`roofline`: HBM; achieved = 88 B/pair x 2^24 / mean kernel time, peak from
-            MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the oracle port (oracle/gd_oracle.py, the
-            reference's eager-torch algorithm) in fp32 on the host cores.
+`value`   : device-resident throughput through the DEFAULT module -- `GDLoss(loss_type, fun=,
+            tau=, loss_weight=)`, the reference's constructor keys only -- forward +
+            `backward()`, CUDA events around K steps, max over ranks.
+            N > 1: one process per GPU (torchrun), every rank owns 2^24 rows (weak scaling),
+            the scalar loss is summed over the GPUs INSIDE the fused launch through peer
+            memory (sharded.ShardedGDLoss(fused=True); NCCL all-reduce if symmetric memory is
+            unavailable -- `config.parallelism` says which).
+`e2e`     : the same four evaluations through the C ABI with HOST (pinned) buffers: H2D of
+            pred/target/weight, kernels, D2H of grad and loss inside the timed region
+            (gd_loss_fwd_bwd_host).
+`roofline`: HBM; achieved = 88 B/pair x 2^24 / mean kernel time of the four configurations
+            (CUDA events around bare C-ABI launches), peak from MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference file
+            (mmdet3d_gaussian/models/losses/gaussian_distance_loss.py, staged by
+            oracle/build_ref.py under oracle/_ref/, loaded with a stub mmdet) in fp32 on the
+            host cores, forward + autograd backward; `kind: "port"` (oracle/gd_oracle.py) only
+            if the staged file is missing.
+Sub-records (BASELINE.json configs[0,2,3,4]; N=1 unless stated): `c1` (100k gwd3d/log1p through
+the module), `c3_strong` (786,432 weighted nuScenes rows split over the N ranks, cross-GPU sum
+included), `c5` (2^10 .. 2^28 pairs x {gwd3d, kld3d, bd3d}, rows split over the N ranks),
+`pairwise` (200k x 256 matrix and fused assignment), `layouts` ([N,7] weights, reduction='none',
+row-strided views).
 """
 import argparse
 import ctypes
@@ -39,25 +51,28 @@ BYTES_PER_PAIR = 88          # pred 28 + target 28 + weight 4 read, grad 28 writ
 COMBOS = (('kld3d', 'none'), ('kld3d', 'log1p'), ('bd3d', 'none'), ('bd3d', 'log1p'))
 LOSS_WEIGHT = 5.0
 METRIC = 'box pairs/s, GD loss fwd+bwd (KLD+BCD, tau=0, f=x|log1p)'
+C3_ROWS = 786_432
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs', type=int, default=N_PAIRS)
-    ap.add_argument('--variant', default='auto', choices=['auto', 'bulk', 'bulk_packed', 'bulk_r2', 'staged'])
+    ap.add_argument('--variant', default='auto',
+                    choices=['auto', 'bulk', 'bulk_packed', 'bulk_any', 'bulk_r2', 'staged'])
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-chunk-log2', type=int, default=20,
+    ap.add_argument('--e2e-chunk-log2', type=int, default=21,
                     help='rows per chunk of the host-buffer pipeline (e2e), as a power of two')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the c1/c3/c5/pairwise/layout sub-records')
+    ap.add_argument('--c5-max-log2', type=int, default=28)
+    ap.add_argument('--nccl', action='store_true', help='N > 1: separate NCCL all-reduce instead of the in-kernel sum')
     ap.add_argument('--eager-gpu', action='store_true',
-                    help='also time the reference algorithm (oracle port, eager torch + autograd) '
-                         'on THIS GPU: the incumbent a user of the reference runs today')
-    ap.add_argument('--detail', action='store_true', help='extra per-config lines on stderr')
-    ap.add_argument('--watchdog', type=float, default=900.0,
+                    help='also time the reference algorithm (eager torch + autograd) on THIS GPU')
+    ap.add_argument('--watchdog', type=float, default=1500.0,
                     help='seconds after which all thread stacks are dumped and the process exits')
     ap.add_argument('--verbose', action='store_true', help='phase log with timestamps on stderr')
     return ap.parse_args()
@@ -73,19 +88,21 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture."""
+    """DRAM bytes per launch of the dominant kernel: NOT measured in this run -- read from the
+    committed ncu capture (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            return json.load(f).get('dram_bytes_per_launch')
+            d = json.load(f)
+            return d.get('dram_bytes_per_launch'), d.get('source', 'recorded ncu capture')
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load."""
+    """nvidia-smi clocks / power / throttle reasons sampled while the GPU is under load."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+         'clocks_event_reasons.sw_power_cap,power.draw')
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -113,7 +130,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
         for ts, line in self.rows:
             if not (t0 <= ts <= t1 + 0.05):
@@ -124,26 +141,42 @@ class ClockSampler:
                 mx.append(float(parts[1]))
             except Exception:
                 continue
-            for name, val in zip(names, parts[2:]):
+            for name, val in zip(names, parts[2:6]):
                 if val.lower().startswith('active'):
                     reasons.add(name)
+            try:
+                pw.append(float(parts[6]))
+            except Exception:
+                pass
         return {'sm_mhz': statistics.median(sm) if sm else None,
                 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'power_w': statistics.median(pw) if pw else None, 'samples': len(sm)}
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port (reference algorithm, eager torch, fp32, all host threads)
+# CPU arm: the reference's own file (oracle/_ref), else the oracle port; fp32, all host threads
 # ---------------------------------------------------------------------------
-def cpu_pairs_per_s(sample_rows, chunk_rows, repeats, threads=None):
+def cpu_modules(combos, **extra):
+    """[(module, kind)] -- the unmodified reference GDLoss when the staged file is there."""
+    from oracle import gd_oracle, ref_loader
+    kind = 'port'
+    cls = gd_oracle.GDLossOracle
+    try:
+        if ref_loader.reference_available():
+            cls = ref_loader.load_reference().GDLoss
+            kind = 'reference'
+    except Exception as exc:                                  # noqa: BLE001
+        sys.stderr.write(f'bench: reference file not loadable ({exc!r}); timing the port\n')
+    return [cls(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT, **extra) for lt, fun in combos], kind
+
+
+def cpu_pairs_per_s(sample_rows, chunk_rows, repeats, threads=None, combos=COMBOS):
     import torch
-    from oracle import gd_oracle
     from mmdet3d_gaussian_b200 import synth
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     pred, target, w = synth.make_pairs(sample_rows, 'kitti', seed=0)
-    mods = [gd_oracle.GDLossOracle(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT)
-            for lt, fun in COMBOS]
+    mods, kind = cpu_modules(combos)
     best = float('inf')
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -154,7 +187,7 @@ def cpu_pairs_per_s(sample_rows, chunk_rows, repeats, threads=None):
                            avg_factor=float(sample_rows))
                 loss.backward()
         best = min(best, time.perf_counter() - t0)
-    return len(COMBOS) * sample_rows / best, cores, best
+    return len(combos) * sample_rows / best, cores, best, kind
 
 
 def run_reference(args):
@@ -166,30 +199,47 @@ def run_reference(args):
     # in the autograd engine's thread)
     os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
     os.environ.pop('MKL_NUM_THREADS', None)
-    sample, chunk = 1 << 21, 1 << 17
-    steps = max(args.steps, 1)
-    for _ in range(min(args.warmup, 1)):
-        cpu_pairs_per_s(1 << 16, 1 << 16, 1)
-    t_budget = time.perf_counter()
+    chunk = 1 << 17
+    # size one step so that the whole --steps/--warmup run stays within ~3 minutes: probe the
+    # host's speed on 2^19 pairs per configuration first
+    cpu_pairs_per_s(1 << 16, 1 << 16, 1)
+    probe, cores, _, kind = cpu_pairs_per_s(1 << 19, chunk, 1)
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    budget = 170.0
+    rows = args.pairs
+    while rows > (1 << 19) and len(COMBOS) * rows / probe * (min(steps, 20) + min(warm, 2)) > budget:
+        rows >>= 1
+    n_steps = min(steps, 20)
+    while n_steps > 3 and len(COMBOS) * rows / probe * (n_steps + min(warm, 2)) > budget:
+        n_steps -= 1
+    for _ in range(min(warm, 2)):
+        cpu_pairs_per_s(rows, chunk, 1)
     vals = []
-    for _ in range(min(steps, 5)):
-        v, cores, _ = cpu_pairs_per_s(sample, chunk, 1)
+    t_budget = time.perf_counter()
+    for _ in range(n_steps):
+        v, cores, _, kind = cpu_pairs_per_s(rows, chunk, 1)
         vals.append(v)
-        if time.perf_counter() - t_budget > 120:
+        if time.perf_counter() - t_budget > budget:
             break
-    value = max(vals)
-    ms = len(COMBOS) * sample / value * 1e3
-    desc = (f'oracle port (reference algorithm in eager torch, fp32, autograd backward), '
-            f'4 configs x 2^21 pairs per step in 2^17-row chunks, best of {len(vals)} steps')
+    value = statistics.median(vals)
+    ms = len(COMBOS) * rows / value * 1e3
+    what = ('UNMODIFIED reference file (oracle/_ref/gaussian_distance_loss.py under a stub mmdet)'
+            if kind == 'reference' else 'oracle port (oracle/gd_oracle.py: the staged reference file is missing)')
+    desc = (f'{what}, eager torch fp32 + autograd backward, {cores} threads, 4 configs x '
+            f'{rows} pairs per step in 2^17-row chunks, median of {len(vals)} steps')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s',
-        'n_gpus': args.gpus, 'steps': len(vals), 'warmup': min(args.warmup, 1),
+        'n_gpus': args.gpus, 'steps': len(vals), 'warmup': min(warm, 2),
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'C2: kld3d+bd3d x fun{none,log1p}, tau=0, bounded sample of '
-                               '2^21 pairs per config (full workload 2^24)',
-                   'pairs_per_step': len(COMBOS) * sample},
-        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+        'config': {'workload': 'C2: kld3d+bd3d x fun{none,log1p}, tau=0, KITTI-prior box pairs, '
+                               f'weights [N], loss_weight=5, mean/avg_factor; {rows} pairs per '
+                               f'configuration and step'
+                               + ('' if rows == args.pairs else
+                                  f' (bounded sample of the {args.pairs}-pair workload: the CPU '
+                                  f'arm is sized to finish in ~3 min)'),
+                   'pairs_per_step': len(COMBOS) * rows},
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': kind,
                          'sample': desc},
         'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -202,7 +252,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mmdet3d_gaussian_b200 import GDLoss, _lib, ops, synth
+    from mmdet3d_gaussian_b200 import GDLoss, GDPairwiseDistance, _lib, ops, sharded, synth
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -220,54 +270,67 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
+    _lib.shim()
     n = args.pairs
-    log('process group and library ready')
-
-    pred, target, weight = synth.make_pairs(n, 'kitti', seed=rank, device=dev)
-    pred.requires_grad_(True)
-    # host_sync=False: the early-return probe of GDLoss.forward (reference
-    # gaussian_distance_loss.py:290, a device->host sync per call) is folded into the
-    # kernel, so launches queue back to back; `value_default_module` below times the
-    # faithful default (host_sync=True) for comparison.
-    mods = [GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT, variant=args.variant,
-                   host_sync=False) for lt, fun in COMBOS]
-    mods_sync = [GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT, variant=args.variant)
-                 for lt, fun in COMBOS]
-    avg = float(n * world)
-    losses = [None] * len(mods)
-    pending = []
-
-    def one_eval(i, modules=None, collective=True):
-        pred.grad = None
-        loss = (modules or mods)[i](pred, target, weight, avg_factor=avg)
-        if world > 1 and collective:
-            tot = loss.detach().clone()
-            # the one collective of the path (4 bytes).  Asynchronous: its result is only read
-            # at the end of the step, so the next evaluation's kernel need not wait for it
-            pending.append(dist.all_reduce(tot, async_op=True))
-            losses[i] = tot
-        elif world == 1:
-            losses[i] = loss.detach()
-        loss.backward()                        # grad_output == 1: scale kernel exits at once
-
-    def drain():
-        while pending:
-            pending.pop(0).wait()              # stream-side wait: no host sync
-
-    def step():
-        for i in range(len(mods)):
-            one_eval(i)
-        drain()
+    log('process group and libraries ready')
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def event_ms(fn, reps, warm=3):
+        """mean ms per call of fn(); CUDA events; max over ranks."""
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    pred, target, weight = synth.make_pairs(n, 'kitti', seed=rank, device=dev)
+    pred.requires_grad_(True)
+    avg = float(n * world)
+    # The headline module: the reference's constructor keys, nothing else.
+    if world == 1:
+        mods = [GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT, variant=args.variant)
+                for lt, fun in COMBOS]
+        module_desc = 'GDLoss(loss_type, fun=, tau=0.0, loss_weight=5.0) -- reference ctor keys only'
+        parallelism = 'single GPU'
+    else:
+        # one process per GPU; rows sharded; the scalar summed over the GPUs inside the launch
+        mods = [sharded.ShardedGDLoss(GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT,
+                                             variant=args.variant, host_sync=False),
+                                      fused=not args.nccl) for lt, fun in COMBOS]
+        fused = all(m.fused for m in mods)
+        module_desc = 'ShardedGDLoss(GDLoss(..., host_sync=False))'
+        parallelism = (f'rows sharded x{world}; scalar loss summed over the GPUs '
+                       + ('INSIDE the fused launch over NVLink peer memory (no NCCL on the path)'
+                          if fused else 'by one NCCL all-reduce per evaluation'))
+    losses = [None] * len(mods)
+
+    def one_eval(i, modules=None, w=None):
+        pred.grad = None
+        loss = (modules or mods)[i](pred, target, weight if w is None else w, avg_factor=avg)
+        losses[i] = loss.detach()
+        loss.backward()                        # grad_output == 1: the fold kernel exits at once
+
+    def step(modules=None, w=None):
+        for i in range(len(mods)):
+            one_eval(i, modules, w)
+
     log('inputs generated')
     for _ in range(max(args.warmup, 3)):
         step()
-    log('warm-up enqueued')
     sync_all()
     log('warm-up done')
 
@@ -294,46 +357,22 @@ def run_ours(args):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = len(COMBOS) * n * world / (ms_step * 1e-3)
+    final_losses = [float(x) for x in losses]
 
-    # ---- same step through the default module (host sync per evaluation, as the reference)
-    sync_all()
-    evs0, evs1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_sync = max(2, min(args.steps, 20))
-    evs0.record()
-    for _ in range(k_sync):
-        for i in range(len(mods_sync)):
-            one_eval(i, mods_sync)
-        drain()
-    evs1.record()
-    sync_all()
-    value_sync = len(COMBOS) * n * world / (evs0.elapsed_time(evs1) / k_sync * 1e-3)
-    log('default-module pass done')
-
-    # ---- same semantics as the default, the fused launch queued before the host waits for the
-    # probe (host_sync='overlap', opt-in).  Informational; never allowed to break the run.
-    value_overlap = None
-    try:
-        if world > 1:
-            raise RuntimeError('single-GPU runs only')
-        mods_ov = [GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT, variant=args.variant,
-                          host_sync='overlap') for lt, fun in COMBOS]
-        for i in range(len(mods_ov)):
-            one_eval(i, mods_ov)
-        drain()
-        sync_all()
-        evo0, evo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        evo0.record()
-        for _ in range(k_sync):
-            for i in range(len(mods_ov)):
-                one_eval(i, mods_ov)
-            drain()
-        evo1.record()
-        sync_all()
-        value_overlap = len(COMBOS) * n * world / (evo0.elapsed_time(evo1) / k_sync * 1e-3)
-    except Exception as exc:                       # noqa: BLE001
-        if world == 1:
-            sys.stderr.write(f'bench: overlap-mode pass skipped: {exc!r}\n')
-    log('overlap-module pass done')
+    # ---- the same step with the other module modes (informational)
+    other = {}
+    if world == 1:
+        k_other = max(2, min(args.steps, 20))
+        w7 = weight[:, None].expand(n, 7).contiguous()
+        for name, ms_mod, wt in (
+                ('value_weights_n7', mods, w7),
+                ('value_host_sync_false', [GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT,
+                                                  variant=args.variant, host_sync=False)
+                                           for lt, fun in COMBOS], None)):
+            ms = event_ms(lambda: step(ms_mod, wt), k_other, warm=2)     # noqa: B023
+            other[name] = len(COMBOS) * n / (ms * 1e-3)
+        del w7
+        log('other module modes done')
 
     # ---- kernel-only durations per config (CUDA events around bare C-ABI launches)
     per_cfg = {}
@@ -343,7 +382,6 @@ def run_ours(args):
     ws = ops._workspace(dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     pd, td, wd = pred.detach(), target, weight
-    reps = 20
     for (lt, fun) in COMBOS + (('gwd3d', 'log1p'),):
         cfg = _lib.make_config(lt, fun, True, 0.0, 1.0, (0, 0, 0.5))
 
@@ -359,27 +397,30 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
+        for _ in range(20):
             launch()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+        ms = e0.elapsed_time(e1) / 20
         per_cfg[f'{lt}/{fun}'] = {'ms': round(ms, 4),
                                   'GBps': round(BYTES_PER_PAIR * n / ms / 1e6, 1),
                                   'Gpairs_per_s': round(n / ms / 1e6, 2)}
         if (lt, fun) in COMBOS:
             fused_ms.append(ms)
     kernel_ms = sum(fused_ms) / len(fused_ms)
+    del grad_buf
     log('kernel-only timings done')
 
-    # keep the device busy ~1.5 s more so the clock sampler sees it under load (rank 0
-    # only, so NO collective in here: the other ranks are already past this point)
-    t_end = time.time() + 1.5
-    while rank == 0 and time.time() < t_end:
-        for _ in range(20):
-            for i in range(len(mods)):
-                one_eval(i, collective=False)
-        torch.cuda.synchronize()
+    # keep the device busy ~1.5 s more so the clock sampler sees it under load (rank 0 only and
+    # plain single-GPU modules: NO exchange with other ranks in here)
+    if rank == 0:
+        busy = [GDLoss(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT, variant=args.variant,
+                       host_sync=False) for lt, fun in COMBOS]
+        t_end = time.time() + 1.5
+        while time.time() < t_end:
+            for _ in range(20):
+                step(busy)
+            torch.cuda.synchronize()
     t_wall_load = time.time()
     clocks = sampler.stop(t_wall0, t_wall_load) if rank == 0 else None
     log('clock sampling done')
@@ -401,7 +442,6 @@ def run_ours(args):
                 _lib.check(code, 'gd_loss_fwd_bwd_host')
         log('host buffers pinned')
         e2e_step()
-        log('first e2e step done')
         k = max(2, min(args.steps, 5))
         sync_all()
         t0 = time.perf_counter()
@@ -417,33 +457,172 @@ def run_ours(args):
                'h2d_bytes_per_step': len(COMBOS) * n * 60,
                'd2h_bytes_per_step': len(COMBOS) * (n * 28 + 4),
                'steps': k, 'ms_per_step': dt / k * 1e3,
+               'h2d_GBps_per_gpu': len(COMBOS) * n * 60 * k / dt / 1e9,
                'api': f'gd_loss_fwd_bwd_host (C ABI, pinned host buffers, 2^{args.e2e_chunk_log2}-row '
                       f'chunks, 3 streams)'}
-
+        del hp, ht, hw, hgrad
     log('e2e done')
+
+    extras = {}
+    if not args.no_extras:
+        # ---- C1: KITTI-like batch through the module (BASELINE configs[0])
+        if world == 1:
+            n1 = 100_000
+            p1, t1, w1 = synth.make_pairs(n1, 'kitti', seed=1, device=dev)
+            p1.requires_grad_(True)
+            w17 = w1[:, None].expand(n1, 7).contiguous()          # the KITTI head's [P,7] ones
+            m1 = GDLoss('gwd3d', fun='log1p', tau=0.0, loss_weight=LOSS_WEIGHT)
+
+            def c1_call():
+                p1.grad = None
+                m1(p1, t1, w17, avg_factor=float(n1)).backward()
+            for _ in range(50):
+                c1_call()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(500):
+                c1_call()
+            torch.cuda.synchronize()
+            us = (time.perf_counter() - t0) / 500 * 1e6
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                ps = p1.detach().clone().requires_grad_(True)
+                torch.autograd.grad(m1(ps, t1, w17, avg_factor=float(n1)), ps)
+                s.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=s):
+                    gl = m1(ps, t1, w17, avg_factor=float(n1))
+                    torch.autograd.grad(gl, ps)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(1000):
+                graph.replay()
+            torch.cuda.synchronize()
+            us_graph = (time.perf_counter() - t0) / 1000 * 1e6
+            extras['c1'] = {'workload': 'C1: gwd3d, tau=0, log1p, 100,000 KITTI-prior pairs, [P,7] weights, '
+                                        'default GDLoss module, forward + backward()',
+                            'us_per_call_wall': round(us, 2), 'pairs_per_s': n1 / us * 1e6,
+                            'us_per_call_cuda_graph_replay': round(us_graph, 2),
+                            'pairs_per_s_cuda_graph': n1 / us_graph * 1e6}
+            del p1, t1, w1, w17, graph
+            log('c1 done')
+
+        # ---- C3: nuScenes-scale weighted rows, STRONG scaling over the N ranks
+        p3, t3, w3 = synth.make_pairs(C3_ROWS, 'nuscenes', seed=3, weights='bernoulli')
+        lo, hi = sharded.shard_bounds(C3_ROWS, rank, world)
+        avg3 = float(max(int((w3 > 0).sum()), 1))
+        p3l = p3[lo:hi].to(dev).requires_grad_(True)
+        t3l, w3l = t3[lo:hi].to(dev), w3[lo:hi].to(dev)
+        base3 = GDLoss('gwd3d', fun='log1p', tau=0.0, loss_weight=LOSS_WEIGHT, host_sync=world == 1)
+        m3 = base3 if world == 1 else sharded.ShardedGDLoss(base3, fused=not args.nccl)
+
+        def c3_call():
+            p3l.grad = None
+            m3(p3l, t3l, w3l, avg_factor=avg3).backward()
+        ms3 = event_ms(c3_call, 200, warm=20)
+        extras['c3_strong'] = {
+            'workload': f'C3: gwd3d, tau=0, log1p, {C3_ROWS} nuScenes-prior rows, Bernoulli(0.5)xU(0,1) '
+                        f'[N] weights, avg_factor=#positive, rows split over {world} rank(s), '
+                        'forward + backward() + cross-GPU sum',
+            'scaling': 'strong', 'n_gpus': world, 'us_per_call_max_over_ranks': round(ms3 * 1e3, 2),
+            'pairs_per_s': C3_ROWS / (ms3 * 1e-3),
+            'cross_gpu_sum': ('none (1 GPU)' if world == 1 else
+                              ('in-kernel over peer memory' if m3.fused else 'NCCL all-reduce'))}
+        del p3, t3, w3, p3l, t3l, w3l
+        log('c3 done')
+
+        # ---- C5: size sweep, rows split over the ranks (strong), through the module
+        max_log2 = args.c5_max_log2
+        free, _ = torch.cuda.mem_get_info()
+        while max_log2 > 20 and (1 << max_log2) // world * 100 > free * 0.8:
+            max_log2 -= 2
+        nmax = (1 << max_log2) // world
+        torch.cuda.empty_cache()
+        p5, t5, w5 = synth.make_pairs(nmax, 'kitti', seed=100 + rank, device=dev)
+        p5.requires_grad_(True)
+        sweep = []
+        for lt in ('gwd3d', 'kld3d', 'bd3d'):
+            base5 = GDLoss(lt, fun='log1p', tau=0.0, loss_weight=LOSS_WEIGHT, host_sync=world == 1)
+            m5 = base5 if world == 1 else sharded.ShardedGDLoss(base5, fused=not args.nccl)
+            for lg in range(10, max_log2 + 1, 2):
+                tot = 1 << lg
+                nl = tot // world
+                if nl < 4:
+                    continue
+                pv, tv, wv = p5[:nl], t5[:nl], w5[:nl]
+
+                def c5_call():
+                    p5.grad = None
+                    m5(pv, tv, wv, avg_factor=float(tot)).backward()       # noqa: B023
+                reps = max(3, min(200, (1 << 27) // tot))
+                ms = event_ms(c5_call, reps, warm=2)
+                sweep.append({'loss': lt, 'pairs': tot, 'us_per_call': round(ms * 1e3, 2),
+                              'Gpairs_per_s': round(tot / ms / 1e6, 3),
+                              'GBps_88B': round(88 * tot / ms / 1e6, 1)})
+        extras['c5'] = {'workload': f'C5: 2^10..2^{max_log2} pairs x gwd3d/kld3d/bd3d (log1p, tau=0, [N] weights), '
+                                    f'rows split over {world} rank(s), default module forward + backward() '
+                                    '(+ cross-GPU sum), CUDA events, max over ranks',
+                        'n_gpus': world, 'rows': sweep}
+        del p5, t5, w5
+        torch.cuda.empty_cache()
+        log('c5 done')
+
+        if world == 1:
+            # ---- C4: pairwise matrix / fused assignment
+            na, m = 200_000, 256
+            anchors = synth.make_anchor_grid(na, 'waymo', device=dev)
+            gts = synth.make_targets(m, 'waymo', seed=5, device=dev)
+            gts[:, 0] = gts[:, 0] * 2.0 - 70.0
+            mat = torch.empty(na, m, device=dev)
+            pw_rows = []
+            for lt in ('gwd3d', 'kld3d', 'bd3d'):
+                pw = GDPairwiseDistance(lt, fun='log1p', tau=1.0)
+                ms_mat = event_ms(lambda: ops.pairwise_distance(anchors, gts, pw.cfg, out=mat), 30)   # noqa: B023
+                ms_asg = event_ms(lambda: pw.assign(anchors, gts), 30)                                # noqa: B023
+                pw_rows.append({'loss': lt, 'matrix_ms': round(ms_mat, 4),
+                                'matrix_Gpairs_per_s': round(na * m / ms_mat / 1e6, 1),
+                                'matrix_write_GBps': round(4 * na * m / ms_mat / 1e6, 1),
+                                'fused_assign_ms': round(ms_asg, 4),
+                                'fused_assign_Gpairs_per_s': round(na * m / ms_asg / 1e6, 1)})
+            pair = {'workload': 'C4: 200,000 Waymo-prior anchors x 256 GT boxes, fun=log1p, tau=1: full [N,M] '
+                                'matrix, and row+column (min, argmin) fused without writing the matrix',
+                    'rows': pw_rows}
+            if not args.no_cpu:
+                from oracle import gd_oracle
+                torch.set_num_threads(os.cpu_count() or 1)
+                sa, sg = anchors[:4096].cpu(), gts.cpu()
+                t0 = time.perf_counter()
+                gd_oracle.pairwise_distance(sa, sg, 'gwd3d', fun='log1p', tau=1.0, chunk_rows=1024)
+                dt = time.perf_counter() - t0
+                pair['cpu_port'] = {'sample': '4096 x 256 pairs of the same call, oracle port (the reference '
+                                              'has no pairwise entry: its element-wise path on expanded pairs), '
+                                              f'fp32, {os.cpu_count()} threads',
+                                    'seconds': round(dt, 3), 'Gpairs_per_s': round(4096 * m / dt / 1e9, 5)}
+            extras['pairwise'] = pair
+            del mat, anchors
+            log('pairwise done')
+
     cpu = None
     # CPU baseline: rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 in its workers,
-    # which would serialise the autograd thread of the CPU port)
+    # which would serialise the autograd thread of the CPU path)
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_pairs_per_s(1 << 17, 1 << 17, 1)                     # warm the thread pool
-        v, cores, secs = cpu_pairs_per_s(1 << 23, 1 << 17, 2)
-        cpu = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-               'sample': 'oracle port (reference algorithm, eager torch fp32 + autograd), 4 '
-                         f'configs x 2^23 pairs (half the batch) in 2^17-row chunks, best of 2 '
-                         f'passes ({secs:.2f} s per pass)'}
-        # the single-thread row of SURVEY.md section 8d (bounded: 4 x 2^20 pairs, one pass)
-        v1, _, secs1 = cpu_pairs_per_s(1 << 20, 1 << 17, 1, threads=1)
+        v, cores, secs, kind = cpu_pairs_per_s(1 << 23, 1 << 17, 2)
+        what = ('UNMODIFIED reference file (oracle/_ref, stub mmdet)' if kind == 'reference'
+                else 'oracle port (staged reference file missing)')
+        cpu = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': kind,
+               'sample': f'{what}, eager torch fp32 + autograd, 4 configs x 2^23 pairs (half the batch) in '
+                         f'2^17-row chunks, best of 2 passes ({secs:.2f} s per pass)'}
+        v1, _, secs1, _ = cpu_pairs_per_s(1 << 20, 1 << 17, 1, threads=1)
         cpu['value_1thread'] = v1
         cpu['sample_1thread'] = f'4 configs x 2^20 pairs, one pass ({secs1:.2f} s)'
         torch.set_num_threads(os.cpu_count() or 1)
 
     eager = None
     if rank == 0 and world == 1 and args.eager_gpu:
-        # baseline leg only: the reference's own op sequence (oracle port) on CUDA tensors
-        from oracle import gd_oracle
+        # baseline leg only: the reference's own op sequence on CUDA tensors
         rows, chunk = min(n, 1 << 22), 1 << 20
-        emods = [gd_oracle.GDLossOracle(lt, fun=fun, tau=0.0, loss_weight=LOSS_WEIGHT)
-                 for lt, fun in COMBOS]
+        emods, ekind = cpu_modules(COMBOS)
 
         def eager_pass():
             for mod in emods:
@@ -459,12 +638,13 @@ def run_ours(args):
         g1.record()
         torch.cuda.synchronize()
         eager = {'value': len(COMBOS) * rows / (g0.elapsed_time(g1) * 1e-3), 'unit': 'pairs/s',
-                 'kind': 'port on cuda (eager torch + autograd, fp32)',
+                 'kind': f'{ekind} on cuda (eager torch + autograd, fp32)',
                  'sample': f'4 configs x 2^{rows.bit_length() - 1} pairs in 2^20-row chunks'}
         log('eager-gpu baseline done')
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic, traffic_src = recorded_traffic()
         achieved = BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
         out = {
             'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
@@ -473,27 +653,26 @@ def run_ours(args):
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'C2: kld3d+bd3d x fun{none,log1p}, tau=0, 2^24 KITTI-prior '
                                    'box pairs per GPU, weights [N], loss_weight=5, mean/avg_factor',
-                       'pairs_per_step_per_gpu': len(COMBOS) * n, 'launches_per_step': 2 * len(COMBOS),
+                       'pairs_per_step_per_gpu': len(COMBOS) * n,
                        'l2': 'inputs 1.0 GB per launch >> 126 MB L2, no flush needed',
-                       'variant': args.variant, 'module': 'GDLoss(host_sync=False)',
-                       'parallelism': f'rows sharded x{world}, 1 NCCL all-reduce of the scalar per evaluation '
-                                      f'(async, waited at the end of the step)'
-                       if world > 1 else 'single GPU'},
+                       'variant': args.variant, 'module': module_desc, 'parallelism': parallelism},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': recorded_traffic(),
-                         'peak_source': peak_src, 'kernel': 'gd_warp_kernel (fused fwd+bwd, bulk-copy warp pipelines)',
+                         'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                         'peak_source': peak_src,
+                         'kernel': 'gd_warp_kernel (fused fwd+bwd, bulk-copy warp pipelines, packed-FP32 math)',
                          'bytes_per_pair': BYTES_PER_PAIR, 'pairs_per_launch': n,
                          'kernel_ms': kernel_ms, 'frac_of_8TBps_nominal': achieved / 8000.0,
-                         # the same figure from the timed region itself (module calls: the
-                         # fused launch + the grad_output fold that exits at once + Python)
+                         # the same figure from the timed region itself (module calls: probe,
+                         # fused launch, grad_output fold that exits at once, Python + C++ shim)
                          'achieved_timed_region': BYTES_PER_PAIR * len(COMBOS) * n / (ms_step * 1e-3) / 1e9,
                          'per_config': per_cfg},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
-            'value_default_module': value_sync, 'value_overlap_module': value_overlap,
             'gpu_eager_baseline': eager,
             'lib': os.path.relpath(_lib.loaded_path(), ROOT),
-            'losses': [float(x) for x in losses],
+            'losses': final_losses,
         }
+        out.update(other)
+        out.update(extras)
         print(json.dumps(out))
     log('report printed')
     if world > 1:

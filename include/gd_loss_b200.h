@@ -138,6 +138,25 @@ GD_API int gd_loss_fwd_bwd(const gd_loss_config* cfg,
                     void* workspace, size_t workspace_bytes,
                     int32_t variant, int32_t flags, void* stream);
 
+/* Cross-GPU sum of the scalar loss INSIDE the fused launch (the one
+ * collective of the row-sharded path), over peer memory instead of a separate NCCL launch.
+ * Every rank owns an exchange buffer of gd_peer_sum_buffer_bytes() bytes that all ranks of
+ * the box can address (a symmetric / P2P-mapped allocation, e.g. torch symmetric memory),
+ * zero-filled once before first use.  The last CTA of the launch stores its scaled partial
+ * into slot [rank] of EVERY peer's buffer over NVLink (one 8-byte store + one release flag per
+ * peer), waits until all `world` flags of its own buffer carry the call's sequence number, and
+ * adds the `world` partials in rank order -- so loss_sum is the global sum, bit-identical on
+ * all ranks, deterministic.  All ranks must issue the same sequence of launches with the same
+ * buffers, one stream per buffer (as for any collective); the launch completes on a rank only
+ * once every rank has contributed.  Gradients stay local (DDP semantics). */
+#define GD_MAX_PEERS 16
+typedef struct gd_peer_sum {
+  int32_t world;                       /* 0 or 1: no exchange */
+  int32_t rank;
+  void* peer_buf[GD_MAX_PEERS];        /* rank r's exchange buffer as addressable from THIS device */
+} gd_peer_sum;
+GD_API size_t gd_peer_sum_buffer_bytes(void);
+
 /* The same launch with every argument in one struct, plus what the positional entry point
  * cannot express (ABI >= 2).  Zero-initialise the struct, then fill what applies. */
 typedef struct gd_loss_io {
@@ -154,29 +173,26 @@ typedef struct gd_loss_io {
   float* loss_sum; float* row_loss; float* grad_pred;
   /* nullable, 1 fp32 := 1 if ANY element of `weight` is > 0 else 0 -- the reference's
    * early-return condition `torch.any(weight > 0)` (ref:290) evaluated inside the same
-   * launch (needs loss_sum).  Feed it to gd_early_return_fix. */
+   * launch (needs loss_sum). */
   float* status;
+  /* Early-return branch of GDLoss.forward WITHOUT a host sync (ref:290-292; needs loss_sum and
+   * a weight).  Non-zero: when no weight element is > 0, the last CTA of the launch replaces
+   * the outputs by what the reference returns on that branch,
+   *   loss_sum := sum_{i,c} pred[i,c] * weight(i,c)          (pred * weight).sum(), ref:292
+   *   grad_pred[i,c] := weight(i,c)                          its autograd gradient
+   * with weight(i,c) = weight[i * er_weight_row_stride + c * er_weight_col_stride]
+   * ([n,7] weights: (row stride, 1); a [7] weight against [7,7] rows broadcasts over columns:
+   * (0, 1); [1]: (0, 0)) and no loss_weight / avg_factor (the reference applies none there).
+   * The branch is rare (an empty batch in practice), so one CTA doing the rewrite is fine. */
+  int32_t early_return;
+  int64_t er_weight_row_stride, er_weight_col_stride;
   void* workspace; size_t workspace_bytes;
   int32_t variant; int32_t flags;
+  /* nullable HOST pointer: sum loss_sum over the ranks of the box inside the launch */
+  const gd_peer_sum* peer_sum;
 } gd_loss_io;
 
 GD_API int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream);
-
-/* Early-return branch of GDLoss.forward WITHOUT a host sync (ref:290-292): launched right
- * after gd_loss_launch on the same stream.  Reads *status on the device; when it is non-zero
- * (some weight element > 0: the normal case) the kernel exits at once.  Otherwise it
- * overwrites the outputs with what the reference returns:
- *   loss_sum := sum_{i,c} pred[i,c] * weight(i,c)          (pred * weight).sum(), ref:292
- *   grad_pred[i,c] := weight(i,c)                          its autograd gradient
- * with weight(i,c) = weight[i * weight_row_stride + c * weight_col_stride]: ([n,7]: (s,1);
- * a [7] weight against [7,7] rows broadcasts over columns: (0,1); [1]: (0,0)).  No
- * loss_weight / avg_factor (the reference applies none on this branch).  grad_pred nullable. */
-GD_API int gd_early_return_fix(const float* status,
-                               const float* pred, int64_t pred_row_stride,
-                               const float* weight, int64_t weight_row_stride,
-                               int64_t weight_col_stride, int64_t n,
-                               float* loss_sum, float* grad_pred,
-                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Autograd fold: grad[i,:] *= *grad_output (0-dim upstream gradient; replaces the
  * first step of the reference's autograd backward).  Reads the scalar on the
@@ -198,15 +214,16 @@ GD_API int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_r
 GD_API int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* stream);
 
 /* The same probe without stalling the GPU (the host-visible form of ref:290 for weight
- * shapes where the reference's early return RAISES, so the host has to know): queues the
- * probe kernel (it stops at the first positive element it sees), a 4-byte copy of the flag
- * into `flag_host` (PINNED host memory) and records `event` behind it.  The caller then
- * queues the fused launch and only afterwards waits with gd_probe_event_wait -- the GPU
- * stays busy during the wait.  `event` comes from gd_probe_event_create (a cudaEvent_t
- * without timing; one per stream, reusable, lives as long as the process). */
+ * shapes where the reference's early return RAISES, so the host has to know): ONE small
+ * kernel (it stops at the first positive element any CTA sees) whose last CTA writes the
+ * answer straight into `flag_host` -- PINNED host memory, device-addressable under UVA -- and
+ * `event` recorded behind it.  The caller then queues the fused launch and only afterwards
+ * waits with gd_probe_event_wait: the GPU stays busy during the wait.  `event` comes from
+ * gd_probe_event_create (a cudaEvent_t without timing; one per stream, reusable, lives as long
+ * as the process); workspace as gd_loss_workspace_bytes (zeroed once, left zeroed). */
 GD_API int gd_probe_event_create(void** event);
-GD_API int gd_probe_begin(const float* weight, int64_t count, int32_t* flag, int32_t* flag_host,
-                          void* event, void* stream);
+GD_API int gd_probe_begin(const float* weight, int64_t count, int32_t* flag_host, void* event,
+                          void* workspace, size_t workspace_bytes, void* stream);
 GD_API int gd_probe_event_wait(void* event);
 
 /* out[0] := max(#{i : 0 <= labels[i] < num_classes}, 1) as fp32 -- the avg_factor of the

@@ -33,6 +33,15 @@ class GDLossConfig(ctypes.Structure):
                 ('alpha', ctypes.c_float), ('center_offset', ctypes.c_float * 3)]
 
 
+MAX_PEERS = 16
+
+
+class GDPeerSum(ctypes.Structure):
+    """``struct gd_peer_sum``."""
+    _fields_ = [('world', ctypes.c_int32), ('rank', ctypes.c_int32),
+                ('peer_buf', ctypes.c_void_p * MAX_PEERS)]
+
+
 class GDLossIO(ctypes.Structure):
     """``struct gd_loss_io``."""
     _fields_ = [('pred', ctypes.c_void_p), ('pred_row_stride', ctypes.c_int64),
@@ -42,8 +51,11 @@ class GDLossIO(ctypes.Structure):
                 ('scale', ctypes.c_float), ('scale_div', ctypes.c_void_p),
                 ('loss_sum', ctypes.c_void_p), ('row_loss', ctypes.c_void_p),
                 ('grad_pred', ctypes.c_void_p), ('status', ctypes.c_void_p),
+                ('early_return', ctypes.c_int32), ('er_weight_row_stride', ctypes.c_int64),
+                ('er_weight_col_stride', ctypes.c_int64),
                 ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t),
-                ('variant', ctypes.c_int32), ('flags', ctypes.c_int32)]
+                ('variant', ctypes.c_int32), ('flags', ctypes.c_int32),
+                ('peer_sum', ctypes.POINTER(GDPeerSum))]
 
 
 class GDCenterCoder(ctypes.Structure):
@@ -63,10 +75,9 @@ SIGNATURES = {
                                        _i64, _f32, _vp, _vp, _vp, _vp,
                                        ctypes.c_size_t, _i32, _i32, _vp]),
     'gd_loss_launch': (ctypes.c_int, [_cfgp, ctypes.POINTER(GDLossIO), _vp]),
-    'gd_early_return_fix': (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp,
-                                           ctypes.c_size_t, _vp]),
+    'gd_peer_sum_buffer_bytes': (ctypes.c_size_t, []),
     'gd_probe_event_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
-    'gd_probe_begin': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    'gd_probe_begin': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     'gd_probe_event_wait': (ctypes.c_int, [_vp]),
     'gd_count_positive_labels': (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.c_size_t, _vp]),
     'gd_scale_grad': (ctypes.c_int, [_vp, _i64, _vp, _vp]),

@@ -150,7 +150,33 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- system-scope accesses to peer memory (NVLink P2P) ----------------------
+__device__ __forceinline__ void st_relaxed_sys(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 #elif defined(GD_HOST_EMULATION)
+inline void st_relaxed_sys(double* p, double v) { __atomic_store(p, &v, __ATOMIC_RELAXED); }
+inline double ld_relaxed_sys(const double* p) {
+  double v;
+  __atomic_load(p, &v, __ATOMIC_RELAXED);
+  return v;
+}
+inline void st_release_sys(unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned int ld_acquire_sys(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 // Host stand-ins for the copy-engine / mbarrier primitives (tests/host_math/loss_emul.cpp
 // runs the kernels' SOURCE with one OS thread per CUDA thread).  A bulk copy is a memcpy
 // done by the issuing thread; the mbarrier keeps its phase bit and pending byte count in the

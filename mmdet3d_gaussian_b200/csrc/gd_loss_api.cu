@@ -64,62 +64,41 @@ __global__ void __launch_bounds__(kThreads) gd_any_positive_kernel(const float* 
   const long long stride = (long long)gridDim.x * kThreads;
   bool any = false;
   for (long long i0 = (long long)blockIdx.x * kThreads; i0 < count; i0 += stride) {
-    if (*reinterpret_cast<volatile int*>(flag) != 0) return;      // CTA-uniform
+    // ONE thread looks at the flag; the vote makes the decision CTA-uniform
+    const bool stop = threadIdx.x == 0 && *reinterpret_cast<volatile int*>(flag) != 0;
     const long long i = i0 + threadIdx.x;
-    if (i < count) any = w[i] > 0.0f;
-    if (__syncthreads_or(any)) {
-      if (threadIdx.x == 0) atomicOr(flag, 1);
-      return;
-    }
+    any = i < count && w[i] > 0.0f;
+    const int vote = __syncthreads_or((any ? 1 : 0) | (stop ? 2 : 0));
+    if ((vote & 1) && threadIdx.x == 0) atomicOr(flag, 1);
+    if (vote) return;
   }
 }
 
-// ref:290-292 decided on the device: *status == 0 (no weight element > 0) -> the outputs of
-// the fused launch are replaced by (pred * weight).sum() and its gradient `weight`.
-struct EarlyArgs {
-  const float* status;
-  const float* pred;
-  long long pstride;
-  const float* weight;
-  long long wrow, wcol;
-  long long nel;
-  float* loss_sum;
-  float* grad;
-  double* partials;
-  unsigned int* ticket;
-};
-
-__global__ void __launch_bounds__(kThreads) gd_early_return_kernel(const EarlyArgs e) {
-  if (__ldg(e.status) != 0.0f) return;     // the normal case: one launch, no traffic
-  __shared__ double s_part[kThreads / 32];
-  __shared__ bool s_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Early-return probe whose LAST CTA writes the answer into pinned host memory: ticket[4] =
+// any-positive word, ticket[5] = CTA ticket (both left zero).
+__global__ void __launch_bounds__(kThreads) gd_probe_kernel(const float* __restrict__ w,
+                                                            long long count, unsigned int* ticket,
+                                                            volatile int* flag_host) {
   const long long stride = (long long)gridDim.x * kThreads;
-  double acc = 0.0;
-  for (long long i = (long long)blockIdx.x * kThreads + tid; i < e.nel; i += stride) {
-    const long long r = i / 7;
-    const int c = (int)(i - r * 7);
-    const float w = e.weight[r * e.wrow + c * e.wcol];
-    acc += (double)(e.pred[r * e.pstride + c] * w);
-    if (e.grad) e.grad[i] = w;
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) s_part[warp] = acc;
-  __syncthreads();
-  if (tid == 0) {
-    double s = 0.0;
-    for (int w = 0; w < kThreads / 32; ++w) s += s_part[w];
-    e.partials[blockIdx.x] = s;
-    __threadfence();
-    s_last = atomicAdd(e.ticket, 1u) == gridDim.x - 1;
+  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < count; i0 += stride) {
+    // ONE thread looks at the flag; the vote makes the decision CTA-uniform
+    const bool stop = threadIdx.x == 0 && *reinterpret_cast<volatile unsigned int*>(ticket + 4) != 0u;
+    const long long i = i0 + threadIdx.x;
+    const bool any = i < count && w[i] > 0.0f;
+    const int vote = __syncthreads_or((any ? 1 : 0) | (stop ? 2 : 0));
+    if ((vote & 1) && threadIdx.x == 0) atomicOr(ticket + 4, 1u);
+    if (vote) break;
   }
   __syncthreads();
-  if (s_last && tid == 0) {
+  if (threadIdx.x == 0) {
     __threadfence();
-    double tot = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(e.partials + b);
-    *e.loss_sum = (float)tot;
-    *e.ticket = 0u;
+    if (atomicAdd(ticket + 5, 1u) == gridDim.x - 1) {
+      __threadfence();
+      *flag_host = __ldcg(ticket + 4) ? 1 : 0;
+      __threadfence_system();
+      ticket[4] = 0u;
+      ticket[5] = 0u;
+    }
   }
 }
 
@@ -233,12 +212,28 @@ int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream
   a.scale = io->scale;
   a.scale_div = io->scale_div;
   a.status = io->status;
+  if (io->early_return) {
+    if (!io->loss_sum || weight_mode == GD_WEIGHT_NONE || io->er_weight_row_stride < 0 ||
+        io->er_weight_col_stride < 0)
+      return GD_ERR_BAD_ARG;
+    a.early_return = 1;
+    a.er_wrow = io->er_weight_row_stride;
+    a.er_wcol = io->er_weight_col_stride;
+  }
   a.loss_sum = io->loss_sum;
   a.row_loss = io->row_loss;
   a.grad = io->grad_pred;
   a.ticket = reinterpret_cast<unsigned int*>(io->workspace);
   a.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(io->workspace) + 256);
   a.pp = make_pair_params(*cfg);
+  if (io->peer_sum && io->peer_sum->world > 1) {
+    const gd_peer_sum& ps = *io->peer_sum;
+    if (!io->loss_sum || ps.world > GD_MAX_PEERS || ps.rank < 0 || ps.rank >= ps.world)
+      return GD_ERR_BAD_ARG;
+    for (int r = 0; r < ps.world; ++r)
+      if (!ps.peer_buf[r]) return GD_ERR_BAD_ARG;
+    a.peer = ps;
+  }
 
   // Row-strided / unaligned inputs: bulk copies of whole wide rows (GD_VARIANT_BULK_ANY) when
   // the strides are sane and a useful number of warps fits the shared memory.
@@ -280,35 +275,7 @@ int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream
   return GD_ERR_BAD_ARG;
 }
 
-int gd_early_return_fix(const float* status, const float* pred, int64_t pred_row_stride,
-                        const float* weight, int64_t weight_row_stride, int64_t weight_col_stride,
-                        int64_t n, float* loss_sum, float* grad_pred, void* workspace,
-                        size_t workspace_bytes, void* stream) {
-  using namespace gdk;
-  if (!status || n < 0 || !loss_sum || (n > 0 && (!pred || !weight)) || weight_row_stride < 0 ||
-      weight_col_stride < 0)
-    return GD_ERR_BAD_ARG;
-  if (!workspace || workspace_bytes < gd_loss_workspace_bytes(n)) return GD_ERR_WORKSPACE;
-  EarlyArgs e;
-  e.status = status;
-  e.pred = pred;
-  e.pstride = pred_row_stride;
-  e.weight = weight;
-  e.wrow = weight_row_stride;
-  e.wcol = weight_col_stride;
-  e.nel = n * 7;
-  e.loss_sum = loss_sum;
-  e.grad = grad_pred;
-  e.ticket = reinterpret_cast<unsigned int*>(workspace);
-  e.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + 256);
-  long long grid = (e.nel + kThreads * 8 - 1) / (kThreads * 8);
-  const long long cap = (long long)device_info().sm_count * 4;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-  gd_early_return_kernel<<<(int)grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
-}
+size_t gd_peer_sum_buffer_bytes(void) { return sizeof(gdk::PeerBuf); }
 
 int gd_scale_grad(float* grad, int64_t n, const float* grad_output_scalar, void* stream) {
   using namespace gdk;
@@ -378,13 +345,21 @@ int gd_probe_event_create(void** event) {
   return 0;
 }
 
-int gd_probe_begin(const float* weight, int64_t count, int32_t* flag, int32_t* flag_host,
-                   void* event, void* stream) {
-  if (!flag_host || !event) return GD_ERR_BAD_ARG;
-  const int rc = gd_any_positive(weight, count, flag, stream);
-  if (rc != 0) return rc;
+int gd_probe_begin(const float* weight, int64_t count, int32_t* flag_host, void* event,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace gdk;
+  if (!flag_host || !event || count < 0 || (count > 0 && !weight)) return GD_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < gd_loss_workspace_bytes(0)) return GD_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemcpyAsync(flag_host, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  long long grid = (count + kThreads - 1) / kThreads;
+  const long long cap = (long long)device_info().sm_count * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  gd_probe_kernel<<<(int)grid, kThreads, 0, st>>>(weight, count,
+                                                  reinterpret_cast<unsigned int*>(workspace),
+                                                  flag_host);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   return (int)cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), st);
 }

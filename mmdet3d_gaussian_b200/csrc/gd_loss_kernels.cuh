@@ -87,15 +87,62 @@ struct LossArgs {
   // device: gd_centerpoint_head.py:407 without its .item())
   const float* scale_div = nullptr;
   // nullable, 1 fp32 := any(weight > 0) ? 1 : 0 over every weight ELEMENT (ref:290), written by
-  // the last CTA together with loss_sum; consumed by gd_early_return_fix
+  // the last CTA together with loss_sum
   float* status = nullptr;
+  // early return of GDLoss.forward decided on the device (ref:290-292): when no weight
+  // element is > 0 the last CTA replaces the outputs by (pred * weight).sum() and its gradient
+  // `weight`, with weight(i, c) = weight[i * er_wrow + c * er_wcol]
+  int early_return = 0;
+  long long er_wrow = 0, er_wcol = 0;
   // gd_warp_kernel<..., ANY = true> (row-strided and/or 16-byte-unaligned inputs): rows
   // [row_lo, row_lo + n_bulk) go through the bulk-copy tiles, the <= 8 rows around them are
   // read straight from global memory; *shift = words between the 16-byte aligned copy
   // window and the first element of a tile (constant: tiles are multiples of 4 rows)
   long long row_lo = 0, n_bulk = 0;
   int pshift = 0, tshift = 0, wshift = 0;
+  // cross-GPU sum of loss_sum over peer memory (world <= 1: none); include/gd_loss_b200.h
+  gd_peer_sum peer = {};
 };
+
+// Exchange buffer of one rank (gd_peer_sum_buffer_bytes()).  Two value / flag sets, used
+// alternately by consecutive calls: a rank can be at most one call ahead of its slowest peer
+// (it cannot finish call s + 1 without that peer's flag for s + 1), so the set of call s is
+// never overwritten before everybody has read it.
+struct PeerBuf {
+  unsigned int seq;                          // calls completed by the owning rank
+  unsigned int pad[3];
+  double val[2][GD_MAX_PEERS];
+  unsigned int flag[2][GD_MAX_PEERS];
+};
+
+// Called by every thread of the LAST CTA of a launch (uniformly).  Returns the global sum.
+__device__ __forceinline__ double peer_exchange_sum(const gd_peer_sum& ps, double mine) {
+  __shared__ double s_total;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_total = mine;              // thread 0 holds the partial; every talker sends it
+  __syncthreads();
+  mine = s_total;
+  __syncthreads();
+  PeerBuf* own = reinterpret_cast<PeerBuf*>(ps.peer_buf[ps.rank]);
+  const unsigned int seq = own->seq + 1u;    // written only by this rank's previous launch
+  const int par = (int)(seq & 1u);
+  if (tid < ps.world) {                      // thread p talks to peer p
+    PeerBuf* dst = reinterpret_cast<PeerBuf*>(ps.peer_buf[tid]);
+    st_relaxed_sys(&dst->val[par][ps.rank], mine);
+    st_release_sys(&dst->flag[par][ps.rank], seq);      // orders the value before the flag
+    while (ld_acquire_sys(&own->flag[par][tid]) != seq) {
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int r = 0; r < ps.world; ++r) tot += ld_relaxed_sys(&own->val[par][r]);   // rank order
+    own->seq = seq;
+    s_total = tot;
+  }
+  __syncthreads();
+  return s_total;
+}
 
 __device__ __forceinline__ float effective_scale(const LossArgs& a) {
   return a.scale_div ? a.scale / __ldg(a.scale_div) : a.scale;
@@ -120,7 +167,7 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a, float s
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += (double)s_warp[w];
     a.partials[blockIdx.x] = s;
-    if (a.status && cta_any) atomicOr(a.ticket + 1, 1u);
+    if ((a.status || a.early_return) && cta_any) atomicOr(a.ticket + 1, 1u);
     __threadfence();
     const unsigned int t = atomicAdd(a.ticket, 1u);
     s_last = (t == gridDim.x - 1);
@@ -133,14 +180,42 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a, float s
     s = warp_sum(s);
     if (lane == 0) s_dwarp[warp] = s;
     __syncthreads();
+    double tot = 0.0;
     if (tid == 0) {
-      double tot = 0.0;
       for (int w = 0; w < nwarps; ++w) tot += s_dwarp[w];
-      *a.loss_sum = (float)(tot * (double)scale);
-      if (a.status) {
-        *a.status = __ldcg(a.ticket + 1) ? 1.0f : 0.0f;
-        a.ticket[1] = 0u;
+      tot *= (double)scale;
+    }
+    if (a.peer.world > 1) tot = peer_exchange_sum(a.peer, tot);    // thread 0's partial is sent
+    const bool probe = a.status != nullptr || a.early_return != 0;
+    // ONE thread reads the any-positive word (it is reset below) and the vote makes the
+    // decision CTA-uniform
+    const bool none_positive =
+        probe && __syncthreads_or(tid == 0 && __ldcg(a.ticket + 1) == 0u ? 1 : 0) != 0;
+    if (a.early_return && none_positive) {
+      // ref:292, the rare branch (in practice an EMPTY batch): every other CTA has finished
+      // (ticket), so this one rewrites the gradient and sums pred * weight on its own
+      __syncthreads();
+      double acc = 0.0;
+      const long long nel = a.n * 7;
+      for (long long i = tid; i < nel; i += nthreads) {
+        const long long r = i / 7;
+        const int c = (int)(i - r * 7);
+        const float w = a.weight[r * a.er_wrow + c * a.er_wcol];
+        acc += (double)(a.pred[r * a.pstride + c] * w);
+        if (a.grad) a.grad[i] = w;
       }
+      acc = warp_sum(acc);
+      if (lane == 0) s_dwarp[warp] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        tot = 0.0;
+        for (int w = 0; w < nwarps; ++w) tot += s_dwarp[w];
+      }
+    }
+    if (tid == 0) {
+      *a.loss_sum = (float)tot;
+      if (a.status) *a.status = none_positive ? 0.0f : 1.0f;
+      if (probe) a.ticket[1] = 0u;
       *a.ticket = 0u;                     // leave the workspace reusable
     }
   }
@@ -224,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
   const int tid = threadIdx.x;
   const long long ntiles = (a.n + kTile - 1) / kTile;
   const float scale = effective_scale(a);
-  const bool probe = a.status != nullptr;   // any(weight > 0) over every weight element, ref:290
+  const bool probe = a.status != nullptr || a.early_return != 0;   // any(weight > 0) over every weight element, ref:290
   bool anyp = false;
   float acc = 0.0f;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -375,7 +450,7 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   gd::PairParams<float> pp = a.pp;
   const bool mask_zero = a.mask_zero_w != 0;
   const float scale = effective_scale(a);
-  const bool probe = a.status != nullptr;     // any(weight > 0), ref:290
+  const bool probe = a.status != nullptr || a.early_return != 0;     // any(weight > 0), ref:290
   bool anyp = false;
   const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
   // row strides in floats / lead-in words of a tile in shared memory

@@ -40,7 +40,6 @@ struct Abi {
   GD_SYM(gd_abi_version)
   GD_SYM(gd_loss_workspace_bytes)
   GD_SYM(gd_loss_launch)
-  GD_SYM(gd_early_return_fix)
   GD_SYM(gd_scale_grad)
   GD_SYM(gd_scale_buffer)
   GD_SYM(gd_scale_grad_rows)
@@ -48,6 +47,7 @@ struct Abi {
   GD_SYM(gd_probe_event_create)
   GD_SYM(gd_probe_event_wait)
   GD_SYM(gd_count_positive_labels)
+  GD_SYM(gd_peer_sum_buffer_bytes)
   GD_SYM(gd_anchor_decoded_loss_fwd_bwd)
   GD_SYM(gd_center_decoded_loss_fwd_bwd)
   GD_SYM(gd_error_string)
@@ -67,7 +67,6 @@ void bind(const std::string& path) {
   GD_SYM(gd_abi_version)
   GD_SYM(gd_loss_workspace_bytes)
   GD_SYM(gd_loss_launch)
-  GD_SYM(gd_early_return_fix)
   GD_SYM(gd_scale_grad)
   GD_SYM(gd_scale_buffer)
   GD_SYM(gd_scale_grad_rows)
@@ -75,6 +74,7 @@ void bind(const std::string& path) {
   GD_SYM(gd_probe_event_create)
   GD_SYM(gd_probe_event_wait)
   GD_SYM(gd_count_positive_labels)
+  GD_SYM(gd_peer_sum_buffer_bytes)
   GD_SYM(gd_anchor_decoded_loss_fwd_bwd)
   GD_SYM(gd_center_decoded_loss_fwd_bwd)
   GD_SYM(gd_error_string)
@@ -84,7 +84,7 @@ void bind(const std::string& path) {
   g_abi = a;
 }
 
-inline const Abi& abi() {
+inline const Abi& gd_abi() {
   if (!g_abi.handle)
     throw std::runtime_error("gd_loss_b200: the CUDA library is not bound (no CPU fallback exists)");
   return g_abi;
@@ -93,7 +93,7 @@ inline const Abi& abi() {
 inline void check(int code, const char* what) {
   if (code != 0)
     throw std::runtime_error(std::string("gd_loss_b200.") + what + " failed (" +
-                             std::to_string(code) + "): " + abi().gd_error_string(code));
+                             std::to_string(code) + "): " + gd_abi().gd_error_string(code));
 }
 
 [[noreturn]] void raise_not_implemented(const char* msg) {
@@ -106,7 +106,6 @@ inline void check(int code, const char* what) {
 // ---------------------------------------------------------------------------
 struct StreamState {
   Tensor workspace;            // ticket + per-CTA partials
-  Tensor probe_flag;           // int32[1] on the device
   Tensor probe_host;           // int32[1] pinned
   void* probe_event = nullptr;
 };
@@ -125,7 +124,7 @@ std::shared_ptr<StreamState> stream_state(const c10::cuda::CUDAStream& s) {
   // entry whose kernels are still queued is safe)
   if (g_state.size() >= kMaxStreamStates) g_state.clear();
   auto st = std::make_shared<StreamState>();
-  const auto nbytes = static_cast<int64_t>(abi().gd_loss_workspace_bytes(0));
+  const auto nbytes = static_cast<int64_t>(gd_abi().gd_loss_workspace_bytes(0));
   st->workspace = at::zeros({nbytes}, at::TensorOptions().dtype(at::kByte).device(at::kCUDA, s.device_index()));
   g_state.emplace(key, st);
   return st;
@@ -166,6 +165,7 @@ struct LossCall {
   int flags = 0;
   bool device_early_return = false;           // ref:290-292 decided on the device
   int64_t er_wrow = 0, er_wcol = 0;           // weight(i, c) strides for (pred * weight)
+  gd_peer_sum peer = {};                      // world > 1: loss summed over the box in-kernel
 };
 
 struct LossOut {
@@ -173,7 +173,7 @@ struct LossOut {
 };
 
 LossOut launch_loss(const LossCall& k, bool want_grad) {
-  const Abi& lib = abi();
+  const Abi& lib = gd_abi();
   const int64_t n = k.pred.size(0);
   const auto opts = k.pred.options();
   LossOut o;
@@ -181,8 +181,6 @@ LossOut launch_loss(const LossCall& k, bool want_grad) {
   if (want_sum) o.loss = at::empty({}, opts);
   if (k.rows_out) o.rows = at::empty({n}, opts);
   if (want_grad) o.grad = at::empty({n, 7}, opts);
-  Tensor status;
-  if (k.device_early_return) status = at::empty({1}, opts);
   const auto stream = at::cuda::getCurrentCUDAStream(k.pred.get_device());
   gd_loss_io io{};
   io.pred = fptr(k.pred);
@@ -199,7 +197,11 @@ LossOut launch_loss(const LossCall& k, bool want_grad) {
   io.loss_sum = fptr_mut(o.loss);
   io.row_loss = fptr_mut(o.rows);
   io.grad_pred = fptr_mut(o.grad);
-  io.status = fptr_mut(status);
+  if (k.device_early_return) {
+    io.early_return = 1;
+    io.er_weight_row_stride = k.er_wrow;
+    io.er_weight_col_stride = k.er_wcol;
+  }
   std::shared_ptr<StreamState> st;
   if (want_sum) {
     st = stream_state(stream);
@@ -208,13 +210,8 @@ LossOut launch_loss(const LossCall& k, bool want_grad) {
   }
   io.variant = k.variant;
   io.flags = k.flags;
+  io.peer_sum = (k.peer.world > 1 && want_sum) ? &k.peer : nullptr;
   check(lib.gd_loss_launch(&k.cfg, &io, stream.stream()), "gd_loss_launch");
-  if (k.device_early_return) {
-    check(lib.gd_early_return_fix(io.status, io.pred, io.pred_row_stride, io.weight, k.er_wrow,
-                                  k.er_wcol, n, io.loss_sum, io.grad_pred, io.workspace,
-                                  io.workspace_bytes, stream.stream()),
-          "gd_early_return_fix");
-  }
   return o;
 }
 
@@ -231,7 +228,7 @@ struct LossNode : public torch::autograd::Node {
       throw std::runtime_error(
           "Trying to backward through the graph a second time (gd_loss_b200: the saved tensors "
           "of the fused loss were freed; pass retain_graph=True to the first backward)");
-    const Abi& lib = abi();
+    const Abi& lib = gd_abi();
     c10::cuda::CUDAGuard guard(call.pred.device());
     Tensor grad = std::move(grad_buf);
     grad_buf = Tensor();
@@ -273,6 +270,10 @@ Tensor attach_history(Tensor out, const Tensor& pred, const LossCall& call, Tens
   return out;
 }
 
+struct PeerSum {
+  gd_peer_sum c;
+};
+
 enum Reduction { kNone = 0, kMean = 1, kSum = 2 };
 enum SyncMode {
   kMaskZero = 0,   // host_sync=False: never probe, rows with weight exactly 0 masked in-kernel
@@ -282,7 +283,7 @@ enum SyncMode {
 // GDLoss.forward after the Python-only steps (reduction_override assert, kwargs merge).
 Tensor gd_loss(const Tensor& pred_in, const Tensor& target_in, const c10::optional<Tensor>& weight_in,
                const Config& cfg, double loss_weight, int reduction, const py::object& avg_factor,
-               int variant, int sync_mode) {
+               int variant, int sync_mode, const PeerSum* peer) {
   require_cuda(pred_in, "pred");
   require_cuda(target_in, "target");
   if (target_in.requires_grad())
@@ -373,6 +374,15 @@ Tensor gd_loss(const Tensor& pred_in, const Tensor& target_in, const c10::option
     if (n == 0) return (pred_in * *weight_in).sum();
   }
   if (sync_mode == kMaskZero) k.flags |= GD_FLAG_MASK_ZERO_WEIGHT;
+  if (peer != nullptr && peer->c.world > 1 && !k.rows_out) {
+    // the early-return branch is a per-process decision in the reference (one process per
+    // GPU); its replacement value would bypass the exchange, so the fused cross-GPU sum is
+    // offered for the sync-free semantics only
+    if (k.device_early_return || host_probe)
+      throw py::value_error(
+          "gd_loss_b200: the in-kernel cross-GPU sum needs weight=None or GDLoss(host_sync=False)");
+    k.peer = peer->c;
+  }
 
   const bool need_grad = at::GradMode::is_enabled() && k.pred.requires_grad();
   void* probe_event = nullptr;
@@ -384,19 +394,18 @@ Tensor gd_loss(const Tensor& pred_in, const Tensor& target_in, const c10::option
           "gd_loss_b200: GDLoss with [N] weights keeps the reference's early-return check "
           "(gaussian_distance_loss.py:290), whose outcome (an exception) needs a host wait and "
           "cannot be captured in a CUDA graph; pass [N,7] weights, weight=None or host_sync=False");
-    const Abi& lib = abi();
+    const Abi& lib = gd_abi();
     const auto stream = at::cuda::getCurrentCUDAStream(k.pred.get_device());
     probe_state = stream_state(stream);
     StreamState& st = *probe_state;
     if (!st.probe_event) {
-      st.probe_flag = at::zeros({1}, k.pred.options().dtype(at::kInt));
       st.probe_host = at::zeros({1}, at::TensorOptions().dtype(at::kInt).pinned_memory(true));
       check(lib.gd_probe_event_create(&st.probe_event), "gd_probe_event_create");
     }
     Tensor wc = k.weight.is_contiguous() ? k.weight : k.weight.contiguous();
-    check(lib.gd_probe_begin(fptr(wc), wc.numel(), st.probe_flag.mutable_data_ptr<int32_t>(),
-                             st.probe_host.mutable_data_ptr<int32_t>(), st.probe_event,
-                             stream.stream()),
+    check(lib.gd_probe_begin(fptr(wc), wc.numel(), st.probe_host.mutable_data_ptr<int32_t>(),
+                             st.probe_event, st.workspace.mutable_data_ptr(),
+                             static_cast<size_t>(st.workspace.numel()), stream.stream()),
           "gd_probe_begin");
     probe_event = st.probe_event;
     probe_host = st.probe_host.const_data_ptr<int32_t>();
@@ -408,7 +417,7 @@ Tensor gd_loss(const Tensor& pred_in, const Tensor& target_in, const c10::option
     int code;
     {
       py::gil_scoped_release nogil;
-      code = abi().gd_probe_event_wait(probe_event);
+      code = gd_abi().gd_probe_event_wait(probe_event);
     }
     check(code, "gd_probe_event_wait");
     if (*probe_host == 0) return (pred_in * *weight_in).sum();      // ref:292 (raises like the reference)
@@ -439,7 +448,7 @@ struct BufferNode : public torch::autograd::Node {
     Tensor go = grads[0];
     if (go.scalar_type() != at::kFloat) go = go.to(at::kFloat);
     const auto stream = at::cuda::getCurrentCUDAStream(grad.get_device());
-    check(abi().gd_scale_buffer(fptr_mut(grad), grad.numel(), fptr(go), stream.stream()),
+    check(gd_abi().gd_scale_buffer(fptr_mut(grad), grad.numel(), fptr(go), stream.stream()),
           "gd_scale_buffer");
     out[0] = std::move(grad);
     return out;
@@ -497,7 +506,7 @@ Tensor anchor_decoded_loss(const Tensor& anchors_in, const Tensor& bbox_pred, co
                            const c10::optional<Tensor>& pos_inds_in, const c10::optional<Tensor>& labels_in,
                            int64_t num_classes, const Config& cfg, double loss_weight, int scale_mode,
                            const py::object& avg_factor, bool mask_zero_weight) {
-  const Abi& lib = abi();
+  const Abi& lib = gd_abi();
   const bool index_mode = pos_inds_in.has_value() && pos_inds_in->defined();
   const bool label_mode = labels_in.has_value() && labels_in->defined();
   if (index_mode == label_mode) throw py::value_error("pass exactly one of pos_inds / labels");
@@ -581,7 +590,7 @@ Tensor center_decoded_loss(const Tensor& pred_in, const Tensor& pos_ind, const T
                            const c10::optional<Tensor>& weight_in, const CenterCoder& coder,
                            const Config& cfg, double loss_weight, int scale_mode,
                            const py::object& avg_factor, bool mask_zero_weight) {
-  const Abi& lib = abi();
+  const Abi& lib = gd_abi();
   Tensor p = rows_f32(pred_in, "pred", 7);
   Tensor t = rows_f32(target_box.requires_grad() ? target_box.detach() : target_box, "target_box", 7);
   require_cuda(pos_ind, "pos_ind");
@@ -669,9 +678,23 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       }))
       .def_property_readonly("norm_bbox", [](const CenterCoder& c) { return c.c.norm_bbox; })
       .def_property_readonly("out_size_factor", [](const CenterCoder& c) { return c.c.out_size_factor; });
+  py::class_<PeerSum>(m, "PeerSum")
+      .def(py::init([](int world, int rank, const std::vector<uint64_t>& bufs) {
+        if (world < 1 || world > GD_MAX_PEERS || rank < 0 || rank >= world ||
+            static_cast<int>(bufs.size()) != world)
+          throw py::value_error("PeerSum(world, rank, one buffer pointer per rank)");
+        PeerSum p{};
+        p.c.world = world;
+        p.c.rank = rank;
+        for (int r = 0; r < world; ++r) p.c.peer_buf[r] = reinterpret_cast<void*>(bufs[r]);
+        return p;
+      }))
+      .def_property_readonly("world", [](const PeerSum& p) { return p.c.world; })
+      .def_property_readonly("rank", [](const PeerSum& p) { return p.c.rank; });
+  m.def("peer_sum_buffer_bytes", []() { return gd_abi().gd_peer_sum_buffer_bytes(); });
   m.def("gd_loss", &gd_loss, py::arg("pred"), py::arg("target"), py::arg("weight"), py::arg("cfg"),
         py::arg("loss_weight"), py::arg("reduction"), py::arg("avg_factor"), py::arg("variant"),
-        py::arg("sync_mode"));
+        py::arg("sync_mode"), py::arg("peer_sum") = nullptr);
   m.def("anchor_decoded_loss", &anchor_decoded_loss);
   m.def("center_decoded_loss", &center_decoded_loss);
   m.def("stream_states", []() {

@@ -96,6 +96,7 @@ class GDLoss(nn.Module):
         self.host_sync = True if hs == 'overlap' else bool(hs)
         self.kwargs = kwargs                                      # ref:278
         self._cfg_cache = {}
+        self._peer_sum = None        # set by sharded.ShardedGDLoss(fused=True)
 
     def _key(self, extra):
         name, default = _FLAG[self.loss_type]
@@ -139,7 +140,7 @@ class GDLoss(nn.Module):
         # ref:290-292 (early return), ref:295-310 and mmdet's weighted_loss: in the shim
         return ops.gd_loss(pred, target, weight, self._shim_config(_kwargs), self.loss_weight,
                            reduction, avg_factor, self.variant,
-                           mask_zero_weight=not self.host_sync)
+                           mask_zero_weight=not self.host_sync, peer_sum=self._peer_sum)
 
     def extra_repr(self):
         return (f'loss_type={self.loss_type!r}, fun={self.fun!r}, tau={self.tau}, '

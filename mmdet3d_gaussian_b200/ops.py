@@ -79,7 +79,7 @@ SYNC_MASK_ZERO, SYNC_EXACT = 0, 1
 
 
 def gd_loss(pred, target, weight, cfg, loss_weight=1.0, reduction='mean', avg_factor=None,
-            variant='auto', mask_zero_weight=False):
+            variant='auto', mask_zero_weight=False, peer_sum=None):
     """``GDLoss.forward`` after its Python-only steps: the torch C++ shim
     (``csrc/torch_shim.cpp``) flattens ``[..., 7]``, dispatches the weight shape
     (``None`` / ``[N]`` / ``[N,7]``: mean over the last dim, reference
@@ -88,10 +88,11 @@ def gd_loss(pred, target, weight, cfg, loss_weight=1.0, reduction='mean', avg_fa
     gradient into autograd.  ``cfg``: ``_lib.make_shim_config(...)``.
     ``mask_zero_weight=False`` keeps the reference's early return (ref:290-292), decided on
     the device where its result is shape-valid; ``True`` never probes and masks rows whose
-    weight is exactly 0."""
+    weight is exactly 0.  ``peer_sum`` (``sharded.PeerSumContext``): the reduced loss is summed
+    over the GPUs of the box inside the launch."""
     return _lib.shim().gd_loss(pred, target, weight, cfg, float(loss_weight),
                                REDUCTIONS[reduction], avg_factor, _lib.VARIANTS[variant],
-                               SYNC_MASK_ZERO if mask_zero_weight else SYNC_EXACT)
+                               SYNC_MASK_ZERO if mask_zero_weight else SYNC_EXACT, peer_sum)
 
 
 def any_positive(weight):

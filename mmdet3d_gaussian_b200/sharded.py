@@ -27,6 +27,48 @@ def shard_bounds(n, rank, world_size, align=ROW_ALIGN):
     return lo, hi
 
 
+class PeerSumContext:
+    """Exchange buffers for the in-kernel cross-GPU sum (``gd_peer_sum``,
+    ``include/gd_loss_b200.h``): one small symmetric-memory allocation per rank
+    (``torch.distributed._symmetric_memory``: every rank's buffer is mapped into every other
+    rank's address space over NVLink), zero-filled, rendezvoused once.  The fused kernel's last
+    CTA then writes its partial straight into the peers' buffers -- no NCCL launch on the path.
+
+    ``PeerSumContext.create(group)`` returns ``None`` when symmetric memory is unavailable
+    (single process, gloo, no P2P): callers then keep the NCCL all-reduce."""
+
+    def __init__(self, handle, buf, shim_obj, world, rank):
+        self.handle, self.buf, self.shim_obj = handle, buf, shim_obj     # keep the mapping alive
+        self.world, self.rank = world, rank
+
+    @classmethod
+    def create(cls, group=None, device=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        group = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or dist.get_backend(group) != 'nccl':
+            return None
+        from . import _lib
+        sh = _lib.shim()
+        ok = torch.ones(1, device=device or torch.device('cuda', torch.cuda.current_device()))
+        ctx = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = int(sh.peer_sum_buffer_bytes())
+            buf = symm_mem.empty(max(nbytes, 1024), dtype=torch.uint8, device=ok.device)
+            buf.zero_()
+            handle = symm_mem.rendezvous(buf, group.group_name)
+            ptrs = [int(p) for p in handle.buffer_ptrs]
+            ctx = cls(handle, buf, sh.PeerSum(world, rank, ptrs), world, rank)
+            torch.cuda.synchronize()
+        except Exception:                              # noqa: BLE001 -- capability probe
+            ok.zero_()
+        # all ranks take the same path: fused only if EVERY rank could map the buffers
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        return ctx if float(ok.item()) > 0 else None
+
+
 class ShardedGDLoss(torch.nn.Module):
     """Wraps a ``GDLoss``-like module: every rank passes ITS rows; the returned
     scalar is the loss over ALL ranks' rows.
@@ -38,10 +80,16 @@ class ShardedGDLoss(torch.nn.Module):
     ``pred`` is the local shard's gradient, as with DDP.
     """
 
-    def __init__(self, loss_module, group=None):
+    def __init__(self, loss_module, group=None, fused=False):
+        """``fused=True``: sum the loss over the GPUs INSIDE the fused launch through peer
+        memory (``PeerSumContext``) instead of a separate NCCL all-reduce; needs
+        ``GDLoss(host_sync=False)`` (or ``weight=None`` calls) and falls back to NCCL when
+        symmetric memory is unavailable (``self.fused`` tells which)."""
         super().__init__()
         self.loss_module = loss_module
         self.group = group
+        self.peer = PeerSumContext.create(group) if fused else None
+        self.fused = self.peer is not None
 
     def forward(self, pred, target, weight=None, avg_factor=None,
                 reduction_override=None, **kwargs):
@@ -62,6 +110,15 @@ class ShardedGDLoss(torch.nn.Module):
             total = packed[0] / n_global
             # value = global mean; gradient = d(local sum)/d pred / n_global
             return total + (local - local.detach()) / n_global
+        if self.fused:
+            # the kernel's last CTA exchanges the scaled partials over NVLink: the value IS the
+            # global sum (identical bits on every rank), the gradient is the local shard's
+            self.loss_module._peer_sum = self.peer.shim_obj
+            try:
+                return self.loss_module(pred, target, weight, avg_factor=avg_factor,
+                                        reduction_override=reduction, **kwargs)
+            finally:
+                self.loss_module._peer_sum = None
         local = self.loss_module(pred, target, weight, avg_factor=avg_factor,
                                  reduction_override=reduction, **kwargs)
         total = local.detach().clone()

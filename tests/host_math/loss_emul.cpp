@@ -122,7 +122,8 @@ extern "C" int gd_emul_loss_any(int loss, int kind, int grid, int warps, const f
                                 long long pstride, const float* target, long long tstride,
                                 const float* weight, int wmode, long long wstride, long long n,
                                 float scale, const float* scale_div, float tau, float* status,
-                                float* loss_sum, float* row_loss, float* grad) {
+                                float* loss_sum, float* row_loss, float* grad, int early_return,
+                                long long er_wrow, long long er_wcol) {
   gd_loss_config cfg{};
   cfg.loss_type = loss;
   cfg.fun = GD_FUN_LOG1P;
@@ -144,6 +145,9 @@ extern "C" int gd_emul_loss_any(int loss, int kind, int grid, int warps, const f
   a.scale = scale;
   a.scale_div = scale_div;
   a.status = status;
+  a.early_return = early_return;
+  a.er_wrow = er_wrow;
+  a.er_wcol = er_wcol;
   a.loss_sum = loss_sum;
   a.row_loss = row_loss;
   a.grad = grad;

@@ -251,8 +251,8 @@ def test_strided_views_at_size(loss_type):
     pc = pred.clone().requires_grad_(True)
     oc = GDLoss(variant='bulk', **kw)(pc, target, w, avg_factor=1234.0)
     oc.backward()
-    lo, hi = 4, 4 + ((n - 1 - 4) & ~3)
-    assert torch.equal(pc.grad[lo:hi], outs['auto'][1][lo:hi])
+    gn = pc.grad.norm(dim=1).clamp_min(1e-3 * 5.0 / 1234.0)
+    assert ((pc.grad - outs['auto'][1]).norm(dim=1) / gn).max().item() <= 2e-6
     assert abs(oc.item() - outs['auto'][0]) <= 2e-6 * abs(oc.item())
     # sampled rows vs the fp64 oracle
     idx = torch.randint(0, n, (20000,), device='cuda')

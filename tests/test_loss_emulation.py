@@ -50,7 +50,8 @@ def emul(bits):
         lib.gd_emul_loss_any.argtypes = [ctypes.c_int] * 4 + [
             ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
             ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p,
-            ctypes.c_float] + [ctypes.c_void_p] * 4
+            ctypes.c_float] + [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_longlong,
+                                                       ctypes.c_longlong]
         _LIBS[bits] = lib
     return _LIBS[bits]
 
@@ -207,7 +208,7 @@ def test_sum_is_deterministic_and_grid_dependent_only():
 
 def run_any(loss, kind, grid, warps, pred, target, weight, pstride=7, tstride=7, wstride=None,
             offsets=(0, 0, 0), scale=1.0, scale_div=None, want_status=False, want_rows=False,
-            want_grad=True, tau=0.0):
+            want_grad=True, tau=0.0, early_return=None):
     """gd_warp_kernel<..., ANY> (kind 1) or gd_staged_kernel (kind 0) on row-strided inputs that
     start `offsets` floats into 16-byte aligned buffers; the gaps between the rows and around
     the arrays are NaN, so any read of a byte that is not a box element shows."""
@@ -247,7 +248,10 @@ def run_any(loss, kind, grid, warps, pred, target, weight, pstride=7, tstride=7,
     ptr = lambda x: x.ctypes.data_as(ctypes.c_void_p) if x is not None else None   # noqa: E731
     rc = emul(0).gd_emul_loss_any(LOSS[loss], kind, grid, warps, ptr(pv), pstride, ptr(tv), tstride,
                                   ptr(wv), wmode, wstride or 0, n, scale, ptr(sdiv), tau,
-                                  ptr(status), ptr(total), ptr(rows), ptr(grad))
+                                  ptr(status), ptr(total), ptr(rows), ptr(grad),
+                                  0 if early_return is None else 1,
+                                  0 if early_return is None else early_return[0],
+                                  0 if early_return is None else early_return[1])
     assert rc == 0, rc
     for name, (full, count) in bufs.items():
         assert (full[:G] == 91.0).all() and (full[G + count:] == 91.0).all(), f'write outside {name}'
@@ -307,3 +311,30 @@ def test_status_word_and_device_scale(kind):
         w1 = -torch.rand(n)
         w1[r] = 1e-3
         assert run_any('gwd3d', kind, 2, 3, pred, target, w1, want_status=True)[3] == 1.0
+
+
+@pytest.mark.parametrize('kind', [0, 1])
+def test_early_return_rewrite_by_the_last_cta(kind):
+    """ref:290-292 decided inside the launch: with no positive weight element the last CTA
+    replaces the outputs by (pred * weight).sum() and grad = weight (element strides given by the
+    caller: [N,7] weights, possibly row-strided, or a [7] weight broadcast over columns); with a
+    positive element anywhere nothing changes."""
+    n = 333
+    pred, target, w = make(n, seed=4)
+    w7 = -torch.rand(n, 7)
+    for wstride in (7, 9):
+        tot, _, grad, st = run_any('kld3d', kind, 3, 4, pred, target, w7, wstride=wstride, scale=5.0,
+                                   want_status=True, early_return=(wstride, 1))
+        want = float((pred.double() * w7.double()).sum())
+        assert st == 0.0 and abs(tot - want) <= 1e-6 * abs(want)
+        assert np.array_equal(grad, w7.numpy())
+    w7p = w7.clone()
+    w7p[n - 1, 6] = 0.5
+    a = run_any('kld3d', kind, 3, 4, pred, target, w7p, scale=5.0, want_status=True,
+                early_return=(7, 1))
+    b = run_any('kld3d', kind, 3, 4, pred, target, w7p, scale=5.0, want_status=True)
+    assert a[3] == 1.0 and a[0] == b[0] and np.array_equal(a[2], b[2])
+    # forward only (no gradient buffer)
+    tot, _, _, st = run_any('kld3d', kind, 3, 4, pred, target, w7, scale=5.0, want_status=True,
+                            want_grad=False, early_return=(7, 1))
+    assert st == 0.0 and abs(tot - want) <= 1e-6 * abs(want)

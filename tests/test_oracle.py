@@ -4,6 +4,8 @@ checks that need no oracle."""
 import math
 
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -211,7 +213,7 @@ def test_head_oracles_match_decode_golden():
         assert _close(p.grad.numpy(), z[f'{cid}/grad_f64'], 1e-9, 1e-12), case
 
 
-@pytest.mark.skipif(not ref_loader.reference_available(), reason='needs /root/reference')
+@pytest.mark.skipif(not os.path.isdir(ref_loader.CODER_DIR), reason='needs /root/reference')
 def test_center_decode_matches_live_reference_coder():
     coder_cls = ref_loader.load_reference_center_coder()
     c = synth.make_center_head_batch(500, seed=77)

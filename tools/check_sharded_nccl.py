@@ -34,15 +34,24 @@ def main():
     avg = float(max(int((w > 0).sum()), 1))
     report = {'world_size': world, 'rows': N, 'cases': []}
     ok = True
-    for lt, red, af in (('gwd3d', 'mean', avg), ('kld3d', 'mean', None), ('bd3d', 'sum', None)):
+    fused_flag = '--fused' in sys.argv
+    report['fused_requested'] = fused_flag
+    for lt, red, af, fused in (('gwd3d', 'mean', avg, False), ('gwd3d', 'mean', avg, fused_flag),
+                               ('kld3d', 'mean', None, False), ('bd3d', 'sum', None, fused_flag),
+                               ('kld3d', 'mean', torch.tensor(avg, device=dev), fused_flag)):
         kw = dict(loss_type=lt, fun='log1p', tau=0.0, loss_weight=5.0, reduction=red)
-        mod = sharded.ShardedGDLoss(GDLoss(host_sync=False, **kw))
+        mod = sharded.ShardedGDLoss(GDLoss(host_sync=False, **kw), fused=fused)
         p = pred[lo:hi].to(dev).requires_grad_(True)
         t, ww = target[lo:hi].to(dev), w[lo:hi].to(dev)
         loss = mod(p, t, ww, avg_factor=af)
         loss.backward()
         grads = [None] * world                 # shards may be ragged: gather as objects
         dist.all_gather_object(grads, p.grad.cpu())
+        vals = [None] * world
+        dist.all_gather_object(vals, float(loss.item()))
+        if rank == 0 and len(set(vals)) != 1:
+            ok = False
+            report.setdefault('rank_disagreement', []).append(vals)
         # timing of the sharded call (forward + backward + the collective)
         for _ in range(5):
             p.grad = None
@@ -60,15 +69,18 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         if rank == 0:
             full = torch.cat([g.cpu() for g in grads]).double()
+            af_host = float(af) if torch.is_tensor(af) else af
             ref_l, ref_g = gd_oracle.loss_and_grad(gd_oracle.GDLossOracle(**kw), pred.double(),
-                                                   target.double(), w.double(), avg_factor=af)
+                                                   target.double(), w.double(), avg_factor=af_host)
             rel = abs(loss.item() - ref_l.item()) / abs(ref_l.item())
             gn = ref_g.norm(dim=1).clamp_min(1e-2 * ref_g.norm(dim=1).max().item() * 1e-3)
             fin = torch.isfinite(ref_g).all(dim=1)
             gerr = ((full - ref_g).norm(dim=1) / gn)[fin].max().item()
             good = rel <= 1e-5 and gerr <= 1e-5
             ok = ok and good
-            report['cases'].append({'loss_type': lt, 'reduction': red, 'avg_factor': af,
+            report['cases'].append({'loss_type': lt, 'reduction': red,
+                                    'avg_factor': af_host, 'avg_factor_on_device': torch.is_tensor(af),
+                                    'fused_in_kernel_sum': bool(mod.fused),
                                     'loss': loss.item(), 'oracle': ref_l.item(),
                                     'loss_rel_err': rel, 'grad_max_row_rel_err': gerr,
                                     'ms_per_call_max_over_ranks': round(float(ms.item()), 4),

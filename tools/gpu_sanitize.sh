@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over the library's kernels: memcheck, racecheck,
-# synccheck, initcheck on tools/sanitize_target.py.  Only OUR library is instrumented
+# synccheck on tools/sanitize_target.py (initcheck needs >15 min on this workload: left out).  Only OUR library is instrumented
 # (--kernel-name kns=3gdk: the mangled namespace of every kernel in csrc/).
 #   bash tools/gpu_sanitize.sh [tag] [workloads ...]
 TAG=${1:-r02s}
@@ -10,7 +10,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
 CS=/usr/local/cuda/bin/compute-sanitizer
-for tool in memcheck racecheck synccheck initcheck; do
+for tool in memcheck racecheck synccheck; do
   extra=""
   [ $tool = racecheck ] && extra="--racecheck-report all"
   [ $tool = initcheck ] && extra=""
