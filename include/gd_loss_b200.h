@@ -256,14 +256,8 @@ enum {
   GD_PAIR_SIMILARITY = 1,  /* the optional matrix holds 1 - value ("larger is closer", the
                               iou_calculator convention of mmdet assigners); the minima
                               are always minima of the distance value                   */
-  GD_PAIR_PACKED = 2       /* OPT-IN, not GPU-validated yet: packed-FP32 kernel (two rows per
-                              lane and pass, FFMA2); gwd3d / kld3d / bd3d with fun in
-                              {none, log1p} and the default normalize / sqrt flag, anything
-                              else silently runs the scalar kernel.  Values may differ from
-                              the scalar kernel in the last bit; matrix and minima of one
-                              call stay bit-consistent with each other.  The environment
-                              variable GD_B200_PAIRWISE_PACKED=1 turns it on for every
-                              pairwise entry point of the process.                      */
+  GD_PAIR_CPL1 = 2         /* measurement / test aid: one column per lane (the round-1 mapping)
+                              instead of two; same per-pair arithmetic, bit-identical results */
 };
 
 /* Bytes of device workspace gd_pairwise_assign needs for m columns.  Zero-filled ONCE

@@ -22,7 +22,7 @@ VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3, 'bulk_packed': 4, '
 FLAG_MASK_ZERO_WEIGHT = 1
 ABI_VERSION = 2
 PAIR_SIMILARITY = 1
-PAIR_PACKED = 2            # opt-in packed-FP32 pairwise kernel (not GPU-validated yet)
+PAIR_CPL1 = 2              # one column per lane (measurement / test aid)
 GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3
 
 

@@ -24,6 +24,7 @@
 // verification only, on the host (tests/host_math builds it with g++ in float
 // and double).  The shipped library contains no host compute path.
 #pragma once
+#include <type_traits>
 
 #include <math.h>
 #include <stdint.h>
@@ -63,6 +64,7 @@ struct PairParams {
   int fun;       // Fun
   int tau_on;    // tau >= 1.0 decided on the host     ref:36
   int flag;      // 'normalize' (gwd) or 'sqrt' (others)   ref:43,110,145
+  int lean = 0;  // pairwise value path: log1p of the post map by Mth::log1p_lean (~4e-7)
 };
 
 // Optional compile-time "diet" of the FAST cores (template parameter DIET, default 0 =
@@ -289,6 +291,28 @@ struct Mth<float> {
     const float lo = fmaf(kf, 1.428606765330187e-06f, 2.0f * s * z * p);
     return fmaf(kf, 0.693145751953125f, fmaf(2.0f, s, lo));
   }
+  // log(1+x) for 0 <= x < ~1e30 in ~15 instructions instead of ~25, branch free, relative
+  // error <= ~5e-7 (the pairwise value path: N x M evaluations, issue bound):
+  //   x <= 0.5 : 2 atanh(s), s = x / (2 + x) <= 0.2, series to s^9 (next term < 1e-8)
+  //   x >  0.5 : ln2 * lg2(1 + x): MUFU.LG2 (abs. error 2^-22 below 2, relative above) on a
+  //              sum whose rounding is <= 6e-8 of a result >= 0.405
+  static GD_HD float log1p_lean(float x) {
+    const float s = x * rcp(2.0f + x);
+    const float z = s * s;
+    float p = fmaf(z, 1.0f / 9.0f, 1.0f / 7.0f);
+    p = fmaf(z, p, 1.0f / 5.0f);
+    p = fmaf(z, p, 1.0f / 3.0f);
+    const float t = s + s;
+    const float small = fmaf(t * z, p, t);
+#if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + x));
+    const float big = l * 0.693147180559945f;
+#else
+    const float big = ::log1pf(x);
+#endif
+    return x <= 0.5f ? small : big;
+  }
   // x^(-1/6) for normal positive x: one MUFU.LG2 + one MUFU.EX2 (rel. err ~5e-7)
   static GD_HD float rsixthroot(float x) {
 #if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
@@ -352,7 +376,11 @@ GD_HD T post_map(T d, const PairParams<T>& P, T* dfac, typename Mth<T>::mask* ra
   if (P.fun == kFunLog1p) {
     if constexpr (FAST) {
       *rare |= !(d < (T)1e30);                 // inf / nan distance: robust path
-      f = Mth<T>::log1p_pos(d);
+      if constexpr (std::is_same<T, float>::value) {
+        f = P.lean ? Mth<float>::log1p_lean(d) : Mth<float>::log1p_pos(d);
+      } else {
+        f = Mth<T>::log1p_pos(d);
+      }
     } else {
       f = Mth<T>::log1p(d);                    // ref:26
     }

@@ -10,9 +10,6 @@ extern template int launch_pairwise<gd::kSymMax>(const PairwiseArgs&, cudaStream
 extern template int launch_pairwise<gd::kSymMin>(const PairwiseArgs&, cudaStream_t);
 extern template int launch_pairwise<gd::kBd>(const PairwiseArgs&, cudaStream_t);
 extern template int launch_pairwise<gd::kKfiou>(const PairwiseArgs&, cudaStream_t);
-extern template int launch_pairwise_packed<gd::kGwd>(const PairwiseArgs&, cudaStream_t);
-extern template int launch_pairwise_packed<gd::kKld>(const PairwiseArgs&, cudaStream_t);
-extern template int launch_pairwise_packed<gd::kBd>(const PairwiseArgs&, cudaStream_t);
 
 // --- MaxIoUAssigner-style labels from the fused minima (similarity = 1 - distance) ---
 __global__ void __launch_bounds__(kThreads) gd_assign_lowq_kernel(
@@ -43,28 +40,7 @@ __global__ void __launch_bounds__(kThreads) gd_assign_rows_kernel(
   if (max_overlaps) max_overlaps[i] = sim;
 }
 
-// GD_B200_PAIRWISE_PACKED=1 routes EVERY pairwise entry point through the opt-in packed
-// kernels (so the whole GPU test suite can be pointed at them); read once per process.
-static bool packed_forced() {
-  static const bool on = [] {
-    const char* e = getenv("GD_B200_PAIRWISE_PACKED");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
-static int dispatch_pairwise(const gd_loss_config* cfg, const PairwiseArgs& a, cudaStream_t st,
-                             bool packed = false) {
-  if (packed || packed_forced()) {
-    int code = kNoPackedKernel;
-    switch (cfg->loss_type) {
-      case GD_LOSS_GWD3D: code = launch_pairwise_packed<gd::kGwd>(a, st); break;
-      case GD_LOSS_KLD3D: code = launch_pairwise_packed<gd::kKld>(a, st); break;
-      case GD_LOSS_BD3D: code = launch_pairwise_packed<gd::kBd>(a, st); break;
-      default: break;
-    }
-    if (code != kNoPackedKernel) return code;
-  }
+static int dispatch_pairwise(const gd_loss_config* cfg, const PairwiseArgs& a, cudaStream_t st) {
   switch (cfg->loss_type) {
     case GD_LOSS_GWD3D: return launch_pairwise<gd::kGwd>(a, st);
     case GD_LOSS_KLD3D: return launch_pairwise<gd::kKld>(a, st);
@@ -125,7 +101,7 @@ int gd_pairwise_assign(const gd_loss_config* cfg, const float* boxes1, int64_t n
                        float* col_min, int32_t* col_argmin, float* out, int64_t out_row_stride,
                        int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace gdk;
-  if (!config_ok(cfg) || n < 0 || m <= 0 || (flags & ~(GD_PAIR_SIMILARITY | GD_PAIR_PACKED)))
+  if (!config_ok(cfg) || n < 0 || m <= 0 || (flags & ~(GD_PAIR_SIMILARITY | GD_PAIR_CPL1)))
     return GD_ERR_BAD_ARG;
   if (out && out_row_stride < m) return GD_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < gd_pairwise_workspace_bytes(m)) return GD_ERR_WORKSPACE;
@@ -140,6 +116,7 @@ int gd_pairwise_assign(const gd_loss_config* cfg, const float* boxes1, int64_t n
   a.out = out;
   a.out_stride = out ? out_row_stride : m;
   a.similarity = (flags & GD_PAIR_SIMILARITY) ? 1 : 0;
+  a.force_cpl1 = (flags & GD_PAIR_CPL1) ? 1 : 0;
   a.row_min = row_min;
   a.row_argmin = row_argmin;
   a.ticket = reinterpret_cast<unsigned int*>(workspace);
@@ -147,8 +124,7 @@ int gd_pairwise_assign(const gd_loss_config* cfg, const float* boxes1, int64_t n
   a.col_min = col_min;
   a.col_argmin = col_argmin;
   a.pp = make_pair_params(*cfg);
-  return dispatch_pairwise(cfg, a, reinterpret_cast<cudaStream_t>(stream),
-                           (flags & GD_PAIR_PACKED) != 0);
+  return dispatch_pairwise(cfg, a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin, int64_t n,

@@ -2,5 +2,4 @@
 #include "gd_pairwise.cuh"
 namespace gdk {
 template int launch_pairwise<gd::kBd>(const PairwiseArgs&, cudaStream_t);
-template int launch_pairwise_packed<gd::kBd>(const PairwiseArgs&, cudaStream_t);
 }  // namespace gdk

@@ -175,12 +175,10 @@ class GDPairwiseDistance(nn.Module):
         return ops.pairwise_distance(boxes1, boxes2, self.cfg)
 
     @torch.no_grad()
-    def assign(self, boxes1, boxes2, want_matrix=False, packed=False):
+    def assign(self, boxes1, boxes2, want_matrix=False, cpl1=False):
         """Row and column ``(min, argmin)`` in one launch, matrix optional:
-        ``(row_min, row_argmin, col_min, col_argmin, matrix | None)``.  ``packed`` =
-        opt-in packed-FP32 kernel."""
-        return ops.pairwise_assign(boxes1, boxes2, self.cfg, want_matrix=want_matrix,
-                                   packed=packed)
+        ``(row_min, row_argmin, col_min, col_argmin, matrix | None)``."""
+        return ops.pairwise_assign(boxes1, boxes2, self.cfg, want_matrix=want_matrix, cpl1=cpl1)
 
     @torch.no_grad()
     def row_argmin(self, boxes1, boxes2):

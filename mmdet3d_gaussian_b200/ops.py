@@ -215,12 +215,12 @@ def _pair_workspace(device, m):
     return ws
 
 
-def pairwise_assign(boxes1, boxes2, cfg, want_matrix=False, similarity=False, packed=False):
+def pairwise_assign(boxes1, boxes2, cfg, want_matrix=False, similarity=False, cpl1=False):
     """Row and column minima / arg-minima of the pairwise distance matrix in one launch
     (``gd_pairwise_assign``); the matrix itself is written only when ``want_matrix``.
     Returns ``(row_min [N], row_argmin [N] int64, col_min [M], col_argmin [M] int64,
-    matrix | None)``.  Indices are -1 / values +inf on an empty axis.  ``packed=True``
-    selects the opt-in packed-FP32 kernel (``GD_PAIR_PACKED``)."""
+    matrix | None)``.  Indices are -1 / values +inf on an empty axis.  ``cpl1=True`` pins the
+    one-column-per-lane mapping (``GD_PAIR_CPL1``: same arithmetic, bit-identical results)."""
     b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
     n, m = b1.shape[0], b2.shape[0]
     dev = b1.device
@@ -240,7 +240,7 @@ def pairwise_assign(boxes1, boxes2, cfg, want_matrix=False, similarity=False, pa
         code = _lib.load().gd_pairwise_assign(
             ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m, _ptr(row_min), _ptr(row_idx),
             _ptr(col_min), _ptr(col_idx), _ptr(mat), m,
-            (_lib.PAIR_SIMILARITY if similarity else 0) | (_lib.PAIR_PACKED if packed else 0),
+            (_lib.PAIR_SIMILARITY if similarity else 0) | (_lib.PAIR_CPL1 if cpl1 else 0),
             _ptr(ws), ws.numel(), _stream_ptr())
     _lib.check(code, 'gd_pairwise_assign')
     return row_min, row_idx.long(), col_min, col_idx.long(), mat

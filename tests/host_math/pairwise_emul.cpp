@@ -1,5 +1,5 @@
-// TEST-ONLY: runs the pairwise CUDA kernels' SOURCE (csrc/gd_pairwise.cuh: the scalar
-// gd_pairwise_kernel and the opt-in gd_pairwise_packed_kernel) on the host, so their index,
+// TEST-ONLY: runs the pairwise CUDA kernel's SOURCE (csrc/gd_pairwise.cuh: gd_pairwise_kernel
+// with one and with two columns per lane) on the host, so their index,
 // tiling, tie-breaking and reduction logic can be checked on a machine without a GPU.
 //
 // How: the header is compiled by g++ under the execution-model emulation of cuda_emul.h (one
@@ -43,11 +43,11 @@ static gdk::PairwiseArgs make_args(const gd_loss_config* cfg, const float* b1, l
   return a;
 }
 
-template <int LOSS, int SPEC, bool REDUCE>
-static void run_scalar(const gdk::PairwiseArgs& a, unsigned cap) {
-  // the grid rules of launch_pairwise_inst (csrc/gd_pairwise.cuh), with the SM count as input
+template <int LOSS, int SPEC, bool REDUCE, int CPL>
+static void run_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
+  // the grid rules of launch_pairwise_cpl (csrc/gd_pairwise.cuh), with the SM count as input
   const long long ntiles = (a.n + gdk::kRowsPerCta - 1) / gdk::kRowsPerCta;
-  const int wx = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
+  const int wx = gdk::pairwise_wx(a.m, 32 * CPL);
   unsigned gx, gy = 1;
   if (REDUCE) {
     long long g = ntiles;
@@ -55,45 +55,15 @@ static void run_scalar(const gdk::PairwiseArgs& a, unsigned cap) {
     gx = (unsigned)g;
   } else {
     gx = (unsigned)ntiles;
-    gy = (unsigned)((a.m + 32LL * wx - 1) / (32LL * wx));
+    gy = (unsigned)((a.m + 32LL * CPL * wx - 1) / (32LL * CPL * wx));
   }
-  emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE>, gx, gy, gdk::kThreads, a);
-}
-
-template <int LOSS, int SPEC, bool REDUCE, int CPL>
-static void run_packed_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
-  // the grid rules of launch_pairwise_packed_cpl
-  const long long ntiles = (a.n + gdk::kRowsPerCta - 1) / gdk::kRowsPerCta;
-  unsigned gx, gy = 1;
-  if (REDUCE) {
-    long long g = ntiles;
-    if (a.col_keys && g > cap) g = cap;
-    gx = (unsigned)g;
-  } else {
-    long long y = (a.m + 32LL * CPL - 1) / (32LL * CPL);
-    long long g = (cap + y - 1) / y;
-    if (g > ntiles) g = ntiles;
-    if (g < 1) g = 1;
-    gx = (unsigned)g;
-    gy = (unsigned)y;
-  }
-  emu_launch(gdk::gd_pairwise_packed_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, gdk::kThreads, a);
-}
-
-template <int LOSS, int SPEC, bool REDUCE>
-static void run_packed(const gdk::PairwiseArgs& a, unsigned cap, int force_cpl) {
-  int cpl = a.m <= 32 ? 1 : (a.m <= 64 ? 2 : (a.m <= 128 ? 4 : 8));
-  if (force_cpl) cpl = force_cpl;              // smaller CPL than needed = several chunks
-  switch (cpl) {
-    case 1: run_packed_cpl<LOSS, SPEC, REDUCE, 1>(a, cap); break;
-    case 2: run_packed_cpl<LOSS, SPEC, REDUCE, 2>(a, cap); break;
-    case 4: run_packed_cpl<LOSS, SPEC, REDUCE, 4>(a, cap); break;
-    default: run_packed_cpl<LOSS, SPEC, REDUCE, 8>(a, cap); break;
-  }
+  emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, gdk::kThreads, a);
 }
 
 // loss: 0 gwd3d, 1 kld3d, 5 bd3d; fun log1p, tau >= 1 (SPEC 13), flag on -- the C4 configuration.
-// packed: 0 = scalar kernel, 1 = packed kernel.  reduce: fused minima (+ the matrix when `out`).
+// packed: 0 = one column per lane (CPL 1), 1 = two columns per lane (CPL 2; the default mapping
+// for m > 32).  force_cpl is unused (kept for the ctypes signature).  reduce: fused minima
+// (+ the matrix when `out`).
 // cap: CTA cap of the persistent reductions (the library uses 6 x SM count).
 extern "C" int gd_emul_pairwise(int loss, int packed, int reduce, int force_cpl, unsigned cap,
                                 const float* b1, long long n, const float* b2, long long m,
@@ -117,11 +87,11 @@ extern "C" int gd_emul_pairwise(int loss, int packed, int reduce, int force_cpl,
 #define GD_EMU_CASE(L)                                                          \
   if (loss == L) {                                                              \
     if (packed) {                                                               \
-      if (reduce) run_packed<L, S, true>(a, cap, force_cpl);                    \
-      else run_packed<L, S, false>(a, cap, force_cpl);                          \
+      if (reduce) run_cpl<L, S, true, 2>(a, cap);                               \
+      else run_cpl<L, S, false, 2>(a, cap);                                     \
     } else {                                                                    \
-      if (reduce) run_scalar<L, S, true>(a, cap);                               \
-      else run_scalar<L, S, false>(a, cap);                                     \
+      if (reduce) run_cpl<L, S, true, 1>(a, cap);                               \
+      else run_cpl<L, S, false, 1>(a, cap);                                     \
     }                                                                           \
   }
   GD_EMU_CASE(0) GD_EMU_CASE(1) GD_EMU_CASE(5)

@@ -1,7 +1,8 @@
 """GPU parity of the packed-FP32 variant of the fused kernel (``variant='bulk_packed'`` =
 GD_VARIANT_BULK_PACKED, csrc/gd_packed.cuh -- what ``variant='auto'`` runs for gwd3d / kld3d /
 bd3d since round 2, build_ext.TUNE_DEFAULT) against the fp64 oracle and the scalar kernel
-(``variant='bulk'``), of the opt-in packed pairwise kernel, and of the ``host_sync`` aliases."""
+(``variant='bulk'``), of the two column mappings of the pairwise kernel, and of the ``host_sync``
+aliases."""
 import numpy as np
 import pytest
 import torch
@@ -59,9 +60,10 @@ def test_packed_falls_back_for_other_configurations():
 @pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (700, 64), (1001, 129), (2050, 256), (400, 700),
                                  (60001, 40)])
 def test_packed_pairwise(loss_type, fun, tau, n, m):
-    """Opt-in packed pairwise kernel (GD_PAIR_PACKED): its matrix vs the fp64 oracle (1e-5)
-    and vs the scalar kernel (last-bit differences only); its fused minima equal the minima
-    of ITS OWN matrix bit for bit (ties -> lowest index, NaN first), odd row counts and
+    """The two column mappings of the pairwise kernel (two columns per lane: the default for
+    m > 32; one column per lane: GD_PAIR_CPL1) run the same per-pair arithmetic: matrices and
+    fused minima agree BIT FOR BIT; the matrix vs the fp64 oracle (1e-5); the fused minima equal
+    the minima of the matrix bit for bit (ties -> lowest index, NaN first), odd row counts and
     ragged column counts included; degenerate boxes take the robust path."""
     from mmdet3d_gaussian_b200 import GDPairwiseDistance
     b1 = synth.make_anchor_grid(n, 'waymo', device='cuda')
@@ -75,13 +77,18 @@ def test_packed_pairwise(loss_type, fun, tau, n, m):
         b1[10, 4] = 1e-9                        # rows the FAST cores must hand over
         b1[11, 6] = 1000.0
     mod = GDPairwiseDistance(loss_type, fun=fun, tau=tau)
-    scalar = mod(b1, b2)
-    rmin, ridx, cmin, cidx, mat = mod.assign(b1, b2, want_matrix=True, packed=True)
+    plain = mod(b1, b2)
+    rmin, ridx, cmin, cidx, mat = mod.assign(b1, b2, want_matrix=True)
+    r1, i1, c1, j1, mat1 = mod.assign(b1, b2, want_matrix=True, cpl1=True)
     ref = gd_oracle.pairwise_distance(b1.cpu().double(), b2.cpu().double(), loss_type, fun=fun,
                                       tau=tau)
     err = (mat.cpu().double() - ref).abs() / ref.abs().clamp_min(1e-3)
     assert err.max() < RTOL
-    assert ((mat - scalar).abs() / scalar.abs().clamp_min(1e-3)).max() < 2e-6
+
+    def same(a, b):
+        return torch.equal(a.view(torch.int32), b.view(torch.int32))
+    assert same(mat, plain) and same(mat, mat1)
+    assert same(rmin, r1) and torch.equal(ridx, i1) and same(cmin, c1) and torch.equal(cidx, j1)
 
     def first_argmin(x, dim):
         key = torch.where(torch.isnan(x), torch.full_like(x, -float('inf')), x)
@@ -93,7 +100,7 @@ def test_packed_pairwise(loss_type, fun, tau, n, m):
         cv, ci = first_argmin(mat, 0)
         assert torch.equal(rmin.view(torch.int32), rv.view(torch.int32)) and torch.equal(ridx, ri)
         assert torch.equal(cmin.view(torch.int32), cv.view(torch.int32)) and torch.equal(cidx, ci)
-        rmin, ridx, cmin, cidx, none = mod.assign(b1, b2, packed=True)
+        rmin, ridx, cmin, cidx, none = mod.assign(b1, b2)
         assert none is None
 
 

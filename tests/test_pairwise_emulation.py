@@ -1,14 +1,12 @@
-"""CPU run of the pairwise CUDA kernels' SOURCE under a thread-per-CUDA-thread emulation
-(tests/host_math/pairwise_emul.cpp): the scalar ``gd_pairwise_kernel`` (GPU-validated) and the
-opt-in ``gd_pairwise_packed_kernel`` (written after the round's GPU budget was spent).
+"""CPU run of the pairwise CUDA kernel's SOURCE under a thread-per-CUDA-thread emulation
+(tests/host_math/pairwise_emul.cpp): ``gd_pairwise_kernel`` with one column per lane (``packed``
+= 0 below: the round-1 mapping) and with two (``packed`` = 1: the default for m > 32).
 
-What this pins without a GPU: tiling and partial tiles, odd row counts, dead lanes, 1/2/4/8
-columns per lane and chunked columns, persistent CTAs walking several tiles, the column-key
-workspace protocol, NaN-first and lowest-index tie rules -- i.e. everything around the
-per-pair arithmetic.  The arithmetic itself runs as the host instantiation (plain float), for
-which scalar and packed cores are bit-identical (tests/host_math/packed_harness.cpp), so the
-packed kernel's matrix must equal the scalar kernel's matrix BIT FOR BIT here; on the device
-they may differ in the last place (FFMA2 contraction) and the GPU tests bound that."""
+What this pins without a GPU: tiling and partial tiles, odd row counts, dead lanes, 1/2
+columns per lane and chunked columns, persistent CTAs walking several tiles, the advanced
+store pointer, the column-key workspace protocol, NaN-first and lowest-index tie rules -- i.e.
+everything around the per-pair arithmetic.  Both mappings run the same per-pair instruction
+sequence, so their matrices and minima must agree BIT FOR BIT (here and on the device)."""
 import ctypes
 import os
 import subprocess
@@ -139,18 +137,19 @@ def test_fused_minima_equal_matrix_minima(emul, loss, n, m):
     assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
 
 
-@pytest.mark.parametrize('n,m,cpl', [(131, 70, 1), (131, 129, 2), (70, 300, 4), (200, 600, 8)])
+@pytest.mark.parametrize('n,m,cpl', [(131, 70, 0), (131, 129, 1), (70, 300, 0), (200, 600, 1),
+                                     (67, 513, 1), (130, 577, 1)])
 def test_packed_chunked_columns(emul, n, m, cpl):
-    """More columns than one pass of a warp covers (m > 32 CPL): the tile-outer loop order,
+    """More columns than one pass of the CTA covers (m > 256 CPL) and ragged column counts:
     row minima carried across chunks in shared memory, column minima flushed per chunk."""
     b1, b2 = boxes(n, m, degenerate=False)
-    mat, rmin, ridx, cmin, cidx = run(emul, 'gwd3d', 1, 1, b1, b2, force_cpl=cpl, cap=2)
+    mat, rmin, ridx, cmin, cidx = run(emul, 'gwd3d', cpl, 1, b1, b2, cap=2)
     rv, ri = first_argmin(mat, 1)
     cv, ci = first_argmin(mat, 0)
     assert not (mat == -7.0).any()
     assert same_bits(rmin, rv) and np.array_equal(ridx, ri)
     assert same_bits(cmin, cv) and np.array_equal(cidx, ci)
-    only = run(emul, 'gwd3d', 1, 0, b1, b2, force_cpl=cpl, cap=2)[0]       # matrix-only launch
+    only = run(emul, 'gwd3d', cpl, 0, b1, b2, cap=2)[0]                    # matrix-only launch
     assert same_bits(only, mat)
 
 

@@ -57,6 +57,12 @@ def main():
                 with torch.no_grad():
                     mod(pred, target, wt, avg_factor=float(n))
             res[name + '_fwd_us'] = round(wall_us(fwd_only, 300), 2)
+        # what torch's autograd engine charges for ANY CUDA backward() (thread hand-off to the
+        # device worker): the smallest possible graph, one elementwise op + sum
+        def trivial():
+            pred.grad = None
+            (pred * 1.0).sum().backward()
+        res['torch_trivial_fwd_bwd_us'] = round(wall_us(trivial, 300), 2)
         # bare C ABI
         cfg = _lib.make_config('gwd3d', 'log1p', True, 0.0, 1.0, (0, 0, 0.5))
         grad = torch.empty(n, 7, device='cuda')

@@ -32,8 +32,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', choices=['all', 'elementwise', 'pairwise'], default='all')
     ap.add_argument('--max-log2n', type=int, default=26)
-    ap.add_argument('--packed', action='store_true',
-                    help='also time the opt-in packed-FP32 pairwise kernel (GD_PAIR_PACKED)')
+    ap.add_argument('--packed', '--cpl1', dest='packed', action='store_true',
+                    help='also time the one-column-per-lane mapping of the pairwise kernel (GD_PAIR_CPL1)')
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device('cuda', 0)
@@ -95,7 +95,7 @@ def main():
         pairs = 200_000 * 256
         packed = {}
         if args.packed and lt in ('gwd3d', 'kld3d', 'bd3d'):
-            # opt-in packed-FP32 kernel (GD_PAIR_PACKED = 2): reductions only, and with the matrix
+            # one column per lane (GD_PAIR_CPL1 = 2): reductions only, and with the matrix
             ms4 = time_launch(lambda: _lib.check(lib.gd_pairwise_assign(
                 ctypes.byref(cfg), anchors.data_ptr(), 200_000, gts.data_ptr(), 256,
                 vmin.data_ptr(), idx.data_ptr(), cmin.data_ptr(), cidx.data_ptr(), None, 256, 2,
@@ -108,10 +108,10 @@ def main():
                 ctypes.byref(cfg), anchors.data_ptr(), 200_000, gts.data_ptr(), 256,
                 vmin.data_ptr(), idx.data_ptr(), cmin.data_ptr(), cidx.data_ptr(), mat.data_ptr(),
                 256, 0, pws.data_ptr(), pws.numel(), stream), 'gd_pairwise_assign'), 20)
-            packed = {'packed_assign_ms': round(ms4, 4),
-                      'packed_assign_Gpairs_per_s': round(pairs / ms4 / 1e6, 2),
-                      'packed_assign_matrix_ms': round(ms5, 4),
-                      'scalar_assign_matrix_ms': round(ms6, 4)}
+            packed = {'cpl1_assign_ms': round(ms4, 4),
+                      'cpl1_assign_Gpairs_per_s': round(pairs / ms4 / 1e6, 2),
+                      'cpl1_assign_matrix_ms': round(ms5, 4),
+                      'assign_matrix_ms': round(ms6, 4)}
         out['pairwise'].append({'loss': lt, 'n': 200_000, 'm': 256, 'matrix_ms': round(ms, 4), **packed,
                                 'matrix_Gpairs_per_s': round(pairs / ms / 1e6, 2),
                                 'matrix_write_GBps': round(4 * pairs / ms / 1e6, 1),
