@@ -246,6 +246,56 @@ def run_reference(args):
         'gpu_launches': 0}))
 
 
+def bind_numa(local_rank, world):
+    """e2e with N ranks is bound by host DRAM / PCIe roots: pin each rank (its threads AND,
+    by first touch, its pinned staging buffers) to one NUMA node -- the GPU's own node when
+    sysfs knows it, else round robin over the nodes -- instead of leaving all ranks on node 0.
+    Returns a description for the JSON line; never fails the run."""
+    info = {'bound': False}
+    try:
+        import glob
+        import re
+        nodes = sorted(int(re.search(r'node(\d+)$', p).group(1))
+                       for p in glob.glob('/sys/devices/system/node/node[0-9]*'))
+        info['numa_nodes'] = len(nodes)
+        if len(nodes) < 2 or world < 2 or not hasattr(os, 'sched_setaffinity'):
+            return info
+        node = None
+        try:
+            import torch
+            bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+            dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+            devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+            path = f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node'
+            with open(path) as f:
+                v = int(f.read().strip())
+            if v >= 0:
+                node = v
+                info['source'] = 'sysfs numa_node of the GPU'
+        except Exception:
+            node = None
+        if node is None:
+            node = nodes[local_rank % len(nodes)]
+            info['source'] = 'round robin over NUMA nodes (sysfs reports none for the GPU)'
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, node=node, cpus=len(cpus))
+    except Exception as exc:                                   # noqa: BLE001
+        info['error'] = repr(exc)
+    return info
+
+
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
@@ -428,6 +478,7 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
+        numa = bind_numa(local_rank, world)
         hp, ht, hw = (x.detach().cpu().pin_memory() for x in (pred, target, weight))
         hgrad = torch.empty(n, 7).pin_memory()
         hloss = torch.zeros(1).pin_memory()
@@ -457,7 +508,7 @@ def run_ours(args):
                'h2d_bytes_per_step': len(COMBOS) * n * 60,
                'd2h_bytes_per_step': len(COMBOS) * (n * 28 + 4),
                'steps': k, 'ms_per_step': dt / k * 1e3,
-               'h2d_GBps_per_gpu': len(COMBOS) * n * 60 * k / dt / 1e9,
+               'h2d_GBps_per_gpu': len(COMBOS) * n * 60 * k / dt / 1e9, 'numa': numa,
                'api': f'gd_loss_fwd_bwd_host (C ABI, pinned host buffers, 2^{args.e2e_chunk_log2}-row '
                       f'chunks, 3 streams)'}
         del hp, ht, hw, hgrad

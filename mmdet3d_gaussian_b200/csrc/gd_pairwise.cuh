@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
           if (lane == 0 && mn != 0xffffffffu) {
             const unsigned long long k64 =
                 ((unsigned long long)mn << 32) | (unsigned int)(jb + col);
-            if (k64 < s_best[r][warp]) s_best[r][warp] = k64;
+            // one chunk: this (row, warp) slot is visited once per tile -- plain store
+            if (one_chunk || k64 < s_best[r][warp]) s_best[r][warp] = k64;
           }
           if (want_col) {
 #pragma unroll
@@ -233,6 +234,15 @@ inline int pairwise_cpl(long long m) {
   if (forced == 1 || forced == 2) return forced;
   return m > 32 ? 2 : 1;
 }
+// Two columns per lane pay for the two light distances only (matrix: gwd3d +2.5 %, kld3d
+// +2.7 % at 200k x 256, fused reductions: no difference; bd3d -9 %: register pressure) --
+// profiles/r02_pairwise.md.  The choice depends on the distance alone, so the matrix-only and
+// the fused-reduction launches of one distance run the same mapping (their values are compared
+// bit for bit by the tests: indices derived from either must agree).
+template <int LOSS>
+constexpr bool pairwise_cpl2_pays() {
+  return LOSS == gd::kGwd || LOSS == gd::kKld;
+}
 
 template <int LOSS, int SPEC, bool REDUCE, int CPL>
 int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
@@ -259,9 +269,11 @@ int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
 
 template <int LOSS, int SPEC, bool REDUCE>
 int launch_pairwise_inst(const PairwiseArgs& a, cudaStream_t st) {
-  return (pairwise_cpl(a.m) == 2 && !a.force_cpl1)
-             ? launch_pairwise_cpl<LOSS, SPEC, REDUCE, 2>(a, st)
-             : launch_pairwise_cpl<LOSS, SPEC, REDUCE, 1>(a, st);
+  if constexpr (pairwise_cpl2_pays<LOSS>()) {
+    if (pairwise_cpl(a.m) == 2 && !a.force_cpl1)
+      return launch_pairwise_cpl<LOSS, SPEC, REDUCE, 2>(a, st);
+  }
+  return launch_pairwise_cpl<LOSS, SPEC, REDUCE, 1>(a, st);
 }
 
 // compile-time specialisation for the shipped configurations of the three headline
