@@ -294,6 +294,36 @@ GD_API int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin
                           int32_t match_low_quality, int64_t* assigned_gt_inds,
                           float* max_overlaps, void* stream);
 
+/* SimOTA-style consumer without the N x M matrix (second branch;
+ * mmdet3d_gaussian/core/bbox/assigners/sim_ota_3d_assigner.py:184-211 dynamic_k_matching with the
+ * Gaussian similarity 1 - D in the role of the IoU and a cost monotone in D).
+ *
+ * gd_pairwise_col_topk: for every column j the k (<= 16) smallest D[i,j] over the rows, ascending
+ * (NaN first, ties -> lowest row):  topk_val [k,m] fp32, topk_row [k,m] int32 (-1 / +inf where
+ * n < k) -- what ref:187-188 `torch.topk(pairwise_ious, candidate_topk, dim=0)` and the per-GT
+ * `torch.topk(cost[:, gt], k=dynamic_k, largest=False)` of ref:192-193 read -- plus the row
+ * (min, argmin) that the conflict rule ref:198-203 needs.  Workspace: scratch, no zeroing
+ * needed, gd_pairwise_topk_workspace_bytes(n, m) bytes. */
+GD_API size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m);
+GD_API int gd_pairwise_col_topk(const gd_loss_config* cfg,
+                                const float* boxes1, int64_t n,
+                                const float* boxes2, int64_t m, int32_t k,
+                                float* row_min, int32_t* row_argmin,
+                                float* topk_val, int32_t* topk_row,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* dynamic_k_matching (ref:184-211) from those lists:
+ *   dynamic_ks[j] = clamp(int(sum_i (1 - topk_val[i,j])), min=1)                    ref:188-190
+ *   rows topk_row[0..dynamic_ks[j]) , j  are matched                                ref:191-194
+ *   a row matched by several GTs keeps row_argmin (its lowest cost over ALL GTs)    ref:198-203
+ * assigned_gt_inds [n] int64: 0 = background, else GT index + 1 (ref:64-66,112);
+ * matched_sim [n] nullable: 1 - D of the kept match, `unmatched_sim` elsewhere (ref:116-118 uses
+ * -INF); dynamic_ks [m] nullable; scratch: 3 * n int32, any content. */
+GD_API int gd_simota_from_topk(const float* topk_val, const int32_t* topk_row, int64_t m, int32_t k,
+                               const float* row_min, const int32_t* row_argmin, int64_t n,
+                               int64_t* assigned_gt_inds, float* matched_sim, int32_t* dynamic_ks,
+                               float unmatched_sim, int32_t* scratch, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Head front ends: positive-row gather + box decode +
  * GD loss + gradient w.r.t. the RAW network outputs in one launch.

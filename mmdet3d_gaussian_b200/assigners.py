@@ -90,3 +90,56 @@ class GDMaxSimAssigner(nn.Module):
                     gt_max_overlaps=1.0 - col_min, gt_argmax_overlaps=col_arg)
 
     forward = assign
+
+
+class GDSimOTAAssigner(nn.Module):
+    """SimOTA's dynamic-k matching on the Gaussian similarity without the N x M matrix
+    (the reference's ``SimOTABEVAssigner.dynamic_k_matching``,
+    ``core/bbox/assigners/sim_ota_3d_assigner.py:184-211``, fed with ``pairwise_ious = 1 - D`` and
+    a cost monotone in ``D``; the reference builds both from a materialised BEV-IoU matrix,
+    :91-107).
+
+    Per GT the ``candidate_topk`` most similar boxes give ``dynamic_k = clamp(int(sum of their
+    similarities), min=1)`` (:187-190); the ``dynamic_k`` cheapest boxes of that GT are matched
+    (:191-194); a box matched by several GTs keeps the GT of its own lowest cost (:198-203).
+    Everything this reads is the column top-k and the row minima of the distance matrix, which
+    the fused kernel reduces on the fly (``gd_pairwise_col_topk`` + ``gd_simota_from_topk``).
+    ``tau >= 1`` keeps ``D`` in ``[0, 1)`` so that ``1 - D`` is an IoU-like score.  Ties between
+    equal distances go to the lowest box index (``torch.topk`` leaves them unspecified).
+
+    ``assign(bboxes [N,>=7], gt_bboxes [M,>=7]) -> dict(assigned_gt_inds [N] int64 (0 background,
+    k+1 = GT k), max_overlaps [N] (similarity of the kept match, -INF elsewhere as :116-118),
+    dynamic_ks [M], topk_overlaps [k,M], topk_inds [k,M])``.  The class / centre-prior terms of
+    the reference's cost (:94-107) are the caller's: this assigner is the GD-only core."""
+
+    INF = 100000000                                   # ref:12
+
+    def __init__(self, candidate_topk=10, loss_type='gwd3d', center_offset=(0, 0, 0.5), fun='log1p',
+                 tau=1.0, alpha=1.0, **kwargs):
+        super().__init__()
+        if not 1 <= int(candidate_topk) <= 16:
+            raise ValueError('candidate_topk must be in [1, 16]')
+        if float(tau) < 1.0:
+            raise ValueError('GDSimOTAAssigner needs tau >= 1 (similarity 1 - D in (0, 1])')
+        self.candidate_topk = int(candidate_topk)
+        self.cfg = _make_cfg(loss_type, fun, tau, alpha, center_offset, kwargs)
+
+    @torch.no_grad()
+    def assign(self, bboxes, gt_bboxes):
+        n, m = bboxes.shape[0], gt_bboxes.shape[0]
+        dev = bboxes.device
+        if n == 0 or m == 0:                          # ref:67-79
+            return dict(assigned_gt_inds=torch.zeros(n, dtype=torch.int64, device=dev),
+                        max_overlaps=torch.zeros(n, device=dev),
+                        dynamic_ks=torch.zeros(m, dtype=torch.int64, device=dev),
+                        topk_overlaps=torch.zeros(0, m, device=dev),
+                        topk_inds=torch.zeros(0, m, dtype=torch.int64, device=dev))
+        k = min(self.candidate_topk, n)               # ref:187
+        row_min, row_arg, tv, tr = ops.pairwise_col_topk(bboxes[..., :7], gt_bboxes[..., :7],
+                                                         self.cfg, k)
+        assigned, sim, dks = ops.simota_from_topk(tv, tr, row_min, row_arg,
+                                                  unmatched_sim=-float(self.INF))
+        return dict(assigned_gt_inds=assigned, max_overlaps=sim, dynamic_ks=dks,
+                    topk_overlaps=1.0 - tv, topk_inds=tr)
+
+    forward = assign

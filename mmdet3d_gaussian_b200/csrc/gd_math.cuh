@@ -565,22 +565,13 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
   const T amb = g.amb;                                             // A - B
   const T cmd = g.cmd;                                             // C - D
   const T eps = amb * cmd * s2;                                    // V^2 - U
-  T U, kU, rU;                                                     // kU = 1/(2 sqrt U)
-  if (!GRAD && FAST && P.lean) {
-    // pairwise value path (issue bound): U = V^2 - eps with V^2 = AC + BD + 2K summed from
-    // positive terms -- 7 instructions fewer than the form below (no cos, no c2).  The one
-    // subtraction costs relative accuracy only for elongated boxes at right angles, where
-    // sqrt U << V and U enters the result through V + sqrt U alone: <= eps_f32 * aspect / 4 of
-    // the value (1.5e-6 at 100:1).
-    U = (A * C + B * D + (T)2 * K) - eps;
-    rU = Mth<T>::sqrt(Mth<T>::sel(U > (T)0, U, (T)0));
-    kU = (T)0;
-  } else {
-    const T c2 = g.cd * g.cd;
-    // U = tr(Sigma_p Sigma_t) + 2 sqrt(det det): all terms positive    ref:88-95
-    U = (A * C + B * D) * c2 + (A * D + B * C) * s2 + (T)2 * K;
-    rU = sqrt_clamp0(U, &kU);                                      // ref:95
-  }
+  const T c2 = g.cd * g.cd;
+  // U = tr(Sigma_p Sigma_t) + 2 sqrt(det det): all terms positive    ref:88-95
+  // (the shorter U = V^2 - eps was measured on the pairwise path: no gain, one subtraction
+  // that costs digits for elongated crossing boxes -- not used)
+  const T U = (A * C + B * D) * c2 + (A * D + B * C) * s2 + (T)2 * K;
+  T kU;                                                            // 1/(2 sqrt U)
+  const T rU = sqrt_clamp0(U, &kU);                                // ref:95
   const T eta = eps * Mth<T>::rcp(V + rU);                         // V - sqrt U
   const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
   const T W = da * da + db * db + (T)2 * eta + de * de;            // ref:81-97
@@ -1065,10 +1056,8 @@ GD_HD BoxGauss<T> box_gauss(const T* row, const PairParams<T>& P) {
   b.ib = Mth<T>::rcp(b.b);
   b.ie = Mth<T>::rcp(b.e);
   const T lo = (T)1e-4, hi = (T)1e4;
-  // BEV aspect ratio <= 64: the short form of U in gwd_core (P.lean) loses eps_f32 * aspect / 4
-  // of the value for crossing boxes; anything more elongated takes the robust cores
   b.nice = (row[3] >= lo && row[3] <= hi && row[4] >= lo && row[4] <= hi && row[5] >= lo &&
-            row[5] <= hi && row[3] <= (T)64 * row[4] && row[4] <= (T)64 * row[3]) ? 1 : 0;
+            row[5] <= hi) ? 1 : 0;
   return b;
 }
 

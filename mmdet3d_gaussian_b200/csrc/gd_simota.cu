@@ -1,0 +1,302 @@
+// SimOTA-style consumer of the pairwise Gaussian distance WITHOUT the N x M matrix
+// (second branch).
+//
+// The reference's SimOTA (mmdet3d_gaussian/core/bbox/assigners/sim_ota_3d_assigner.py, "ref")
+// materialises an IoU matrix (ref:91-93), builds a cost from it (ref:94-107) and runs
+// dynamic_k_matching (ref:184-211):
+//     topk_ious = topk(pairwise_ious, candidate_topk, dim=0)            ref:187-188
+//     dynamic_ks = clamp(topk_ious.sum(0).int(), min=1)                 ref:190
+//     per GT: the dynamic_k rows of lowest cost are matched             ref:191-194
+//     a row matched by several GTs keeps argmin_j cost[row, j]          ref:198-203
+// With the Gaussian similarity s = 1 - D (D in [0, 1) for tau >= 1) in the role of the IoU and
+// the cost monotone in D, everything the matching reads lives in (a) the candidate_topk
+// smallest D of every COLUMN and (b) the (min, argmin) of every ROW.  Both are reductions of
+// the pairwise kernel's value stream:
+//   gd_pairwise_topk_kernel  -- the pairwise value loop (lane <-> column box in registers, row
+//                               Gaussians broadcast from shared memory) with a K-deep sorted
+//                               list of (value key, row) per lane and the row minima of the
+//                               assign kernel; lists of all CTAs / row phases go to a scratch
+//   gd_topk_merge_kernel     -- one warp per column merges the scratch lists
+//   gd_simota_cols_kernel / gd_simota_rows_kernel -- dynamic k, matching, conflict rule
+// Keys are the pairwise kernel's: order-preserving 32-bit value key (NaN lowest) in the high
+// word, row index in the low word -- ties go to the lowest row, deterministically (torch.topk
+// leaves tie order unspecified).
+#include "gd_pairwise.cuh"
+
+namespace gdk {
+
+constexpr int kTopK = 16;                    // list depth kept per column (candidate_topk <= 16)
+
+struct TopkArgs {
+  unsigned long long* cand;                  // [slots][kTopK][m] scratch
+  long long slots;
+};
+
+// sorted insert of x into the ascending list best[0..K): branch-free bubble
+template <int K>
+__device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsigned long long x) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const unsigned long long lo = best[i] < x ? best[i] : x;
+    x = best[i] < x ? x : best[i];
+    best[i] = lo;
+  }
+}
+
+template <int LOSS>
+__global__ void __launch_bounds__(kThreads) gd_pairwise_topk_kernel(const PairwiseArgs a,
+                                                                    const TopkArgs tk) {
+  __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
+  __shared__ unsigned long long s_best[kRowsPerCta][kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  gd::PairParams<float> pp = a.pp;
+  pp.lean = 1;
+  const int wx = pairwise_wx(a.m, 32);
+  const int wy = kWarps / wx;
+  const int cgrp = warp % wx, ry = warp / wx;
+  const long long chunk = 32LL * wx;
+  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  const long long slot = (long long)blockIdx.x * wy + ry;
+
+  // columns outer (each lane's list lives across all row tiles of this CTA), tiles inner
+  for (long long c0 = 0; c0 < a.m; c0 += chunk) {
+    const long long j = c0 + 32LL * cgrp + lane;
+    const bool warp_live = c0 + 32LL * cgrp < a.m;
+    const bool live = j < a.m;
+    unsigned long long best[kTopK];
+#pragma unroll
+    for (int i = 0; i < kTopK; ++i) best[i] = ~0ull;
+    gd::BoxGauss<float> t;
+    if (warp_live) t = gd::box_gauss(a.b2 + (live ? j : 0) * 7, pp);   // dead lanes: any valid box
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = tile * kRowsPerCta;
+      const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
+      __syncthreads();                         // previous tile fully consumed
+      if (tid < rows) s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
+      for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads) (&s_best[0][0])[i] = ~0ull;
+      __syncthreads();
+      if (warp_live) {
+        for (int r = ry; r < rows; r += wy) {
+          const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t, pp);
+          const unsigned int key = live ? order_key(v) : 0xffffffffu;
+          const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
+          const unsigned int who = __ballot_sync(0xffffffffu, key == mn);
+          if (lane == 0 && mn != 0xffffffffu)
+            s_best[r][warp] = ((unsigned long long)mn << 32) |
+                              (unsigned int)(c0 + 32LL * cgrp + (__ffs(who) - 1));
+          if (live) {
+            const unsigned long long k64 =
+                ((unsigned long long)key << 32) | (unsigned int)(row0 + r);
+            if (k64 < best[kTopK - 1]) topk_insert<kTopK>(best, k64);
+          }
+        }
+      }
+      // row minima of this tile over this chunk of columns, merged into the outputs (chunks are
+      // walked in ascending column order by every CTA, so "strictly smaller wins" keeps the
+      // lowest column on ties)
+      __syncthreads();
+      if (tid < rows) {
+        unsigned long long k = s_best[tid][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
+        const unsigned int key = (unsigned int)(k >> 32);
+        if (c0 == 0) {
+          a.row_min[row0 + tid] = key_value(key);
+          a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
+        } else if (k != ~0ull && key < order_key(a.row_min[row0 + tid])) {
+          a.row_min[row0 + tid] = key_value(key);
+          a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < kTopK; ++i) tk.cand[(slot * kTopK + i) * a.m + j] = best[i];
+    }
+  }
+}
+
+// one warp per column: K smallest of the slots x K candidates (each slot's list is sorted, but
+// the merge does not rely on it)
+__global__ void __launch_bounds__(128) gd_topk_merge_kernel(const unsigned long long* __restrict__ cand,
+                                                            long long slots, long long m, int k,
+                                                            float* __restrict__ topk_val,
+                                                            int* __restrict__ topk_row) {
+  const int lane = threadIdx.x & 31;
+  const long long j = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (j >= m) return;                          // whole warp
+  unsigned long long best[kTopK];
+#pragma unroll
+  for (int i = 0; i < kTopK; ++i) best[i] = ~0ull;
+  const long long total = slots * kTopK;
+  for (long long c = lane; c < total; c += 32) {
+    const unsigned long long x = __ldcs(cand + c * m + j);
+    if (x < best[kTopK - 1]) topk_insert<kTopK>(best, x);
+  }
+  for (int i = 0; i < k; ++i) {
+    unsigned long long head = best[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, head, o);
+      head = other < head ? other : head;
+    }
+    if (best[0] == head && head != ~0ull) {    // the owner pops (keys are unique: one row, one slot)
+#pragma unroll
+      for (int q = 0; q + 1 < kTopK; ++q) best[q] = best[q + 1];
+      best[kTopK - 1] = ~0ull;
+    }
+    if (lane == 0) {
+      const bool none = head == ~0ull;
+      topk_val[(long long)i * m + j] = none ? __uint_as_float(0x7f800000u) : key_value((unsigned int)(head >> 32));
+      topk_row[(long long)i * m + j] = none ? -1 : (int)(unsigned int)(head & 0xffffffffu);
+    }
+  }
+}
+
+// ref:187-194 per GT column: dynamic k from the k largest similarities (= 1 - the k smallest
+// distances), then the dynamic_k lowest-cost rows are matched
+__global__ void __launch_bounds__(kThreads) gd_simota_cols_kernel(
+    const float* __restrict__ topk_val, const int* __restrict__ topk_row, long long m, int k,
+    int* __restrict__ match_count, int* __restrict__ match_gt, float* __restrict__ match_val,
+    int* __restrict__ dynamic_ks) {
+  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= m) return;
+  float sum = 0.0f;
+  int have = 0;
+  for (int i = 0; i < k; ++i) {
+    if (topk_row[(long long)i * m + j] < 0) break;
+    sum += 1.0f - topk_val[(long long)i * m + j];                  // topk_ious.sum(0)      ref:188-190
+    ++have;
+  }
+  int dk = (int)sum;                                               // .int(): truncation     ref:190
+  dk = dk < 1 ? 1 : dk;                                            // clamp(min=1)
+  dk = dk > have ? have : dk;
+  if (dynamic_ks) dynamic_ks[j] = dk;
+  for (int i = 0; i < dk; ++i) {                                   // topk(cost[:, j], k=dk, largest=False)  ref:191-194
+    const int row = topk_row[(long long)i * m + j];
+    atomicAdd(match_count + row, 1);
+    match_gt[row] = (int)j;                   // read back only where the count is exactly 1
+    match_val[row] = topk_val[(long long)i * m + j];
+  }
+}
+
+// ref:198-211 per prior row: several GTs -> the row's own argmin over ALL GTs; one -> that GT
+__global__ void __launch_bounds__(kThreads) gd_simota_rows_kernel(
+    const int* __restrict__ match_count, const int* __restrict__ match_gt,
+    const float* __restrict__ match_val, const float* __restrict__ row_min,
+    const int* __restrict__ row_argmin, long long n, long long* __restrict__ assigned_gt_inds,
+    float* __restrict__ matched_sim, float unmatched_sim) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int c = match_count[i];
+  long long gt = 0;                                                // background          ref:64-66
+  float sim = unmatched_sim;
+  if (c > 1) {                                                     // ref:198-203
+    gt = (long long)row_argmin[i] + 1;
+    sim = 1.0f - row_min[i];
+  } else if (c == 1) {
+    gt = (long long)match_gt[i] + 1;
+    sim = 1.0f - match_val[i];
+  }
+  assigned_gt_inds[i] = gt;                                        // matched_gt_inds + 1   ref:112
+  if (matched_sim) matched_sim[i] = sim;                           // matched_pred_ious     ref:209-210
+}
+
+template <int LOSS>
+static int launch_topk(const PairwiseArgs& a, const TopkArgs& tk, long long gx, cudaStream_t st) {
+  gd_pairwise_topk_kernel<LOSS><<<(unsigned)gx, kThreads, 0, st>>>(a, tk);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+static long long topk_grid(long long n) {
+  const long long ntiles = (n + kRowsPerCta - 1) / kRowsPerCta;
+  long long gx = (long long)device_info().sm_count * 2;            // persistent: bounds the scratch
+  if (gx > ntiles) gx = ntiles;
+  return gx < 1 ? 1 : gx;
+}
+
+}  // namespace gdk
+
+extern "C" {
+
+size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m) {
+  using namespace gdk;
+  if (n < 0 || m < 0) return 0;
+  const long long slots = topk_grid(n) * kWarps;                   // wy <= kWarps row phases
+  return 256 + sizeof(unsigned long long) * (size_t)(slots * kTopK * (m > 0 ? m : 0));
+}
+
+int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t n,
+                         const float* boxes2, int64_t m, int32_t k, float* row_min,
+                         int32_t* row_argmin, float* topk_val, int32_t* topk_row, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  using namespace gdk;
+  if (!config_ok(cfg) || n < 0 || m <= 0 || k < 1 || k > kTopK) return GD_ERR_BAD_ARG;
+  if (n > 0x7fffffffLL || m > 0x7fffffffLL) return GD_ERR_BAD_ARG;
+  if (!topk_val || !topk_row || (n > 0 && (!boxes1 || !boxes2 || !row_min || !row_argmin)))
+    return GD_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < gd_pairwise_topk_workspace_bytes(n, m)) return GD_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PairwiseArgs a{};
+  a.b1 = boxes1;
+  a.n = n;
+  a.b2 = boxes2;
+  a.m = m;
+  a.out_stride = m;
+  a.row_min = row_min;
+  a.row_argmin = row_argmin;
+  a.pp = make_pair_params(*cfg);
+  TopkArgs tk;
+  tk.cand = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  const long long gx = topk_grid(n);
+  const int wy = kWarps / pairwise_wx(m, 32);
+  tk.slots = n > 0 ? gx * wy : 0;
+  int rc = 0;
+  if (n > 0) {
+    switch (cfg->loss_type) {
+      case GD_LOSS_GWD3D: rc = launch_topk<gd::kGwd>(a, tk, gx, st); break;
+      case GD_LOSS_KLD3D: rc = launch_topk<gd::kKld>(a, tk, gx, st); break;
+      case GD_LOSS_JD3D: rc = launch_topk<gd::kJd>(a, tk, gx, st); break;
+      case GD_LOSS_KLD3D_SYMMAX: rc = launch_topk<gd::kSymMax>(a, tk, gx, st); break;
+      case GD_LOSS_KLD3D_SYMMIN: rc = launch_topk<gd::kSymMin>(a, tk, gx, st); break;
+      case GD_LOSS_BD3D: rc = launch_topk<gd::kBd>(a, tk, gx, st); break;
+      case GD_LOSS_KFIOU3D: rc = launch_topk<gd::kKfiou>(a, tk, gx, st); break;
+      default: return GD_ERR_BAD_ARG;
+    }
+    if (rc != 0) return rc;
+  }
+  gd_topk_merge_kernel<<<(unsigned)((m + 3) / 4), 128, 0, st>>>(tk.cand, tk.slots, m, k, topk_val,
+                                                                topk_row);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int gd_simota_from_topk(const float* topk_val, const int32_t* topk_row, int64_t m, int32_t k,
+                        const float* row_min, const int32_t* row_argmin, int64_t n,
+                        int64_t* assigned_gt_inds, float* matched_sim, int32_t* dynamic_ks,
+                        float unmatched_sim, int32_t* scratch, void* stream) {
+  using namespace gdk;
+  if (n < 0 || m < 0 || k < 1 || k > kTopK) return GD_ERR_BAD_ARG;
+  if (n == 0) return 0;
+  if (!assigned_gt_inds || !scratch || !row_min || !row_argmin || (m > 0 && (!topk_val || !topk_row)))
+    return GD_ERR_BAD_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int* count = scratch;
+  int* mgt = scratch + n;
+  float* mval = reinterpret_cast<float*>(scratch + 2 * n);
+  cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int) * (size_t)n, st);
+  if (e != cudaSuccess) return (int)e;
+  if (m > 0) {
+    gd_simota_cols_kernel<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+        topk_val, topk_row, m, k, count, mgt, mval, dynamic_ks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  gd_simota_rows_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+      count, mgt, mval, row_min, row_argmin, n, reinterpret_cast<long long*>(assigned_gt_inds),
+      matched_sim, unmatched_sim);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -262,3 +262,61 @@ def assign_from_minima(row_min, row_argmin, col_min, col_argmin, pos_thr, neg_lo
             _ptr(assigned), _ptr(max_ov), _stream_ptr())
     _lib.check(code, 'gd_assign_from_minima')
     return assigned, max_ov
+
+
+# ---------------------------------------------------------------------------
+# SimOTA-style consumer: column top-k + dynamic-k matching, no matrix (f2)
+# ---------------------------------------------------------------------------
+_TOPK_WORKSPACES = {}
+
+
+def pairwise_col_topk(boxes1, boxes2, cfg, k):
+    """``(row_min [N], row_argmin [N] int64, topk_val [k,M], topk_row [k,M] int64)``: per column
+    of the (never materialised) distance matrix its ``k`` smallest entries, ascending (NaN first,
+    ties -> lowest row; -1 / +inf where N < k), and per row its minimum -- ``gd_pairwise_col_topk``."""
+    b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
+    n, m = b1.shape[0], b2.shape[0]
+    if m == 0:
+        raise ValueError('pairwise_col_topk needs at least one column box')
+    if not 1 <= int(k) <= 16:
+        raise ValueError('k must be in [1, 16]')
+    dev = b1.device
+    lib = _lib.load()
+    row_min = torch.empty((n,), dtype=torch.float32, device=dev)
+    row_idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    val = torch.empty((int(k), m), dtype=torch.float32, device=dev)
+    row = torch.empty((int(k), m), dtype=torch.int32, device=dev)
+    need = lib.gd_pairwise_topk_workspace_bytes(n, m)
+    key = (dev.index, _raw_stream(dev.index))
+    ws = _TOPK_WORKSPACES.get(key)
+    if ws is None or ws.numel() < need:
+        if len(_TOPK_WORKSPACES) >= _MAX_WORKSPACES:
+            _TOPK_WORKSPACES.clear()
+        ws = _TOPK_WORKSPACES[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+    with _on_device(dev):
+        code = lib.gd_pairwise_col_topk(ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m, int(k),
+                                        _ptr(row_min), _ptr(row_idx), _ptr(val), _ptr(row),
+                                        _ptr(ws), ws.numel(), _stream_ptr())
+    _lib.check(code, 'gd_pairwise_col_topk')
+    return row_min, row_idx.long(), val, row.long()
+
+
+def simota_from_topk(topk_val, topk_row, row_min, row_argmin, unmatched_sim=-1e8):
+    """SimOTA ``dynamic_k_matching`` (reference ``sim_ota_3d_assigner.py:184-211``) from the
+    column top-k lists: ``(assigned_gt_inds [N] int64 (0 = background, else GT + 1),
+    matched_sim [N], dynamic_ks [M] int64)`` -- ``gd_simota_from_topk``."""
+    k, m = topk_val.shape
+    n = row_min.shape[0]
+    dev = row_min.device
+    assigned = torch.empty((n,), dtype=torch.int64, device=dev)
+    sim = torch.empty((n,), dtype=torch.float32, device=dev)
+    dks = torch.empty((m,), dtype=torch.int32, device=dev)
+    scratch = torch.empty((3 * max(n, 1),), dtype=torch.int32, device=dev)
+    tr = topk_row.to(torch.int32).contiguous()
+    ri = row_argmin.to(torch.int32)
+    with _on_device(dev):
+        code = _lib.load().gd_simota_from_topk(
+            _ptr(topk_val.contiguous()), _ptr(tr), m, k, _ptr(row_min), _ptr(ri), n, _ptr(assigned),
+            _ptr(sim), _ptr(dks), float(unmatched_sim), _ptr(scratch), _stream_ptr())
+    _lib.check(code, 'gd_simota_from_topk')
+    return assigned, sim, dks.long()

@@ -399,3 +399,45 @@ def loss_and_grad(module, pred, target, weight=None, avg_factor=None,
         loss.backward(torch.ones_like(loss) if grad_output is None
                       else grad_output)
     return loss.detach(), pred.grad
+
+
+# --------------------------------------------------------------------------
+# f2 (second branch): SimOTA's dynamic-k matching, restated from
+# core/bbox/assigners/sim_ota_3d_assigner.py:184-211 ("sim:LINE").  Pinned against the
+# reference's own method by tests/test_oracle.py (golden fixture written by
+# oracle/make_simota_golden.py from the unmodified file).
+# --------------------------------------------------------------------------
+def simota_dynamic_k_matching(cost, pairwise_ious, candidate_topk=10):
+    """``cost`` / ``pairwise_ious`` ``[num_priors, num_gt]``.  Returns
+    ``(assigned_gt_inds [num_priors] int64 -- 0 background, k+1 = GT k (sim:112) --,
+    matched_ious [num_priors] (0 where unmatched), dynamic_ks [num_gt])``.
+
+    Ties: ``torch.topk`` leaves the order of equal entries unspecified; this restatement (and
+    the CUDA kernels) take the LOWEST row index first, which is one of the reference's
+    admissible outcomes."""
+    n, num_gt = cost.shape
+    matching = torch.zeros_like(cost)                                    # sim:185
+    topk = min(candidate_topk, n)                                        # sim:187
+    rows = torch.arange(n, device=cost.device)
+
+    def lowest(values, k, largest):
+        # k smallest / largest entries, ties -> lowest row (stable sort on the value)
+        order = torch.sort(-values if largest else values, stable=True).indices
+        return order[:k]
+    dynamic_ks = torch.empty(num_gt, dtype=torch.int64, device=cost.device)
+    for j in range(num_gt):
+        top = lowest(pairwise_ious[:, j], topk, True)                    # sim:188
+        dynamic_ks[j] = max(int(pairwise_ious[top, j].sum().int()), 1)   # sim:190
+    for j in range(num_gt):                                              # sim:191-194
+        pos = lowest(cost[:, j], int(dynamic_ks[j]), False)
+        matching[pos, j] = 1.0
+    multi = matching.sum(1) > 1                                          # sim:198
+    if multi.sum() > 0:                                                  # sim:199-203
+        cost_argmin = torch.min(cost[multi, :], dim=1).indices
+        matching[multi, :] *= 0.0
+        matching[rows[multi], cost_argmin] = 1.0
+    fg = matching.sum(1) > 0.0                                           # sim:205
+    assigned = torch.zeros(n, dtype=torch.int64, device=cost.device)
+    assigned[fg] = matching[fg, :].argmax(1) + 1                         # sim:208, sim:112
+    matched = (matching * pairwise_ious).sum(1)                          # sim:209-210
+    return assigned, matched, dynamic_ks

@@ -187,3 +187,45 @@ def load_reference_center_coder():
     pkg.CenterPointBBoxCoderRev = _load('centerpoint_bbox_coders').CenterPointBBoxCoderRev
     _CODER = _load('centerpoint_bbox_yaw_coders').CenterPointBBoxYawCoder
     return _CODER
+
+
+# ---------------------------------------------------------------------------
+# SimOTABEVAssigner: only its pure-torch method
+# dynamic_k_matching (sim_ota_3d_assigner.py:184-211) is on our path; the module's imports
+# (mmdet assigner base classes, mmdet3d ops / box structures) are stubbed.
+# ---------------------------------------------------------------------------
+SIMOTA_FILE = os.path.join(REFERENCE_ROOT, 'mmdet3d_gaussian', 'core', 'bbox', 'assigners',
+                           'sim_ota_3d_assigner.py')
+_SIMOTA = None
+
+
+def load_reference_simota():
+    """Import ``core/bbox/assigners/sim_ota_3d_assigner.py`` by path, unmodified; returns the
+    class ``SimOTABEVAssigner``."""
+    global _SIMOTA
+    if _SIMOTA is not None:
+        return _SIMOTA
+    if not os.path.isfile(SIMOTA_FILE):
+        raise FileNotFoundError(f'{SIMOTA_FILE} not found: build container only')
+    _install_stub_mmdet()
+    stubs = ['mmdet.core', 'mmdet.core.bbox', 'mmdet.core.bbox.assigners', 'mmdet.core.bbox.builder',
+             'mmdet3d', 'mmdet3d.ops', 'mmdet3d.core', 'mmdet3d.core.bbox',
+             'mmdet3d.core.bbox.structures', 'mmdet3d.core.bbox.structures.lidar_box3d']
+    for name in stubs:
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            sys.modules[name] = mod
+            if '.' in name:
+                parent, child = name.rsplit('.', 1)
+                setattr(sys.modules[parent], child, mod)
+    sys.modules['mmdet.core.bbox.assigners'].BaseAssigner = type('BaseAssigner', (), {})
+    sys.modules['mmdet.core.bbox.assigners'].AssignResult = type('AssignResult', (), {})
+    if not hasattr(sys.modules['mmdet.core.bbox.builder'], 'BBOX_ASSIGNERS'):
+        sys.modules['mmdet.core.bbox.builder'].BBOX_ASSIGNERS = _StubRegistry('bbox_assigner')
+    sys.modules['mmdet3d.ops'].points_in_boxes_all = None
+    sys.modules['mmdet3d.core.bbox.structures.lidar_box3d'].LiDARInstance3DBoxes = None
+    spec = importlib.util.spec_from_file_location('_gd_reference_simota', SIMOTA_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _SIMOTA = mod.SimOTABEVAssigner
+    return _SIMOTA

@@ -262,3 +262,40 @@ def test_oracle_matches_reference_on_mismatched_boxes():
         assert np.allclose(loss.numpy(), rl, rtol=1e-11, atol=1e-300), c
         gn = np.abs(rg).max(1, keepdims=True)
         assert (np.abs(grad.numpy() - rg) <= 1e-10 * gn + 1e-300).all(), c
+
+
+# ---------------------------------------------------------------------------
+# SimOTA dynamic-k matching: restatement vs the reference method
+# ---------------------------------------------------------------------------
+def test_simota_restatement_matches_reference_goldens():
+    """``gd_oracle.simota_dynamic_k_matching`` against fixtures written by the UNMODIFIED
+    ``SimOTABEVAssigner.dynamic_k_matching`` (oracle/make_simota_golden.py; tie-free inputs)."""
+    import json
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'gd_simota_golden.npz'))
+    manifest = json.loads(bytes(z['manifest']).decode())
+    assert len(manifest) >= 7
+    for c in manifest:
+        cid = c['id']
+        cost, ious = torch.from_numpy(z[f'{cid}/cost']), torch.from_numpy(z[f'{cid}/ious'])
+        assigned, matched, dks = gd_oracle.simota_dynamic_k_matching(cost, ious, c['candidate_topk'])
+        assert torch.equal(assigned, torch.from_numpy(z[f'{cid}/assigned'])), c
+        assert torch.allclose(matched, torch.from_numpy(z[f'{cid}/matched_ious']), rtol=0, atol=1e-15)
+        assert int(dks.min()) >= 1 and (assigned > 0).sum() >= 1
+
+
+@pytest.mark.skipif(not os.path.isfile(ref_loader.SIMOTA_FILE), reason='needs /root/reference')
+def test_simota_restatement_matches_live_reference():
+    cls = ref_loader.load_reference_simota()
+    g = torch.Generator().manual_seed(5)
+    for n, m, topk in ((400, 9, 10), (33, 4, 10), (7, 2, 10), (800, 25, 6)):
+        d = torch.rand(n, m, generator=g, dtype=torch.float64)
+        ious = 1.0 / (1.0 + torch.where(torch.rand(n, m, generator=g) < 0.1, d * 0.03, 0.2 + d))
+        cost = -torch.log(ious)                       # the reference's own cost shape (sim:94)
+        valid = torch.ones(n, dtype=torch.bool)
+        mi, mg = cls(candidate_topk=topk).dynamic_k_matching(cost.clone(), ious.clone(), m, valid)
+        want = torch.zeros(n, dtype=torch.int64)
+        want[valid] = mg + 1
+        assigned, matched, _ = gd_oracle.simota_dynamic_k_matching(cost, ious, topk)
+        assert torch.equal(assigned, want)
+        assert torch.allclose(matched[valid], mi, rtol=0, atol=1e-15)
