@@ -302,14 +302,17 @@ GD_API int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin
  * (NaN first, ties -> lowest row):  topk_val [k,m] fp32, topk_row [k,m] int32 (-1 / +inf where
  * n < k) -- what ref:187-188 `torch.topk(pairwise_ious, candidate_topk, dim=0)` and the per-GT
  * `torch.topk(cost[:, gt], k=dynamic_k, largest=False)` of ref:192-193 read -- plus the row
- * (min, argmin) that the conflict rule ref:198-203 needs.  Workspace: scratch, no zeroing
- * needed, gd_pairwise_topk_workspace_bytes(n, m) bytes. */
+ * (min, argmin) that the conflict rule ref:198-203 needs.  `out` (nullable, row stride in
+ * elements) additionally receives the matrix from the same instruction sequence, so lists and
+ * matrix of one launch are bit-consistent (tests).  Workspace: scratch, no zeroing needed,
+ * gd_pairwise_topk_workspace_bytes(n, m) bytes. */
 GD_API size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m);
 GD_API int gd_pairwise_col_topk(const gd_loss_config* cfg,
                                 const float* boxes1, int64_t n,
                                 const float* boxes2, int64_t m, int32_t k,
                                 float* row_min, int32_t* row_argmin,
                                 float* topk_val, int32_t* topk_row,
+                                float* out, int64_t out_row_stride,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* dynamic_k_matching (ref:184-211) from those lists:

@@ -91,7 +91,7 @@ SIGNATURES = {
                                           _i64, _i32, _vp, ctypes.c_size_t, _vp]),
     'gd_pairwise_topk_workspace_bytes': (ctypes.c_size_t, [_i64, _i64]),
     'gd_pairwise_col_topk': (ctypes.c_int, [_cfgp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp,
-                                            _vp, ctypes.c_size_t, _vp]),
+                                            _vp, _i64, _vp, ctypes.c_size_t, _vp]),
     'gd_simota_from_topk': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp,
                                            _f32, _vp, _vp]),
     'gd_assign_from_minima': (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _f32, _f32, _f32, _f32,

@@ -125,7 +125,7 @@ class GDSimOTAAssigner(nn.Module):
         self.cfg = _make_cfg(loss_type, fun, tau, alpha, center_offset, kwargs)
 
     @torch.no_grad()
-    def assign(self, bboxes, gt_bboxes):
+    def assign(self, bboxes, gt_bboxes, want_matrix=False):
         n, m = bboxes.shape[0], gt_bboxes.shape[0]
         dev = bboxes.device
         if n == 0 or m == 0:                          # ref:67-79
@@ -135,11 +135,14 @@ class GDSimOTAAssigner(nn.Module):
                         topk_overlaps=torch.zeros(0, m, device=dev),
                         topk_inds=torch.zeros(0, m, dtype=torch.int64, device=dev))
         k = min(self.candidate_topk, n)               # ref:187
-        row_min, row_arg, tv, tr = ops.pairwise_col_topk(bboxes[..., :7], gt_bboxes[..., :7],
-                                                         self.cfg, k)
+        row_min, row_arg, tv, tr, mat = ops.pairwise_col_topk(
+            bboxes[..., :7], gt_bboxes[..., :7], self.cfg, k, want_matrix=want_matrix)
         assigned, sim, dks = ops.simota_from_topk(tv, tr, row_min, row_arg,
                                                   unmatched_sim=-float(self.INF))
-        return dict(assigned_gt_inds=assigned, max_overlaps=sim, dynamic_ks=dks,
-                    topk_overlaps=1.0 - tv, topk_inds=tr)
+        out = dict(assigned_gt_inds=assigned, max_overlaps=sim, dynamic_ks=dks,
+                   topk_overlaps=1.0 - tv, topk_inds=tr)
+        if want_matrix:
+            out['distance_matrix'] = mat              # debugging / tests: the values the lists hold
+        return out
 
     forward = assign

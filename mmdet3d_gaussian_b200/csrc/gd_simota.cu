@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_topk_kernel(const Pairwi
       if (warp_live) {
         for (int r = ry; r < rows; r += wy) {
           const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t, pp);
+          if (a.out != nullptr && live) __stcs(a.out + (row0 + r) * a.out_stride + j, v);
           const unsigned int key = live ? order_key(v) : 0xffffffffu;
           const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
           const unsigned int who = __ballot_sync(0xffffffffu, key == mn);
@@ -229,10 +230,12 @@ size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m) {
 
 int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t n,
                          const float* boxes2, int64_t m, int32_t k, float* row_min,
-                         int32_t* row_argmin, float* topk_val, int32_t* topk_row, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         int32_t* row_argmin, float* topk_val, int32_t* topk_row, float* out,
+                         int64_t out_row_stride, void* workspace, size_t workspace_bytes,
+                         void* stream) {
   using namespace gdk;
   if (!config_ok(cfg) || n < 0 || m <= 0 || k < 1 || k > kTopK) return GD_ERR_BAD_ARG;
+  if (out && out_row_stride < m) return GD_ERR_BAD_ARG;
   if (n > 0x7fffffffLL || m > 0x7fffffffLL) return GD_ERR_BAD_ARG;
   if (!topk_val || !topk_row || (n > 0 && (!boxes1 || !boxes2 || !row_min || !row_argmin)))
     return GD_ERR_BAD_ARG;
@@ -243,7 +246,8 @@ int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t
   a.n = n;
   a.b2 = boxes2;
   a.m = m;
-  a.out_stride = m;
+  a.out = out;
+  a.out_stride = out ? out_row_stride : m;
   a.row_min = row_min;
   a.row_argmin = row_argmin;
   a.pp = make_pair_params(*cfg);

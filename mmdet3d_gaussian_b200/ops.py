@@ -270,10 +270,11 @@ def assign_from_minima(row_min, row_argmin, col_min, col_argmin, pos_thr, neg_lo
 _TOPK_WORKSPACES = {}
 
 
-def pairwise_col_topk(boxes1, boxes2, cfg, k):
-    """``(row_min [N], row_argmin [N] int64, topk_val [k,M], topk_row [k,M] int64)``: per column
-    of the (never materialised) distance matrix its ``k`` smallest entries, ascending (NaN first,
-    ties -> lowest row; -1 / +inf where N < k), and per row its minimum -- ``gd_pairwise_col_topk``."""
+def pairwise_col_topk(boxes1, boxes2, cfg, k, want_matrix=False):
+    """``(row_min [N], row_argmin [N] int64, topk_val [k,M], topk_row [k,M] int64, matrix | None)``:
+    per column of the distance matrix its ``k`` smallest entries, ascending (NaN first, ties ->
+    lowest row; -1 / +inf where N < k), and per row its minimum -- ``gd_pairwise_col_topk``.  The
+    matrix is only written when ``want_matrix`` (same instruction sequence: bit-consistent)."""
     b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
     n, m = b1.shape[0], b2.shape[0]
     if m == 0:
@@ -286,6 +287,7 @@ def pairwise_col_topk(boxes1, boxes2, cfg, k):
     row_idx = torch.empty((n,), dtype=torch.int32, device=dev)
     val = torch.empty((int(k), m), dtype=torch.float32, device=dev)
     row = torch.empty((int(k), m), dtype=torch.int32, device=dev)
+    mat = torch.empty((n, m), dtype=torch.float32, device=dev) if want_matrix else None
     need = lib.gd_pairwise_topk_workspace_bytes(n, m)
     key = (dev.index, _raw_stream(dev.index))
     ws = _TOPK_WORKSPACES.get(key)
@@ -296,9 +298,9 @@ def pairwise_col_topk(boxes1, boxes2, cfg, k):
     with _on_device(dev):
         code = lib.gd_pairwise_col_topk(ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m, int(k),
                                         _ptr(row_min), _ptr(row_idx), _ptr(val), _ptr(row),
-                                        _ptr(ws), ws.numel(), _stream_ptr())
+                                        _ptr(mat), m, _ptr(ws), ws.numel(), _stream_ptr())
     _lib.check(code, 'gd_pairwise_col_topk')
-    return row_min, row_idx.long(), val, row.long()
+    return row_min, row_idx.long(), val, row.long(), mat
 
 
 def simota_from_topk(topk_val, topk_row, row_min, row_argmin, unmatched_sim=-1e8):

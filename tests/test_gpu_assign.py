@@ -191,9 +191,11 @@ def test_sharded_assigner_emulated_shards():
 def test_simota_assigner_equals_matching_on_the_matrix(loss_type, n, m, topk):
     """The fused path (column top-k lists + row minima, no matrix) against the restated
     reference matching (gd_oracle.simota_dynamic_k_matching = sim_ota_3d_assigner.py:184-211)
-    run on OUR materialised fp32 matrix: identical assignment, similarities and dynamic k --
-    exact ties included (both take the lowest index first).  The lists themselves equal a
-    stable sort of the matrix columns bit for bit."""
+    run on the fp32 matrix the SAME kernel writes on request (one instruction sequence for lists
+    and matrix): identical assignment, similarities and dynamic k -- exact ties included (both
+    take the lowest index first); the lists equal a stable sort of the matrix columns bit for
+    bit; the result does not depend on whether the matrix is written; and the matrix agrees with
+    the plain pairwise kernel's to the last place (another instantiation)."""
     from mmdet3d_gaussian_b200 import GDSimOTAAssigner
     b1 = synth.make_anchor_grid(n, 'waymo', device='cuda')
     b2 = synth.make_targets(m, 'waymo', seed=n + m, device='cuda')
@@ -204,7 +206,12 @@ def test_simota_assigner_equals_matching_on_the_matrix(loss_type, n, m, topk):
         b1[68] = b1[3]
     asg = GDSimOTAAssigner(candidate_topk=topk, loss_type=loss_type, fun='log1p', tau=1.0)
     res = asg.assign(b1, b2)
-    mat = GDPairwiseDistance(loss_type, fun='log1p', tau=1.0)(b1, b2)
+    resm = asg.assign(b1, b2, want_matrix=True)
+    for key in ('assigned_gt_inds', 'max_overlaps', 'dynamic_ks', 'topk_overlaps', 'topk_inds'):
+        assert torch.equal(res[key], resm[key]), key
+    mat = resm['distance_matrix']
+    plain = GDPairwiseDistance(loss_type, fun='log1p', tau=1.0)(b1, b2)
+    assert ((plain - mat).abs() / mat.abs().clamp_min(1e-3)).max().item() < 2e-6
     k = min(topk, n)
     order = torch.sort(mat, dim=0, stable=True).indices[:k]           # ties -> lowest row
     assert torch.equal(res['topk_inds'], order)
