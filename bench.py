@@ -504,11 +504,23 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # host-side ceiling next to it: what a plain CPU copy between two pinned buffers gets on
+        # this rank while all ranks copy at the same time (read + write bytes)
+        hsrc = torch.empty(1 << 26, dtype=torch.uint8).pin_memory()
+        hdst = torch.empty(1 << 26, dtype=torch.uint8).pin_memory()
+        hdst.copy_(hsrc)
+        sync_all()
+        th = time.perf_counter()
+        for _ in range(8):
+            hdst.copy_(hsrc)
+        host_copy = 8 * 2 * (1 << 26) / (time.perf_counter() - th) / 1e9
+        del hsrc, hdst
         e2e = {'value': len(COMBOS) * n * world * k / dt, 'unit': 'pairs/s',
                'h2d_bytes_per_step': len(COMBOS) * n * 60,
                'd2h_bytes_per_step': len(COMBOS) * (n * 28 + 4),
                'steps': k, 'ms_per_step': dt / k * 1e3,
                'h2d_GBps_per_gpu': len(COMBOS) * n * 60 * k / dt / 1e9, 'numa': numa,
+               'host_copy_GBps_this_rank_all_ranks_busy': round(host_copy, 1),
                'api': f'gd_loss_fwd_bwd_host (C ABI, pinned host buffers, 2^{args.e2e_chunk_log2}-row '
                       f'chunks, 3 streams)'}
         del hp, ht, hw, hgrad

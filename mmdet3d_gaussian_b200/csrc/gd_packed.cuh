@@ -285,44 +285,6 @@ GD_HD PairParams<f2> broadcast_params(const PairParams<float>& P) {
   return Q;
 }
 
-// ---- pairwise path: two ROW boxes against one COLUMN box per packed evaluation ----------
-// Field order of BoxGauss as a flat array (the packed pairwise kernel keeps the row tile
-// in shared memory as float2 {row 2k, row 2k+1} per field, so one 64-bit broadcast load
-// yields a packed operand).
-enum GaussField : int {
-  kGfCx, kGfCy, kGfCz, kGfA, kGfB, kGfE, kGfS, kGfC, kGfAA, kGfBB, kGfEE, kGfAb, kGfAmb, kGfR6,
-  kGfIa, kGfIb, kGfIe, kGaussFields
-};
-GD_HD void gauss_to_fields(const BoxGauss<float>& b, float* f) {
-  f[kGfCx] = b.cx; f[kGfCy] = b.cy; f[kGfCz] = b.cz;
-  f[kGfA] = b.a; f[kGfB] = b.b; f[kGfE] = b.e;
-  f[kGfS] = b.s; f[kGfC] = b.c;
-  f[kGfAA] = b.A; f[kGfBB] = b.B; f[kGfEE] = b.E;
-  f[kGfAb] = b.ab; f[kGfAmb] = b.amb; f[kGfR6] = b.r6;
-  f[kGfIa] = b.ia; f[kGfIb] = b.ib; f[kGfIe] = b.ie;
-}
-template <typename T>
-GD_HD BoxGauss<T> gauss_from_fields(const T* f) {
-  BoxGauss<T> b;
-  b.cx = f[kGfCx]; b.cy = f[kGfCy]; b.cz = f[kGfCz];
-  b.a = f[kGfA]; b.b = f[kGfB]; b.e = f[kGfE];
-  b.s = f[kGfS]; b.c = f[kGfC];
-  b.A = f[kGfAA]; b.B = f[kGfBB]; b.E = f[kGfEE];
-  b.ab = f[kGfAb]; b.amb = f[kGfAmb]; b.r6 = f[kGfR6];
-  b.ia = f[kGfIa]; b.ib = f[kGfIb]; b.ie = f[kGfIe];
-  b.nice = 0;                                  // carried separately by the callers
-  return b;
-}
-// FAST value of (row box lo, column box) and (row box hi, column box) in one packed stream;
-// `rare` comes in as "this half may not use the FAST cores" and is OR-ed with the guards.
-template <int LOSS>
-GD_HD f2 pair_value_fast2(const BoxGauss<f2>& rows, const BoxGauss<f2>& col,
-                          const PairParams<f2>& P, m2* rare) {
-  static_assert(LOSS == kGwd || LOSS == kKld || LOSS == kBd, "packed cores: gwd3d, kld3d, bd3d");
-  const PairGeom<f2> g = geom_from_gauss(rows, col);
-  return core_eval<f2, LOSS, false, true>(g, P, f2(1.0f), (f2*)0, rare);
-}
-
 // Two (pred, target) rows through the FAST cores at once.  pa/ta, pb/tb: the two rows;
 // wsa/wsb their weight*scale factors; ga/gb receive the gradients; rare_a/rare_b are
 // OR-ed with "this row must be redone on the robust path".  Returns the two values.

@@ -62,62 +62,8 @@ long run(int fun, int tau_on, int flag, long n, unsigned seed, long* nrare) {
   }
   return bad;
 }
-// Pairwise path: two row boxes against one column box through pair_value_fast2 (what
-// gd_pairwise_packed_kernel runs) vs the scalar FAST value core on each (row, column) pair.
-template <int LOSS>
-long run_pairwise(int fun, int tau_on, int flag, long n, unsigned seed, long* nrare) {
-  std::mt19937 rng(seed);
-  std::normal_distribution<float> N01(0.f, 1.f);
-  std::uniform_real_distribution<float> U(0.f, 1.f);
-  gd::PairParams<float> P;
-  P.off[0] = 0; P.off[1] = 0; P.off[2] = 0.5f; P.alpha2 = 1; P.inv_alpha2 = 1; P.tau = tau_on ? 1.0f : 0.f;
-  P.fun = fun; P.tau_on = tau_on; P.flag = flag;
-  const gd::PairParams<gd::f2> Q = gd::broadcast_params(P);
-  long bad = 0;
-  for (long i = 0; i < n; ++i) {
-    float b[3][7];                                   // two rows + one column
-    for (int h = 0; h < 3; ++h) {
-      b[h][0] = 70 * U(rng); b[h][1] = 80 * U(rng) - 40; b[h][2] = -1 + 0.5f * N01(rng);
-      b[h][3] = 1.7f * expf(0.3f * N01(rng)); b[h][4] = 0.7f * expf(0.3f * N01(rng)); b[h][5] = 1.6f * expf(0.2f * N01(rng));
-      b[h][6] = 6.2831853f * U(rng) - 3.1415927f;
-    }
-    if (i % 5 == 0) for (int c = 0; c < 7; ++c) b[1][c] = b[2][c] * (1.0f + 1e-3f * N01(rng));  // near-identical pair
-    if (i % 7 == 0) for (int c = 0; c < 7; ++c) b[0][c] = b[2][c];                                // identical pair
-    if (i % 991 == 0) b[1][4] = 1e-9f;               // not nice: must be flagged, never silently wrong
-    gd::BoxGauss<float> g[3];
-    float f[3][gd::kGaussFields];
-    for (int h = 0; h < 3; ++h) { g[h] = gd::box_gauss(b[h], P); gd::gauss_to_fields(g[h], f[h]); }
-    gd::f2 rf[gd::kGaussFields], cf[gd::kGaussFields];
-    for (int k = 0; k < gd::kGaussFields; ++k) { rf[k] = gd::mk2(f[0][k], f[1][k]); cf[k] = gd::mk2(f[2][k], f[2][k]); }
-    const gd::BoxGauss<gd::f2> rows = gd::gauss_from_fields<gd::f2>(rf), col = gd::gauss_from_fields<gd::f2>(cf);
-    gd::m2 rare{!(g[0].nice && g[2].nice), !(g[1].nice && g[2].nice)};
-    const gd::f2 v2 = gd::pair_value_fast2<LOSS>(rows, col, Q, &rare);
-    const float v[2] = {gd::lo2(v2), gd::hi2(v2)};
-    const bool r2[2] = {rare.lo, rare.hi};
-    for (int h = 0; h < 2; ++h) {
-      bool rs = !(g[h].nice && g[2].nice);
-      const gd::PairGeom<float> pg = gd::geom_from_gauss(g[h], g[2]);
-      const float vs = gd::core_eval<float, LOSS, false, true>(pg, P, 1.0f, (float*)0, &rs);
-      if (rs != r2[h]) { ++bad; continue; }
-      if (rs) { ++*nrare; continue; }
-      if (memcmp(&vs, &v[h], 4)) ++bad;
-      // and the round trip through the field array loses nothing
-      const gd::BoxGauss<float> back = gd::gauss_from_fields<float>(f[h]);
-      if (memcmp(&back.cx, &g[h].cx, sizeof(float) * 3) || back.r6 != g[h].r6 || back.ie != g[h].ie) ++bad;
-    }
-  }
-  return bad;
-}
 int main() {
   long total_bad = 0;
-  for (int fun = 0; fun < 2; ++fun) for (int tau = 0; tau < 2; ++tau) {
-    long nr = 0;
-    long b0 = run_pairwise<gd::kGwd>(fun, tau, 1, 20000, 11, &nr);
-    long b1 = run_pairwise<gd::kKld>(fun, tau, 1, 20000, 12, &nr);
-    long b5 = run_pairwise<gd::kBd>(fun, tau, 1, 20000, 13, &nr);
-    printf("pairwise fun %d tau %d: mismatches gwd %ld kld %ld bd %ld (rare pairs %ld)\n", fun, tau, b0, b1, b5, nr);
-    total_bad += b0 + b1 + b5;
-  }
   for (int fun = 0; fun < 2; ++fun) for (int tau = 0; tau < 2; ++tau) for (int flag = 0; flag < 2; ++flag) {
     long nr = 0;
     long b0 = run<gd::kGwd>(fun, tau, flag, 20000, 1, &nr);

@@ -1,0 +1,40 @@
+#!/bin/bash
+# Round-2 evidence run on one GPU: smoke, full GPU suite, bench (both arms), ncu full captures
+# (fused kernel: headline, [N,7] weights, strided) + launch list of the bench command, layouts,
+# latency, heads, sanitizer.   bash tools/gpu_final2.sh [tag]
+TAG=${1:-r02z}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+T0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - T0 ))s] $*"; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit,memory.total --format=csv > $OUT/gpu.txt 2>&1
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1
+stamp "smoke exit $?"; tail -6 $OUT/smoke.log
+timeout -s KILL 1500 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1
+stamp "pytest exit $?"; tail -6 $OUT/pytest_gpu.log
+timeout -s KILL 600 python bench.py --eager-gpu > $OUT/bench_auto.json 2> $OUT/bench_auto.err
+stamp "bench exit $?"; head -c 1200 $OUT/bench_auto.json; echo; tail -2 $OUT/bench_auto.err
+timeout -s KILL 400 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+stamp "bench reference exit $?"; head -c 600 $OUT/bench_reference.json; echo
+timeout -s KILL 500 ncu --set full --clock-control none --import-source on -k regex:gd_warp_kernel \
+  -c 10 -o $OUT/prof_bulk -f python tools/ncu_target.py > $OUT/ncu_full.log 2>&1
+stamp "ncu full exit $?"; tail -2 $OUT/ncu_full.log
+if [ -f $OUT/prof_bulk.ncu-rep ]; then
+  ncu -i $OUT/prof_bulk.ncu-rep --page raw --csv > $OUT/prof_bulk_raw.csv 2>/dev/null
+  SZ=$(stat -c %s $OUT/prof_bulk.ncu-rep); if [ $SZ -gt 40000000 ]; then rm $OUT/prof_bulk.ncu-rep; fi
+fi
+timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+  --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extras > $OUT/ncu_launches.log 2>&1
+stamp "ncu launches exit $?"
+timeout -s KILL 300 python tools/bench_layouts.py > $OUT/layouts.json 2> $OUT/layouts.err
+stamp "layouts exit $?"
+timeout -s KILL 300 python tools/latency.py > $OUT/latency.json 2> $OUT/latency.err
+stamp "latency exit $?"; cat $OUT/latency.json
+timeout -s KILL 300 python tools/bench_heads.py > $OUT/bench_heads.json 2> $OUT/bench_heads.err
+stamp "bench_heads exit $?"
+timeout -s KILL 300 python tools/sweep.py --only pairwise --cpl1 > $OUT/sweep_pairwise.json 2> $OUT/sweep_pairwise.err
+stamp "sweep pairwise exit $?"
+bash tools/gpu_sanitize.sh ${TAG}_san loss strided pairwise
+stamp "sanitizer done"
+du -sh $OUT

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""A handful of launches for `ncu --set full` (round evidence): the fused kernel at 2^24 pairs
+in the layouts that matter -- contiguous [N] weights (headline; kld3d/none, bd3d/log1p),
+contiguous [N,7] weights, row-strided 9/11-wide views (CenterGDHead) -- through bare C-ABI
+launches, two of each (ncu keeps both; the second is warm)."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmdet3d_gaussian_b200 import _lib, ops, synth  # noqa: E402
+
+
+def main():
+    n = 1 << 24
+    torch.cuda.set_device(0)
+    lib = _lib.load()
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=0, device='cuda')
+    w7 = w[:, None].expand(n, 7).contiguous()
+    wide_p = torch.zeros(n, 9, device='cuda')
+    wide_p[:, :7] = pred
+    wide_t = torch.zeros(n, 11, device='cuda')
+    wide_t[:, :7] = target
+    grad = torch.empty(n, 7, device='cuda')
+    loss = torch.empty((), device='cuda')
+    ws = ops._workspace(pred.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(lt, fun, p, ps, t, ts, wt, wmode, wstride):
+        cfg = _lib.make_config(lt, fun, True, 0.0, 1.0, (0, 0, 0.5))
+        io = _lib.GDLossIO()
+        io.pred, io.pred_row_stride = p.data_ptr(), ps
+        io.target, io.target_row_stride = t.data_ptr(), ts
+        io.weight = wt.data_ptr() if wt is not None else None
+        io.weight_mode, io.weight_row_stride = wmode, wstride
+        io.n, io.scale = n, 5.0 / n
+        io.loss_sum, io.grad_pred = loss.data_ptr(), grad.data_ptr()
+        io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
+        for _ in range(2):
+            code = lib.gd_loss_launch(ctypes.byref(cfg), ctypes.byref(io), stream)
+            assert code == 0, code
+        torch.cuda.synchronize()
+
+    run('kld3d', 'none', pred, 7, target, 7, w, 1, 1)
+    run('bd3d', 'log1p', pred, 7, target, 7, w, 1, 1)
+    run('kld3d', 'none', pred, 7, target, 7, w7, 2, 7)
+    run('kld3d', 'none', wide_p, 9, wide_t, 11, None, 0, 0)
+    run('bd3d', 'log1p', wide_p, 9, wide_t, 11, None, 0, 0)
+    print('ncu_target done')
+
+
+if __name__ == '__main__':
+    main()

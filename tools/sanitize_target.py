@@ -54,6 +54,10 @@ def main():
             mat = mod(b1, b2)
             rmin, ridx, cmin, cidx, _ = mod.assign(b1, b2)
             ok = ok and bool(torch.isfinite(mat).all()) and int(ridx.max()) < 97
+        from mmdet3d_gaussian_b200 import GDSimOTAAssigner
+        res = GDSimOTAAssigner(candidate_topk=10, loss_type='gwd3d', fun='log1p', tau=1.0).assign(
+            b1, b2, want_matrix=True)
+        ok = ok and int(res['assigned_gt_inds'].max()) <= 97 and int(res['topk_inds'].min()) >= 0
     torch.cuda.synchronize()
     print('sanitize_target finished, ok =', ok)
     sys.exit(0 if ok else 1)
