@@ -583,11 +583,32 @@ def run_ours(args):
             p3l.grad = None
             m3(p3l, t3l, w3l, avg_factor=avg3).backward()
         ms3 = event_ms(c3_call, 200, warm=20)
+        # the same sharded call captured into a CUDA graph (the in-kernel exchange keeps its
+        # sequence counter on the device, so it replays): what is left once torch's autograd
+        # engine hand-off (~45 us of the wall time above) is out of the loop
+        graph_us = None
+        try:
+            base3g = GDLoss('gwd3d', fun='log1p', tau=0.0, loss_weight=LOSS_WEIGHT, host_sync=False)
+            m3g = base3g if world == 1 else sharded.ShardedGDLoss(base3g, fused=not args.nccl)
+            gs = torch.cuda.Stream()
+            with torch.cuda.stream(gs):
+                psg = p3l.detach().clone().requires_grad_(True)
+                torch.autograd.grad(m3g(psg, t3l, w3l, avg_factor=avg3), psg)
+                gs.synchronize()
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg, stream=gs):
+                    gl3 = m3g(psg, t3l, w3l, avg_factor=avg3)
+                    torch.autograd.grad(gl3, psg)
+            torch.cuda.synchronize()
+            graph_us = event_ms(cg.replay, 200, warm=20) * 1e3
+        except Exception as exc:                                  # noqa: BLE001
+            sys.stderr.write(f'bench: c3 graph capture skipped: {exc!r}\n')
         extras['c3_strong'] = {
             'workload': f'C3: gwd3d, tau=0, log1p, {C3_ROWS} nuScenes-prior rows, Bernoulli(0.5)xU(0,1) '
                         f'[N] weights, avg_factor=#positive, rows split over {world} rank(s), '
                         'forward + backward() + cross-GPU sum',
             'scaling': 'strong', 'n_gpus': world, 'us_per_call_max_over_ranks': round(ms3 * 1e3, 2),
+            'us_per_call_cuda_graph_replay': None if graph_us is None else round(graph_us, 2),
             'pairs_per_s': C3_ROWS / (ms3 * 1e-3),
             'cross_gpu_sum': ('none (1 GPU)' if world == 1 else
                               ('in-kernel over peer memory' if m3.fused else 'NCCL all-reduce'))}

@@ -44,8 +44,8 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsig
 }
 
 template <int LOSS>
-__global__ void __launch_bounds__(kThreads) gd_pairwise_topk_kernel(const PairwiseArgs a,
-                                                                    const TopkArgs tk) {
+__global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const PairwiseArgs a,
+                                                                       const TopkArgs tk) {
   __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
   __shared__ unsigned long long s_best[kRowsPerCta][kWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -212,7 +212,7 @@ static int launch_topk(const PairwiseArgs& a, const TopkArgs& tk, long long gx, 
 
 static long long topk_grid(long long n) {
   const long long ntiles = (n + kRowsPerCta - 1) / kRowsPerCta;
-  long long gx = (long long)device_info().sm_count * 2;            // persistent: bounds the scratch
+  long long gx = (long long)device_info().sm_count * 3;            // persistent: bounds the scratch
   if (gx > ntiles) gx = ntiles;
   return gx < 1 ? 1 : gx;
 }
