@@ -37,7 +37,7 @@ struct Pipe {
 };
 
 static Pipe g_pipe[64];
-static std::mutex g_mu;
+static std::mutex g_mu[64];          // one pipeline per device: callers on different GPUs do not serialise
 
 #define GD_TRY(expr)                          \
   do {                                        \
@@ -47,16 +47,31 @@ static std::mutex g_mu;
 
 static int ensure(Pipe& p, long long chunk_rows, long long w_floats) {
   if (!p.init) {
+    // every resource is created at most once: a call that fails half way leaves what it got in
+    // place and the next call continues from there (nothing is leaked, nothing is created twice)
     for (int s = 0; s < kSlots; ++s) {
-      GD_TRY(cudaStreamCreateWithFlags(&p.slot[s].stream, cudaStreamNonBlocking));
-      GD_TRY(cudaMalloc(&p.slot[s].loss, sizeof(float)));
-      p.slot[s].ws_bytes = gd_loss_workspace_bytes(chunk_rows);
-      GD_TRY(cudaMalloc(&p.slot[s].ws, p.slot[s].ws_bytes));
-      GD_TRY(cudaMemset(p.slot[s].ws, 0, p.slot[s].ws_bytes));
+      Slot& sl = p.slot[s];
+      if (!sl.stream) GD_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+      if (!sl.loss) GD_TRY(cudaMalloc(&sl.loss, sizeof(float)));
+      if (!sl.ws) {
+        const size_t bytes = gd_loss_workspace_bytes(chunk_rows);
+        void* ws = nullptr;
+        GD_TRY(cudaMalloc(&ws, bytes));
+        const cudaError_t e = cudaMemset(ws, 0, bytes);
+        if (e != cudaSuccess) {
+          cudaFree(ws);
+          return (int)e;
+        }
+        sl.ws = ws;
+        sl.ws_bytes = bytes;
+      }
     }
-    GD_TRY(cudaMallocHost(&p.loss_pinned, sizeof(float) * kMaxChunks));
+    if (!p.loss_pinned) GD_TRY(cudaMallocHost(&p.loss_pinned, sizeof(float) * kMaxChunks));
     p.init = true;
   }
+  // staging buffers only ever grow (to the largest chunk this process has used): a steady
+  // workload allocates once; cudaFree / cudaMalloc below are the documented sync points of a
+  // chunk-size increase
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = p.slot[s];
     if (sl.cap_rows < chunk_rows) {
@@ -144,7 +159,7 @@ extern "C" int gd_loss_fwd_bwd_host(const gd_loss_config* cfg, const float* pred
   const long long nchunks = nplan;
   const int wcols = weight_mode == GD_WEIGHT_ROW7 ? 7 : (weight_mode == GD_WEIGHT_ROW ? 1 : 0);
 
-  std::lock_guard<std::mutex> lock(g_mu);
+  std::lock_guard<std::mutex> lock(g_mu[device]);
   int prev_dev = 0;
   GD_TRY(cudaGetDevice(&prev_dev));
   GD_TRY(cudaSetDevice(device));
