@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GD_ABI_VERSION 2
+#define GD_ABI_VERSION 3
 
 /* loss_type: keys of GDLoss.BAG_GD_LOSS                                ref:253-259 */
 enum {
@@ -190,6 +190,14 @@ typedef struct gd_loss_io {
   int32_t variant; int32_t flags;
   /* nullable HOST pointer: sum loss_sum over the ranks of the box inside the launch */
   const gd_peer_sum* peer_sum;
+  /* ABI >= 3.  Nullable, one int32 of PINNED host memory (cudaHostAlloc: device-addressable under
+   * UVA) that the CALLER sets to 0 before the launch: the host-visible form of
+   * `torch.any(weight > 0)` (ref:290) for the weight shapes where the reference's early return
+   * RAISES, reported from inside the fused launch instead of by a probe launch in front of it.
+   * The kernel stores 1 as soon as the first tile of its first warp holds a positive weight
+   * (microseconds after it starts: the common case), otherwise its last CTA stores 1 (some
+   * element > 0) or 2 (none).  Wait with gd_host_flag_wait.  Needs loss_sum and a weight. */
+  int32_t* any_positive_host;
 } gd_loss_io;
 
 GD_API int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream);
@@ -213,18 +221,10 @@ GD_API int gd_scale_grad_rows(float* grad, int64_t n, const float* grad_output_r
  * flattened by the caller) so the shim can take that branch. */
 GD_API int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* stream);
 
-/* The same probe without stalling the GPU (the host-visible form of ref:290 for weight
- * shapes where the reference's early return RAISES, so the host has to know): ONE small
- * kernel (it stops at the first positive element any CTA sees) whose last CTA writes the
- * answer straight into `flag_host` -- PINNED host memory, device-addressable under UVA -- and
- * `event` recorded behind it.  The caller then queues the fused launch and only afterwards
- * waits with gd_probe_event_wait: the GPU stays busy during the wait.  `event` comes from
- * gd_probe_event_create (a cudaEvent_t without timing; one per stream, reusable, lives as long
- * as the process); workspace as gd_loss_workspace_bytes (zeroed once, left zeroed). */
-GD_API int gd_probe_event_create(void** event);
-GD_API int gd_probe_begin(const float* weight, int64_t count, int32_t* flag_host, void* event,
-                          void* workspace, size_t workspace_bytes, void* stream);
-GD_API int gd_probe_event_wait(void* event);
+/* Spins (no CUDA call on the fast path) until *flag != 0, `flag` being the
+ * gd_loss_io.any_positive_host word of a launch queued on `stream`.  Returns 0 once the flag is
+ * set; if the stream drains or fails with the flag still 0, the CUDA error (or GD_ERR_BAD_ARG). */
+GD_API int gd_host_flag_wait(const int32_t* flag, void* stream);
 
 /* out[0] := max(#{i : 0 <= labels[i] < num_classes}, 1) as fp32 -- the avg_factor of the
  * anchor head's labels mode when the caller passes none (reduction='mean' over the positives,

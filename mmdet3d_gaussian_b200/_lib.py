@@ -20,7 +20,7 @@ FUNS = {'none': 0, 'log1p': 1, 'expm1': 2, 'nlog': 3}
 WEIGHT_NONE, WEIGHT_ROW, WEIGHT_ROW7 = 0, 1, 2
 VARIANTS = {'auto': 0, 'staged': 1, 'bulk': 2, 'bulk_r2': 3, 'bulk_packed': 4, 'bulk_any': 5}
 FLAG_MASK_ZERO_WEIGHT = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 PAIR_SIMILARITY = 1
 PAIR_CPL1 = 2              # one column per lane (measurement / test aid)
 GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3
@@ -55,7 +55,8 @@ class GDLossIO(ctypes.Structure):
                 ('er_weight_col_stride', ctypes.c_int64),
                 ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t),
                 ('variant', ctypes.c_int32), ('flags', ctypes.c_int32),
-                ('peer_sum', ctypes.POINTER(GDPeerSum))]
+                ('peer_sum', ctypes.POINTER(GDPeerSum)),
+                ('any_positive_host', ctypes.c_void_p)]
 
 
 class GDCenterCoder(ctypes.Structure):
@@ -76,9 +77,7 @@ SIGNATURES = {
                                        ctypes.c_size_t, _i32, _i32, _vp]),
     'gd_loss_launch': (ctypes.c_int, [_cfgp, ctypes.POINTER(GDLossIO), _vp]),
     'gd_peer_sum_buffer_bytes': (ctypes.c_size_t, []),
-    'gd_probe_event_create': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
-    'gd_probe_begin': (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
-    'gd_probe_event_wait': (ctypes.c_int, [_vp]),
+    'gd_host_flag_wait': (ctypes.c_int, [_vp, _vp]),
     'gd_count_positive_labels': (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, ctypes.c_size_t, _vp]),
     'gd_scale_grad': (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     'gd_scale_buffer': (ctypes.c_int, [_vp, _i64, _vp, _vp]),

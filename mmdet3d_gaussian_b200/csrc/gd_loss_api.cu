@@ -74,34 +74,6 @@ __global__ void __launch_bounds__(kThreads) gd_any_positive_kernel(const float* 
   }
 }
 
-// Early-return probe whose LAST CTA writes the answer into pinned host memory: ticket[4] =
-// any-positive word, ticket[5] = CTA ticket (both left zero).
-__global__ void __launch_bounds__(kThreads) gd_probe_kernel(const float* __restrict__ w,
-                                                            long long count, unsigned int* ticket,
-                                                            volatile int* flag_host) {
-  const long long stride = (long long)gridDim.x * kThreads;
-  for (long long i0 = (long long)blockIdx.x * kThreads; i0 < count; i0 += stride) {
-    // ONE thread looks at the flag; the vote makes the decision CTA-uniform
-    const bool stop = threadIdx.x == 0 && *reinterpret_cast<volatile unsigned int*>(ticket + 4) != 0u;
-    const long long i = i0 + threadIdx.x;
-    const bool any = i < count && w[i] > 0.0f;
-    const int vote = __syncthreads_or((any ? 1 : 0) | (stop ? 2 : 0));
-    if ((vote & 1) && threadIdx.x == 0) atomicOr(ticket + 4, 1u);
-    if (vote) break;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(ticket + 5, 1u) == gridDim.x - 1) {
-      __threadfence();
-      *flag_host = __ldcg(ticket + 4) ? 1 : 0;
-      __threadfence_system();
-      ticket[4] = 0u;
-      ticket[5] = 0u;
-    }
-  }
-}
-
 // positives of the anchor head's labels mode; ticket[0] = CTA ticket, ticket[2] = count
 __global__ void __launch_bounds__(kThreads) gd_count_labels_kernel(
     const long long* __restrict__ labels, long long total, long long num_classes,
@@ -220,6 +192,10 @@ int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream
     a.er_wrow = io->er_weight_row_stride;
     a.er_wcol = io->er_weight_col_stride;
   }
+  if (io->any_positive_host) {
+    if (!io->loss_sum || weight_mode == GD_WEIGHT_NONE) return GD_ERR_BAD_ARG;
+    a.host_flag = reinterpret_cast<int*>(io->any_positive_host);
+  }
   a.loss_sum = io->loss_sum;
   a.row_loss = io->row_loss;
   a.grad = io->grad_pred;
@@ -336,37 +312,22 @@ int gd_any_positive(const float* weight, int64_t count, int32_t* flag, void* str
   return (int)cudaGetLastError();
 }
 
-int gd_probe_event_create(void** event) {
-  if (!event) return GD_ERR_BAD_ARG;
-  cudaEvent_t ev;
-  const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  if (e != cudaSuccess) return (int)e;
-  *event = ev;
-  return 0;
-}
-
-int gd_probe_begin(const float* weight, int64_t count, int32_t* flag_host, void* event,
-                   void* workspace, size_t workspace_bytes, void* stream) {
-  using namespace gdk;
-  if (!flag_host || !event || count < 0 || (count > 0 && !weight)) return GD_ERR_BAD_ARG;
-  if (!workspace || workspace_bytes < gd_loss_workspace_bytes(0)) return GD_ERR_WORKSPACE;
+int gd_host_flag_wait(const int32_t* flag, void* stream) {
+  if (!flag) return GD_ERR_BAD_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  long long grid = (count + kThreads - 1) / kThreads;
-  const long long cap = (long long)device_info().sm_count * 8;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-  gd_probe_kernel<<<(int)grid, kThreads, 0, st>>>(weight, count,
-                                                  reinterpret_cast<unsigned int*>(workspace),
-                                                  flag_host);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  const cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
-  return (int)cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), st);
-}
-
-int gd_probe_event_wait(void* event) {
-  if (!event) return GD_ERR_BAD_ARG;
-  return (int)cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event));
+  for (unsigned long long spin = 1;; ++spin) {
+    if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) != 0) return 0;
+    if ((spin & 0x3fffu) == 0) {           // now and then: did the launch die / the stream drain?
+      const cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {              // everything queued has run: the flag is final
+        return __atomic_load_n(flag, __ATOMIC_ACQUIRE) != 0 ? 0 : GD_ERR_BAD_ARG;
+      }
+      if (e != cudaErrorNotReady) return (int)e;
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
 }
 
 int gd_count_positive_labels(const int64_t* labels, int64_t total, int64_t num_classes, float* out,

@@ -94,6 +94,12 @@ struct LossArgs {
   // `weight`, with weight(i, c) = weight[i * er_wrow + c * er_wcol]
   int early_return = 0;
   long long er_wrow = 0, er_wcol = 0;
+  // nullable, PINNED host memory (device-addressable under UVA), zeroed by the caller before the
+  // launch: any(weight > 0) reported to a waiting host thread from inside THIS launch -- 1 as
+  // soon as the first tile of the first warp holds a positive weight (a few microseconds after
+  // the kernel starts), else 1 / 2 (some / none positive) from the last CTA.  Replaces the
+  // separate probe launch of the host-visible early-return check (ref:290-292).
+  int* host_flag = nullptr;
   // gd_warp_kernel<..., ANY = true> (row-strided and/or 16-byte-unaligned inputs): rows
   // [row_lo, row_lo + n_bulk) go through the bulk-copy tiles, the <= 8 rows around them are
   // read straight from global memory; *shift = words between the 16-byte aligned copy
@@ -167,7 +173,7 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a, float s
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += (double)s_warp[w];
     a.partials[blockIdx.x] = s;
-    if ((a.status || a.early_return) && cta_any) atomicOr(a.ticket + 1, 1u);
+    if ((a.status || a.early_return || a.host_flag) && cta_any) atomicOr(a.ticket + 1, 1u);
     __threadfence();
     const unsigned int t = atomicAdd(a.ticket, 1u);
     s_last = (t == gridDim.x - 1);
@@ -186,7 +192,7 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a, float s
       tot *= (double)scale;
     }
     if (a.peer.world > 1) tot = peer_exchange_sum(a.peer, tot);    // thread 0's partial is sent
-    const bool probe = a.status != nullptr || a.early_return != 0;
+    const bool probe = a.status != nullptr || a.early_return != 0 || a.host_flag != nullptr;
     // ONE thread reads the any-positive word (it is reset below) and the vote makes the
     // decision CTA-uniform
     const bool none_positive =
@@ -215,6 +221,10 @@ __device__ __forceinline__ void finish_sum(float acc, const LossArgs& a, float s
     if (tid == 0) {
       *a.loss_sum = (float)tot;
       if (a.status) *a.status = none_positive ? 0.0f : 1.0f;
+      if (a.host_flag) {
+        *reinterpret_cast<volatile int*>(a.host_flag) = none_positive ? 2 : 1;
+        __threadfence_system();
+      }
       if (probe) a.ticket[1] = 0u;
       *a.ticket = 0u;                     // leave the workspace reusable
     }
@@ -299,7 +309,8 @@ __global__ void __launch_bounds__(kThreads) gd_staged_kernel(const LossArgs a) {
   const int tid = threadIdx.x;
   const long long ntiles = (a.n + kTile - 1) / kTile;
   const float scale = effective_scale(a);
-  const bool probe = a.status != nullptr || a.early_return != 0;   // any(weight > 0) over every weight element, ref:290
+  const bool probe = a.status != nullptr || a.early_return != 0 ||
+                     a.host_flag != nullptr;   // any(weight > 0) over every weight element, ref:290
   bool anyp = false;
   float acc = 0.0f;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -450,7 +461,8 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
   gd::PairParams<float> pp = a.pp;
   const bool mask_zero = a.mask_zero_w != 0;
   const float scale = effective_scale(a);
-  const bool probe = a.status != nullptr || a.early_return != 0;     // any(weight > 0), ref:290
+  const bool probe = a.status != nullptr || a.early_return != 0 ||
+                     a.host_flag != nullptr;                         // any(weight > 0), ref:290
   bool anyp = false;
   const int wcols = wmode == GD_WEIGHT_ROW7 ? 7 : 1;
   // row strides in floats / lead-in words of a tile in shared memory
@@ -615,6 +627,16 @@ __global__ void __launch_bounds__(R >= 4 ? 384 : 768, 1) gd_warp_kernel(const Lo
       if (wmode != GD_WEIGHT_ROW7) {
 #pragma unroll
         for (int k = 0; k < R; ++k) wpos[k] = w[k] > 0.0f;
+      }
+    }
+    if (a.host_flag != nullptr && i == 0 && gwarp == 0) {
+      // a host thread is waiting for any(weight > 0): the common answer is in the first tile
+      bool pos = false;
+#pragma unroll
+      for (int k = 0; k < R; ++k) pos |= wpos[k] && ((strided ? lane + 32 * k : R * lane + k) < rows);
+      if (__any_sync(0xffffffffu, pos) && lane == 0) {
+        *reinterpret_cast<volatile int*>(a.host_flag) = 1;
+        __threadfence_system();
       }
     }
     // the previous tile's store must have finished READING the output buffer

@@ -109,11 +109,15 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
     const long long row0 = tile * kRowsPerCta;
     const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
     __syncthreads();                           // previous tile fully consumed
-    if (tid < rows) s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
+    int row_nice = 1;
+    if (tid < rows) {
+      s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
+      row_nice = s_rows[tid].nice;
+    }
     if (REDUCE) {
       for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads) (&s_best[0][0])[i] = ~0ull;
     }
-    __syncthreads();
+    const bool tile_nice = __syncthreads_and(row_nice) != 0;   // also publishes the tile
     for (long long c0 = (long long)blockIdx.y * chunk; c0 < a.m; c0 += (long long)gridDim.y * chunk) {
       const long long jb = c0 + (long long)kWarpCols * cgrp;     // first column of this warp
       if (jb >= a.m) continue;                 // this warp's columns are all past the end
@@ -130,6 +134,45 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
       // row pointer of this lane's first column, advanced by wy rows per iteration
       float* orow = a.out != nullptr ? a.out + (row0 + ry) * a.out_stride + jb + lane : nullptr;
       const long long ostep = (long long)wy * a.out_stride;
+      if constexpr (!REDUCE && LOSS != gd::kKfiou) {
+        // Matrix only, every column of the warp in range, every box of the tile and of the
+        // warp's columns nice (the common case): straight-line FAST cores and unconditional
+        // coalesced stores, no per-pair screen, range check or branch.  A guard tripping inside
+        // a FAST core (rare) is remembered and the lane's columns are rewritten afterwards
+        // through pair_value_auto -- the same thread stored them, so program order decides.
+        bool ok = tile_nice;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) ok = ok && live[q] && t[q].nice != 0;
+        if (__all_sync(0xffffffffu, ok)) {
+          // 1 - v and v as one FMA with hoisted constants: identical bits (single rounding)
+          const float sgn = a.similarity ? -1.0f : 1.0f, off = a.similarity ? 1.0f : 0.0f;
+          bool redo = false;
+          float* o = orow;
+#pragma unroll 2
+          for (int r = ry; r < rows; r += wy) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              bool rare = false;
+              const float f = gd::pair_value_fast<float, LOSS>(s_rows[r], t[q], pp, &rare);
+              redo |= rare;
+              __stcs(o + 32 * q, fmaf(f, sgn, off));
+            }
+            o += ostep;
+          }
+          if (redo) {
+            o = orow;
+            for (int r = ry; r < rows; r += wy) {
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) {
+                const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t[q], pp);
+                __stcs(o + 32 * q, a.similarity ? 1.0f - v : v);
+              }
+              o += ostep;
+            }
+          }
+          continue;
+        }
+      }
 #pragma unroll 2
       for (int r = ry; r < rows; r += wy) {
         float v[CPL];
@@ -219,6 +262,242 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused reductions WITHOUT the matrix (row f2, the assigner's launch): lanes map to ROWS.
+//
+// With lanes on columns (the kernel above, needed for coalesced matrix stores) a row minimum
+// costs a REDUX, ballots and a shared-memory update per warp and row, and every value goes
+// through the key mapping -- the fused launch ran 35-40 % slower than writing the matrix it
+// avoids (profiles/r02_pairwise.md).  Here a lane keeps RPL row Gaussians in registers and the
+// column Gaussians (m <= kRowLaneCols) sit in shared memory, read as broadcasts:
+//   * row minimum: NaN-sticky FMNMX + compare/select per pair, in the lane, no collective;
+//     a NaN result (rare) is resolved on a cold pass (first NaN column, as torch.min);
+//   * column minimum: two integer ops for the order key, one REDUX.MIN per warp and column,
+//     compared with the CTA's running minimum in shared memory; only when a warp improves it
+//     (O(log rows) times per column) does it find the row and issue the 64-bit shared atomic;
+//   * when every box of the warp's rows and every column box is "nice" (the common case) the
+//     loop carries no per-pair screen at all.
+// Work is handed out per WARP in units of 32 RPL rows, dynamically through a counter when the
+// caller gave a workspace (ticket[1]), so the 4 schedulers of an SM stay evenly loaded at
+// sizes that give each only a handful of units (C4: 3125 units over 592 schedulers).
+// Values come out of the same gd::core_eval instruction sequence as the matrix kernel's.
+// ---------------------------------------------------------------------------
+constexpr int kRowLaneCols = 512;
+struct alignas(16) ColBox {
+  gd::BoxGauss<float> g;
+};
+struct CleanLoop { static constexpr bool value = true; };
+struct GeneralLoop { static constexpr bool value = false; };
+
+__device__ __forceinline__ float min_nan(float a, float b) {     // NaN propagates, and sticks
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
+  return (a != a || b != b) ? __uint_as_float(0x7fc00000u) : (b < a ? b : a);
+#endif
+}
+// order-preserving float -> uint32 for non-NaN values (NaNs are handled on the cold pass)
+__device__ __forceinline__ unsigned int order_key_fast(float v) {
+  const unsigned int b = __float_as_uint(v);
+  return b ^ ((unsigned int)((int)b >> 31) | 0x80000000u);
+}
+
+template <int LOSS, int SPEC, int RPL>
+__global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const PairwiseArgs a) {
+  __shared__ ColBox s_cols[kRowLaneCols];
+  __shared__ unsigned long long s_colbest[kRowLaneCols];      // key << 32 | row; ~0: none yet
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  gd::PairParams<float> pp = a.pp;
+  if (SPEC >= 0) {
+    pp.fun = SPEC & 3;
+    pp.tau_on = (SPEC >> 2) & 1;
+    pp.flag = (SPEC >> 3) & 1;
+  }
+  pp.lean = 1;
+  const bool want_col = a.col_keys != nullptr;
+  const int cnt = (int)a.m;                                    // <= kRowLaneCols (launcher)
+  constexpr int kUnitRows = 32 * RPL;
+  const long long nunits = (a.n + kUnitRows - 1) / kUnitRows;
+
+  int nice = 1;
+  for (int j = tid; j < cnt; j += kThreads) {
+    s_cols[j].g = gd::box_gauss(a.b2 + (long long)j * 7, pp);
+    nice &= s_cols[j].g.nice;
+    s_colbest[j] = ~0ull;
+  }
+  const bool cols_nice = __syncthreads_and(nice) != 0;         // also publishes the columns
+
+  // unit schedule: dynamic (one atomic per unit, lane 0) or interleaved static
+  const bool dynamic = a.ticket != nullptr;
+  const long long gwarps = (long long)gridDim.x * kWarps;
+  long long unit = dynamic ? 0 : (long long)blockIdx.x + (long long)gridDim.x * warp;
+  for (;;) {
+    if (dynamic) {
+      unsigned int u = 0;
+      if (lane == 0) u = atomicAdd(a.ticket + 1, 1u);
+      unit = (long long)__shfl_sync(0xffffffffu, u, 0);
+    }
+    if (unit >= nunits) break;
+    const long long row0 = unit * kUnitRows;
+    gd::BoxGauss<float> rb[RPL];
+    bool live[RPL];
+    float best[RPL];
+    int bj[RPL];
+    bool clean = cols_nice;
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const long long r = row0 + 32 * q + lane;
+      live[q] = r < a.n;
+      rb[q] = gd::box_gauss(a.b1 + (live[q] ? r : a.n - 1) * 7, pp);   // dead lane: any valid box
+      clean = clean && live[q] && rb[q].nice;
+      best[q] = __uint_as_float(0x7f800000u);
+      bj[q] = 0;
+    }
+    const bool warp_clean = __all_sync(0xffffffffu, clean);
+    const unsigned int rowbase = (unsigned int)row0;
+
+    // hi words of the CTA's running column minima (key << 32 | row)
+    const volatile unsigned int* colhi = reinterpret_cast<const volatile unsigned int*>(s_colbest) + 1;
+    bool redo = false;                           // CLEAN sweep: a guard of the FAST core tripped
+    auto sweep = [&](auto clean_tag, auto col_tag) {
+      constexpr bool CLEAN = decltype(clean_tag)::value;
+      constexpr bool COLS = decltype(col_tag)::value;
+#pragma unroll 2
+      for (int j = 0; j < cnt; ++j) {
+        const gd::BoxGauss<float>& t = s_cols[j].g;
+        float v[RPL];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+          if constexpr (CLEAN && LOSS != gd::kKfiou) {
+            // straight-line FAST core; a tripped guard turns the value into +inf (it cannot
+            // lower any minimum) and the whole unit is redone below on the general path
+            bool rare = false;
+            const float f = gd::pair_value_fast<float, LOSS>(rb[q], t, pp, &rare);
+            v[q] = rare ? __uint_as_float(0x7f800000u) : f;
+            redo |= rare;
+          } else {
+            v[q] = gd::pair_value_auto<float, LOSS>(rb[q], t, pp);
+          }
+          const float old = best[q];
+          best[q] = min_nan(old, v[q]);
+          bj[q] = v[q] < old ? j : bj[q];        // strict: the lowest column keeps a tie
+        }
+        if constexpr (COLS) {
+          unsigned int key[RPL];
+#pragma unroll
+          for (int q = 0; q < RPL; ++q) {
+            key[q] = order_key_fast(v[q]);
+            if (!CLEAN) key[q] = live[q] ? key[q] : 0xffffffffu;
+          }
+          unsigned int kmin = key[0];
+#pragma unroll
+          for (int q = 1; q < RPL; ++q) kmin = key[q] < kmin ? key[q] : kmin;
+          const unsigned int mn = __reduce_min_sync(0xffffffffu, kmin);
+          if (__any_sync(0xffffffffu, mn <= colhi[2 * j])) {   // rare after the first few units
+            unsigned int row = 0u;
+            bool found = false;
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {                    // lowest row holding the minimum
+              const unsigned int who = __ballot_sync(0xffffffffu, key[q] == mn);
+              if (!found && who) {
+                row = rowbase + 32u * q + (unsigned int)(__ffs(who) - 1);
+                found = true;
+              }
+            }
+            if (lane == 0 && mn != 0xffffffffu)
+              atomicMin(&s_colbest[j], ((unsigned long long)mn << 32) | row);
+          }
+        }
+      }
+    };
+    auto sweep_cols = [&](auto clean_tag) {
+      if (want_col) sweep(clean_tag, CleanLoop{});
+      else sweep(clean_tag, GeneralLoop{});
+    };
+    if (warp_clean) {
+      sweep_cols(CleanLoop{});
+      if (__any_sync(0xffffffffu, redo)) {       // start over: every pair through its own screen
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+          best[q] = __uint_as_float(0x7f800000u);
+          bj[q] = 0;
+        }
+        sweep_cols(GeneralLoop{});
+      }
+    } else {
+      sweep_cols(GeneralLoop{});
+    }
+
+    // cold pass: a NaN in the row.  torch.min returns NaN with the first NaN column; every
+    // column holding a NaN gets the lowest key (0) with the lowest such row.
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      if (live[q] && best[q] != best[q]) {
+        bool first = true;
+        for (int j = 0; j < cnt; ++j) {
+          const float v = gd::pair_value_auto<float, LOSS>(rb[q], s_cols[j].g, pp);
+          if (v != v) {
+            if (first) bj[q] = j;
+            first = false;
+            if (want_col) atomicMin(&s_colbest[j], (unsigned long long)(rowbase + 32u * q + lane));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const long long r = row0 + 32 * q + lane;
+      if (live[q]) {
+        a.row_min[r] = best[q];
+        a.row_argmin[r] = bj[q];
+      }
+    }
+    if (!dynamic) {
+      // CTA-interleaved: consecutive units go to different CTAs, then to the next warp slot
+      unit += gwarps;
+    }
+  }
+
+  if (want_col) {
+    __syncthreads();
+    for (int j = tid; j < cnt; j += kThreads) {
+      const unsigned long long k = s_colbest[j];
+      if (k != ~0ull) atomicMax(a.col_keys + j, ~k);
+    }
+    // last CTA to finish unpacks the column keys and restores the workspace
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (long long j = tid; j < a.m; j += kThreads) {
+        const unsigned long long k = ~__ldcg(a.col_keys + j);
+        a.col_min[j] = key_value((unsigned int)(k >> 32));
+        a.col_argmin[j] = (int)(unsigned int)(k & 0xffffffffu);
+        a.col_keys[j] = 0ull;
+      }
+      if (tid == 0) {
+        a.ticket[1] = 0u;
+        *a.ticket = 0u;
+      }
+    }
+  } else if (dynamic) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+        a.ticket[1] = 0u;
+        __threadfence();
+        *a.ticket = 0u;
+      }
+    }
+  }
+}
+
 // Host-side launchers.  tests/host_math/pairwise_emul.cpp compiles THIS header with g++
 // (GD_HOST_EMULATION: one OS thread per CUDA thread, barriers for __syncthreads and the
 // warp collectives) to run the kernels' index / reduction logic on a machine without a GPU;
@@ -296,8 +575,64 @@ int launch_pairwise_spec(const PairwiseArgs& a, cudaStream_t st) {
   return launch_pairwise_inst<LOSS, -1, REDUCE>(a, st);
 }
 
+// GD_B200_PAIR_ROWLANE=0 keeps the column-lane kernel for the fused reductions (measurements)
+inline bool pairwise_rowlane_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("GD_B200_PAIR_ROWLANE");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+
+template <int LOSS, int SPEC>
+int launch_rowlane_inst(const PairwiseArgs& a, cudaStream_t st) {
+  // two rows per lane halve the shared-memory reads per pair; bd3d / the symmetric KLDs hold
+  // too many per-box terms in registers for that
+  constexpr int RPL = pairwise_cpl2_pays<LOSS>() ? 2 : 1;
+  auto kern = gd_pairwise_rowlane_kernel<LOSS, SPEC, RPL>;
+  static int occ[kMaxDevices] = {};
+  const int dev = current_device();
+  if (occ[dev] == 0) {
+    int per_sm = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0);
+    if (e != cudaSuccess) return (int)e;
+    occ[dev] = per_sm > 0 ? per_sm : 1;
+  }
+  const long long nunits = (a.n + 32 * RPL - 1) / (32 * RPL);
+  if (nunits > 0xffffffffLL || a.n > 0xffffffffLL) return GD_ERR_BAD_ARG;
+  long long grid = (nunits + kWarps - 1) / kWarps;
+  const long long cap = (long long)device_info().sm_count * occ[dev];
+  if (grid > cap) grid = cap;
+  kern<<<(unsigned)grid, kThreads, 0, st>>>(a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <int LOSS>
+int launch_rowlane(const PairwiseArgs& a, cudaStream_t st) {
+  constexpr bool kHasSpec = (LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd);
+  if constexpr (kHasSpec) {
+    const gd::PairParams<float>& pp = a.pp;
+    if (pp.flag == 1 && (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p)) {
+      switch (pp.fun | (pp.tau_on << 2) | (1 << 3)) {
+        case 8: return launch_rowlane_inst<LOSS, 8>(a, st);
+        case 9: return launch_rowlane_inst<LOSS, 9>(a, st);
+        case 12: return launch_rowlane_inst<LOSS, 12>(a, st);
+        case 13: return launch_rowlane_inst<LOSS, 13>(a, st);
+        default: break;
+      }
+    }
+  }
+  return launch_rowlane_inst<LOSS, -1>(a, st);
+}
+
 template <int LOSS>
 int launch_pairwise(const PairwiseArgs& a, cudaStream_t st) {
+  // reductions without the matrix: lanes on rows (no per-row collective); with the matrix (or
+  // more columns than the shared-memory stage holds): lanes on columns, coalesced stores
+  if (a.row_min && a.out == nullptr && a.m <= kRowLaneCols && !a.force_cpl1 &&
+      pairwise_rowlane_enabled())
+    return launch_rowlane<LOSS>(a, st);
   return a.row_min ? launch_pairwise_spec<LOSS, true>(a, st)
                    : launch_pairwise_spec<LOSS, false>(a, st);
 }

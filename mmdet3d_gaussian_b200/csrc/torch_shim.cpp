@@ -44,9 +44,7 @@ struct Abi {
   GD_SYM(gd_scale_grad)
   GD_SYM(gd_scale_buffer)
   GD_SYM(gd_scale_grad_rows)
-  GD_SYM(gd_probe_begin)
-  GD_SYM(gd_probe_event_create)
-  GD_SYM(gd_probe_event_wait)
+  GD_SYM(gd_host_flag_wait)
   GD_SYM(gd_count_positive_labels)
   GD_SYM(gd_peer_sum_buffer_bytes)
   GD_SYM(gd_anchor_decoded_loss_fwd_bwd)
@@ -71,9 +69,7 @@ void bind(const std::string& path) {
   GD_SYM(gd_scale_grad)
   GD_SYM(gd_scale_buffer)
   GD_SYM(gd_scale_grad_rows)
-  GD_SYM(gd_probe_begin)
-  GD_SYM(gd_probe_event_create)
-  GD_SYM(gd_probe_event_wait)
+  GD_SYM(gd_host_flag_wait)
   GD_SYM(gd_count_positive_labels)
   GD_SYM(gd_peer_sum_buffer_bytes)
   GD_SYM(gd_anchor_decoded_loss_fwd_bwd)
@@ -107,9 +103,10 @@ inline void check(int code, const char* what) {
 // ---------------------------------------------------------------------------
 struct StreamState {
   Tensor workspace;            // ticket + per-CTA partials
-  Tensor probe_host;           // int32[1] pinned
-  void* probe_event = nullptr;
+  Tensor probe_host;           // int32[kProbeSlots] pinned: any(weight > 0) words written by the launches
+  unsigned probe_next = 0;     // guarded by g_mutex
 };
+constexpr int kProbeSlots = 16;
 std::mutex g_mutex;
 std::unordered_map<uint64_t, std::shared_ptr<StreamState>> g_state;
 constexpr size_t kMaxStreamStates = 256;
@@ -181,7 +178,7 @@ struct LossOut {
   Tensor loss, rows, grad;
 };
 
-LossOut launch_loss(const LossCall& k, bool want_grad) {
+LossOut launch_loss(const LossCall& k, bool want_grad, int32_t* any_positive_host = nullptr) {
   const Abi& lib = gd_abi();
   const int64_t n = k.pred.size(0);
   const auto opts = k.pred.options();
@@ -220,6 +217,7 @@ LossOut launch_loss(const LossCall& k, bool want_grad) {
   io.variant = k.variant;
   io.flags = k.flags;
   io.peer_sum = (k.peer.world > 1 && want_sum) ? &k.peer : nullptr;
+  io.any_positive_host = any_positive_host;
   check(lib.gd_loss_launch(&k.cfg, &io, stream.stream()), "gd_loss_launch");
   return o;
 }
@@ -396,42 +394,39 @@ Tensor gd_loss(const Tensor& pred_in, const Tensor& target_in, const c10::option
   }
 
   const bool need_grad = at::GradMode::is_enabled() && k.pred.requires_grad();
-  void* probe_event = nullptr;
-  const int32_t* probe_host = nullptr;
-  std::shared_ptr<StreamState> probe_state;
+  int32_t* probe_host = nullptr;
   if (host_probe) {
     if (c10::cuda::currentStreamCaptureStatusMayInitCtx() != c10::cuda::CaptureStatus::None)
       throw std::runtime_error(
           "gd_loss_b200: GDLoss with [N] weights keeps the reference's early-return check "
           "(gaussian_distance_loss.py:290), whose outcome (an exception) needs a host wait and "
           "cannot be captured in a CUDA graph; pass [N,7] weights, weight=None or host_sync=False");
-    const Abi& lib = gd_abi();
     const auto stream = at::cuda::getCurrentCUDAStream(k.pred.get_device());
-    probe_state = stream_state(stream);
-    StreamState& st = *probe_state;
-    if (!st.probe_event) {
-      st.probe_host = at::zeros({1}, at::TensorOptions().dtype(at::kInt).pinned_memory(true));
-      check(lib.gd_probe_event_create(&st.probe_event), "gd_probe_event_create");
+    std::shared_ptr<StreamState> st = stream_state(stream);
+    {
+      std::lock_guard<std::mutex> lock(g_mutex);
+      if (!st->probe_host.defined())
+        st->probe_host = at::zeros({kProbeSlots}, at::TensorOptions().dtype(at::kInt).pinned_memory(true));
+      probe_host = st->probe_host.mutable_data_ptr<int32_t>() + (st->probe_next++ % kProbeSlots);
     }
-    Tensor wc = k.weight.is_contiguous() ? k.weight : k.weight.contiguous();
-    check(lib.gd_probe_begin(fptr(wc), wc.numel(), st.probe_host.mutable_data_ptr<int32_t>(),
-                             st.probe_event, st.workspace.mutable_data_ptr(),
-                             static_cast<size_t>(st.workspace.numel()), stream.stream()),
-          "gd_probe_begin");
-    probe_event = st.probe_event;
-    probe_host = st.probe_host.const_data_ptr<int32_t>();
+    __atomic_store_n(probe_host, 0, __ATOMIC_RELEASE);
   }
 
-  LossOut o = launch_loss(k, need_grad);
+  // any(weight > 0) comes back from INSIDE the fused launch (its first warp reports a positive
+  // weight of the first tile microseconds after the kernel starts): no probe launch, and the
+  // GPU is already working on the loss while the host waits for the word.
+  LossOut o = launch_loss(k, need_grad, probe_host);
 
   if (host_probe) {
     int code;
     {
       py::gil_scoped_release nogil;
-      code = gd_abi().gd_probe_event_wait(probe_event);
+      code = gd_abi().gd_host_flag_wait(
+          probe_host, at::cuda::getCurrentCUDAStream(k.pred.get_device()).stream());
     }
-    check(code, "gd_probe_event_wait");
-    if (*probe_host == 0) return (pred_in * *weight_in).sum();      // ref:292 (raises like the reference)
+    check(code, "gd_host_flag_wait");
+    if (__atomic_load_n(probe_host, __ATOMIC_ACQUIRE) == 2)
+      return (pred_in * *weight_in).sum();      // ref:292 (raises like the reference)
   }
 
   Tensor out = k.rows_out ? o.rows : o.loss;

@@ -56,7 +56,17 @@ static inline int __syncthreads_or(int p) {
   g_cta->all.arrive_and_wait();
   return r;
 }
+static inline int __syncthreads_and(int p) {
+  if (!p) __atomic_fetch_or(&g_cta->vote, 1, __ATOMIC_SEQ_CST);
+  g_cta->all.arrive_and_wait();
+  const int r = __atomic_load_n(&g_cta->vote, __ATOMIC_SEQ_CST);
+  g_cta->all.arrive_and_wait();
+  if (threadIdx.x == 0) g_cta->vote = 0;
+  g_cta->all.arrive_and_wait();
+  return !r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline EmuCta::Warp& emu_warp() { return *g_cta->warps[threadIdx.x >> 5]; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp().bar.arrive_and_wait(); }
 
@@ -98,6 +108,8 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
     return m;
   });
 }
+static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0u; }
+static inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline unsigned __float_as_uint(float f) {
   unsigned u;
@@ -125,6 +137,12 @@ static inline double __ldcg(const double* p) {
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
   unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
   }
   return old;
 }

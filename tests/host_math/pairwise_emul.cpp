@@ -60,10 +60,21 @@ static void run_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
   emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, gdk::kThreads, a);
 }
 
+// the row-lane kernel of the fused reductions (no matrix), with launch_rowlane_inst's grid rule
+template <int LOSS, int SPEC, int RPL>
+static void run_rowlane(const gdk::PairwiseArgs& a, unsigned cap) {
+  const long long nunits = (a.n + 32 * RPL - 1) / (32 * RPL);
+  long long grid = (nunits + gdk::kWarps - 1) / gdk::kWarps;
+  if (grid > cap) grid = cap;
+  emu_launch(gdk::gd_pairwise_rowlane_kernel<LOSS, SPEC, RPL>, (unsigned)grid, 1, gdk::kThreads, a);
+}
+
 // loss: 0 gwd3d, 1 kld3d, 5 bd3d; fun log1p, tau >= 1 (SPEC 13), flag on -- the C4 configuration.
 // packed: 0 = one column per lane (CPL 1), 1 = two columns per lane (CPL 2; the default mapping
-// for m > 32).  force_cpl is unused (kept for the ctypes signature).  reduce: fused minima
-// (+ the matrix when `out`).
+// for m > 32).  reduce: fused minima (+ the matrix when `out`).
+// force_cpl: 3 / 4 = the ROW-lane kernel with two / one rows per lane (reduce only, no matrix,
+// m <= 512; dynamic unit schedule), 5 = the same without column minima (static schedule, as
+// gd_pairwise_row_argmin launches it); else unused.
 // cap: CTA cap of the persistent reductions (the library uses 6 x SM count).
 extern "C" int gd_emul_pairwise(int loss, int packed, int reduce, int force_cpl, unsigned cap,
                                 const float* b1, long long n, const float* b2, long long m,
@@ -79,11 +90,30 @@ extern "C" int gd_emul_pairwise(int loss, int packed, int reduce, int force_cpl,
   cfg.center_offset[1] = 0.0f;
   cfg.center_offset[2] = 0.5f;
   std::vector<unsigned long long> keys((size_t)m + 1, 0ull);
-  unsigned ticket = 0;
-  const gdk::PairwiseArgs a =
+  unsigned ticket[8] = {};
+  gdk::PairwiseArgs a =
       make_args(&cfg, b1, n, b2, m, out, reduce ? row_min : nullptr, reduce ? row_argmin : nullptr,
-                col_min, col_argmin, reduce ? keys.data() : nullptr, &ticket, similarity);
+                col_min, col_argmin, reduce ? keys.data() : nullptr, ticket, similarity);
   constexpr int S = 13;
+  if (force_cpl >= 3) {
+    if (!reduce || m > gdk::kRowLaneCols) return -1;
+    a.out = nullptr;
+    if (force_cpl == 5) {
+      a.col_keys = nullptr;
+      a.ticket = nullptr;
+    }
+#define GD_EMU_ROWLANE(L)                                                       \
+    if (loss == L) {                                                            \
+      if (force_cpl == 4) run_rowlane<L, S, 1>(a, cap);                         \
+      else run_rowlane<L, S, 2>(a, cap);                                        \
+    }
+    GD_EMU_ROWLANE(0) GD_EMU_ROWLANE(1) GD_EMU_ROWLANE(5)
+#undef GD_EMU_ROWLANE
+    int dirty = 0;
+    for (unsigned t : ticket) dirty |= (t != 0u);
+    for (auto k : keys) dirty |= (k != 0ull);
+    return dirty;
+  }
 #define GD_EMU_CASE(L)                                                          \
   if (loss == L) {                                                              \
     if (packed) {                                                               \
@@ -97,7 +127,8 @@ extern "C" int gd_emul_pairwise(int loss, int packed, int reduce, int force_cpl,
   GD_EMU_CASE(0) GD_EMU_CASE(1) GD_EMU_CASE(5)
 #undef GD_EMU_CASE
   // workspace protocol: the kernels must leave keys and ticket zeroed again
-  int dirty = ticket != 0;
+  int dirty = 0;
+  for (unsigned t : ticket) dirty |= (t != 0u);
   for (auto k : keys) dirty |= (k != 0ull);
   return dirty;
 }

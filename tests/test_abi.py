@@ -25,7 +25,7 @@ def test_library_is_in_tree_and_current(lib):
     assert _lib.loaded_path() == build_ext.lib_path()
     assert os.path.dirname(_lib.loaded_path()).endswith('mmdet3d_gaussian_b200')
     assert build_ext.is_current()
-    assert lib.gd_abi_version() == 2
+    assert lib.gd_abi_version() == 3
 
 
 def test_every_declared_symbol_is_exported(lib):

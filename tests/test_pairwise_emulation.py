@@ -166,3 +166,51 @@ def test_nan_and_degenerate_boxes(emul):
         assert np.isnan(rmin).all() and np.isnan(cmin).all()          # NaN is the minimum
         assert np.array_equal(ridx, ri) and np.array_equal(cidx, ci)
         assert ridx[0] == 11 and cidx[0] == 7
+
+
+@pytest.mark.parametrize('loss', ['gwd3d', 'kld3d', 'bd3d'])
+@pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (131, 129), (200, 256), (700, 40), (90, 512)])
+@pytest.mark.parametrize('mode', [3, 4, 5])
+def test_rowlane_minima_equal_matrix_minima(emul, loss, n, m, mode):
+    """The ROW-lane kernel of the fused reductions (lanes on rows, column Gaussians in shared
+    memory; what gd_pairwise_assign / gd_pairwise_row_argmin launch when no matrix is asked
+    for): row / column (min, argmin) == those of the matrix the column-lane kernel writes, bit
+    for bit, lowest index on ties.  mode 3 / 4: two / one rows per lane with the dynamic unit
+    counter; 5: no column minima, static unit schedule.  Covers partial units, dead lanes,
+    duplicate rows / columns (ties) and rows that leave the FAST cores (general sweep)."""
+    b1, b2 = boxes(n, m)
+    mat = run(emul, loss, 1, 0, b1, b2)[0]
+    rv, ri = first_argmin(mat, 1)
+    cv, ci = first_argmin(mat, 0)
+    for cap in (1, 3):
+        _, rmin, ridx, cmin, cidx = run(emul, loss, 1, 1, b1, b2, want_matrix=False,
+                                        force_cpl=mode, cap=cap)
+        assert same_bits(rmin, rv) and np.array_equal(ridx, ri), (loss, mode, cap, 'rows')
+        if mode != 5:
+            assert same_bits(cmin, cv) and np.array_equal(cidx, ci), (loss, mode, cap, 'cols')
+
+
+@pytest.mark.parametrize('mode', [3, 4])
+def test_rowlane_nan_and_degenerate_boxes(emul, mode):
+    b1, b2 = boxes(130, 40)
+    b1[7, 0] = float('nan')
+    b2[11, 3] = float('nan')
+    b1[20, 3:6] = 1e-7
+    b2[5, 4] = -1.0
+    mat = run(emul, 'gwd3d', 1, 0, b1, b2)[0]
+    rv, ri = first_argmin(mat, 1)
+    cv, ci = first_argmin(mat, 0)
+    _, rmin, ridx, cmin, cidx = run(emul, 'gwd3d', 1, 1, b1, b2, want_matrix=False, force_cpl=mode)
+    assert np.isnan(rmin).all() and np.isnan(cmin).all()              # NaN is the minimum
+    assert np.array_equal(ridx, ri) and np.array_equal(cidx, ci)
+    assert ridx[0] == 11 and cidx[0] == 7
+    # one NaN row only: the other rows keep their finite minima
+    b1, b2 = boxes(130, 40)
+    b1[7, 0] = float('nan')
+    mat = run(emul, 'gwd3d', 1, 0, b1, b2)[0]
+    rv, ri = first_argmin(mat, 1)
+    cv, ci = first_argmin(mat, 0)
+    _, rmin, ridx, cmin, cidx = run(emul, 'gwd3d', 1, 1, b1, b2, want_matrix=False, force_cpl=mode)
+    assert np.isnan(rmin[7]) and ridx[7] == 0 and np.isfinite(np.delete(rmin, 7)).all()
+    assert same_bits(np.delete(rmin, 7), np.delete(rv, 7)) and np.array_equal(ridx, ri)
+    assert np.isnan(cmin).all() and (cidx == 7).all()
