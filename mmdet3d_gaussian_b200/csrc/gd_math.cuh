@@ -567,21 +567,9 @@ GD_HD T gwd_core(const PairGeom<T>& g, const PairParams<T>& P, T gscale, T* grad
   const T eps = amb * cmd * s2;                                    // V^2 - U
   const T c2 = g.cd * g.cd;
   // U = tr(Sigma_p Sigma_t) + 2 sqrt(det det): all terms positive    ref:88-95
-  T U, kU, rU;                                                     // kU = 1/(2 sqrt U)
-  if constexpr (FAST && !GRAD) {
-    // Value only (the pairwise kernels; both boxes "nice", which there includes an in-plane
-    // aspect ratio <= 256, box_gauss): tr + 2K = (AC + BD) + 2K - (A-B)(C-D) s2 = V^2 - eps, one
-    // FMA instead of eight operations.  U >= 4K >= V^2 / 2^15 under the aspect bound, so the
-    // subtraction keeps >= 9 bits more than the 1e-5 of the final value needs (error sweep:
-    // equal or better quantiles than the long form up to 1000:1, profiles/r03_pairwise.md);
-    // U > 0, so the clamp of ref:95 could only act on a NaN, which the root propagates anyway.
-    U = V * V - eps;
-    kU = (T)0;
-    rU = Mth<T>::sqrt(U);
-  } else {
-    U = (A * C + B * D) * c2 + (A * D + B * C) * s2 + (T)2 * K;
-    rU = sqrt_clamp0(U, &kU);                                      // ref:95
-  }
+  const T U = (A * C + B * D) * c2 + (A * D + B * C) * s2 + (T)2 * K;
+  T kU;                                                            // 1/(2 sqrt U)
+  const T rU = sqrt_clamp0(U, &kU);                                // ref:95
   const T eta = eps * Mth<T>::rcp(V + rU);                         // V - sqrt U
   const T da = g.ap - g.at, db = g.bp - g.bt, de = g.ep - g.et;
   const T W = da * da + db * db + (T)2 * eta + de * de;            // ref:81-97
@@ -1103,29 +1091,159 @@ GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<
   return core_eval<T, LOSS, false, false>(g, P, (T)1, (T*)0, &unused);
 }
 
+// ---------------------------------------------------------------------------
+// Pairwise value path with the rounding of every operation FIXED IN THE SOURCE.
+//
+// The matrix kernel, the fused-reduction kernels and the top-k kernel are different
+// instantiations, with the two boxes in different roles (registers / shared memory, loop
+// invariant / variant).  Left to the compiler, the same formula is contracted into FMAs
+// differently from one context to the next (a product that is loop invariant or shared with the
+// cold robust path stays a separate multiply), and the values differ in the last place -- so an
+// index derived in one kernel need not be the index of the matrix written by another.  Here
+// every multiply, add and FMA is an explicit round-to-nearest intrinsic (mul.rn / add.rn /
+// fma.rn are never re-fused by ptxas) and the MUFU approximations are functions of their input
+// bits: the value of a pair is the same in every kernel BY CONSTRUCTION, which is what
+// "assignment indices bit-exact with the matrix" rests on.
+// ---------------------------------------------------------------------------
+namespace pw {
+GD_HD float mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+GD_HD float add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+GD_HD float sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+GD_HD float fma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return ::fmaf(a, b, c);
+#endif
+}
+// Mth<float>::log1p_lean, operation by operation
+GD_HD float log1p_lean(float x) {
+  const float s = mul(x, Mth<float>::rcp(add(2.0f, x)));
+  const float z = mul(s, s);
+  float q = fma(z, 1.0f / 9.0f, 1.0f / 7.0f);
+  q = fma(z, q, 1.0f / 5.0f);
+  q = fma(z, q, 1.0f / 3.0f);
+  const float t = add(s, s);
+  const float small = fma(mul(t, z), q, t);
+#if defined(__CUDA_ARCH__) && !GD_PRECISE_MATH
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(add(1.0f, x)));
+  const float big = mul(l, 0.693147180559945f);
+#else
+  const float big = ::log1pf(x);
+#endif
+  return x <= 0.5f ? small : big;
+}
+// post map of the FAST value path (fun in {none, log1p}; anything else is left to the robust
+// path), ref:24-39
+GD_HD float post(float d, const PairParams<float>& P, bool* rare) {
+  float f = d;
+  if (P.fun == kFunLog1p) {
+    *rare |= !(d < 1e30f);                     // inf / nan distance: robust path
+    f = log1p_lean(d);
+  } else if (P.fun != kFunNone) {
+    *rare = true;
+  }
+  if (P.tau_on) f = mul(f, Mth<float>::rcp(add(P.tau, f)));       // 1 - tau/(tau+f)   ref:36-37
+  return f;
+}
+// GWD (ref:42-106) for two NICE boxes (box_gauss: extents in [1e-4, 1e4], in-plane aspect
+// ratio <= 256).  tr(Sp St) + 2K = (AC + BD) + 2K - (A-B)(C-D) s2 = V^2 - eps: under the
+// aspect bound U >= 4K >= V^2 / 2^15, so the one subtraction keeps >= 9 bits more than the 1e-5
+// of the result needs (error sweep against fp64: equal or better quantiles than the
+// all-positive long form up to 1000:1, profiles/r03_pairwise.md), and U > 0: the clamp of
+// ref:95 could only act on a NaN, which the root propagates anyway.
+GD_HD float gwd_value(const BoxGauss<float>& p, const BoxGauss<float>& t,
+                      const PairParams<float>& P, bool* rare) {
+  const float dx = sub(p.cx, t.cx), dy = sub(p.cy, t.cy), dz = sub(p.cz, t.cz);
+  const float sd = fma(p.s, t.c, -mul(p.c, t.s));                  // sin(r_p - r_t)
+  const float s2 = mul(sd, sd);
+  const float V = fma(p.a, t.a, mul(p.b, t.b));
+  const float eps = mul(mul(p.amb, t.amb), s2);                    // V^2 - U
+  const float U = fma(V, V, -eps);
+  const float rU = Mth<float>::sqrt(U);                            // ref:95
+  const float eta = mul(eps, Mth<float>::rcp(add(V, rU)));         // V - sqrt U
+  const float da = sub(p.a, t.a), db = sub(p.b, t.b), de = sub(p.e, t.e);
+  float W = fma(da, da, mul(db, db));                              // ref:81-97
+  W = fma(2.0f, eta, W);
+  W = fma(de, de, W);
+  float d2 = fma(dx, dx, mul(dy, dy));                             // ref:79,99
+  d2 = fma(dz, dz, d2);
+  d2 = fma(P.alpha2, W, d2);
+  d2 = d2 < 0.0f ? 0.0f : d2;                                      // clamp(0); NaN falls through
+  float d = Mth<float>::sqrt(d2);
+  if (P.flag) d = mul(d, mul(0.5f, mul(p.r6, t.r6)));              // ref:101-104
+  return post(d, P, rare);
+}
+}  // namespace pw
+
+// losses whose pairwise FAST value is the explicit-rounding form above
+template <int LOSS>
+struct PairwiseExact { static constexpr bool value = (LOSS == kGwd); };
+
+// The robust value behind a call: ONE body per translation unit, the same machine code for
+// every kernel that reaches it (cold: degenerate boxes, tripped guards).
+template <int LOSS>
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+float pair_value_robust(const BoxGauss<float> p, const BoxGauss<float> t,
+                        const PairParams<float> P) {       // by value: no address of the
+  return pair_value<float, LOSS>(p, t, P);                 // caller's registers escapes
+}
+
+// FAST value for two boxes the caller knows to be nice (exact-form losses only): *rare is
+// OR-ed with "a guard inside the distance tripped" -- the value is then meaningless and the
+// caller must redo the pair with pair_value_auto.
+template <typename T, int LOSS>
+GD_HD T pair_value_fast(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P,
+                        bool* rare) {
+  static_assert(PairwiseExact<LOSS>::value && std::is_same<T, float>::value,
+                "only the explicit-rounding value cores may be called outside pair_value_auto");
+  return pw::gwd_value(p, t, P, rare);
+}
+
 // value through the branch-free FAST cores when both boxes are nice and no guard
 // trips, else through the robust cores (a cold branch).
 template <typename T, int LOSS>
 GD_HD T pair_value_auto(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P) {
-  const PairGeom<T> g = geom_from_gauss(p, t);
-  if (LOSS != kKfiou) {
+  if constexpr (PairwiseExact<LOSS>::value && std::is_same<T, float>::value) {
     bool rare = !(p.nice && t.nice);
-    const T v = core_eval<T, LOSS, false, true>(g, P, (T)1, (T*)0, &rare);
-    if (!rare) return v;
+    if (!rare) {
+      const T v = pw::gwd_value(p, t, P, &rare);
+      if (!rare) return v;
+    }
+    return pair_value_robust<LOSS>(p, t, P);
+  } else {
+    const PairGeom<T> g = geom_from_gauss(p, t);
+    if (LOSS != kKfiou) {
+      bool rare = !(p.nice && t.nice);
+      const T v = core_eval<T, LOSS, false, true>(g, P, (T)1, (T*)0, &rare);
+      if (!rare) return v;
+    }
+    bool unused = false;
+    return core_eval<T, LOSS, false, false>(g, P, (T)1, (T*)0, &unused);
   }
-  bool unused = false;
-  return core_eval<T, LOSS, false, false>(g, P, (T)1, (T*)0, &unused);
-}
-
-// FAST core only, for two boxes the caller knows to be nice: *rare is OR-ed with "a guard inside
-// the distance tripped" -- the value is then meaningless and the caller must redo the pair with
-// pair_value_auto (which runs this very sequence first, so values agree bit for bit otherwise).
-template <typename T, int LOSS>
-GD_HD T pair_value_fast(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P,
-                        bool* rare) {
-  static_assert(LOSS != kKfiou, "kfiou3d has no FAST core");
-  const PairGeom<T> g = geom_from_gauss(p, t);
-  return core_eval<T, LOSS, false, true>(g, P, (T)1, (T*)0, rare);
 }
 
 }  // namespace gd

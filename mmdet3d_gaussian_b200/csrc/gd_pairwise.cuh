@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
       // row pointer of this lane's first column, advanced by wy rows per iteration
       float* orow = a.out != nullptr ? a.out + (row0 + ry) * a.out_stride + jb + lane : nullptr;
       const long long ostep = (long long)wy * a.out_stride;
-      if constexpr (!REDUCE && LOSS != gd::kKfiou) {
+      if constexpr (!REDUCE && gd::PairwiseExact<LOSS>::value) {
         // Matrix only, every column of the warp in range, every box of the tile and of the
         // warp's columns nice (the common case): straight-line FAST cores and unconditional
         // coalesced stores, no per-pair screen, range check or branch.  A guard tripping inside
@@ -272,17 +272,21 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
 // column Gaussians (m <= kRowLaneCols) sit in shared memory, read as broadcasts:
 //   * row minimum: NaN-sticky FMNMX + compare/select per pair, in the lane, no collective;
 //     a NaN result (rare) is resolved on a cold pass (first NaN column, as torch.min);
-//   * column minimum: two integer ops for the order key, one REDUX.MIN per warp and column,
-//     compared with the CTA's running minimum in shared memory; only when a warp improves it
-//     (O(log rows) times per column) does it find the row and issue the 64-bit shared atomic;
+//   * column minimum: two integer ops for the order key, one REDUX.MIN per warp and column for
+//     the key and one for the lowest row holding it, merged into a WARP-PRIVATE (key, row) table
+//     in shared memory by a compare and a predicated store -- no branch, no atomic, the same
+//     cost whatever the history (a "did it improve?" pre-check does not pay: at C4 a warp sees
+//     one or two units, so most columns improve every time); the 8 tables are merged once per
+//     CTA at the end;
 //   * when every box of the warp's rows and every column box is "nice" (the common case) the
 //     loop carries no per-pair screen at all.
-// Work is handed out per WARP in units of 32 RPL rows, dynamically through a counter when the
-// caller gave a workspace (ticket[1]), so the 4 schedulers of an SM stay evenly loaded at
-// sizes that give each only a handful of units (C4: 3125 units over 592 schedulers).
+// Work is handed out per WARP in units of 32 RPL rows: the first unit of every warp statically
+// (CTA-interleaved), further ones through a counter when the caller gave a workspace
+// (ticket[1]), so the 4 schedulers of an SM stay evenly loaded at sizes that give each only a
+// handful of units (C4: 3125 units over 592 schedulers).
 // Values come out of the same gd::core_eval instruction sequence as the matrix kernel's.
 // ---------------------------------------------------------------------------
-constexpr int kRowLaneCols = 512;
+constexpr int kRowLaneCols = 256;
 struct alignas(16) ColBox {
   gd::BoxGauss<float> g;
 };
@@ -307,7 +311,7 @@ __device__ __forceinline__ unsigned int order_key_fast(float v) {
 template <int LOSS, int SPEC, int RPL>
 __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const PairwiseArgs a) {
   __shared__ ColBox s_cols[kRowLaneCols];
-  __shared__ unsigned long long s_colbest[kRowLaneCols];      // key << 32 | row; ~0: none yet
+  __shared__ unsigned long long s_wbest[kWarps][kRowLaneCols];   // per warp: key << 32 | row; ~0: none
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   gd::PairParams<float> pp = a.pp;
@@ -326,19 +330,27 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
   for (int j = tid; j < cnt; j += kThreads) {
     s_cols[j].g = gd::box_gauss(a.b2 + (long long)j * 7, pp);
     nice &= s_cols[j].g.nice;
-    s_colbest[j] = ~0ull;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s_wbest[w][j] = ~0ull;
   }
   const bool cols_nice = __syncthreads_and(nice) != 0;         // also publishes the columns
 
-  // unit schedule: dynamic (one atomic per unit, lane 0) or interleaved static
+  // unit schedule: the first unit of a warp is static and CTA-interleaved (consecutive units
+  // go to different CTAs, then to the next warp slot); further units come from the counter when
+  // there is one (else the static stride continues)
   const bool dynamic = a.ticket != nullptr;
   const long long gwarps = (long long)gridDim.x * kWarps;
-  long long unit = dynamic ? 0 : (long long)blockIdx.x + (long long)gridDim.x * warp;
-  for (;;) {
-    if (dynamic) {
-      unsigned int u = 0;
-      if (lane == 0) u = atomicAdd(a.ticket + 1, 1u);
-      unit = (long long)__shfl_sync(0xffffffffu, u, 0);
+  long long unit = (long long)blockIdx.x + (long long)gridDim.x * warp;
+  unsigned long long* wbest = s_wbest[warp];
+  for (bool first = true;; first = false) {
+    if (!first) {
+      if (dynamic) {
+        unsigned int u = 0;
+        if (lane == 0) u = atomicAdd(a.ticket + 1, 1u);
+        unit = gwarps + (long long)__shfl_sync(0xffffffffu, u, 0);
+      } else {
+        unit += gwarps;
+      }
     }
     if (unit >= nunits) break;
     const long long row0 = unit * kUnitRows;
@@ -356,11 +368,9 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
       best[q] = __uint_as_float(0x7f800000u);
       bj[q] = 0;
     }
-    const bool warp_clean = __all_sync(0xffffffffu, clean);
+    const bool warp_clean = gd::PairwiseExact<LOSS>::value && __all_sync(0xffffffffu, clean);
     const unsigned int rowbase = (unsigned int)row0;
 
-    // hi words of the CTA's running column minima (key << 32 | row)
-    const volatile unsigned int* colhi = reinterpret_cast<const volatile unsigned int*>(s_colbest) + 1;
     bool redo = false;                           // CLEAN sweep: a guard of the FAST core tripped
     auto sweep = [&](auto clean_tag, auto col_tag) {
       constexpr bool CLEAN = decltype(clean_tag)::value;
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
         float v[RPL];
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
-          if constexpr (CLEAN && LOSS != gd::kKfiou) {
+          if constexpr (CLEAN && gd::PairwiseExact<LOSS>::value) {
             // straight-line FAST core; a tripped guard turns the value into +inf (it cannot
             // lower any minimum) and the whole unit is redone below on the general path
             bool rare = false;
@@ -396,20 +406,14 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
 #pragma unroll
           for (int q = 1; q < RPL; ++q) kmin = key[q] < kmin ? key[q] : kmin;
           const unsigned int mn = __reduce_min_sync(0xffffffffu, kmin);
-          if (__any_sync(0xffffffffu, mn <= colhi[2 * j])) {   // rare after the first few units
-            unsigned int row = 0u;
-            bool found = false;
+          // lowest row of the unit holding the minimum: rows 32 q + lane
+          unsigned int rr = 0xffffffffu;
 #pragma unroll
-            for (int q = 0; q < RPL; ++q) {                    // lowest row holding the minimum
-              const unsigned int who = __ballot_sync(0xffffffffu, key[q] == mn);
-              if (!found && who) {
-                row = rowbase + 32u * q + (unsigned int)(__ffs(who) - 1);
-                found = true;
-              }
-            }
-            if (lane == 0 && mn != 0xffffffffu)
-              atomicMin(&s_colbest[j], ((unsigned long long)mn << 32) | row);
-          }
+          for (int q = RPL - 1; q >= 0; --q) rr = key[q] == mn ? 32u * q + (unsigned int)lane : rr;
+          const unsigned int rlow = __reduce_min_sync(0xffffffffu, rr);
+          // warp-private table: every lane writes the same word (no divergence, no atomic)
+          const unsigned long long cand = ((unsigned long long)mn << 32) | (rowbase + rlow);
+          if (cand < wbest[j] && mn != 0xffffffffu) wbest[j] = cand;
         }
       }
     };
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
           if (v != v) {
             if (first) bj[q] = j;
             first = false;
-            if (want_col) atomicMin(&s_colbest[j], (unsigned long long)(rowbase + 32u * q + lane));
+            if (want_col) atomicMin(&wbest[j], (unsigned long long)(rowbase + 32u * q + lane));
           }
         }
       }
@@ -455,16 +459,14 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
         a.row_argmin[r] = bj[q];
       }
     }
-    if (!dynamic) {
-      // CTA-interleaved: consecutive units go to different CTAs, then to the next warp slot
-      unit += gwarps;
-    }
   }
 
   if (want_col) {
     __syncthreads();
     for (int j = tid; j < cnt; j += kThreads) {
-      const unsigned long long k = s_colbest[j];
+      unsigned long long k = s_wbest[0][j];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) k = s_wbest[w][j] < k ? s_wbest[w][j] : k;
       if (k != ~0ull) atomicMax(a.col_keys + j, ~k);
     }
     // last CTA to finish unpacks the column keys and restores the workspace
@@ -630,9 +632,13 @@ template <int LOSS>
 int launch_pairwise(const PairwiseArgs& a, cudaStream_t st) {
   // reductions without the matrix: lanes on rows (no per-row collective); with the matrix (or
   // more columns than the shared-memory stage holds): lanes on columns, coalesced stores
-  if (a.row_min && a.out == nullptr && a.m <= kRowLaneCols && !a.force_cpl1 &&
-      pairwise_rowlane_enabled())
-    return launch_rowlane<LOSS>(a, st);
+  // (for the distances whose pair value is fixed to the last bit in the source,
+  // gd::PairwiseExact: the two kernels must agree exactly)
+  if constexpr (gd::PairwiseExact<LOSS>::value) {
+    if (a.row_min && a.out == nullptr && a.m <= kRowLaneCols && !a.force_cpl1 &&
+        pairwise_rowlane_enabled())
+      return launch_rowlane<LOSS>(a, st);
+  }
   return a.row_min ? launch_pairwise_spec<LOSS, true>(a, st)
                    : launch_pairwise_spec<LOSS, false>(a, st);
 }

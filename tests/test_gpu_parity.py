@@ -301,6 +301,42 @@ def test_early_return_and_weight_shapes():
         GDLoss('gwd3d')(pred, target)                 # CPU tensors: no fallback
 
 
+def test_early_return_flag_reported_from_inside_the_launch():
+    """[N] weights (the reference RAISES on its early-return branch, so the host must learn
+    any(weight > 0)): the answer comes back from the fused launch itself through a pinned word
+    (gd_loss_io.any_positive_host) -- from its first tile when that holds a positive weight,
+    else from the last CTA.  Every kernel variant, small and large batches, positives only at
+    the far end of the batch, no positives at all (raises like the reference), repeated calls
+    (the slots are reused), and a loss identical to the sync-free module's."""
+    kw = dict(loss_type='kld3d', fun='log1p', tau=0.0, loss_weight=5.0)
+    for n in (5, 500, 100_003, 1 << 21):
+        pred, target, w = synth.make_pairs(n, 'kitti', seed=n, weights='bernoulli')
+        pc, tc = pred.cuda(), target.cuda()
+        w[0] = 0.5                              # at least one positive weight
+        w_late = torch.zeros(n)
+        w_late[n - 1] = 0.7                     # the only positive weight is the last row
+        w_neg = -torch.rand(n)
+        for variant in ('auto', 'bulk', 'bulk_any', 'staged'):
+            if variant == 'bulk' and n < 16:
+                continue
+            for wt in (w, w_late):
+                p = pc.clone().requires_grad_(True)
+                out = GDLoss(variant=variant, **kw)(p, tc, wt.cuda(), avg_factor=7.0)
+                out.backward()
+                q = pc.clone().requires_grad_(True)
+                ref = GDLoss(variant=variant, host_sync=False, **kw)(q, tc, wt.cuda(), avg_factor=7.0)
+                ref.backward()
+                assert out.item() == ref.item() and torch.equal(p.grad, q.grad), (n, variant)
+            for _ in range(3):
+                with pytest.raises(RuntimeError):         # [N,7] * [N]: broadcasting error, ref:292
+                    GDLoss(variant=variant, **kw)(pc, tc, w_neg.cuda(), avg_factor=7.0)
+    # many calls back to back: more than the ring of flag words
+    pred, target, w = synth.make_pairs(4096, 'kitti', seed=1, weights='bernoulli')
+    mod = GDLoss(**kw)
+    outs = [mod(pred.cuda(), target.cuda(), w.cuda()).item() for _ in range(40)]
+    assert len(set(outs)) == 1
+
+
 def test_early_return_decided_on_the_device():
     """The default module (reference ctor keys only) takes the early return of ref:290-292
     without any host involvement wherever `pred * weight` has the shape of pred: value

@@ -169,7 +169,7 @@ def test_nan_and_degenerate_boxes(emul):
 
 
 @pytest.mark.parametrize('loss', ['gwd3d', 'kld3d', 'bd3d'])
-@pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (131, 129), (200, 256), (700, 40), (90, 512)])
+@pytest.mark.parametrize('n,m', [(1, 1), (63, 5), (65, 33), (131, 129), (200, 256), (700, 40), (90, 256)])
 @pytest.mark.parametrize('mode', [3, 4, 5])
 def test_rowlane_minima_equal_matrix_minima(emul, loss, n, m, mode):
     """The ROW-lane kernel of the fused reductions (lanes on rows, column Gaussians in shared
