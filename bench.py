@@ -691,6 +691,14 @@ def run_ours(args):
                                               'has no pairwise entry: its element-wise path on expanded pairs), '
                                               f'fp32, {os.cpu_count()} threads',
                                     'seconds': round(dt, 3), 'Gpairs_per_s': round(4096 * m / dt / 1e9, 5)}
+            # pipe utilisation cannot be measured inside a timed run: recorded ncu capture of the
+            # same two launches (tools/summarize_pairwise_ncu.py), marked as such
+            rec = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'pairwise_ncu.json')
+            if os.path.exists(rec):
+                with open(rec) as f:
+                    pair['ncu_recorded'] = {'source': 'profiles/pairwise_ncu.json (recorded ncu --set full '
+                                                      'capture, not measured in this run)',
+                                            'kernels': json.load(f)}
             extras['pairwise'] = pair
             del mat, anchors
             log('pairwise done')

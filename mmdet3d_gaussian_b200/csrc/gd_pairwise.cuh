@@ -48,6 +48,8 @@ struct PairwiseArgs {
   long long out_stride;
   int similarity;                  // write 1 - value (assigners' "larger is closer")
   int force_cpl1;                  // GD_PAIR_CPL1: one column per lane
+  int tile_rows;                   // rows per tile of the column-lane kernel (0: kRowsPerCta);
+                                   // the matrix launcher sizes it so the waves come out even
   float* row_min;                  // [n]   REDUCE only
   int* row_argmin;                 // [n]
   unsigned long long* col_keys;    // [m] workspace holding ~key (so zero is the identity of the
@@ -77,8 +79,10 @@ __host__ __device__ inline int pairwise_wx(long long m, int warp_cols) {
 
 // SPEC < 0: fun / tau_on / flag at run time; SPEC >= 0: bits [1:0] fun, [2] tau_on,
 // [3] flag compile-time (as gd_warp_kernel).  CPL: columns per lane (1 or 2).
+// (matrix only, two columns per lane: capped at 85 registers so three CTAs stay resident)
 template <int LOSS, int SPEC, bool REDUCE, int CPL>
-__global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArgs a) {
+__global__ void __launch_bounds__(kThreads, (!REDUCE && CPL == 2) ? 3 : 1)
+gd_pairwise_kernel(const PairwiseArgs a) {
   __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
   __shared__ unsigned long long s_best[REDUCE ? kRowsPerCta : 1][kWarps];
   __shared__ bool s_last;
@@ -97,7 +101,14 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
   const long long chunk = (long long)kWarpCols * wx;
   const bool want_col = REDUCE && a.col_keys != nullptr;
   const bool one_chunk = a.m <= chunk;         // column minima can stay in registers across tiles
-  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  const int tile_rows = a.tile_rows > 0 ? a.tile_rows : kRowsPerCta;       // <= kRowsPerCta
+  const long long ntiles = (a.n + tile_rows - 1) / tile_rows;
+  // one column chunk for the whole launch: the lane's column Gaussians are converted once and
+  // kept across the CTA's tiles
+  const bool keep_cols = gridDim.y == 1 && one_chunk;
+  bool cols_ready = false;
+  gd::BoxGauss<float> t[CPL];
+  bool live[CPL];
   unsigned int cbest[CPL], crow[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
@@ -106,8 +117,8 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
   }
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * kRowsPerCta;
-    const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
+    const long long row0 = tile * tile_rows;
+    const int rows = (int)min((long long)tile_rows, a.n - row0);
     __syncthreads();                           // previous tile fully consumed
     int row_nice = 1;
     if (tid < rows) {
@@ -121,16 +132,19 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArg
     for (long long c0 = (long long)blockIdx.y * chunk; c0 < a.m; c0 += (long long)gridDim.y * chunk) {
       const long long jb = c0 + (long long)kWarpCols * cgrp;     // first column of this warp
       if (jb >= a.m) continue;                 // this warp's columns are all past the end
-      gd::BoxGauss<float> t[CPL];
-      bool live[CPL];
+      if (!(keep_cols && cols_ready)) {
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        const long long j = jb + 32 * q + lane;
-        live[q] = j < a.m;
-        if (live[q]) t[q] = gd::box_gauss(a.b2 + j * 7, pp);
-        else t[q] = s_rows[0];                 // any valid box: the result is discarded
-        if (want_col && !one_chunk) cbest[q] = 0xffffffffu;
+        for (int q = 0; q < CPL; ++q) {
+          const long long j = jb + 32 * q + lane;
+          live[q] = j < a.m;
+          if (live[q]) t[q] = gd::box_gauss(a.b2 + j * 7, pp);
+          else t[q] = s_rows[0];               // any valid box: the result is discarded
+        }
+        cols_ready = true;
       }
+#pragma unroll
+      for (int q = 0; q < CPL; ++q)
+        if (want_col && !one_chunk) cbest[q] = 0xffffffffu;
       // row pointer of this lane's first column, advanced by wy rows per iteration
       float* orow = a.out != nullptr ? a.out + (row0 + ry) * a.out_stride + jb + lane : nullptr;
       const long long ostep = (long long)wy * a.out_stride;
@@ -370,6 +384,9 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
     }
     const bool warp_clean = gd::PairwiseExact<LOSS>::value && __all_sync(0xffffffffu, clean);
     const unsigned int rowbase = (unsigned int)row0;
+    unsigned int rowid[RPL];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) rowid[q] = rowbase + 32u * q + (unsigned int)lane;
 
     bool redo = false;                           // CLEAN sweep: a guard of the FAST core tripped
     auto sweep = [&](auto clean_tag, auto col_tag) {
@@ -406,14 +423,19 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
 #pragma unroll
           for (int q = 1; q < RPL; ++q) kmin = key[q] < kmin ? key[q] : kmin;
           const unsigned int mn = __reduce_min_sync(0xffffffffu, kmin);
-          // lowest row of the unit holding the minimum: rows 32 q + lane
+          // lowest row holding the minimum (rowid[q] = this lane's rows, hoisted)
           unsigned int rr = 0xffffffffu;
 #pragma unroll
-          for (int q = RPL - 1; q >= 0; --q) rr = key[q] == mn ? 32u * q + (unsigned int)lane : rr;
+          for (int q = RPL - 1; q >= 0; --q) rr = key[q] == mn ? rowid[q] : rr;
           const unsigned int rlow = __reduce_min_sync(0xffffffffu, rr);
-          // warp-private table: every lane writes the same word (no divergence, no atomic)
-          const unsigned long long cand = ((unsigned long long)mn << 32) | (rowbase + rlow);
-          if (cand < wbest[j] && mn != 0xffffffffu) wbest[j] = cand;
+          // warp-private table: every lane writes the same word (no divergence, no atomic).
+          // mn == ~0 (dead lanes only, or a NaN the cold pass overrides with key 0) never gets in.
+          const unsigned long long cand = ((unsigned long long)mn << 32) | rlow;
+          if (CLEAN) {
+            if (cand < wbest[j]) wbest[j] = cand;
+          } else {
+            if (cand < wbest[j] && mn != 0xffffffffu) wbest[j] = cand;
+          }
         }
       }
     };
@@ -542,6 +564,33 @@ int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
     long long gy = (a.m + 32LL * CPL * wx - 1) / (32LL * CPL * wx);
     if (gy > 65535) gy = 65535;
     grid = dim3((unsigned)ntiles, (unsigned)gy);
+    if (gy == 1) {
+      // One column chunk: persistent CTAs (the lane's column Gaussians are converted once per
+      // CTA, not once per tile) and a tile height chosen so that every CTA slot of the GPU gets
+      // the same number of equal tiles -- 200k rows in 64-row tiles are 7.04 waves of 444 CTAs,
+      // i.e. 8 wave times; in 57-row tiles they are 7.9 waves of shorter tiles.
+      static int occ[kMaxDevices] = {};
+      const int dev = current_device();
+      if (occ[dev] == 0) {
+        int per_sm = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL>, kThreads, 0);
+        if (e != cudaSuccess) return (int)e;
+        occ[dev] = per_sm > 0 ? per_sm : 1;
+      }
+      const long long slots = (long long)device_info().sm_count * occ[dev];
+      const long long waves = (ntiles + slots - 1) / slots;
+      long long rows = (a.n + waves * slots - 1) / (waves * slots);     // <= kRowsPerCta
+      if (rows < 16) rows = 16;
+      if (rows > kRowsPerCta) rows = kRowsPerCta;
+      PairwiseArgs b = a;
+      b.tile_rows = (int)rows;
+      const long long nt = (a.n + rows - 1) / rows;
+      grid = dim3((unsigned)(nt < slots ? nt : slots), 1);
+      gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL><<<grid, kThreads, 0, st>>>(b);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      return (int)cudaGetLastError();
+    }
   }
   gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL><<<grid, kThreads, 0, st>>>(a);
   g_launches.fetch_add(1, std::memory_order_relaxed);

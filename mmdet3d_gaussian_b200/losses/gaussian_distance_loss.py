@@ -60,8 +60,9 @@ class GDLoss(nn.Module):
       launch swaps in ``(pred * weight).sum()`` / ``grad = weight`` when it is false -- no
       host involvement at all, CUDA-graph capturable.  For other ``[N]`` weights the
       reference RAISES a broadcasting error when the branch is taken, so the host must learn
-      the answer: a probe kernel and a 4-byte copy are queued, the fused launch is queued
-      right behind them, and only then does the host wait for the probe -- the GPU never
+      the answer: the fused launch itself reports ``any(weight > 0)`` into a word of pinned host
+      memory (its first warp, microseconds after the kernel starts, when the first tile holds a
+      positive weight; its last CTA otherwise) and the host waits for that word -- the GPU never
       idles.  ``weight=None`` and ``reduction='none'`` never probe (as the reference).
       False never waits and never raises: rows whose weight is exactly 0 are masked inside
       the kernel (0 loss, 0 gradient, even where the distance is inf/nan); for non-negative

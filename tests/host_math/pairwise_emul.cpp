@@ -56,6 +56,19 @@ static void run_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
   } else {
     gx = (unsigned)ntiles;
     gy = (unsigned)((a.m + 32LL * CPL * wx - 1) / (32LL * CPL * wx));
+    if (gy == 1) {               // persistent, even waves: launch_pairwise_cpl with `cap` CTA slots
+      const long long slots = cap;
+      const long long waves = (ntiles + slots - 1) / slots;
+      long long rows = (a.n + waves * slots - 1) / (waves * slots);
+      if (rows < 16) rows = 16;
+      if (rows > gdk::kRowsPerCta) rows = gdk::kRowsPerCta;
+      gdk::PairwiseArgs b = a;
+      b.tile_rows = (int)rows;
+      const long long nt = (a.n + rows - 1) / rows;
+      emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL>, (unsigned)(nt < slots ? nt : slots), 1,
+                 gdk::kThreads, b);
+      return;
+    }
   }
   emu_launch(gdk::gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL>, gx, gy, gdk::kThreads, a);
 }

@@ -317,7 +317,7 @@ def test_early_return_flag_reported_from_inside_the_launch():
         w_late[n - 1] = 0.7                     # the only positive weight is the last row
         w_neg = -torch.rand(n)
         for variant in ('auto', 'bulk', 'bulk_any', 'staged'):
-            if variant == 'bulk' and n < 16:
+            if variant in ('bulk', 'bulk_any') and n < 16:
                 continue
             for wt in (w, w_late):
                 p = pc.clone().requires_grad_(True)
