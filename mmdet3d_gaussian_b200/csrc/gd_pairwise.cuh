@@ -79,10 +79,8 @@ __host__ __device__ inline int pairwise_wx(long long m, int warp_cols) {
 
 // SPEC < 0: fun / tau_on / flag at run time; SPEC >= 0: bits [1:0] fun, [2] tau_on,
 // [3] flag compile-time (as gd_warp_kernel).  CPL: columns per lane (1 or 2).
-// (matrix only, two columns per lane: capped at 85 registers so three CTAs stay resident)
 template <int LOSS, int SPEC, bool REDUCE, int CPL>
-__global__ void __launch_bounds__(kThreads, (!REDUCE && CPL == 2) ? 3 : 1)
-gd_pairwise_kernel(const PairwiseArgs a) {
+__device__ __forceinline__ void pairwise_body(const PairwiseArgs& a) {
   __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
   __shared__ unsigned long long s_best[REDUCE ? kRowsPerCta : 1][kWarps];
   __shared__ bool s_last;
@@ -103,12 +101,14 @@ gd_pairwise_kernel(const PairwiseArgs a) {
   const bool one_chunk = a.m <= chunk;         // column minima can stay in registers across tiles
   const int tile_rows = a.tile_rows > 0 ? a.tile_rows : kRowsPerCta;       // <= kRowsPerCta
   const long long ntiles = (a.n + tile_rows - 1) / tile_rows;
-  // one column chunk for the whole launch: the lane's column Gaussians are converted once and
-  // kept across the CTA's tiles
-  const bool keep_cols = gridDim.y == 1 && one_chunk;
+  // One column chunk for the whole launch (matrix kernel of the exact-form distance): the lane's
+  // column Gaussians are converted once and kept across the CTA's tiles.  Compile-time off
+  // elsewhere: the longer live ranges cost kld3d / bd3d a resident CTA (-7 %, gpurun_out/r03c).
+  constexpr bool kKeepCols = !REDUCE && gd::PairwiseExact<LOSS>::value;
+  const bool keep_cols = kKeepCols && gridDim.y == 1 && one_chunk;
   bool cols_ready = false;
-  gd::BoxGauss<float> t[CPL];
-  bool live[CPL];
+  gd::BoxGauss<float> tkeep[kKeepCols ? CPL : 1];
+  bool lkeep[kKeepCols ? CPL : 1];
   unsigned int cbest[CPL], crow[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
@@ -132,19 +132,29 @@ gd_pairwise_kernel(const PairwiseArgs a) {
     for (long long c0 = (long long)blockIdx.y * chunk; c0 < a.m; c0 += (long long)gridDim.y * chunk) {
       const long long jb = c0 + (long long)kWarpCols * cgrp;     // first column of this warp
       if (jb >= a.m) continue;                 // this warp's columns are all past the end
-      if (!(keep_cols && cols_ready)) {
+      gd::BoxGauss<float> t[CPL];
+      bool live[CPL];
+      if (kKeepCols && keep_cols && cols_ready) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          t[q] = tkeep[kKeepCols ? q : 0];
+          live[q] = lkeep[kKeepCols ? q : 0];
+        }
+      } else {
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
           const long long j = jb + 32 * q + lane;
           live[q] = j < a.m;
           if (live[q]) t[q] = gd::box_gauss(a.b2 + j * 7, pp);
           else t[q] = s_rows[0];               // any valid box: the result is discarded
+          if (want_col && !one_chunk) cbest[q] = 0xffffffffu;
+          if (kKeepCols) {
+            tkeep[kKeepCols ? q : 0] = t[q];
+            lkeep[kKeepCols ? q : 0] = live[q];
+          }
         }
         cols_ready = true;
       }
-#pragma unroll
-      for (int q = 0; q < CPL; ++q)
-        if (want_col && !one_chunk) cbest[q] = 0xffffffffu;
       // row pointer of this lane's first column, advanced by wy rows per iteration
       float* orow = a.out != nullptr ? a.out + (row0 + ry) * a.out_stride + jb + lane : nullptr;
       const long long ostep = (long long)wy * a.out_stride;
@@ -276,6 +286,17 @@ gd_pairwise_kernel(const PairwiseArgs a) {
   }
 }
 
+template <int LOSS, int SPEC, bool REDUCE, int CPL>
+__global__ void __launch_bounds__(kThreads) gd_pairwise_kernel(const PairwiseArgs a) {
+  pairwise_body<LOSS, SPEC, REDUCE, CPL>(a);
+}
+// the same body capped at 85 registers so that three CTAs stay resident (the persistent matrix
+// launch of the exact-form distance, two columns per lane)
+template <int LOSS, int SPEC, int CPL>
+__global__ void __launch_bounds__(kThreads, 3) gd_pairwise_kernel_m3(const PairwiseArgs a) {
+  pairwise_body<LOSS, SPEC, false, CPL>(a);
+}
+
 // ---------------------------------------------------------------------------
 // Fused reductions WITHOUT the matrix (row f2, the assigner's launch): lanes map to ROWS.
 //
@@ -326,6 +347,7 @@ template <int LOSS, int SPEC, int RPL>
 __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const PairwiseArgs a) {
   __shared__ ColBox s_cols[kRowLaneCols];
   __shared__ unsigned long long s_wbest[kWarps][kRowLaneCols];   // per warp: key << 32 | row; ~0: none
+  __shared__ unsigned long long s_dummy[kThreads];               // lanes 1..31: sink of the table update
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   gd::PairParams<float> pp = a.pp;
@@ -347,6 +369,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s_wbest[w][j] = ~0ull;
   }
+  s_dummy[tid] = 0ull;                                         // nothing is ever below it: never written
   const bool cols_nice = __syncthreads_and(nice) != 0;         // also publishes the columns
 
   // unit schedule: the first unit of a warp is static and CTA-interleaved (consecutive units
@@ -356,6 +379,8 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
   const long long gwarps = (long long)gridDim.x * kWarps;
   long long unit = (long long)blockIdx.x + (long long)gridDim.x * warp;
   unsigned long long* wbest = s_wbest[warp];
+  unsigned long long* const slot0 = lane == 0 ? wbest : &s_dummy[tid];
+  const int slot_step = lane == 0 ? 1 : 0;
   for (bool first = true;; first = false) {
     if (!first) {
       if (dynamic) {
@@ -428,13 +453,16 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
 #pragma unroll
           for (int q = RPL - 1; q >= 0; --q) rr = key[q] == mn ? rowid[q] : rr;
           const unsigned int rlow = __reduce_min_sync(0xffffffffu, rr);
-          // warp-private table: every lane writes the same word (no divergence, no atomic).
-          // mn == ~0 (dead lanes only, or a NaN the cold pass overrides with key 0) never gets in.
+          // warp-private table, touched by lane 0 only inside the sweep (no atomic, nothing
+          // shared between lanes); the other lanes run the same predicated store on a private
+          // dummy word, so the warp never diverges.  mn == ~0 (dead lanes only, or a NaN the cold pass overrides
+          // with key 0) never gets in.
           const unsigned long long cand = ((unsigned long long)mn << 32) | rlow;
+          unsigned long long* slot = slot0 + (long long)j * slot_step;   // lane 0: wbest[j]
           if (CLEAN) {
-            if (cand < wbest[j]) wbest[j] = cand;
+            if (cand < *slot) *slot = cand;
           } else {
-            if (cand < wbest[j] && mn != 0xffffffffu) wbest[j] = cand;
+            if (cand < *slot && mn != 0xffffffffu) *slot = cand;
           }
         }
       }
@@ -459,6 +487,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
 
     // cold pass: a NaN in the row.  torch.min returns NaN with the first NaN column; every
     // column holding a NaN gets the lowest key (0) with the lowest such row.
+    __syncwarp();                                // lane 0's table updates before other lanes' atomics
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
       if (live[q] && best[q] != best[q]) {
@@ -481,6 +510,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
         a.row_argmin[r] = bj[q];
       }
     }
+    __syncwarp();                                // atomics of the cold pass before lane 0 goes on
   }
 
   if (want_col) {
@@ -564,7 +594,7 @@ int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
     long long gy = (a.m + 32LL * CPL * wx - 1) / (32LL * CPL * wx);
     if (gy > 65535) gy = 65535;
     grid = dim3((unsigned)ntiles, (unsigned)gy);
-    if (gy == 1) {
+    if constexpr (gd::PairwiseExact<LOSS>::value) if (gy == 1) {
       // One column chunk: persistent CTAs (the lane's column Gaussians are converted once per
       // CTA, not once per tile) and a tile height chosen so that every CTA slot of the GPU gets
       // the same number of equal tiles -- 200k rows in 64-row tiles are 7.04 waves of 444 CTAs,
@@ -574,7 +604,7 @@ int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
       if (occ[dev] == 0) {
         int per_sm = 0;
         const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &per_sm, gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL>, kThreads, 0);
+            &per_sm, gd_pairwise_kernel_m3<LOSS, SPEC, CPL>, kThreads, 0);
         if (e != cudaSuccess) return (int)e;
         occ[dev] = per_sm > 0 ? per_sm : 1;
       }
@@ -587,7 +617,7 @@ int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
       b.tile_rows = (int)rows;
       const long long nt = (a.n + rows - 1) / rows;
       grid = dim3((unsigned)(nt < slots ? nt : slots), 1);
-      gd_pairwise_kernel<LOSS, SPEC, REDUCE, CPL><<<grid, kThreads, 0, st>>>(b);
+      gd_pairwise_kernel_m3<LOSS, SPEC, CPL><<<grid, kThreads, 0, st>>>(b);
       g_launches.fetch_add(1, std::memory_order_relaxed);
       return (int)cudaGetLastError();
     }

@@ -56,7 +56,7 @@ static void run_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
   } else {
     gx = (unsigned)ntiles;
     gy = (unsigned)((a.m + 32LL * CPL * wx - 1) / (32LL * CPL * wx));
-    if (gy == 1) {               // persistent, even waves: launch_pairwise_cpl with `cap` CTA slots
+    if (gy == 1 && gd::PairwiseExact<LOSS>::value) {   // persistent, even waves: launch_pairwise_cpl with `cap` CTA slots
       const long long slots = cap;
       const long long waves = (ntiles + slots - 1) / slots;
       long long rows = (a.n + waves * slots - 1) / (waves * slots);
