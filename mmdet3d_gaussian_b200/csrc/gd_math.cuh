@@ -1014,6 +1014,39 @@ GD_HD T pair_eval_fast(const T* p, const T* t, const PairParams<T>& P, T gscale,
   }
 }
 
+// Explicit round-to-nearest operations of the pairwise value path (see the long comment at
+// namespace pw further down): mul.rn / add.rn / fma.rn are never re-fused by ptxas.
+namespace pw {
+GD_HD float mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+GD_HD float add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+GD_HD float sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+GD_HD float fma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return ::fmaf(a, b, c);
+#endif
+}
+}  // namespace pw
+
 // ---------------------------------------------------------------------------
 // a12: pairwise N x M path.  Everything that depends on ONE box is computed
 // once per box (BoxGauss); the per-pair work is the geometry difference and the
@@ -1030,13 +1063,41 @@ struct BoxGauss {
   T amb;            // (a - b)(a + b)
   T r6;             // (a b e)^(-1/6): the box's factor of the gwd normaliser   ref:101-104
   T ia, ib, ie;     // reciprocal half extents
-  int nice;         // extents in [1e-4, 1e4]: the FAST cores may be used for this box
+  T iA, iB, iE;     // their squares
+  T iBmA;           // 1/B - 1/A
+  T iab;            // 1 / (a b)
+  int nice;         // extents in [1e-4, 1e4], aspect <= 256: the FAST cores may be used for this box
 };
 
 template <typename T>
 GD_HD BoxGauss<T> box_gauss(const T* row, const PairParams<T>& P) {
   BoxGauss<T> b;
   T m;
+  if constexpr (std::is_same<T, float>::value) {
+    // float: every operation with its rounding spelled out, so that a box converts to the same
+    // bits in every kernel that inlines this function (see namespace pw below)
+    b.cx = pw::fma(P.off[0], row[3], row[0]);
+    b.cy = pw::fma(P.off[1], row[4], row[1]);
+    b.cz = pw::fma(P.off[2], row[5], row[2]);
+    b.a = pw::mul(0.5f, clamp_extent(row[3], &m));
+    b.b = pw::mul(0.5f, clamp_extent(row[4], &m));
+    b.e = pw::mul(0.5f, clamp_extent(row[5], &m));
+    Mth<T>::sincos(row[6], &b.s, &b.c);
+    b.A = pw::mul(b.a, b.a);
+    b.B = pw::mul(b.b, b.b);
+    b.E = pw::mul(b.e, b.e);
+    b.ab = pw::mul(b.a, b.b);
+    b.amb = pw::mul(pw::sub(b.a, b.b), pw::add(b.a, b.b));
+    b.r6 = Mth<T>::rcbrt(Mth<T>::sqrt(pw::mul(b.ab, b.e)));
+    b.ia = Mth<T>::rcp(b.a);
+    b.ib = Mth<T>::rcp(b.b);
+    b.ie = Mth<T>::rcp(b.e);
+    b.iA = pw::mul(b.ia, b.ia);
+    b.iB = pw::mul(b.ib, b.ib);
+    b.iE = pw::mul(b.ie, b.ie);
+    b.iBmA = pw::sub(b.iB, b.iA);
+    b.iab = pw::mul(b.ia, b.ib);
+  } else {
   b.cx = row[0] + P.off[0] * row[3];
   b.cy = row[1] + P.off[1] * row[4];
   b.cz = row[2] + P.off[2] * row[5];
@@ -1053,6 +1114,12 @@ GD_HD BoxGauss<T> box_gauss(const T* row, const PairParams<T>& P) {
   b.ia = Mth<T>::rcp(b.a);
   b.ib = Mth<T>::rcp(b.b);
   b.ie = Mth<T>::rcp(b.e);
+  b.iA = b.ia * b.ia;
+  b.iB = b.ib * b.ib;
+  b.iE = b.ie * b.ie;
+  b.iBmA = b.iB - b.iA;
+  b.iab = b.ia * b.ib;
+  }
   const T lo = (T)1e-4, hi = (T)1e4;
   // ... and an in-plane aspect ratio <= 256 (the short form of U in gwd_core's value path)
   b.nice = (row[3] >= lo && row[3] <= hi && row[4] >= lo && row[4] <= hi && row[5] >= lo &&
@@ -1106,34 +1173,6 @@ GD_HD T pair_value(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<
 // "assignment indices bit-exact with the matrix" rests on.
 // ---------------------------------------------------------------------------
 namespace pw {
-GD_HD float mul(float a, float b) {
-#if defined(__CUDA_ARCH__)
-  return __fmul_rn(a, b);
-#else
-  return a * b;
-#endif
-}
-GD_HD float add(float a, float b) {
-#if defined(__CUDA_ARCH__)
-  return __fadd_rn(a, b);
-#else
-  return a + b;
-#endif
-}
-GD_HD float sub(float a, float b) {
-#if defined(__CUDA_ARCH__)
-  return __fsub_rn(a, b);
-#else
-  return a - b;
-#endif
-}
-GD_HD float fma(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
-  return __fmaf_rn(a, b, c);
-#else
-  return ::fmaf(a, b, c);
-#endif
-}
 // Mth<float>::log1p_lean, operation by operation
 GD_HD float log1p_lean(float x) {
   const float s = mul(x, Mth<float>::rcp(add(2.0f, x)));
@@ -1152,6 +1191,59 @@ GD_HD float log1p_lean(float x) {
 #endif
   return x <= 0.5f ? small : big;
 }
+// Mth<float>::log1p_pos, operation by operation (log(1+x), 0 <= x < ~1e30, ~1 ulp)
+GD_HD float log1p_pos(float x) {
+  const float y = add(1.0f, x);
+  uint32_t yb;
+  memcpy(&yb, &y, 4);
+  const int k = (int)((int32_t)(yb - 0x3f3504f3u) >> 23);
+  const uint32_t mb = yb - ((uint32_t)k << 23);
+  float m;
+  memcpy(&m, &mb, 4);
+  const float f = (k == 0) ? x : sub(m, 1.0f);
+  const float s = mul(f, Mth<float>::rcp(add(2.0f, f)));
+  const float z = mul(s, s);
+  float q = 1.0f / 13.0f;
+  q = fma(q, z, 1.0f / 11.0f);
+  q = fma(q, z, 1.0f / 9.0f);
+  q = fma(q, z, 1.0f / 7.0f);
+  q = fma(q, z, 1.0f / 5.0f);
+  q = fma(q, z, 1.0f / 3.0f);
+  const float kf = (float)k;
+  const float lo = fma(kf, 1.428606765330187e-06f, mul(mul(mul(2.0f, s), z), q));
+  return fma(kf, 0.693145751953125f, fma(2.0f, s, lo));
+}
+// Mth<float>::sum_minus_log_ratios<FAST>, operation by operation:
+// S - log(r1 r2 r3) with S = q1 + q2 + q3, r_i = 1 + q_i, pair = r1 r2 r3 - 1 - S
+GD_HD float sum_minus_log_ratios(float S, float pair, float r1, float r2, float r3, bool* rare) {
+  const float y = mul(mul(r1, r2), r3);
+  *rare |= !(y > 1.0e-30f && y < 1.0e30f);
+  uint32_t yb;
+  memcpy(&yb, &y, 4);
+  const int k = (int)((int32_t)(yb - 0x3f3504f3u) >> 23);
+  const uint32_t mb = yb - ((uint32_t)k << 23);
+  float m;
+  memcpy(&m, &mb, 4);
+  const float x = add(S, pair);
+  const float f = (k == 0) ? x : sub(m, 1.0f);
+  const float s = mul(f, Mth<float>::rcp(add(2.0f, f)));
+  const float z = mul(s, s);
+  float q = 1.0f / 13.0f;
+  q = fma(q, z, 1.0f / 11.0f);
+  q = fma(q, z, 1.0f / 9.0f);
+  q = fma(q, z, 1.0f / 7.0f);
+  q = fma(q, z, 1.0f / 5.0f);
+  q = fma(q, z, 1.0f / 3.0f);
+  const float tail = mul(mul(mul(2.0f, s), z), q);
+  const float kf = (float)k;
+  float r = fma(-kf, 0.693145751953125f, S);               // ln2 hi (k * hi exact)
+  r = fma(-kf, 1.428606765330187e-06f, r);                 // ln2 lo
+  const float direct = sub(fma(-2.0f, s, r), tail);
+  return (k == 0) ? sub(fma(x, s, -tail), pair) : direct;
+}
+// sqrt(clamp(x, 0)): negative -> 0, NaN propagates                ref:95,99,139,184,197
+GD_HD float sqrt_clamp0(float x) { return Mth<float>::sqrt(x < 0.0f ? 0.0f : x); }
+
 // post map of the FAST value path (fun in {none, log1p}; anything else is left to the robust
 // path), ref:24-39
 GD_HD float post(float d, const PairParams<float>& P, bool* rare) {
@@ -1188,16 +1280,119 @@ GD_HD float gwd_value(const BoxGauss<float>& p, const BoxGauss<float>& t,
   float d2 = fma(dx, dx, mul(dy, dy));                             // ref:79,99
   d2 = fma(dz, dz, d2);
   d2 = fma(P.alpha2, W, d2);
-  d2 = d2 < 0.0f ? 0.0f : d2;                                      // clamp(0); NaN falls through
-  float d = Mth<float>::sqrt(d2);
+  float d = sqrt_clamp0(d2);                                       // NaN falls through
   if (P.flag) d = mul(d, mul(0.5f, mul(p.r6, t.r6)));              // ref:101-104
   return post(d, P, rare);
+}
+// KL divergence with Sigma_p inverted -- what kld3d_loss(pred = p, target = t) evaluates
+// (ref:109-141) before its optional sqrt; the reverse direction of jd / symmax / symmin
+// (kld3d_loss(target, pred), ref:193,207,220) is the same function with the boxes swapped.
+// Same formulas as kld_fwd above (ratios q = (t - p)/p, one log through
+// sum_minus_log_ratios), every operation explicit.
+GD_HD float kld_dir(const BoxGauss<float>& p, const BoxGauss<float>& t,
+                    const PairParams<float>& P, bool* rare) {
+  const float dx = sub(p.cx, t.cx), dy = sub(p.cy, t.cy), dz = sub(p.cz, t.cz);
+  const float u = fma(p.c, dx, mul(p.s, dy));                      // ref:119-123
+  const float v = fma(p.c, dy, -mul(p.s, dx));
+  const float sd = fma(p.s, t.c, -mul(p.c, t.s));
+  const float s2 = mul(sd, sd);
+  const float qa = mul(sub(t.a, p.a), p.ia), qb = mul(sub(t.b, p.b), p.ib),
+              qe = mul(sub(t.e, p.e), p.ie);
+  const float ra = mul(t.a, p.ia), rb = mul(t.b, p.ib), re = mul(t.e, p.ie);   // = 1 + q
+  float mh = mul(mul(u, u), p.iA);
+  mh = fma(mul(v, v), p.iB, mh);
+  mh = fma(mul(dz, dz), p.iE, mh);
+  const float maha = mul(mul(0.5f, P.inv_alpha2), mh);             // ref:122-124,137
+  const float ab = mul(qa, qb);
+  float pr = fma(qa, qe, ab);                                      // Pi(1+q) - 1 - sum q
+  pr = fma(qb, qe, pr);
+  pr = fma(ab, qe, pr);
+  float h = mul(qa, qa);
+  h = fma(qb, qb, h);
+  h = fma(qe, qe, h);
+  const float S = add(add(qa, qb), qe);
+  const float lg = sum_minus_log_ratios(S, pr, ra, rb, re, rare);
+  const float rot = mul(mul(mul(0.5f, t.amb), s2), p.iBmA);        // 0.5 (C-D) s2 (1/B - 1/A)
+  const float shape = add(fma(0.5f, h, lg), rot);
+  return add(maha, shape);
+}
+template <int LOSS>
+GD_HD float kld_family_value(const BoxGauss<float>& p, const BoxGauss<float>& t,
+                             const PairParams<float>& P, bool* rare) {
+  float val;
+  if constexpr (LOSS == kKld) {
+    val = kld_dir(p, t, P, rare);
+    if (P.flag) val = sqrt_clamp0(val);                            // ref:138-139
+  } else {
+    float f = kld_dir(p, t, P, rare);
+    float r = kld_dir(t, p, P, rare);
+    if constexpr (LOSS == kJd) {                                   // ref:191-197
+      val = mul(0.5f, add(f, r));
+      if (P.flag) val = sqrt_clamp0(val);
+    } else {                                                       // ref:204-223
+      if (P.flag) {
+        f = sqrt_clamp0(f);
+        r = sqrt_clamp0(r);
+      }
+      const bool take_f = (LOSS == kSymMax) ? (f > r) : (f < r);
+      val = (f == r) ? f : (take_f ? f : r);
+      if (f != f || r != r) val = add(f, r);   // NaN propagates like torch.max / torch.min
+    }
+  }
+  return post(val, P, rare);
+}
+// Bhattacharyya (ref:144-186), same formulas as bd_core above, every operation explicit.
+GD_HD float bd_value(const BoxGauss<float>& p, const BoxGauss<float>& t,
+                     const PairParams<float>& P, bool* rare) {
+  const float dx = sub(p.cx, t.cx), dy = sub(p.cy, t.cy), dz = sub(p.cz, t.cz);
+  const float u = fma(p.c, dx, mul(p.s, dy));
+  const float v = fma(p.c, dy, -mul(p.s, dx));
+  const float sd = fma(p.s, t.c, -mul(p.c, t.s));                  // sin / cos (r_p - r_t)
+  const float cd = fma(p.c, t.c, mul(p.s, t.s));
+  const float s2 = mul(sd, sd), c2 = mul(cd, cd), sc = mul(sd, cd);
+  // Sigma_t in the pred frame; M = (Sigma_p + Sigma_t)/2              ref:152
+  const float t00 = fma(t.A, c2, mul(t.B, s2)), t11 = fma(t.A, s2, mul(t.B, c2));
+  const float t01 = -mul(t.amb, sc);
+  const float M00 = mul(0.5f, add(p.A, t00)), M11 = mul(0.5f, add(p.B, t11)), M01 = mul(0.5f, t01);
+  const float Ml = mul(0.5f, add(p.E, t.E));                       // ref:153
+  const float eps = mul(mul(p.amb, t.amb), s2);
+  const float detN = fma(add(p.A, t.A), add(p.B, t.B), eps);       // det(Sp + St)
+  const float det = mul(0.25f, detN);                              // ref:155-157
+  *rare |= !(det >= 1e-7f);                                        // clamp active (or nan), ref:158
+  const float idet = Mth<float>::rcp(det), iMl = Mth<float>::rcp(Ml);
+  float Q2 = mul(mul(u, u), M11);                                  // d^T adj(M) d
+  Q2 = fma(mul(-2.0f, mul(u, v)), M01, Q2);
+  Q2 = fma(mul(v, v), M00, Q2);
+  const float mh = fma(Q2, idet, mul(mul(dz, dz), iMl));
+  const float maha = mul(mul(0.125f, P.inv_alpha2), mh);           // ref:170-172,182
+  // shape: 0.5 ln det + 0.5 ln Ml - 0.25 ln(ABE) - 0.25 ln(CDF)    ref:174-180
+  const float da = sub(p.a, t.a), db = sub(p.b, t.b), de = sub(p.e, t.e);
+  const float xe = mul(mul(de, de), mul(0.5f, mul(p.ie, t.ie)));   // Ml/(e_p e_t) - 1
+  const float xa = mul(mul(da, da), mul(0.5f, mul(p.ia, t.ia)));
+  const float xb = mul(mul(db, db), mul(0.5f, mul(p.ib, t.ib)));
+  float q = add(xa, xb);
+  q = fma(xa, xb, q);
+  q = fma(mul(0.25f, eps), mul(p.iab, t.iab), q);
+  const float qq = fma(q, xe, add(q, xe));                         // (1+q)(1+xe) - 1
+  *rare |= !(qq >= 0.0f && qq < 1e30f);
+  const float shape = mul(0.5f, log1p_pos(qq));
+  float val = add(maha, shape);
+  if (P.flag) val = sqrt_clamp0(val);                              // ref:183-184
+  return post(val, P, rare);
+}
+// the FAST value of one pair of NICE boxes for every distance that has one
+template <int LOSS>
+GD_HD float value(const BoxGauss<float>& p, const BoxGauss<float>& t, const PairParams<float>& P,
+                  bool* rare) {
+  if constexpr (LOSS == kGwd) return gwd_value(p, t, P, rare);
+  else if constexpr (LOSS == kBd) return bd_value(p, t, P, rare);
+  else return kld_family_value<LOSS>(p, t, P, rare);
 }
 }  // namespace pw
 
 // losses whose pairwise FAST value is the explicit-rounding form above
 template <int LOSS>
-struct PairwiseExact { static constexpr bool value = (LOSS == kGwd); };
+struct PairwiseExact { static constexpr bool value = (LOSS != kKfiou); };   // kfiou3d: robust only
 
 // The robust value behind a call: ONE body per translation unit, the same machine code for
 // every kernel that reaches it (cold: degenerate boxes, tripped guards).
@@ -1220,7 +1415,7 @@ GD_HD T pair_value_fast(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairPa
                         bool* rare) {
   static_assert(PairwiseExact<LOSS>::value && std::is_same<T, float>::value,
                 "only the explicit-rounding value cores may be called outside pair_value_auto");
-  return pw::gwd_value(p, t, P, rare);
+  return pw::value<LOSS>(p, t, P, rare);
 }
 
 // value through the branch-free FAST cores when both boxes are nice and no guard
@@ -1230,7 +1425,7 @@ GD_HD T pair_value_auto(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairPa
   if constexpr (PairwiseExact<LOSS>::value && std::is_same<T, float>::value) {
     bool rare = !(p.nice && t.nice);
     if (!rare) {
-      const T v = pw::gwd_value(p, t, P, &rare);
+      const T v = pw::value<LOSS>(p, t, P, &rare);
       if (!rare) return v;
     }
     return pair_value_robust<LOSS>(p, t, P);
