@@ -1392,7 +1392,11 @@ GD_HD float value(const BoxGauss<float>& p, const BoxGauss<float>& t, const Pair
 
 // losses whose pairwise FAST value is the explicit-rounding form above
 template <int LOSS>
+#if defined(GD_PW_IMPLICIT)   // host experiments only: the templated cores with implicit contraction
+struct PairwiseExact { static constexpr bool value = false; };
+#else
 struct PairwiseExact { static constexpr bool value = (LOSS != kKfiou); };   // kfiou3d: robust only
+#endif
 
 // The robust value behind a call: ONE body per translation unit, the same machine code for
 // every kernel that reaches it (cold: degenerate boxes, tripped guards).

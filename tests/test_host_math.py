@@ -212,6 +212,45 @@ def test_pairwise_value_path(hostlib, lt):
         assert err.max() < tol, (dt, err.max())
 
 
+@pytest.mark.parametrize('lt', [x for x in LT if x != 'kfiou3d'])
+@pytest.mark.parametrize('fun,tau,flag', [('log1p', 1.0, 1), ('none', 0.0, 1), ('log1p', 0.0, 0),
+                                           ('none', 2.5, 0)])
+def test_pairwise_explicit_rounding_cores(hostlib, lt, fun, tau, flag):
+    """The pairwise FAST value cores with the rounding fixed in the source (gd::pw, what every
+    pairwise kernel evaluates for nice boxes) against the fp64 oracle: anchors vs ground truth at
+    Waymo scale, near-coincident boxes (values down to 1e-6: the ratio forms must not cancel) and
+    elongated crossing boxes, for both post maps and both settings of normalize / sqrt."""
+    b1, near, _ = synth.make_pairs(300, 'waymo', seed=12)
+    b2 = synth.make_targets(41, 'waymo', seed=13)
+    b2[:20] = b1[:20] + 1e-3 * torch.randn(20, 7, generator=torch.Generator().manual_seed(5))
+    b2[20:30] = near[:10]
+    b1[40:60, 3] = b1[40:60, 4] * 40.0                   # elongated, some at right angles
+    b2[30:35, 4] = b2[30:35, 3] * 25.0
+    kw = {('normalize' if lt == 'gwd3d' else 'sqrt'): bool(flag)}
+    ref = gd_oracle.pairwise_distance(b1.double(), b2.double(), lt, fun=fun, tau=tau, **kw).numpy()
+    a1 = np.ascontiguousarray(b1.numpy().astype(np.float32))
+    a2 = np.ascontiguousarray(b2.numpy().astype(np.float32))
+    # the oracle sees the float32-rounded inputs the kernel sees
+    ref = gd_oracle.pairwise_distance(torch.from_numpy(a1).double(), torch.from_numpy(a2).double(),
+                                      lt, fun=fun, tau=tau, **kw).numpy()
+    out = np.zeros((300, 41), np.float32)
+    hostlib.gd_host_pairwise_f32(
+        ctypes.c_int(LT.index(lt)), ctypes.c_long(300), ctypes.c_long(41),
+        a1.ctypes.data_as(ctypes.c_void_p), a2.ctypes.data_as(ctypes.c_void_p),
+        (ctypes.c_double * 3)(0, 0, 0.5), ctypes.c_double(1.0), ctypes.c_double(tau),
+        ctypes.c_int(FUN[fun]), ctypes.c_int(flag), out.ctypes.data_as(ctypes.c_void_p))
+    err = np.abs(out - ref) / np.maximum(np.abs(ref), 1e-3)
+    # Boxes that coincide to ~1e-3 (the diagonal of the first 20 x 20 block; values ~1e-3): the
+    # pairwise path takes sin(r_p - r_t) from per-box sines / cosines, whose ~1e-7 ABSOLUTE error
+    # is ~1e-4 of such a small angle -- 5e-5..7e-5 of the value there (the element-wise loss
+    # kernel forms the difference first and does not have this limit; an assigner never needs
+    # more than the order of such pairs).  Everything else: 1e-5.
+    coincident = np.zeros_like(err, dtype=bool)
+    coincident[np.arange(20), np.arange(20)] = True
+    assert err[~coincident].max() < 1e-5, (lt, fun, tau, flag, err[~coincident].max())
+    assert err[coincident].max() < 1.5e-4, (lt, fun, tau, flag, err[coincident].max())
+
+
 def test_packed_instantiation_is_bit_identical_on_host(tmp_path):
     """csrc/gd_packed.cuh (T = f2, two rows per 64-bit register; the GD_VARIANT_BULK_PACKED
     kernels, the default of 'auto' since round 2): on the host both halves use plain float
