@@ -1053,8 +1053,9 @@ GD_HD float fma(float a, float b, float c) {
 // same value cores as above.  sin/cos of the yaw difference come from the
 // angle-difference identities instead of a per-pair sincos.
 // ---------------------------------------------------------------------------
+// (16-byte aligned: the kernels read it from shared memory with 128-bit loads)
 template <typename T>
-struct BoxGauss {
+struct alignas(16) BoxGauss {
   T cx, cy, cz;     // centre incl. center_offset * unclamped extents   ref:12
   T a, b, e;        // clamped half extents                             ref:13-14,19-20
   T s, c;           // sin / cos yaw                                    ref:16-17
@@ -1427,11 +1428,11 @@ GD_HD T pair_value_fast(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairPa
 template <typename T, int LOSS>
 GD_HD T pair_value_auto(const BoxGauss<T>& p, const BoxGauss<T>& t, const PairParams<T>& P) {
   if constexpr (PairwiseExact<LOSS>::value && std::is_same<T, float>::value) {
+    // the FAST core runs unconditionally (straight-line; on boxes that are not nice its result
+    // is discarded): one cold branch per pair instead of two
     bool rare = !(p.nice && t.nice);
-    if (!rare) {
-      const T v = pw::value<LOSS>(p, t, P, &rare);
-      if (!rare) return v;
-    }
+    const T v = pw::value<LOSS>(p, t, P, &rare);
+    if (!rare) return v;
     return pair_value_robust<LOSS>(p, t, P);
   } else {
     const PairGeom<T> g = geom_from_gauss(p, t);
