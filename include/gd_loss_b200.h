@@ -256,8 +256,13 @@ enum {
   GD_PAIR_SIMILARITY = 1,  /* the optional matrix holds 1 - value ("larger is closer", the
                               iou_calculator convention of mmdet assigners); the minima
                               are always minima of the distance value                   */
-  GD_PAIR_CPL1 = 2         /* measurement / test aid: one column per lane (the round-1 mapping)
-                              instead of two; same per-pair arithmetic, bit-identical results */
+  GD_PAIR_CPL1 = 2         /* measurement / test aid: the column-lane kernel with one column per
+                              lane (the round-1 mapping) also where the row-lane kernel or two
+                              columns per lane would run; same per-pair arithmetic (explicitly
+                              rounded operations), bit-identical results                      */
+  ,
+  GD_PAIR_INDEX64 = 4      /* row_argmin / col_argmin point to int64 arrays (torch's index type:
+                              saves the caller two conversion launches)                       */
 };
 
 /* Bytes of device workspace gd_pairwise_assign needs for m columns.  Zero-filled ONCE

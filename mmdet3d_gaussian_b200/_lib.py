@@ -23,6 +23,7 @@ FLAG_MASK_ZERO_WEIGHT = 1
 ABI_VERSION = 3
 PAIR_SIMILARITY = 1
 PAIR_CPL1 = 2              # one column per lane (measurement / test aid)
+PAIR_INDEX64 = 4           # index outputs are int64 arrays
 GRAD_NONE, GRAD_COMPACT, GRAD_SCATTER, GRAD_DENSE = 0, 1, 2, 3
 
 

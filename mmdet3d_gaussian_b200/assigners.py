@@ -79,7 +79,7 @@ class GDMaxSimAssigner(nn.Module):
     @torch.no_grad()
     def assign(self, bboxes, gt_bboxes):
         row_min, row_arg, col_min, col_arg, _ = ops.pairwise_assign(
-            bboxes[..., :7], gt_bboxes[..., :7], self.cfg)
+            bboxes[..., :7], gt_bboxes[..., :7], self.cfg, index64=False)   # int32: fed straight back
         assigned, max_ov = ops.assign_from_minima(
             row_min, row_arg, col_min, col_arg, self.pos_iou_thr, self.neg_lo, self.neg_hi,
             self.min_pos_iou, self.match_low_quality)
@@ -87,7 +87,7 @@ class GDMaxSimAssigner(nn.Module):
             assigned.zero_()                   # mmdet: no GT -> everything is background
             max_ov.zero_()
         return dict(assigned_gt_inds=assigned, max_overlaps=max_ov,
-                    gt_max_overlaps=1.0 - col_min, gt_argmax_overlaps=col_arg)
+                    gt_max_overlaps=1.0 - col_min, gt_argmax_overlaps=col_arg.long())
 
     forward = assign
 

@@ -101,7 +101,8 @@ int gd_pairwise_assign(const gd_loss_config* cfg, const float* boxes1, int64_t n
                        float* col_min, int32_t* col_argmin, float* out, int64_t out_row_stride,
                        int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace gdk;
-  if (!config_ok(cfg) || n < 0 || m <= 0 || (flags & ~(GD_PAIR_SIMILARITY | GD_PAIR_CPL1)))
+  if (!config_ok(cfg) || n < 0 || m <= 0 ||
+      (flags & ~(GD_PAIR_SIMILARITY | GD_PAIR_CPL1 | GD_PAIR_INDEX64)))
     return GD_ERR_BAD_ARG;
   if (out && out_row_stride < m) return GD_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < gd_pairwise_workspace_bytes(m)) return GD_ERR_WORKSPACE;
@@ -117,6 +118,7 @@ int gd_pairwise_assign(const gd_loss_config* cfg, const float* boxes1, int64_t n
   a.out_stride = out ? out_row_stride : m;
   a.similarity = (flags & GD_PAIR_SIMILARITY) ? 1 : 0;
   a.force_cpl1 = (flags & GD_PAIR_CPL1) ? 1 : 0;
+  a.idx64 = (flags & GD_PAIR_INDEX64) ? 1 : 0;
   a.row_min = row_min;
   a.row_argmin = row_argmin;
   a.ticket = reinterpret_cast<unsigned int*>(workspace);

@@ -48,6 +48,7 @@ struct PairwiseArgs {
   long long out_stride;
   int similarity;                  // write 1 - value (assigners' "larger is closer")
   int force_cpl1;                  // GD_PAIR_CPL1: one column per lane
+  int idx64;                       // GD_PAIR_INDEX64: row_argmin / col_argmin are int64 arrays
   int tile_rows;                   // rows per tile of the column-lane kernel (0: kRowsPerCta);
                                    // the matrix launcher sizes it so the waves come out even
   float* row_min;                  // [n]   REDUCE only
@@ -59,6 +60,12 @@ struct PairwiseArgs {
   unsigned int* ticket;            // zero on entry and on exit
   gd::PairParams<float> pp;
 };
+
+// index outputs: int32 (the C ABI's default) or int64 (torch's index type, GD_PAIR_INDEX64)
+__device__ __forceinline__ void store_index(int* base, long long i, int v, int idx64) {
+  if (idx64) reinterpret_cast<long long*>(base)[i] = (long long)v;
+  else base[i] = v;
+}
 
 // order-preserving float -> uint32 (NaN -> 0: lowest)
 __device__ __forceinline__ unsigned int order_key(float v) {
@@ -255,7 +262,7 @@ __device__ __forceinline__ void pairwise_body(const PairwiseArgs& a) {
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
         a.row_min[row0 + tid] = key_value((unsigned int)(k >> 32));
-        a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
+        store_index(a.row_argmin, row0 + tid, (int)(unsigned int)(k & 0xffffffffu), a.idx64);
       }
     }
   }
@@ -278,7 +285,7 @@ __device__ __forceinline__ void pairwise_body(const PairwiseArgs& a) {
       for (long long j = tid; j < a.m; j += kThreads) {
         const unsigned long long k = ~__ldcg(a.col_keys + j);
         a.col_min[j] = key_value((unsigned int)(k >> 32));
-        a.col_argmin[j] = (int)(unsigned int)(k & 0xffffffffu);
+        store_index(a.col_argmin, j, (int)(unsigned int)(k & 0xffffffffu), a.idx64);
         a.col_keys[j] = 0ull;
       }
       if (tid == 0) *a.ticket = 0u;
@@ -507,7 +514,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
       const long long r = row0 + 32 * q + lane;
       if (live[q]) {
         a.row_min[r] = best[q];
-        a.row_argmin[r] = bj[q];
+        store_index(a.row_argmin, r, bj[q], a.idx64);
       }
     }
     __syncwarp();                                // atomics of the cold pass before lane 0 goes on
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(kThreads) gd_pairwise_rowlane_kernel(const Pai
       for (long long j = tid; j < a.m; j += kThreads) {
         const unsigned long long k = ~__ldcg(a.col_keys + j);
         a.col_min[j] = key_value((unsigned int)(k >> 32));
-        a.col_argmin[j] = (int)(unsigned int)(k & 0xffffffffu);
+        store_index(a.col_argmin, j, (int)(unsigned int)(k & 0xffffffffu), a.idx64);
         a.col_keys[j] = 0ull;
       }
       if (tid == 0) {

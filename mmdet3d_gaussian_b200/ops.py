@@ -215,35 +215,40 @@ def _pair_workspace(device, m):
     return ws
 
 
-def pairwise_assign(boxes1, boxes2, cfg, want_matrix=False, similarity=False, cpl1=False):
+def pairwise_assign(boxes1, boxes2, cfg, want_matrix=False, similarity=False, cpl1=False,
+                    index64=True):
     """Row and column minima / arg-minima of the pairwise distance matrix in one launch
     (``gd_pairwise_assign``); the matrix itself is written only when ``want_matrix``.
     Returns ``(row_min [N], row_argmin [N] int64, col_min [M], col_argmin [M] int64,
     matrix | None)``.  Indices are -1 / values +inf on an empty axis.  ``cpl1=True`` pins the
-    one-column-per-lane mapping (``GD_PAIR_CPL1``: same arithmetic, bit-identical results)."""
+    one-column-per-lane mapping (``GD_PAIR_CPL1``: same arithmetic, bit-identical results).
+    The kernel writes the indices as int64 itself (``GD_PAIR_INDEX64``); ``index64=False`` keeps
+    the C ABI's int32 (what ``assign_from_minima`` consumes: no conversion launch either way)."""
     b1, b2 = _boxes(boxes1, 'boxes1'), _boxes(boxes2, 'boxes2')
     n, m = b1.shape[0], b2.shape[0]
     dev = b1.device
     row_min = torch.empty((n,), dtype=torch.float32, device=dev)
-    row_idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    idt = torch.int64 if index64 else torch.int32
+    row_idx = torch.empty((n,), dtype=idt, device=dev)             # GD_PAIR_INDEX64: no conversion
     col_min = torch.empty((m,), dtype=torch.float32, device=dev)
-    col_idx = torch.empty((m,), dtype=torch.int32, device=dev)
+    col_idx = torch.empty((m,), dtype=idt, device=dev)
     mat = torch.empty((n, m), dtype=torch.float32, device=dev) if want_matrix else None
     if n == 0 or m == 0:
         row_min.fill_(float('inf'))
         col_min.fill_(float('inf'))
         row_idx.fill_(-1)
         col_idx.fill_(-1)
-        return row_min, row_idx.long(), col_min, col_idx.long(), mat
+        return row_min, row_idx, col_min, col_idx, mat
     ws = _pair_workspace(dev, m)
     with _on_device(dev):
         code = _lib.load().gd_pairwise_assign(
             ctypes.byref(cfg), _ptr(b1), n, _ptr(b2), m, _ptr(row_min), _ptr(row_idx),
             _ptr(col_min), _ptr(col_idx), _ptr(mat), m,
-            (_lib.PAIR_SIMILARITY if similarity else 0) | (_lib.PAIR_CPL1 if cpl1 else 0),
+            (_lib.PAIR_SIMILARITY if similarity else 0) | (_lib.PAIR_CPL1 if cpl1 else 0) |
+            (_lib.PAIR_INDEX64 if index64 else 0),
             _ptr(ws), ws.numel(), _stream_ptr())
     _lib.check(code, 'gd_pairwise_assign')
-    return row_min, row_idx.long(), col_min, col_idx.long(), mat
+    return row_min, row_idx, col_min, col_idx, mat
 
 
 def assign_from_minima(row_min, row_argmin, col_min, col_argmin, pos_thr, neg_lo, neg_hi,

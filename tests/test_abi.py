@@ -219,7 +219,7 @@ def test_pairwise_assign_argument_validation_without_gpu(lib):
     assert call(ctypes.byref(cfg), *ok, null, 256, 0, null, 0, null) == -2       # no workspace
     assert call(ctypes.byref(cfg), *ok, null, 256, 0, one, need - 1, null) == -2
     assert call(ctypes.byref(cfg), *ok, one, 255, 0, one, need, null) == -1      # stride < m
-    assert call(ctypes.byref(cfg), *ok, null, 256, 4, one, need, null) == -1     # unknown flag
+    assert call(ctypes.byref(cfg), *ok, null, 256, 8, one, need, null) == -1     # unknown flag
     assert call(ctypes.byref(cfg), one, 8, one, 0, one, one, one, one, null, 0, 0, one, need,
                 null) == -1                                                       # m == 0
     assert call(ctypes.byref(cfg), one, 8, one, 256, one, one, null, one, null, 256, 0, one,

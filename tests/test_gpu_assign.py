@@ -73,6 +73,10 @@ def test_fused_minima_equal_matrix_minima(loss_type, n, m):
     # legacy entry point
     v0, i0 = mod.row_argmin(b1, b2)
     assert same_bits(v0, rmin) and torch.equal(i0, ridx)
+    # int32 index outputs (the C ABI's default) == the int64 ones the kernel writes for torch
+    r32 = ops.pairwise_assign(b1, b2, mod.cfg, index64=False)
+    assert r32[1].dtype == torch.int32 and ridx.dtype == torch.int64
+    assert torch.equal(r32[1].long(), ridx) and torch.equal(r32[3].long(), cidx) and same_bits(r32[0], rmin)
 
 
 def test_nan_and_degenerate_boxes_in_reductions():
