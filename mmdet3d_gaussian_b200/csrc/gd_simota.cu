@@ -117,38 +117,60 @@ __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const Pai
   }
 }
 
-// one warp per column: K smallest of the slots x K candidates (each slot's list is sorted, but
-// the merge does not rely on it)
-__global__ void __launch_bounds__(128) gd_topk_merge_kernel(const unsigned long long* __restrict__ cand,
-                                                            long long slots, long long m, int k,
-                                                            float* __restrict__ topk_val,
-                                                            int* __restrict__ topk_row) {
-  const int lane = threadIdx.x & 31;
-  const long long j = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (j >= m) return;                          // whole warp
+// Merge of the per-slot candidate lists, coalesced and in two stages.  Lane <-> column (a warp
+// reads 32 consecutive columns of one list entry: 256 contiguous bytes), the 8 warps of a CTA
+// and the gridDim.y CTA groups split the slots; every slot list is sorted ascending, so a lane
+// stops walking a list at the first entry that cannot enter its own.  The warps' lists meet in
+// shared memory and warp 0 merges them; with `cand_out` the CTA writes its K-list in the input
+// layout ([gridDim.y][K][m]: stage A, many CTAs), without it the final values / rows (stage B).
+// (Round 2 ran one warp per column over strided 8-byte loads: 256 warps, ~0.15 ms at C4.)
+constexpr int kMergeGroups = 16;
+__global__ void __launch_bounds__(kThreads) gd_topk_merge_kernel(
+    const unsigned long long* __restrict__ cand, long long slots, long long m, int k,
+    unsigned long long* __restrict__ cand_out, float* __restrict__ topk_val,
+    int* __restrict__ topk_row) {
+  __shared__ unsigned long long s_list[kWarps][kTopK][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long j = (long long)blockIdx.x * 32 + lane;
+  const bool live = j < m;
   unsigned long long best[kTopK];
 #pragma unroll
   for (int i = 0; i < kTopK; ++i) best[i] = ~0ull;
-  const long long total = slots * kTopK;
-  for (long long c = lane; c < total; c += 32) {
-    const unsigned long long x = __ldcs(cand + c * m + j);
-    if (x < best[kTopK - 1]) topk_insert<kTopK>(best, x);
+  if (live) {
+    for (long long s = (long long)blockIdx.y * kWarps + warp; s < slots;
+         s += (long long)gridDim.y * kWarps) {
+      const unsigned long long* list = cand + s * kTopK * m + j;
+      for (int i = 0; i < kTopK; ++i) {
+        const unsigned long long x = __ldcs(list + (long long)i * m);
+        if (!(x < best[kTopK - 1])) break;     // sorted list: nothing further can enter
+        topk_insert<kTopK>(best, x);
+      }
+    }
   }
-  for (int i = 0; i < k; ++i) {
-    unsigned long long head = best[0];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, head, o);
-      head = other < head ? other : head;
+  for (int i = 0; i < kTopK; ++i) s_list[warp][i][lane] = best[i];
+  __syncthreads();
+  if (warp != 0 || !live) return;
+  for (int w = 1; w < kWarps; ++w) {
+    for (int i = 0; i < kTopK; ++i) {
+      const unsigned long long x = s_list[w][i][lane];
+      if (!(x < best[kTopK - 1])) break;
+      topk_insert<kTopK>(best, x);
     }
-    if (best[0] == head && head != ~0ull) {    // the owner pops (keys are unique: one row, one slot)
+  }
+  if (cand_out != nullptr) {
 #pragma unroll
-      for (int q = 0; q + 1 < kTopK; ++q) best[q] = best[q + 1];
-      best[kTopK - 1] = ~0ull;
-    }
-    if (lane == 0) {
+    for (int i = 0; i < kTopK; ++i)
+      cand_out[((long long)blockIdx.y * kTopK + i) * m + j] = best[i];
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < kTopK; ++i) {
+    if (i < k) {
+      const unsigned long long head = best[i];
       const bool none = head == ~0ull;
-      topk_val[(long long)i * m + j] = none ? __uint_as_float(0x7f800000u) : key_value((unsigned int)(head >> 32));
+      topk_val[(long long)i * m + j] =
+          none ? __uint_as_float(0x7f800000u) : key_value((unsigned int)(head >> 32));
       topk_row[(long long)i * m + j] = none ? -1 : (int)(unsigned int)(head & 0xffffffffu);
     }
   }
@@ -224,7 +246,7 @@ extern "C" {
 size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m) {
   using namespace gdk;
   if (n < 0 || m < 0) return 0;
-  const long long slots = topk_grid(n) * kWarps;                   // wy <= kWarps row phases
+  const long long slots = topk_grid(n) * kWarps + kMergeGroups;     // wy <= kWarps row phases; + stage A
   return 256 + sizeof(unsigned long long) * (size_t)(slots * kTopK * (m > 0 ? m : 0));
 }
 
@@ -270,9 +292,20 @@ int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t
     }
     if (rc != 0) return rc;
   }
-  gd_topk_merge_kernel<<<(unsigned)((m + 3) / 4), 128, 0, st>>>(tk.cand, tk.slots, m, k, topk_val,
-                                                                topk_row);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const unsigned mx = (unsigned)((m + 31) / 32);
+  if (tk.slots > 2 * kWarps) {
+    // stage A: kMergeGroups CTA groups reduce the slots to kMergeGroups lists behind the inputs
+    unsigned long long* mid = tk.cand + tk.slots * kTopK * m;
+    gd_topk_merge_kernel<<<dim3(mx, kMergeGroups), kThreads, 0, st>>>(tk.cand, tk.slots, m, k, mid,
+                                                                     nullptr, nullptr);
+    gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(mid, kMergeGroups, m, k, nullptr, topk_val,
+                                                          topk_row);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+  } else {
+    gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(tk.cand, tk.slots, m, k, nullptr, topk_val,
+                                                          topk_row);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   return (int)cudaGetLastError();
 }
 
