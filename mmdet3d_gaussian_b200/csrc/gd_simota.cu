@@ -30,6 +30,12 @@ constexpr int kTopK = 16;                    // list depth kept per column (cand
 struct TopkArgs {
   unsigned long long* cand;                  // [slots][kTopK][m] scratch
   long long slots;
+  // Sample pass (row_step > 1): the kernel sees rows 0, row_step, 2 row_step, ... (a.n of them)
+  // and writes no row minima.  Main pass: thr[j] (nullable) = the k-th smallest (key, row) of
+  // column j over the sample -- an upper bound of the k-th smallest over all rows, so only
+  // candidates <= thr[j] can belong to the final top k and only they are inserted.
+  long long row_step;
+  const unsigned long long* thr;
 };
 
 // sorted insert of x into the ascending list best[0..K): branch-free bubble
@@ -66,13 +72,20 @@ __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const Pai
     unsigned long long best[kTopK];
 #pragma unroll
     for (int i = 0; i < kTopK; ++i) best[i] = ~0ull;
+    // insert limit: strictly below it a candidate may still belong to the top k
+    unsigned long long cap = ~0ull;
+    if (tk.thr != nullptr && live) {
+      const unsigned long long t = tk.thr[j];
+      cap = t == ~0ull ? t : t + 1;
+    }
+    unsigned long long lim = cap;
     gd::BoxGauss<float> t;
     if (warp_live) t = gd::box_gauss(a.b2 + (live ? j : 0) * 7, pp);   // dead lanes: any valid box
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = tile * kRowsPerCta;
       const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
       __syncthreads();                         // previous tile fully consumed
-      if (tid < rows) s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
+      if (tid < rows) s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * tk.row_step * 7, pp);
       for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads) (&s_best[0][0])[i] = ~0ull;
       __syncthreads();
       if (warp_live) {
@@ -87,8 +100,11 @@ __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const Pai
                               (unsigned int)(c0 + 32LL * cgrp + (__ffs(who) - 1));
           if (live) {
             const unsigned long long k64 =
-                ((unsigned long long)key << 32) | (unsigned int)(row0 + r);
-            if (k64 < best[kTopK - 1]) topk_insert<kTopK>(best, k64);
+                ((unsigned long long)key << 32) | (unsigned int)((row0 + r) * tk.row_step);
+            if (k64 < lim) {
+              topk_insert<kTopK>(best, k64);
+              lim = best[kTopK - 1] < cap ? best[kTopK - 1] : cap;
+            }
           }
         }
       }
@@ -96,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const Pai
       // walked in ascending column order by every CTA, so "strictly smaller wins" keeps the
       // lowest column on ties)
       __syncthreads();
-      if (tid < rows) {
+      if (tid < rows && a.row_min != nullptr) {
         unsigned long long k = s_best[tid][0];
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
@@ -128,7 +144,7 @@ constexpr int kMergeGroups = 16;
 __global__ void __launch_bounds__(kThreads) gd_topk_merge_kernel(
     const unsigned long long* __restrict__ cand, long long slots, long long m, int k,
     unsigned long long* __restrict__ cand_out, float* __restrict__ topk_val,
-    int* __restrict__ topk_row) {
+    int* __restrict__ topk_row, unsigned long long* __restrict__ thr_out) {
   __shared__ unsigned long long s_list[kWarps][kTopK][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long j = (long long)blockIdx.x * 32 + lane;
@@ -140,10 +156,13 @@ __global__ void __launch_bounds__(kThreads) gd_topk_merge_kernel(
     for (long long s = (long long)blockIdx.y * kWarps + warp; s < slots;
          s += (long long)gridDim.y * kWarps) {
       const unsigned long long* list = cand + s * kTopK * m + j;
+      // the whole list in flight at once (an early exit would serialise 16 DRAM latencies)
+      unsigned long long x[kTopK];
+#pragma unroll
+      for (int i = 0; i < kTopK; ++i) x[i] = __ldcs(list + (long long)i * m);
+#pragma unroll
       for (int i = 0; i < kTopK; ++i) {
-        const unsigned long long x = __ldcs(list + (long long)i * m);
-        if (!(x < best[kTopK - 1])) break;     // sorted list: nothing further can enter
-        topk_insert<kTopK>(best, x);
+        if (x[i] < best[kTopK - 1]) topk_insert<kTopK>(best, x[i]);   // sorted: later ones fail too
       }
     }
   }
@@ -162,6 +181,14 @@ __global__ void __launch_bounds__(kThreads) gd_topk_merge_kernel(
 #pragma unroll
     for (int i = 0; i < kTopK; ++i)
       cand_out[((long long)blockIdx.y * kTopK + i) * m + j] = best[i];
+    return;
+  }
+  if (thr_out != nullptr) {                    // sample pass: only the k-th key is wanted
+    unsigned long long t = ~0ull;
+#pragma unroll
+    for (int i = 0; i < kTopK; ++i)
+      if (i == k - 1) t = best[i];
+    thr_out[j] = t;
     return;
   }
 #pragma unroll
@@ -232,6 +259,9 @@ static int launch_topk(const PairwiseArgs& a, const TopkArgs& tk, long long gx, 
   return (int)cudaGetLastError();
 }
 
+constexpr long long kSampleRows = 2048;      // rows of the threshold sample (strided over all rows)
+constexpr long long kSampleMinRows = 16 * kSampleRows;   // smaller inputs: no sample pass
+
 static long long topk_grid(long long n) {
   const long long ntiles = (n + kRowsPerCta - 1) / kRowsPerCta;
   long long gx = (long long)device_info().sm_count * 3;            // persistent: bounds the scratch
@@ -246,7 +276,8 @@ extern "C" {
 size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m) {
   using namespace gdk;
   if (n < 0 || m < 0) return 0;
-  const long long slots = topk_grid(n) * kWarps + kMergeGroups;     // wy <= kWarps row phases; + stage A
+  // main lists (wy <= kWarps row phases) + stage-A lists + the sample pass's lists + thresholds
+  const long long slots = topk_grid(n) * kWarps + kMergeGroups + topk_grid(kSampleRows) * kWarps + 1;
   return 256 + sizeof(unsigned long long) * (size_t)(slots * kTopK * (m > 0 ? m : 0));
 }
 
@@ -273,39 +304,72 @@ int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t
   a.row_min = row_min;
   a.row_argmin = row_argmin;
   a.pp = make_pair_params(*cfg);
-  TopkArgs tk;
-  tk.cand = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  unsigned long long* ws64 =
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + 256);
   const long long gx = topk_grid(n);
   const int wy = kWarps / pairwise_wx(m, 32);
+  TopkArgs tk;
+  tk.cand = ws64;
   tk.slots = n > 0 ? gx * wy : 0;
-  int rc = 0;
-  if (n > 0) {
+  tk.row_step = 1;
+  tk.thr = nullptr;
+  unsigned long long* mid = tk.cand + (long long)topk_grid(n) * kWarps * kTopK * m;   // stage-A lists
+  const unsigned mx = (unsigned)((m + 31) / 32);
+  auto launch = [&](const PairwiseArgs& pa, const TopkArgs& pt, long long grid) -> int {
     switch (cfg->loss_type) {
-      case GD_LOSS_GWD3D: rc = launch_topk<gd::kGwd>(a, tk, gx, st); break;
-      case GD_LOSS_KLD3D: rc = launch_topk<gd::kKld>(a, tk, gx, st); break;
-      case GD_LOSS_JD3D: rc = launch_topk<gd::kJd>(a, tk, gx, st); break;
-      case GD_LOSS_KLD3D_SYMMAX: rc = launch_topk<gd::kSymMax>(a, tk, gx, st); break;
-      case GD_LOSS_KLD3D_SYMMIN: rc = launch_topk<gd::kSymMin>(a, tk, gx, st); break;
-      case GD_LOSS_BD3D: rc = launch_topk<gd::kBd>(a, tk, gx, st); break;
-      case GD_LOSS_KFIOU3D: rc = launch_topk<gd::kKfiou>(a, tk, gx, st); break;
-      default: return GD_ERR_BAD_ARG;
+      case GD_LOSS_GWD3D: return launch_topk<gd::kGwd>(pa, pt, grid, st);
+      case GD_LOSS_KLD3D: return launch_topk<gd::kKld>(pa, pt, grid, st);
+      case GD_LOSS_JD3D: return launch_topk<gd::kJd>(pa, pt, grid, st);
+      case GD_LOSS_KLD3D_SYMMAX: return launch_topk<gd::kSymMax>(pa, pt, grid, st);
+      case GD_LOSS_KLD3D_SYMMIN: return launch_topk<gd::kSymMin>(pa, pt, grid, st);
+      case GD_LOSS_BD3D: return launch_topk<gd::kBd>(pa, pt, grid, st);
+      case GD_LOSS_KFIOU3D: return launch_topk<gd::kKfiou>(pa, pt, grid, st);
     }
+    return GD_ERR_BAD_ARG;
+  };
+  // merge of `slots` lists at `lists`: two coalesced stages when there are many
+  auto merge = [&](const unsigned long long* lists, long long slots, float* val, int* row,
+                   unsigned long long* thr_out) {
+    if (slots > 2 * kWarps) {
+      gd_topk_merge_kernel<<<dim3(mx, kMergeGroups), kThreads, 0, st>>>(lists, slots, m, k, mid,
+                                                                       nullptr, nullptr, nullptr);
+      gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(mid, kMergeGroups, m, k, nullptr, val,
+                                                            row, thr_out);
+      g_launches.fetch_add(2, std::memory_order_relaxed);
+    } else {
+      gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(lists, slots, m, k, nullptr, val, row,
+                                                            thr_out);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  };
+  int rc = 0;
+  if (n >= kSampleMinRows) {
+    // Threshold pass.  The row tiles of the main pass are spread over ~450 CTAs, each with its own
+    // K-deep list per column: without a bound every list accepts ~K ln(rows / K) candidates and
+    // nearly every warp iteration runs the sorted insert (0.49 ms at C4).  The k-th smallest key of
+    // a 2048-row strided sample bounds the k-th smallest of the column from above, and with it
+    // as the insert limit a list accepts a handful.
+    PairwiseArgs sa = a;
+    TopkArgs sk = tk;
+    sa.n = kSampleRows;
+    sa.out = nullptr;
+    sa.row_min = nullptr;
+    sa.row_argmin = nullptr;
+    sk.row_step = n / kSampleRows;
+    sk.cand = mid + (long long)kMergeGroups * kTopK * m;
+    const long long sgx = topk_grid(kSampleRows);
+    sk.slots = sgx * wy;
+    unsigned long long* thr = sk.cand + (long long)topk_grid(kSampleRows) * kWarps * kTopK * m;
+    rc = launch(sa, sk, sgx);
+    if (rc != 0) return rc;
+    merge(sk.cand, sk.slots, nullptr, nullptr, thr);
+    tk.thr = thr;
+  }
+  if (n > 0) {
+    rc = launch(a, tk, gx);
     if (rc != 0) return rc;
   }
-  const unsigned mx = (unsigned)((m + 31) / 32);
-  if (tk.slots > 2 * kWarps) {
-    // stage A: kMergeGroups CTA groups reduce the slots to kMergeGroups lists behind the inputs
-    unsigned long long* mid = tk.cand + tk.slots * kTopK * m;
-    gd_topk_merge_kernel<<<dim3(mx, kMergeGroups), kThreads, 0, st>>>(tk.cand, tk.slots, m, k, mid,
-                                                                     nullptr, nullptr);
-    gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(mid, kMergeGroups, m, k, nullptr, topk_val,
-                                                          topk_row);
-    g_launches.fetch_add(2, std::memory_order_relaxed);
-  } else {
-    gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(tk.cand, tk.slots, m, k, nullptr, topk_val,
-                                                          topk_row);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-  }
+  merge(tk.cand, tk.slots, topk_val, topk_row, nullptr);
   return (int)cudaGetLastError();
 }
 
