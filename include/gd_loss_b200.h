@@ -308,9 +308,12 @@ GD_API int gd_assign_from_minima(const float* row_min, const int32_t* row_argmin
  * n < k) -- what ref:187-188 `torch.topk(pairwise_ious, candidate_topk, dim=0)` and the per-GT
  * `torch.topk(cost[:, gt], k=dynamic_k, largest=False)` of ref:192-193 read -- plus the row
  * (min, argmin) that the conflict rule ref:198-203 needs.  `out` (nullable, row stride in
- * elements) additionally receives the matrix from the same instruction sequence, so lists and
- * matrix of one launch are bit-consistent (tests).  Workspace: scratch, no zeroing needed,
- * gd_pairwise_topk_workspace_bytes(n, m) bytes. */
+ * elements) additionally receives the matrix.  Row minima, matrix and column lists come from
+ * separate launches (row-lane kernel; matrix kernel; threshold sample + filter + per-column
+ * selection) that evaluate a pair with the same explicitly rounded operations, so they are
+ * reductions of one and the same matrix bit for bit (tests).  Exact for any input: a column
+ * whose candidate buffer overflows (masses of equal values) is recomputed by brute force.
+ * Workspace: scratch, no zeroing needed, gd_pairwise_topk_workspace_bytes(n, m) bytes. */
 GD_API size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m);
 GD_API int gd_pairwise_col_topk(const gd_loss_config* cfg,
                                 const float* boxes1, int64_t n,

@@ -10,32 +10,52 @@
 //     a row matched by several GTs keeps argmin_j cost[row, j]          ref:198-203
 // With the Gaussian similarity s = 1 - D (D in [0, 1) for tau >= 1) in the role of the IoU and
 // the cost monotone in D, everything the matching reads lives in (a) the candidate_topk
-// smallest D of every COLUMN and (b) the (min, argmin) of every ROW.  Both are reductions of
-// the pairwise kernel's value stream:
-//   gd_pairwise_topk_kernel  -- the pairwise value loop (lane <-> column box in registers, row
-//                               Gaussians broadcast from shared memory) with a K-deep sorted
-//                               list of (value key, row) per lane and the row minima of the
-//                               assign kernel; lists of all CTAs / row phases go to a scratch
-//   gd_topk_merge_kernel     -- one warp per column merges the scratch lists
+// smallest D of every COLUMN and (b) the (min, argmin) of every ROW.
+//
+// Every pairwise kernel computes a pair with the same explicitly rounded operations
+// (gd_math.cuh, namespace pw), so the pieces may come from DIFFERENT launches and still be the
+// reductions of one and the same matrix:
+//   (b) row minima           -- the row-lane kernel of gd_pairwise.cuh (launch_pairwise)
+//   (a) column top-k, three small steps:
+//       gd_topk_select_kernel, sample mode -- thr[j] = the k-th smallest (key, row) of column j
+//           over a 2048-row strided sample: an upper bound of the k-th smallest over all rows
+//       gd_topk_filter_kernel -- one lean pass over all pairs (lane <-> column box in registers,
+//           row Gaussians broadcast from shared memory); a pair with (key, row) <= thr[j] is
+//           appended to column j's candidate buffer (~k N / 2048 per column: 0.5 % of the pairs)
+//       gd_topk_select_kernel, buffer mode -- one CTA per column extracts the k smallest
+//           candidates in order; a column whose buffer overflowed (masses of equal values) is
+//           recomputed by brute force over all rows, so the result is exact for any input
 //   gd_simota_cols_kernel / gd_simota_rows_kernel -- dynamic k, matching, conflict rule
-// Keys are the pairwise kernel's: order-preserving 32-bit value key (NaN lowest) in the high
-// word, row index in the low word -- ties go to the lowest row, deterministically (torch.topk
-// leaves tie order unspecified).
+// (Round 2 kept a 16-deep sorted list per lane and CTA inside one fused value loop: 444 lists
+// per column, nearly every warp iteration ran a sorted insert -- 0.49 ms + 0.1 ms of merging at
+// C4 against 0.12 ms for the bare value loop.)
+// Keys: order-preserving 32-bit value key (NaN lowest) in the high word, row index in the low
+// word -- ties go to the lowest row, deterministically (torch.topk leaves tie order unspecified).
 #include "gd_pairwise.cuh"
 
 namespace gdk {
 
-constexpr int kTopK = 16;                    // list depth kept per column (candidate_topk <= 16)
+extern template int launch_pairwise<gd::kGwd>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kKld>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kJd>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kSymMax>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kSymMin>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kBd>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_pairwise<gd::kKfiou>(const PairwiseArgs&, cudaStream_t);
+
+constexpr int kTopK = 16;                    // candidate_topk <= 16
+constexpr long long kSampleRows = 2048;      // rows of the threshold sample (strided over all rows)
+constexpr int kCandCap = 4096;               // candidate slots per column (~k N / 2048 expected)
 
 struct TopkArgs {
-  unsigned long long* cand;                  // [slots][kTopK][m] scratch
-  long long slots;
-  // Sample pass (row_step > 1): the kernel sees rows 0, row_step, 2 row_step, ... (a.n of them)
-  // and writes no row minima.  Main pass: thr[j] (nullable) = the k-th smallest (key, row) of
-  // column j over the sample -- an upper bound of the k-th smallest over all rows, so only
-  // candidates <= thr[j] can belong to the final top k and only they are inserted.
-  long long row_step;
-  const unsigned long long* thr;
+  const unsigned long long* thr;             // [m] insert limit per column (filter pass)
+  unsigned long long* thr_out;               // [m] sample mode: k-th key of the sample
+  unsigned int* count;                       // [m] candidates appended so far (zeroed by the host)
+  unsigned long long* cand;                  // [m][kCandCap]
+  long long row_step, nrows;                 // brute force: rows 0, step, 2 step, ... (nrows of them)
+  int k;
+  float* topk_val;                           // [k][m]
+  int* topk_row;                             // [k][m]
 };
 
 // sorted insert of x into the ascending list best[0..K): branch-free bubble
@@ -49,11 +69,11 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsig
   }
 }
 
+// One pass over all pairs; (key, row) <= thr[column] goes to the column's candidate buffer.
 template <int LOSS>
-__global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const PairwiseArgs a,
-                                                                       const TopkArgs tk) {
+__global__ void __launch_bounds__(kThreads) gd_topk_filter_kernel(const PairwiseArgs a,
+                                                                  const TopkArgs tk) {
   __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
-  __shared__ unsigned long long s_best[kRowsPerCta][kWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   gd::PairParams<float> pp = a.pp;
   pp.lean = 1;
@@ -62,145 +82,94 @@ __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_topk_kernel(const Pai
   const int cgrp = warp % wx, ry = warp / wx;
   const long long chunk = 32LL * wx;
   const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
-  const long long slot = (long long)blockIdx.x * wy + ry;
-
-  // columns outer (each lane's list lives across all row tiles of this CTA), tiles inner
   for (long long c0 = 0; c0 < a.m; c0 += chunk) {
     const long long j = c0 + 32LL * cgrp + lane;
     const bool warp_live = c0 + 32LL * cgrp < a.m;
     const bool live = j < a.m;
-    unsigned long long best[kTopK];
-#pragma unroll
-    for (int i = 0; i < kTopK; ++i) best[i] = ~0ull;
-    // insert limit: strictly below it a candidate may still belong to the top k
-    unsigned long long cap = ~0ull;
-    if (tk.thr != nullptr && live) {
-      const unsigned long long t = tk.thr[j];
-      cap = t == ~0ull ? t : t + 1;
-    }
-    unsigned long long lim = cap;
     gd::BoxGauss<float> t;
-    if (warp_live) t = gd::box_gauss(a.b2 + (live ? j : 0) * 7, pp);   // dead lanes: any valid box
+    unsigned long long lim = 0ull;             // dead lanes: nothing passes
+    if (warp_live) t = gd::box_gauss(a.b2 + (live ? j : 0) * 7, pp);
+    if (live) lim = tk.thr[j];
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = tile * kRowsPerCta;
       const int rows = (int)min((long long)kRowsPerCta, a.n - row0);
       __syncthreads();                         // previous tile fully consumed
-      if (tid < rows) s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * tk.row_step * 7, pp);
-      for (int i = tid; i < kRowsPerCta * kWarps; i += kThreads) (&s_best[0][0])[i] = ~0ull;
+      if (tid < rows) s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
       __syncthreads();
-      if (warp_live) {
-        for (int r = ry; r < rows; r += wy) {
-          const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t, pp);
-          if (a.out != nullptr && live) __stcs(a.out + (row0 + r) * a.out_stride + j, v);
-          const unsigned int key = live ? order_key(v) : 0xffffffffu;
-          const unsigned int mn = __reduce_min_sync(0xffffffffu, key);
-          const unsigned int who = __ballot_sync(0xffffffffu, key == mn);
-          if (lane == 0 && mn != 0xffffffffu)
-            s_best[r][warp] = ((unsigned long long)mn << 32) |
-                              (unsigned int)(c0 + 32LL * cgrp + (__ffs(who) - 1));
-          if (live) {
-            const unsigned long long k64 =
-                ((unsigned long long)key << 32) | (unsigned int)((row0 + r) * tk.row_step);
-            if (k64 < lim) {
-              topk_insert<kTopK>(best, k64);
-              lim = best[kTopK - 1] < cap ? best[kTopK - 1] : cap;
-            }
-          }
+      if (!warp_live) continue;
+#pragma unroll 2
+      for (int r = ry; r < rows; r += wy) {
+        const float v = gd::pair_value_auto<float, LOSS>(s_rows[r], t, pp);
+        const unsigned long long k64 =
+            ((unsigned long long)order_key(v) << 32) | (unsigned int)(row0 + r);
+        if (live && k64 <= lim) {
+          const unsigned int pos = atomicAdd(tk.count + j, 1u);
+          if (pos < (unsigned int)kCandCap) tk.cand[j * kCandCap + pos] = k64;
         }
       }
-      // row minima of this tile over this chunk of columns, merged into the outputs (chunks are
-      // walked in ascending column order by every CTA, so "strictly smaller wins" keeps the
-      // lowest column on ties)
-      __syncthreads();
-      if (tid < rows && a.row_min != nullptr) {
-        unsigned long long k = s_best[tid][0];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) k = s_best[tid][w] < k ? s_best[tid][w] : k;
-        const unsigned int key = (unsigned int)(k >> 32);
-        if (c0 == 0) {
-          a.row_min[row0 + tid] = key_value(key);
-          a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
-        } else if (k != ~0ull && key < order_key(a.row_min[row0 + tid])) {
-          a.row_min[row0 + tid] = key_value(key);
-          a.row_argmin[row0 + tid] = (int)(unsigned int)(k & 0xffffffffu);
-        }
-      }
-    }
-    if (live) {
-#pragma unroll
-      for (int i = 0; i < kTopK; ++i) tk.cand[(slot * kTopK + i) * a.m + j] = best[i];
     }
   }
 }
 
-// Merge of the per-slot candidate lists, coalesced and in two stages.  Lane <-> column (a warp
-// reads 32 consecutive columns of one list entry: 256 contiguous bytes), the 8 warps of a CTA
-// and the gridDim.y CTA groups split the slots; every slot list is sorted ascending, so a lane
-// stops walking a list at the first entry that cannot enter its own.  The warps' lists meet in
-// shared memory and warp 0 merges them; with `cand_out` the CTA writes its K-list in the input
-// layout ([gridDim.y][K][m]: stage A, many CTAs), without it the final values / rows (stage B).
-// (Round 2 ran one warp per column over strided 8-byte loads: 256 warps, ~0.15 ms at C4.)
-constexpr int kMergeGroups = 16;
-__global__ void __launch_bounds__(kThreads) gd_topk_merge_kernel(
-    const unsigned long long* __restrict__ cand, long long slots, long long m, int k,
-    unsigned long long* __restrict__ cand_out, float* __restrict__ topk_val,
-    int* __restrict__ topk_row, unsigned long long* __restrict__ thr_out) {
-  __shared__ unsigned long long s_list[kWarps][kTopK][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long j = (long long)blockIdx.x * 32 + lane;
-  const bool live = j < m;
+// One CTA per column.  Buffer mode (tk.cand): the k smallest of the column's candidates; when the
+// buffer overflowed, or in sample mode (tk.thr_out), the column is evaluated by brute force over
+// rows 0, row_step, ... -- every thread keeps a sorted K-list of its rows.  Then k rounds of
+// "smallest head of all lists" (keys are unique), written in ascending order.
+template <int LOSS>
+__global__ void __launch_bounds__(kThreads) gd_topk_select_kernel(const PairwiseArgs a,
+                                                                  const TopkArgs tk) {
+  __shared__ unsigned long long s_min[kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long j = blockIdx.x;
   unsigned long long best[kTopK];
 #pragma unroll
   for (int i = 0; i < kTopK; ++i) best[i] = ~0ull;
-  if (live) {
-    for (long long s = (long long)blockIdx.y * kWarps + warp; s < slots;
-         s += (long long)gridDim.y * kWarps) {
-      const unsigned long long* list = cand + s * kTopK * m + j;
-      // the whole list in flight at once (an early exit would serialise 16 DRAM latencies)
-      unsigned long long x[kTopK];
-#pragma unroll
-      for (int i = 0; i < kTopK; ++i) x[i] = __ldcs(list + (long long)i * m);
-#pragma unroll
-      for (int i = 0; i < kTopK; ++i) {
-        if (x[i] < best[kTopK - 1]) topk_insert<kTopK>(best, x[i]);   // sorted: later ones fail too
-      }
+  const unsigned int cnt = tk.cand != nullptr ? tk.count[j] : 0u;
+  if (tk.cand != nullptr && cnt <= (unsigned int)kCandCap) {
+    for (unsigned int i = tid; i < cnt; i += kThreads) {
+      const unsigned long long x = tk.cand[j * kCandCap + i];
+      if (x < best[kTopK - 1]) topk_insert<kTopK>(best, x);
+    }
+  } else {
+    gd::PairParams<float> pp = a.pp;
+    pp.lean = 1;
+    const gd::BoxGauss<float> t = gd::box_gauss(a.b2 + j * 7, pp);
+    for (long long i = tid; i < tk.nrows; i += kThreads) {
+      const long long r = i * tk.row_step;
+      const gd::BoxGauss<float> p = gd::box_gauss(a.b1 + r * 7, pp);
+      const float v = gd::pair_value_auto<float, LOSS>(p, t, pp);
+      const unsigned long long x = ((unsigned long long)order_key(v) << 32) | (unsigned int)r;
+      if (x < best[kTopK - 1]) topk_insert<kTopK>(best, x);
     }
   }
+  unsigned long long kth = ~0ull;
+  for (int i = 0; i < tk.k; ++i) {
+    unsigned long long head = best[0];
 #pragma unroll
-  for (int i = 0; i < kTopK; ++i) s_list[warp][i][lane] = best[i];
-  __syncthreads();
-  if (warp != 0 || !live) return;
-  for (int w = 1; w < kWarps; ++w) {
-    for (int i = 0; i < kTopK; ++i) {
-      const unsigned long long x = s_list[w][i][lane];
-      if (!(x < best[kTopK - 1])) break;
-      topk_insert<kTopK>(best, x);
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, head, o);
+      head = other < head ? other : head;
     }
-  }
-  if (cand_out != nullptr) {
+    __syncthreads();                           // s_min of the previous round consumed
+    if (lane == 0) s_min[warp] = head;
+    __syncthreads();
+    head = s_min[0];
 #pragma unroll
-    for (int i = 0; i < kTopK; ++i)
-      cand_out[((long long)blockIdx.y * kTopK + i) * m + j] = best[i];
-    return;
-  }
-  if (thr_out != nullptr) {                    // sample pass: only the k-th key is wanted
-    unsigned long long t = ~0ull;
+    for (int w = 1; w < kWarps; ++w) head = s_min[w] < head ? s_min[w] : head;
+    if (best[0] == head && head != ~0ull) {    // the owner pops (keys are unique)
 #pragma unroll
-    for (int i = 0; i < kTopK; ++i)
-      if (i == k - 1) t = best[i];
-    thr_out[j] = t;
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < kTopK; ++i) {
-    if (i < k) {
-      const unsigned long long head = best[i];
+      for (int q = 0; q + 1 < kTopK; ++q) best[q] = best[q + 1];
+      best[kTopK - 1] = ~0ull;
+    }
+    kth = head;
+    if (tid == 0 && tk.topk_val != nullptr) {
       const bool none = head == ~0ull;
-      topk_val[(long long)i * m + j] =
+      tk.topk_val[(long long)i * a.m + j] =
           none ? __uint_as_float(0x7f800000u) : key_value((unsigned int)(head >> 32));
-      topk_row[(long long)i * m + j] = none ? -1 : (int)(unsigned int)(head & 0xffffffffu);
+      tk.topk_row[(long long)i * a.m + j] = none ? -1 : (int)(unsigned int)(head & 0xffffffffu);
     }
   }
+  if (tid == 0 && tk.thr_out != nullptr) tk.thr_out[j] = kth;
 }
 
 // ref:187-194 per GT column: dynamic k from the k largest similarities (= 1 - the k smallest
@@ -253,20 +222,35 @@ __global__ void __launch_bounds__(kThreads) gd_simota_rows_kernel(
 }
 
 template <int LOSS>
-static int launch_topk(const PairwiseArgs& a, const TopkArgs& tk, long long gx, cudaStream_t st) {
-  gd_pairwise_topk_kernel<LOSS><<<(unsigned)gx, kThreads, 0, st>>>(a, tk);
+static int run_col_topk(const PairwiseArgs& a, TopkArgs tk, unsigned long long* thr,
+                        cudaStream_t st) {
+  const unsigned m = (unsigned)a.m;
+  if (a.n > kSampleRows * 4) {
+    // sample pass -> thr[j]; then the filter pass fills the candidate buffers
+    TopkArgs sk = tk;
+    sk.cand = nullptr;
+    sk.thr_out = thr;
+    sk.topk_val = nullptr;
+    sk.topk_row = nullptr;
+    sk.row_step = a.n / kSampleRows;
+    sk.nrows = kSampleRows;
+    gd_topk_select_kernel<LOSS><<<m, kThreads, 0, st>>>(a, sk);
+    cudaError_t e = cudaMemsetAsync(tk.count, 0, sizeof(unsigned int) * (size_t)a.m, st);
+    if (e != cudaSuccess) return (int)e;
+    tk.thr = thr;
+    const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+    long long gx = (long long)device_info().sm_count * 4;
+    if (gx > ntiles) gx = ntiles;
+    gd_topk_filter_kernel<LOSS><<<(unsigned)gx, kThreads, 0, st>>>(a, tk);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+  } else {
+    tk.cand = nullptr;                         // few rows: brute force per column
+  }
+  tk.row_step = 1;
+  tk.nrows = a.n;
+  gd_topk_select_kernel<LOSS><<<m, kThreads, 0, st>>>(a, tk);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
-}
-
-constexpr long long kSampleRows = 2048;      // rows of the threshold sample (strided over all rows)
-constexpr long long kSampleMinRows = 16 * kSampleRows;   // smaller inputs: no sample pass
-
-static long long topk_grid(long long n) {
-  const long long ntiles = (n + kRowsPerCta - 1) / kRowsPerCta;
-  long long gx = (long long)device_info().sm_count * 3;            // persistent: bounds the scratch
-  if (gx > ntiles) gx = ntiles;
-  return gx < 1 ? 1 : gx;
 }
 
 }  // namespace gdk
@@ -276,9 +260,8 @@ extern "C" {
 size_t gd_pairwise_topk_workspace_bytes(int64_t n, int64_t m) {
   using namespace gdk;
   if (n < 0 || m < 0) return 0;
-  // main lists (wy <= kWarps row phases) + stage-A lists + the sample pass's lists + thresholds
-  const long long slots = topk_grid(n) * kWarps + kMergeGroups + topk_grid(kSampleRows) * kWarps + 1;
-  return 256 + sizeof(unsigned long long) * (size_t)(slots * kTopK * (m > 0 ? m : 0));
+  // per column: threshold (8 B) + counter (4 B, padded to 8) + kCandCap candidates
+  return 256 + sizeof(unsigned long long) * (size_t)((m > 0 ? m : 0) * (2 + (long long)kCandCap));
 }
 
 int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t n,
@@ -299,78 +282,56 @@ int gd_pairwise_col_topk(const gd_loss_config* cfg, const float* boxes1, int64_t
   a.n = n;
   a.b2 = boxes2;
   a.m = m;
-  a.out = out;
-  a.out_stride = out ? out_row_stride : m;
-  a.row_min = row_min;
-  a.row_argmin = row_argmin;
+  a.out_stride = m;
   a.pp = make_pair_params(*cfg);
-  unsigned long long* ws64 =
-      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + 256);
-  const long long gx = topk_grid(n);
-  const int wy = kWarps / pairwise_wx(m, 32);
-  TopkArgs tk;
-  tk.cand = ws64;
-  tk.slots = n > 0 ? gx * wy : 0;
-  tk.row_step = 1;
-  tk.thr = nullptr;
-  unsigned long long* mid = tk.cand + (long long)topk_grid(n) * kWarps * kTopK * m;   // stage-A lists
-  const unsigned mx = (unsigned)((m + 31) / 32);
-  auto launch = [&](const PairwiseArgs& pa, const TopkArgs& pt, long long grid) -> int {
+  auto pairwise = [&](const PairwiseArgs& pa) -> int {
     switch (cfg->loss_type) {
-      case GD_LOSS_GWD3D: return launch_topk<gd::kGwd>(pa, pt, grid, st);
-      case GD_LOSS_KLD3D: return launch_topk<gd::kKld>(pa, pt, grid, st);
-      case GD_LOSS_JD3D: return launch_topk<gd::kJd>(pa, pt, grid, st);
-      case GD_LOSS_KLD3D_SYMMAX: return launch_topk<gd::kSymMax>(pa, pt, grid, st);
-      case GD_LOSS_KLD3D_SYMMIN: return launch_topk<gd::kSymMin>(pa, pt, grid, st);
-      case GD_LOSS_BD3D: return launch_topk<gd::kBd>(pa, pt, grid, st);
-      case GD_LOSS_KFIOU3D: return launch_topk<gd::kKfiou>(pa, pt, grid, st);
+      case GD_LOSS_GWD3D: return launch_pairwise<gd::kGwd>(pa, st);
+      case GD_LOSS_KLD3D: return launch_pairwise<gd::kKld>(pa, st);
+      case GD_LOSS_JD3D: return launch_pairwise<gd::kJd>(pa, st);
+      case GD_LOSS_KLD3D_SYMMAX: return launch_pairwise<gd::kSymMax>(pa, st);
+      case GD_LOSS_KLD3D_SYMMIN: return launch_pairwise<gd::kSymMin>(pa, st);
+      case GD_LOSS_BD3D: return launch_pairwise<gd::kBd>(pa, st);
+      case GD_LOSS_KFIOU3D: return launch_pairwise<gd::kKfiou>(pa, st);
     }
     return GD_ERR_BAD_ARG;
   };
-  // merge of `slots` lists at `lists`: two coalesced stages when there are many
-  auto merge = [&](const unsigned long long* lists, long long slots, float* val, int* row,
-                   unsigned long long* thr_out) {
-    if (slots > 2 * kWarps) {
-      gd_topk_merge_kernel<<<dim3(mx, kMergeGroups), kThreads, 0, st>>>(lists, slots, m, k, mid,
-                                                                       nullptr, nullptr, nullptr);
-      gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(mid, kMergeGroups, m, k, nullptr, val,
-                                                            row, thr_out);
-      g_launches.fetch_add(2, std::memory_order_relaxed);
-    } else {
-      gd_topk_merge_kernel<<<dim3(mx, 1), kThreads, 0, st>>>(lists, slots, m, k, nullptr, val, row,
-                                                            thr_out);
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
-  };
   int rc = 0;
-  if (n >= kSampleMinRows) {
-    // Threshold pass.  The row tiles of the main pass are spread over ~450 CTAs, each with its own
-    // K-deep list per column: without a bound every list accepts ~K ln(rows / K) candidates and
-    // nearly every warp iteration runs the sorted insert (0.49 ms at C4).  The k-th smallest key of
-    // a 2048-row strided sample bounds the k-th smallest of the column from above, and with it
-    // as the insert limit a list accepts a handful.
-    PairwiseArgs sa = a;
-    TopkArgs sk = tk;
-    sa.n = kSampleRows;
-    sa.out = nullptr;
-    sa.row_min = nullptr;
-    sa.row_argmin = nullptr;
-    sk.row_step = n / kSampleRows;
-    sk.cand = mid + (long long)kMergeGroups * kTopK * m;
-    const long long sgx = topk_grid(kSampleRows);
-    sk.slots = sgx * wy;
-    unsigned long long* thr = sk.cand + (long long)topk_grid(kSampleRows) * kWarps * kTopK * m;
-    rc = launch(sa, sk, sgx);
-    if (rc != 0) return rc;
-    merge(sk.cand, sk.slots, nullptr, nullptr, thr);
-    tk.thr = thr;
-  }
   if (n > 0) {
-    rc = launch(a, tk, gx);
+    // (b) row minima, and the matrix when asked for: launches of their own -- the same bits
+    PairwiseArgs ra = a;
+    ra.row_min = row_min;
+    ra.row_argmin = row_argmin;
+    rc = pairwise(ra);
     if (rc != 0) return rc;
+    if (out != nullptr) {
+      PairwiseArgs ma = a;
+      ma.out = out;
+      ma.out_stride = out_row_stride;
+      rc = pairwise(ma);
+      if (rc != 0) return rc;
+    }
   }
-  merge(tk.cand, tk.slots, topk_val, topk_row, nullptr);
-  return (int)cudaGetLastError();
+  // (a) column top-k
+  unsigned long long* ws64 =
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  TopkArgs tk{};
+  unsigned long long* thr = ws64;
+  tk.count = reinterpret_cast<unsigned int*>(ws64 + m);
+  tk.cand = ws64 + 2 * m;
+  tk.k = k;
+  tk.topk_val = topk_val;
+  tk.topk_row = topk_row;
+  switch (cfg->loss_type) {
+    case GD_LOSS_GWD3D: return run_col_topk<gd::kGwd>(a, tk, thr, st);
+    case GD_LOSS_KLD3D: return run_col_topk<gd::kKld>(a, tk, thr, st);
+    case GD_LOSS_JD3D: return run_col_topk<gd::kJd>(a, tk, thr, st);
+    case GD_LOSS_KLD3D_SYMMAX: return run_col_topk<gd::kSymMax>(a, tk, thr, st);
+    case GD_LOSS_KLD3D_SYMMIN: return run_col_topk<gd::kSymMin>(a, tk, thr, st);
+    case GD_LOSS_BD3D: return run_col_topk<gd::kBd>(a, tk, thr, st);
+    case GD_LOSS_KFIOU3D: return run_col_topk<gd::kKfiou>(a, tk, thr, st);
+  }
+  return GD_ERR_BAD_ARG;
 }
 
 int gd_simota_from_topk(const float* topk_val, const int32_t* topk_row, int64_t m, int32_t k,
