@@ -676,8 +676,9 @@ def run_ours(args):
             pair = {'workload': 'C4: 200,000 Waymo-prior anchors x 256 GT boxes, fun=log1p, tau=1: full [N,M] '
                                 'matrix, and row+column (min, argmin) fused without writing the matrix',
                     'rows': pw_rows,
-                    'simota_gwd3d': {'what': 'GDSimOTAAssigner: column top-10 + row minima + dynamic-k '
-                                             'matching, no matrix (4 launches)',
+                    'simota_gwd3d': {'what': 'GDSimOTAAssigner: row minima (row-lane kernel) + column top-10 '
+                                             '(threshold sample, filter pass, per-column selection) + '
+                                             'dynamic-k matching, no matrix',
                                      'ms': round(ms_sim, 4),
                                      'Gpairs_per_s': round(na * m / ms_sim / 1e6, 1)}}
             if not args.no_cpu:

@@ -71,7 +71,7 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsig
 
 // One pass over all pairs; (key, row) <= thr[column] goes to the column's candidate buffer.
 template <int LOSS>
-__global__ void __launch_bounds__(kThreads) gd_topk_filter_kernel(const PairwiseArgs a,
+__global__ void __launch_bounds__(kThreads, 4) gd_topk_filter_kernel(const PairwiseArgs a,
                                                                   const TopkArgs tk) {
   __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -239,7 +239,17 @@ static int run_col_topk(const PairwiseArgs& a, TopkArgs tk, unsigned long long* 
     if (e != cudaSuccess) return (int)e;
     tk.thr = thr;
     const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
-    long long gx = (long long)device_info().sm_count * 4;
+    // persistent, exactly the resident CTA slots: a partial second wave would run alone
+    static int occ[kMaxDevices] = {};
+    const int dev = current_device();
+    if (occ[dev] == 0) {
+      int per_sm = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gd_topk_filter_kernel<LOSS>,
+                                                        kThreads, 0);
+      if (e != cudaSuccess) return (int)e;
+      occ[dev] = per_sm > 0 ? per_sm : 1;
+    }
+    long long gx = (long long)device_info().sm_count * occ[dev];
     if (gx > ntiles) gx = ntiles;
     gd_topk_filter_kernel<LOSS><<<(unsigned)gx, kThreads, 0, st>>>(a, tk);
     g_launches.fetch_add(2, std::memory_order_relaxed);

@@ -193,13 +193,14 @@ def test_sharded_assigner_emulated_shards():
 @pytest.mark.parametrize('n,m,topk', [(5000, 37, 10), (700, 300, 10), (64, 5, 10), (9, 3, 10),
                                       (20001, 256, 13), (300, 1, 4)])
 def test_simota_assigner_equals_matching_on_the_matrix(loss_type, n, m, topk):
-    """The fused path (column top-k lists + row minima, no matrix) against the restated
-    reference matching (gd_oracle.simota_dynamic_k_matching = sim_ota_3d_assigner.py:184-211)
-    run on the fp32 matrix the SAME kernel writes on request (one instruction sequence for lists
-    and matrix): identical assignment, similarities and dynamic k -- exact ties included (both
+    """The matrix-free path (row minima from the row-lane kernel; column top-k lists from the
+    threshold sample + filter pass + per-column selection) against the restated reference
+    matching (gd_oracle.simota_dynamic_k_matching = sim_ota_3d_assigner.py:184-211) run on the
+    fp32 matrix: identical assignment, similarities and dynamic k -- exact ties included (both
     take the lowest index first); the lists equal a stable sort of the matrix columns bit for
-    bit; the result does not depend on whether the matrix is written; and the matrix agrees with
-    the plain pairwise kernel's to the last place (another instantiation)."""
+    bit; the result does not depend on whether the matrix is written; and the matrix IS the plain
+    pairwise kernel's (every launch evaluates a pair with the same explicitly rounded
+    operations)."""
     from mmdet3d_gaussian_b200 import GDSimOTAAssigner
     b1 = synth.make_anchor_grid(n, 'waymo', device='cuda')
     b2 = synth.make_targets(m, 'waymo', seed=n + m, device='cuda')
@@ -215,7 +216,7 @@ def test_simota_assigner_equals_matching_on_the_matrix(loss_type, n, m, topk):
         assert torch.equal(res[key], resm[key]), key
     mat = resm['distance_matrix']
     plain = GDPairwiseDistance(loss_type, fun='log1p', tau=1.0)(b1, b2)
-    assert ((plain - mat).abs() / mat.abs().clamp_min(1e-3)).max().item() < 2e-6
+    assert same_bits(plain, mat)
     k = min(topk, n)
     order = torch.sort(mat, dim=0, stable=True).indices[:k]           # ties -> lowest row
     assert torch.equal(res['topk_inds'], order)
@@ -232,6 +233,34 @@ def test_simota_assigner_equals_matching_on_the_matrix(loss_type, n, m, topk):
     # a second call on the same stream (scratch reuse)
     res2 = asg.assign(b1, b2)
     assert torch.equal(res2['assigned_gt_inds'], res['assigned_gt_inds'])
+
+
+@pytest.mark.parametrize('loss_type', ['gwd3d', 'kld3d'])
+def test_column_topk_at_c4_size_and_with_overflowing_candidate_buffers(loss_type):
+    """gd_pairwise_col_topk at BASELINE's C4 shape (200k x 256): lists == a stable sort of the
+    matrix columns, bit for bit.  Then an input built to defeat the threshold sample: every row
+    the strided sample sees is far away, all the others are close, so nearly every pair passes
+    the filter and every column's candidate buffer overflows -- the brute-force path must give
+    the same exact answer."""
+    n, m, k = 200_000, 256, 10
+    b1 = synth.make_anchor_grid(n, 'waymo', device='cuda')
+    b2 = synth.make_targets(m, 'waymo', seed=5, device='cuda')
+    b2[:, 0] = b2[:, 0] * 2.0 - 70.0
+    cfg = GDPairwiseDistance(loss_type, fun='log1p', tau=1.0).cfg
+
+    def check(b1, b2, k):
+        rmin, ridx, val, row, _ = ops.pairwise_col_topk(b1, b2, cfg, k)
+        mat = ops.pairwise_distance(b1, b2, cfg)
+        order = torch.sort(mat, dim=0, stable=True).indices[:k]
+        assert torch.equal(row, order)
+        assert same_bits(val, torch.gather(mat, 0, order))
+        rv, ri = first_argmin(mat, 1)
+        assert same_bits(rmin, rv) and torch.equal(ridx, ri)
+    check(b1, b2, k)
+    n2 = 40_960                                  # sample step 20: rows 0, 20, 40, ... are sampled
+    c1 = synth.make_anchor_grid(n2, 'waymo', device='cuda')
+    c1[::20, :2] += 500.0                        # the sampled rows sit far from every GT
+    check(c1, b2[:40], 16)
 
 
 def test_simota_assigner_vs_fp64_oracle_and_edge_cases():
