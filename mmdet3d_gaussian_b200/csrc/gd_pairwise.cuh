@@ -305,6 +305,105 @@ __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_kernel_m3(const Pairw
 }
 
 // ---------------------------------------------------------------------------
+// Filter pass of the column top-k (gd_simota.cu): the matrix kernel's loop with the store
+// replaced by "append (key, row) to column j's candidate buffer when it is <= thr[j]".  One
+// column chunk (m <= 32 CPL wx), persistent CTAs, column Gaussians and limits kept in registers;
+// straight-line FAST cores when every box in sight is nice, as in the matrix kernel.
+// ---------------------------------------------------------------------------
+struct FilterArgs {
+  const unsigned long long* thr;             // [m] upper bound of the column's k-th (key, row)
+  unsigned int* count;                       // [m] candidates appended so far (zero on entry)
+  unsigned long long* cand;                  // [m][cap]
+  unsigned int cap;
+};
+
+template <int LOSS, int SPEC, int CPL>
+__global__ void __launch_bounds__(kThreads, 3) gd_pairwise_filter_kernel(const PairwiseArgs a,
+                                                                         const FilterArgs f) {
+  __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  gd::PairParams<float> pp = a.pp;
+  if (SPEC >= 0) {
+    pp.fun = SPEC & 3;
+    pp.tau_on = (SPEC >> 2) & 1;
+    pp.flag = (SPEC >> 3) & 1;
+  }
+  pp.lean = 1;
+  constexpr int kWarpCols = 32 * CPL;
+  const int wx = pairwise_wx(a.m, kWarpCols);
+  const int wy = kWarps / wx;
+  const int cgrp = warp % wx, ry = warp / wx;
+  const long long jb = (long long)kWarpCols * cgrp;            // first column of this warp
+  const bool warp_live = jb < a.m;
+  const int tile_rows = a.tile_rows > 0 ? a.tile_rows : kRowsPerCta;
+  const long long ntiles = (a.n + tile_rows - 1) / tile_rows;
+  gd::BoxGauss<float> t[CPL];
+  bool live[CPL];
+  unsigned long long lim[CPL];
+  bool cols_ok = warp_live;
+#pragma unroll
+  for (int q = 0; q < CPL; ++q) {
+    const long long j = jb + 32 * q + lane;
+    live[q] = j < a.m;
+    t[q] = gd::box_gauss(a.b2 + (live[q] ? j : 0) * 7, pp);     // dead lane: any valid box
+    lim[q] = live[q] ? f.thr[j] : 0ull;                        // dead lane: nothing passes
+    cols_ok = cols_ok && live[q] && t[q].nice != 0;
+  }
+  const bool fast_cols = gd::PairwiseExact<LOSS>::value && __all_sync(0xffffffffu, cols_ok);
+  auto offer = [&](int q, long long row, float v) {
+    const unsigned long long k64 = ((unsigned long long)order_key(v) << 32) | (unsigned int)row;
+    if (k64 <= lim[q]) {
+      const long long j = jb + 32 * q + lane;
+      const unsigned int pos = atomicAdd(f.count + j, 1u);
+      if (pos < f.cap) f.cand[j * f.cap + pos] = k64;
+    }
+  };
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * tile_rows;
+    const int rows = (int)min((long long)tile_rows, a.n - row0);
+    __syncthreads();                           // previous tile fully consumed
+    int row_nice = 1;
+    if (tid < rows) {
+      s_rows[tid] = gd::box_gauss(a.b1 + (row0 + tid) * 7, pp);
+      row_nice = s_rows[tid].nice;
+    }
+    const bool tile_nice = __syncthreads_and(row_nice) != 0;   // also publishes the tile
+    if (!warp_live) continue;
+    if constexpr (gd::PairwiseExact<LOSS>::value) {
+      if (fast_cols && tile_nice) {
+        bool redo = false;
+#pragma unroll 2
+        for (int r = ry; r < rows; r += wy) {
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            bool rare = false;
+            const float v = gd::pair_value_fast<float, LOSS>(s_rows[r], t[q], pp, &rare);
+            redo |= rare;
+            if (!rare) offer(q, row0 + r, v);
+          }
+        }
+        if (redo) {                            // only the pairs whose FAST core gave up
+          for (int r = ry; r < rows; r += wy) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              bool rare = false;
+              (void)gd::pair_value_fast<float, LOSS>(s_rows[r], t[q], pp, &rare);
+              if (rare) offer(q, row0 + r, gd::pair_value_auto<float, LOSS>(s_rows[r], t[q], pp));
+            }
+          }
+        }
+        continue;
+      }
+    }
+    for (int r = ry; r < rows; r += wy) {
+#pragma unroll
+      for (int q = 0; q < CPL; ++q)
+        if (live[q]) offer(q, row0 + r, gd::pair_value_auto<float, LOSS>(s_rows[r], t[q], pp));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Fused reductions WITHOUT the matrix (row f2, the assigner's launch): lanes map to ROWS.
 //
 // With lanes on columns (the kernel above, needed for coalesced matrix stores) a row minimum
@@ -712,6 +811,47 @@ int launch_rowlane(const PairwiseArgs& a, cudaStream_t st) {
     }
   }
   return launch_rowlane_inst<LOSS, -1>(a, st);
+}
+
+// Filter pass: one column chunk only (m <= 256); returns GD_ERR_LAYOUT otherwise (the caller
+// falls back to its own chunked kernel).  Persistent, even waves, like the matrix launch.
+template <int LOSS, int SPEC, int CPL>
+int launch_filter_inst(const PairwiseArgs& a, const FilterArgs& f, cudaStream_t st) {
+  auto kern = gd_pairwise_filter_kernel<LOSS, SPEC, CPL>;
+  static int occ[kMaxDevices] = {};
+  const int dev = current_device();
+  if (occ[dev] == 0) {
+    int per_sm = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0);
+    if (e != cudaSuccess) return (int)e;
+    occ[dev] = per_sm > 0 ? per_sm : 1;
+  }
+  const long long slots = (long long)device_info().sm_count * occ[dev];
+  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  const long long waves = (ntiles + slots - 1) / slots;
+  long long rows = (a.n + waves * slots - 1) / (waves * slots);
+  if (rows < 16) rows = 16;
+  if (rows > kRowsPerCta) rows = kRowsPerCta;
+  PairwiseArgs b = a;
+  b.tile_rows = (int)rows;
+  const long long nt = (a.n + rows - 1) / rows;
+  kern<<<(unsigned)(nt < slots ? nt : slots), kThreads, 0, st>>>(b, f);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <int LOSS>
+int launch_filter(const PairwiseArgs& a, const FilterArgs& f, cudaStream_t st) {
+  constexpr int CPL = pairwise_cpl2_pays<LOSS>() ? 2 : 1;
+  const int cpl = (CPL == 2 && a.m > 32) ? 2 : 1;
+  if (a.m > 32LL * cpl * kWarps || a.n <= 0) return GD_ERR_LAYOUT;
+  const gd::PairParams<float>& pp = a.pp;
+  const bool spec13 = pp.flag == 1 && pp.fun == gd::kFunLog1p && pp.tau_on == 1;   // the SimOTA setting
+  if constexpr (CPL == 2) {
+    if (cpl == 2)
+      return spec13 ? launch_filter_inst<LOSS, 13, 2>(a, f, st) : launch_filter_inst<LOSS, -1, 2>(a, f, st);
+  }
+  return spec13 ? launch_filter_inst<LOSS, 13, 1>(a, f, st) : launch_filter_inst<LOSS, -1, 1>(a, f, st);
 }
 
 template <int LOSS>

@@ -2,4 +2,5 @@
 #include "gd_pairwise.cuh"
 namespace gdk {
 template int launch_pairwise<gd::kKfiou>(const PairwiseArgs&, cudaStream_t);
+template int launch_filter<gd::kKfiou>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
 }  // namespace gdk

@@ -2,4 +2,5 @@
 #include "gd_pairwise.cuh"
 namespace gdk {
 template int launch_pairwise<gd::kSymMax>(const PairwiseArgs&, cudaStream_t);
+template int launch_filter<gd::kSymMax>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
 }  // namespace gdk

@@ -42,6 +42,13 @@ extern template int launch_pairwise<gd::kSymMax>(const PairwiseArgs&, cudaStream
 extern template int launch_pairwise<gd::kSymMin>(const PairwiseArgs&, cudaStream_t);
 extern template int launch_pairwise<gd::kBd>(const PairwiseArgs&, cudaStream_t);
 extern template int launch_pairwise<gd::kKfiou>(const PairwiseArgs&, cudaStream_t);
+extern template int launch_filter<gd::kGwd>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
+extern template int launch_filter<gd::kKld>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
+extern template int launch_filter<gd::kJd>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
+extern template int launch_filter<gd::kSymMax>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
+extern template int launch_filter<gd::kSymMin>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
+extern template int launch_filter<gd::kBd>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
+extern template int launch_filter<gd::kKfiou>(const PairwiseArgs&, const FilterArgs&, cudaStream_t);
 
 constexpr int kTopK = 16;                    // candidate_topk <= 16
 constexpr long long kSampleRows = 2048;      // rows of the threshold sample (strided over all rows)
@@ -238,6 +245,21 @@ static int run_col_topk(const PairwiseArgs& a, TopkArgs tk, unsigned long long* 
     cudaError_t e = cudaMemsetAsync(tk.count, 0, sizeof(unsigned int) * (size_t)a.m, st);
     if (e != cudaSuccess) return (int)e;
     tk.thr = thr;
+    // m <= 256: the matrix kernel's lean loop with an append in place of the store
+    FilterArgs fa;
+    fa.thr = thr;
+    fa.count = tk.count;
+    fa.cand = tk.cand;
+    fa.cap = (unsigned int)kCandCap;
+    const int frc = launch_filter<LOSS>(a, fa, st);
+    if (frc != GD_ERR_LAYOUT) {
+      if (frc != 0) return frc;
+      tk.row_step = 1;
+      tk.nrows = a.n;
+      gd_topk_select_kernel<LOSS><<<m, kThreads, 0, st>>>(a, tk);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      return (int)cudaGetLastError();
+    }
     const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
     // persistent, exactly the resident CTA slots: a partial second wave would run alone
     static int occ[kMaxDevices] = {};
