@@ -37,6 +37,7 @@
 namespace gdk {
 
 constexpr int kRowsPerCta = 64;
+constexpr int kRowsPerCtaBig = 128;     // persistent matrix / filter launches: half the barriers per row
 constexpr int kWarps = kThreads / 32;
 
 struct PairwiseArgs {
@@ -88,7 +89,10 @@ __host__ __device__ inline int pairwise_wx(long long m, int warp_cols) {
 // [3] flag compile-time (as gd_warp_kernel).  CPL: columns per lane (1 or 2).
 template <int LOSS, int SPEC, bool REDUCE, int CPL>
 __device__ __forceinline__ void pairwise_body(const PairwiseArgs& a) {
-  __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
+  // the persistent matrix launch of the exact-form distances may ask for tiles up to
+  // kRowsPerCtaBig rows (a.tile_rows); every other launch stays at kRowsPerCta
+  constexpr int kTileCap = (!REDUCE && gd::PairwiseExact<LOSS>::value) ? kRowsPerCtaBig : kRowsPerCta;
+  __shared__ gd::BoxGauss<float> s_rows[kTileCap];
   __shared__ unsigned long long s_best[REDUCE ? kRowsPerCta : 1][kWarps];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,7 +110,7 @@ __device__ __forceinline__ void pairwise_body(const PairwiseArgs& a) {
   const long long chunk = (long long)kWarpCols * wx;
   const bool want_col = REDUCE && a.col_keys != nullptr;
   const bool one_chunk = a.m <= chunk;         // column minima can stay in registers across tiles
-  const int tile_rows = a.tile_rows > 0 ? a.tile_rows : kRowsPerCta;       // <= kRowsPerCta
+  const int tile_rows = a.tile_rows > 0 ? a.tile_rows : kRowsPerCta;       // <= kTileCap
   const long long ntiles = (a.n + tile_rows - 1) / tile_rows;
   // One column chunk for the whole launch (matrix kernel of the exact-form distance): the lane's
   // column Gaussians are converted once and kept across the CTA's tiles.  Compile-time off
@@ -715,10 +719,11 @@ int launch_pairwise_cpl(const PairwiseArgs& a, cudaStream_t st) {
         occ[dev] = per_sm > 0 ? per_sm : 1;
       }
       const long long slots = (long long)device_info().sm_count * occ[dev];
-      const long long waves = (ntiles + slots - 1) / slots;
-      long long rows = (a.n + waves * slots - 1) / (waves * slots);     // <= kRowsPerCta
+      const long long big_tiles = (a.n + kRowsPerCtaBig - 1) / kRowsPerCtaBig;
+      const long long waves = (big_tiles + slots - 1) / slots;
+      long long rows = (a.n + waves * slots - 1) / (waves * slots);     // <= kRowsPerCtaBig
       if (rows < 16) rows = 16;
-      if (rows > kRowsPerCta) rows = kRowsPerCta;
+      if (rows > kRowsPerCtaBig) rows = kRowsPerCtaBig;
       PairwiseArgs b = a;
       b.tile_rows = (int)rows;
       const long long nt = (a.n + rows - 1) / rows;

@@ -58,10 +58,11 @@ static void run_cpl(const gdk::PairwiseArgs& a, unsigned cap) {
     gy = (unsigned)((a.m + 32LL * CPL * wx - 1) / (32LL * CPL * wx));
     if (gy == 1 && gd::PairwiseExact<LOSS>::value) {   // persistent, even waves: launch_pairwise_cpl with `cap` CTA slots
       const long long slots = cap;
-      const long long waves = (ntiles + slots - 1) / slots;
+      const long long big_tiles = (a.n + gdk::kRowsPerCtaBig - 1) / gdk::kRowsPerCtaBig;
+      const long long waves = (big_tiles + slots - 1) / slots;
       long long rows = (a.n + waves * slots - 1) / (waves * slots);
       if (rows < 16) rows = 16;
-      if (rows > gdk::kRowsPerCta) rows = gdk::kRowsPerCta;
+      if (rows > gdk::kRowsPerCtaBig) rows = gdk::kRowsPerCtaBig;
       gdk::PairwiseArgs b = a;
       b.tile_rows = (int)rows;
       const long long nt = (a.n + rows - 1) / rows;
