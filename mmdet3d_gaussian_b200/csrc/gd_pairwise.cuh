@@ -324,7 +324,7 @@ struct FilterArgs {
 template <int LOSS, int SPEC, int CPL>
 __global__ void __launch_bounds__(kThreads, 3) gd_pairwise_filter_kernel(const PairwiseArgs a,
                                                                          const FilterArgs f) {
-  __shared__ gd::BoxGauss<float> s_rows[kRowsPerCta];
+  __shared__ gd::BoxGauss<float> s_rows[kRowsPerCtaBig];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   gd::PairParams<float> pp = a.pp;
   if (SPEC >= 0) {
@@ -832,11 +832,11 @@ int launch_filter_inst(const PairwiseArgs& a, const FilterArgs& f, cudaStream_t 
     occ[dev] = per_sm > 0 ? per_sm : 1;
   }
   const long long slots = (long long)device_info().sm_count * occ[dev];
-  const long long ntiles = (a.n + kRowsPerCta - 1) / kRowsPerCta;
+  const long long ntiles = (a.n + kRowsPerCtaBig - 1) / kRowsPerCtaBig;
   const long long waves = (ntiles + slots - 1) / slots;
   long long rows = (a.n + waves * slots - 1) / (waves * slots);
   if (rows < 16) rows = 16;
-  if (rows > kRowsPerCta) rows = kRowsPerCta;
+  if (rows > kRowsPerCtaBig) rows = kRowsPerCtaBig;
   PairwiseArgs b = a;
   b.tile_rows = (int)rows;
   const long long nt = (a.n + rows - 1) / rows;
