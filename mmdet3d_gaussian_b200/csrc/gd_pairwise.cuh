@@ -20,16 +20,25 @@
 // log1p of the post map is the short pairwise version (Mth::log1p_lean, ~4e-7).  Stores
 // are coalesced 4 B/pair streaming stores through a row pointer that is advanced, not
 // recomputed.  FP32 CUDA-core math, no tensor cores (not a contraction).
-// The kernel is issue bound, so the design goal is instructions per pair (round 1: ~105
-// matrix / ~160 fused; profiles/r02*_pairwise.md for this version).
+// The kernels are issue bound, so the design goal is instructions per pair (round 1: ~111
+// matrix / ~160 fused; now 61 / 68: profiles/r03_pairwise.md).
 //
-// Reductions.  Values map to order-preserving 32-bit keys (NaN lowest, as torch.min
+// Kernels in this header:
+//   gd_pairwise_kernel / gd_pairwise_kernel_m3 (pairwise_body)  the matrix, lanes on columns;
+//       with REDUCE also the row / column minima of the same launch (column-lane reductions)
+//   gd_pairwise_filter_kernel   the matrix loop with "append candidates below a bound" in place
+//       of the store (column top-k of gd_simota.cu)
+//   gd_pairwise_rowlane_kernel  row / column minima without the matrix, lanes on ROWS
+// Every one of them evaluates a pair through gd::pair_value_auto / gd::pair_value_fast, whose
+// FAST cores are written with explicitly rounded operations (gd_math.cuh, namespace pw): the
+// value of a pair is the same bits in every kernel, whatever the mapping.
+//
+// Reductions of the column-lane kernel.  Values map to order-preserving 32-bit keys (NaN lowest, as torch.min
 // propagates NaN).  Row minimum: in-lane minimum over the CPL columns, one REDUX.MIN and
 // CPL ballots per warp and row, lowest column wins ties.  Column minimum: a compare/select per pair in the owning lane,
 // merged across CTAs with one 64-bit atomic per column on (key << 32 | row) -- lowest
 // row wins ties -- and unpacked by the last CTA to finish (atomic ticket), which also
-// restores the workspace.  Both reductions and the matrix come out of the SAME
-// instruction sequence per pair, so indices derived from either are bit-identical.
+// restores the workspace.
 #pragma once
 #include "gd_common.cuh"
 #include "gd_packed.cuh"

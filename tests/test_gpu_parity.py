@@ -337,6 +337,41 @@ def test_early_return_flag_reported_from_inside_the_launch():
     assert len(set(outs)) == 1
 
 
+def test_default_module_issues_no_synchronizing_cuda_call():
+    """torch's sync debug mode raises on every synchronizing CUDA call made through torch
+    (.item(), nonzero, blocking copies, stream / event synchronize).  The DEFAULT module
+    (reference ctor keys only) must run forward + backward without one for the call patterns
+    of both heads: [N,7] weights with a python and with a device avg_factor (KITTI head), no
+    weight (CenterPoint head), strided views; and for plain [N] weights, whose early-return
+    answer is read from a pinned word the launch writes (a host spin, not a CUDA sync)."""
+    n = 4096
+    pred, target, w = synth.make_pairs(n, 'kitti', seed=4, weights='bernoulli')
+    pc, tc, wc = pred.cuda(), target.cuda(), w.cuda()
+    w[0] = 0.5
+    w7 = wc[:, None].expand(n, 7).contiguous()
+    avg = torch.tensor(37.0, device='cuda')
+    wide = torch.zeros(n, 9, device='cuda')
+    wide[:, :7] = pc
+    mod = GDLoss('gwd3d', fun='log1p', tau=0.0, loss_weight=5.0)
+    for _ in range(2):                            # first call: lazy allocations (workspace, pinned word)
+        cases = [(pc.clone().requires_grad_(True), w7, 3.0), (pc.clone().requires_grad_(True), w7, avg),
+                 (pc.clone().requires_grad_(True), None, avg), (pc.clone().requires_grad_(True), wc, 3.0)]
+        views = wide.clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        torch.cuda.set_sync_debug_mode('error')
+        try:
+            outs = []
+            for p, wt, af in cases:
+                out = mod(p, tc, wt, avg_factor=af)
+                out.backward()
+                outs.append(out)
+            out = mod(views[:, :7], tc, None, avg_factor=avg)
+            out.backward()
+        finally:
+            torch.cuda.set_sync_debug_mode('default')
+        assert all(bool(torch.isfinite(o)) for o in outs) and bool(torch.isfinite(out))
+
+
 def test_early_return_decided_on_the_device():
     """The default module (reference ctor keys only) takes the early return of ref:290-292
     without any host involvement wherever `pred * weight` has the shape of pred: value
