@@ -439,6 +439,12 @@ GD_API int gd_loss_fwd_bwd_host(const gd_loss_config* cfg,
  * `gpu_launches`). */
 GD_API int64_t gd_launch_count(void);
 
+/* CTAs of the persistent fused loss kernel (at most one per SM).  0 restores the built-in policy
+ * (per distance, chosen from interleaved A/B runs under the board's power cap: fewer, faster-
+ * clocked SMs move more bytes for the light distances -- DESIGN.md section 4); a positive value
+ * pins the grid for every later launch of the process (measurements: tools/ab_grid.py). */
+GD_API int gd_set_loss_grid(int32_t ctas);
+
 GD_API const char* gd_error_string(int code);
 
 #ifdef __cplusplus

@@ -106,6 +106,7 @@ SIGNATURES = {
                                             _vp, _vp, _i32, _i64]),
     'gd_host_chunk_plan': (_i64, [_i64, _i64, _vp, _vp, _i64]),
     'gd_launch_count': (_i64, []),
+    'gd_set_loss_grid': (ctypes.c_int, [_i32]),
     'gd_error_string': (ctypes.c_char_p, [ctypes.c_int]),
 }
 

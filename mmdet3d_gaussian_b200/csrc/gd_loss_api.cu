@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kThreads) gd_count_labels_kernel(
   }
 }
 
+std::atomic<int> g_loss_grid{0};           // gd_set_loss_grid(); policy: warp_kernel_ctas()
+
 extern template int launch_loss<gd::kGwd>(const LossArgs&, int, int, cudaStream_t);
 extern template int launch_loss<gd::kKld>(const LossArgs&, int, int, cudaStream_t);
 extern template int launch_loss<gd::kJd>(const LossArgs&, int, int, cudaStream_t);
@@ -344,6 +346,12 @@ int gd_count_positive_labels(const int64_t* labels, int64_t total, int64_t num_c
       reinterpret_cast<unsigned int*>(workspace));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
+}
+
+int gd_set_loss_grid(int32_t ctas) {
+  if (ctas < 0) return GD_ERR_BAD_ARG;
+  gdk::g_loss_grid.store(ctas, std::memory_order_relaxed);
+  return 0;
 }
 
 int64_t gd_launch_count(void) { return gdk::g_launches.load(std::memory_order_relaxed); }

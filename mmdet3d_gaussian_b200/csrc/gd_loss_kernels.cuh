@@ -794,6 +794,22 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// CTAs of the persistent warp kernel (one per SM at most).  gd_set_loss_grid() pins the number;
+// the built-in policy is 128 of the 148 SMs (32/37 of the device).  The board runs this kernel
+// at its 1000 W power cap, and interleaved A/B runs on five boxes of the pool
+// (profiles/r03_grid.md) show the same picture for all five bench configurations: from 148 down
+// to 134 CTAs the delivered bandwidth falls slowly (5.70 -> 5.50 TB/s), at 132 (one box: 130) it
+// JUMPS to 6.1-6.2 TB/s and then falls slowly again (128: 6.0-6.1, 124: 5.85-6.0, 120: 5.75-5.9);
+// 4 s of back-to-back launches at 52-54 C keep the gap (148: 5.58, 132: 6.05, 128: 5.95-6.0).
+// 128 sits two to four CTAs below the lowest jump seen: +5-6 % over one CTA per SM.
+extern std::atomic<int> g_loss_grid;
+inline long long warp_kernel_ctas(long long sms) {
+  const int forced = g_loss_grid.load(std::memory_order_relaxed);
+  if (forced > 0) return forced < sms ? forced : sms;
+  const long long g = sms * 32 / 37;
+  return g < 1 ? 1 : g;
+}
+
 template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false, bool ANY = false>
 int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
 #if GD_TUNE
@@ -827,7 +843,7 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
   if (warps < 1) return GD_ERR_BAD_ARG;
   // Persistent: at most one CTA per SM with `warps` warps.  A batch too small to give
   // every such warp 32 rows uses fewer warps, spread over as many SMs as possible.
-  const long long sms = device_info().sm_count;
+  const long long sms = warp_kernel_ctas(device_info().sm_count);
   const long long n_main = ANY ? a.n_bulk : (a.n & ~3LL);
   long long want = (n_main + 31) / 32;                    // warps that would get >= 32 rows
   if (want < 1) want = 1;
