@@ -802,10 +802,15 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
 // JUMPS to 6.1-6.2 TB/s and then falls slowly again (128: 6.0-6.1, 124: 5.85-6.0, 120: 5.75-5.9);
 // 4 s of back-to-back launches at 52-54 C keep the gap (148: 5.58, 132: 6.05, 128: 5.95-6.0).
 // 128 sits two to four CTAs below the lowest jump seen: +5-6 % over one CTA per SM.
+// The policy applies to the contiguous layouts with [N] / no weights (12 warps per CTA, the
+// headline kernel and reduction='none').  The instantiations with fewer, heavier warps per CTA
+// ([N,7] weights: 9 warps; row-strided / unaligned inputs: 9 warps, run-time parameters) lose
+// 4-12 % on 128 CTAs (profiles/r03_grid.md) and keep one CTA per SM.
 extern std::atomic<int> g_loss_grid;
-inline long long warp_kernel_ctas(long long sms) {
+inline long long warp_kernel_ctas(long long sms, bool light) {
   const int forced = g_loss_grid.load(std::memory_order_relaxed);
   if (forced > 0) return forced < sms ? forced : sms;
+  if (!light) return sms;
   const long long g = sms * 32 / 37;
   return g < 1 ? 1 : g;
 }
@@ -843,7 +848,7 @@ int launch_warp_inst(const LossArgs& a_in, int max_grid, cudaStream_t stream) {
   if (warps < 1) return GD_ERR_BAD_ARG;
   // Persistent: at most one CTA per SM with `warps` warps.  A batch too small to give
   // every such warp 32 rows uses fewer warps, spread over as many SMs as possible.
-  const long long sms = warp_kernel_ctas(device_info().sm_count);
+  const long long sms = warp_kernel_ctas(device_info().sm_count, !ANY && a.wmode != GD_WEIGHT_ROW7);
   const long long n_main = ANY ? a.n_bulk : (a.n & ~3LL);
   long long want = (n_main + 31) / 32;                    // warps that would get >= 32 rows
   if (want < 1) want = 1;
