@@ -806,11 +806,19 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
 // headline kernel and reduction='none').  The instantiations with fewer, heavier warps per CTA
 // ([N,7] weights: 9 warps; row-strided / unaligned inputs: 9 warps, run-time parameters) lose
 // 4-12 % on 128 CTAs (profiles/r03_grid.md) and keep one CTA per SM.
+// It also applies only when the process runs alone on its box: with all 8 GPUs of a box busy
+// (bench.py --gpus 8 under torchrun) the slowest GPU sits on the wrong side of its jump at 128
+// CTAs and the step takes 1.125 ms instead of 1.084 ms (gpurun_out/r03t vs r03s), so ranks of a
+// multi-process job (WORLD_SIZE > 1, as torchrun / dist_train.sh export it) keep one CTA per SM.
 extern std::atomic<int> g_loss_grid;
 inline long long warp_kernel_ctas(long long sms, bool light) {
   const int forced = g_loss_grid.load(std::memory_order_relaxed);
   if (forced > 0) return forced < sms ? forced : sms;
-  if (!light) return sms;
+  static const bool multi_process = [] {
+    const char* e = getenv("WORLD_SIZE");
+    return e != nullptr && atoi(e) > 1;
+  }();
+  if (!light || multi_process) return sms;
   const long long g = sms * 32 / 37;
   return g < 1 ? 1 : g;
 }
