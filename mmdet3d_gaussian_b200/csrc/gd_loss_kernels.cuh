@@ -936,6 +936,29 @@ int launch_loss(const LossArgs& a, int variant, int max_grid, cudaStream_t strea
                 : launch_warp<LOSS, false, 2>(a, max_grid, stream);
   }
   if (variant == GD_VARIANT_BULK_ANY) {
+    // Row-strided / unaligned inputs.  The CenterGDHead call (no weight, gradient, a shipped
+    // fun / tau / flag configuration of one of the three headline losses) gets the specialised
+    // packed-FP32 instantiation: this layout runs 9 warps per CTA and is bound by its
+    // instruction stream (profiles/r03_grid.md), and the run-time-parameter kernel executes
+    // 55 % more instructions per row.  Everything else: run-time parameters, scalar math.
+    if constexpr ((LOSS == gd::kGwd || LOSS == gd::kKld || LOSS == gd::kBd) &&
+                  (GD_TUNE_DEFAULT & kTunePacked) != 0) {
+      const gd::PairParams<float>& pp = a.pp;
+      bool spec_ok = grad && !a.row_loss && a.wmode == GD_WEIGHT_NONE && pp.flag == 1 &&
+                     (pp.fun == gd::kFunNone || pp.fun == gd::kFunLog1p);
+      if (GD_TUNE_DEFAULT & kTuneStd)
+        spec_ok = spec_ok && pp.alpha2 == 1.0f && pp.inv_alpha2 == 1.0f && pp.off[0] == 0.0f &&
+                  pp.off[1] == 0.0f && pp.off[2] == 0.5f;
+      if (spec_ok) {
+        switch (pp.fun | (pp.tau_on << 2) | (1 << 3)) {
+          case 8: return launch_warp_inst<LOSS, true, 4, 8, 0, true, true>(a, max_grid, stream);
+          case 9: return launch_warp_inst<LOSS, true, 4, 9, 0, true, true>(a, max_grid, stream);
+          case 12: return launch_warp_inst<LOSS, true, 4, 12, 0, true, true>(a, max_grid, stream);
+          case 13: return launch_warp_inst<LOSS, true, 4, 13, 0, true, true>(a, max_grid, stream);
+          default: break;
+        }
+      }
+    }
     return grad ? launch_warp_inst<LOSS, true, 4, -1, -1, false, true>(a, max_grid, stream)
                 : launch_warp_inst<LOSS, false, 4, -1, -1, false, true>(a, max_grid, stream);
   }
