@@ -439,10 +439,15 @@ GD_API int gd_loss_fwd_bwd_host(const gd_loss_config* cfg,
  * `gpu_launches`). */
 GD_API int64_t gd_launch_count(void);
 
-/* CTAs of the persistent fused loss kernel (at most one per SM).  0 restores the built-in policy
- * (per distance, chosen from interleaved A/B runs under the board's power cap: fewer, faster-
- * clocked SMs move more bytes for the light distances -- DESIGN.md section 4); a positive value
- * pins the grid for every later launch of the process (measurements: tools/ab_grid.py). */
+/* CTAs of the persistent fused loss kernel (at most one per SM).  Built-in policy (0): the board
+ * runs this kernel at its power cap and on most chips 128 of the 148 SMs deliver 5-6 % more
+ * bandwidth than all of them, on some they deliver less (profiles/r03_grid.md) -- so the first
+ * launch of a process with >= 2^22 rows on a contiguous [N] / no-weight layout TIMES the launch it
+ * was asked for on both grids (~13 ms once per device; this one call synchronises with the host)
+ * and keeps the faster one.  Never calibrated, one CTA per SM: [N,7] weights, row-strided /
+ * unaligned inputs, ranks of a multi-process job (WORLD_SIZE > 1), launches captured into a CUDA
+ * graph.  A positive value pins the grid for every later launch of the process and switches the
+ * calibration off (measurements: tools/ab_grid.py; latency-critical callers). */
 GD_API int gd_set_loss_grid(int32_t ctas);
 
 GD_API const char* gd_error_string(int code);

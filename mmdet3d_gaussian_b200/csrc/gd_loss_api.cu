@@ -2,6 +2,8 @@
 // early-return probe).  The heavy kernel templates live in gd_loss_kernels.cuh and
 // are instantiated one loss type per translation unit (gd_loss_inst_*.cu) so the
 // build parallelises.
+#include <mutex>
+
 #include "gd_loss_kernels.cuh"
 
 namespace gdk {
@@ -100,6 +102,41 @@ __global__ void __launch_bounds__(kThreads) gd_count_labels_kernel(
 }
 
 std::atomic<int> g_loss_grid{0};           // gd_set_loss_grid(); policy: warp_kernel_ctas()
+std::atomic<int> g_loss_grid_cal[kMaxDevices];
+thread_local int t_loss_grid_try = 0;
+static std::mutex g_cal_mutex;
+
+// Times `launch` (the launch the caller asked for: idempotent, it writes its outputs) on one CTA
+// per SM and on 32/37 of the SMs, twice each and interleaved, and keeps the faster grid for the
+// device.  Host-synchronising, once per device and process; any failure keeps one CTA per SM.
+template <typename F>
+static void calibrate_grid(F&& launch, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_cal_mutex);
+  const int dev = current_device();
+  if (g_loss_grid_cal[dev].load(std::memory_order_relaxed) > 0) return;
+  const int sms = device_info().sm_count;
+  const int cand[2] = {sms, sms * 32 / 37 > 0 ? sms * 32 / 37 : 1};
+  float ms[2] = {0.0f, 0.0f};
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool ok = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+  for (int round = 0; ok && round < 2; ++round) {
+    for (int c = 0; ok && c < 2; ++c) {
+      t_loss_grid_try = cand[c];
+      for (int i = 0; ok && i < 2; ++i) ok = launch() == 0;
+      ok = ok && cudaEventRecord(e0, st) == cudaSuccess;
+      for (int i = 0; ok && i < 8; ++i) ok = launch() == 0;
+      ok = ok && cudaEventRecord(e1, st) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
+      float t = 0.0f;
+      ok = ok && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess;
+      ms[c] += t;
+    }
+  }
+  t_loss_grid_try = 0;
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (!ok) (void)cudaGetLastError();
+  g_loss_grid_cal[dev].store(ok && ms[1] < ms[0] ? cand[1] : cand[0], std::memory_order_relaxed);
+}
 
 extern template int launch_loss<gd::kGwd>(const LossArgs&, int, int, cudaStream_t);
 extern template int launch_loss<gd::kKld>(const LossArgs&, int, int, cudaStream_t);
@@ -241,16 +278,29 @@ int gd_loss_launch(const gd_loss_config* cfg, const gd_loss_io* io, void* stream
                 : (any_ok ? GD_VARIANT_BULK_ANY : GD_VARIANT_STAGED);
   if (v == GD_VARIANT_BULK_ANY) plan_any(&a);
 
-  switch (cfg->loss_type) {
-    case GD_LOSS_GWD3D: return launch_loss<gd::kGwd>(a, v, kMaxGrid, st);
-    case GD_LOSS_KLD3D: return launch_loss<gd::kKld>(a, v, kMaxGrid, st);
-    case GD_LOSS_JD3D: return launch_loss<gd::kJd>(a, v, kMaxGrid, st);
-    case GD_LOSS_KLD3D_SYMMAX: return launch_loss<gd::kSymMax>(a, v, kMaxGrid, st);
-    case GD_LOSS_KLD3D_SYMMIN: return launch_loss<gd::kSymMin>(a, v, kMaxGrid, st);
-    case GD_LOSS_BD3D: return launch_loss<gd::kBd>(a, v, kMaxGrid, st);
-    case GD_LOSS_KFIOU3D: return launch_loss<gd::kKfiou>(a, v, kMaxGrid, st);
+  auto dispatch = [&]() -> int {
+    switch (cfg->loss_type) {
+      case GD_LOSS_GWD3D: return launch_loss<gd::kGwd>(a, v, kMaxGrid, st);
+      case GD_LOSS_KLD3D: return launch_loss<gd::kKld>(a, v, kMaxGrid, st);
+      case GD_LOSS_JD3D: return launch_loss<gd::kJd>(a, v, kMaxGrid, st);
+      case GD_LOSS_KLD3D_SYMMAX: return launch_loss<gd::kSymMax>(a, v, kMaxGrid, st);
+      case GD_LOSS_KLD3D_SYMMIN: return launch_loss<gd::kSymMin>(a, v, kMaxGrid, st);
+      case GD_LOSS_BD3D: return launch_loss<gd::kBd>(a, v, kMaxGrid, st);
+      case GD_LOSS_KFIOU3D: return launch_loss<gd::kKfiou>(a, v, kMaxGrid, st);
+    }
+    return GD_ERR_BAD_ARG;
+  };
+  // grid of the persistent kernel: measured once per device (gd_loss_kernels.cuh, warp_kernel_ctas)
+  const bool light = (v == GD_VARIANT_BULK || v == GD_VARIANT_BULK_PACKED || v == GD_VARIANT_BULK_R2) &&
+                     weight_mode != GD_WEIGHT_ROW7;
+  if (light && n >= (1LL << 22) && g_loss_grid.load(std::memory_order_relaxed) == 0 &&
+      !loss_multi_process() && !a.peer.world &&
+      g_loss_grid_cal[current_device()].load(std::memory_order_relaxed) == 0) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+      calibrate_grid(dispatch, st);
   }
-  return GD_ERR_BAD_ARG;
+  return dispatch();
 }
 
 size_t gd_peer_sum_buffer_bytes(void) { return sizeof(gdk::PeerBuf); }

@@ -794,33 +794,43 @@ int launch_staged(const LossArgs& a, int grid, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-// CTAs of the persistent warp kernel (one per SM at most).  gd_set_loss_grid() pins the number;
-// the built-in policy is 128 of the 148 SMs (32/37 of the device).  The board runs this kernel
-// at its 1000 W power cap, and interleaved A/B runs on five boxes of the pool
-// (profiles/r03_grid.md) show the same picture for all five bench configurations: from 148 down
-// to 134 CTAs the delivered bandwidth falls slowly (5.70 -> 5.50 TB/s), at 132 (one box: 130) it
-// JUMPS to 6.1-6.2 TB/s and then falls slowly again (128: 6.0-6.1, 124: 5.85-6.0, 120: 5.75-5.9);
-// 4 s of back-to-back launches at 52-54 C keep the gap (148: 5.58, 132: 6.05, 128: 5.95-6.0).
-// 128 sits two to four CTAs below the lowest jump seen: +5-6 % over one CTA per SM.
-// The policy applies to the contiguous layouts with [N] / no weights (12 warps per CTA, the
-// headline kernel and reduction='none').  The instantiations with fewer, heavier warps per CTA
-// ([N,7] weights: 9 warps; row-strided / unaligned inputs: 9 warps, run-time parameters) lose
-// 4-12 % on 128 CTAs (profiles/r03_grid.md) and keep one CTA per SM.
-// It also applies only when the process runs alone on its box: with all 8 GPUs of a box busy
-// (bench.py --gpus 8 under torchrun) the slowest GPU sits on the wrong side of its jump at 128
-// CTAs and the step takes 1.125 ms instead of 1.084 ms (gpurun_out/r03t vs r03s), so ranks of a
-// multi-process job (WORLD_SIZE > 1, as torchrun / dist_train.sh export it) keep one CTA per SM.
-extern std::atomic<int> g_loss_grid;
-inline long long warp_kernel_ctas(long long sms, bool light) {
-  const int forced = g_loss_grid.load(std::memory_order_relaxed);
-  if (forced > 0) return forced < sms ? forced : sms;
-  static const bool multi_process = [] {
+// CTAs of the persistent warp kernel (at most one per SM).
+//
+// The board runs this kernel at its 1000 W power cap, and the delivered bandwidth is not
+// monotone in the number of busy SMs: interleaved A/B runs on the pool's boxes
+// (profiles/r03_grid.md) show it falling slowly from 148 CTAs (5.70 TB/s) to 134 (5.50), JUMPING
+// to 6.1-6.2 TB/s at 132 (one box: 130) and falling slowly again (128: 6.0-6.1, 120: 5.8-5.9);
+// 4 s of back-to-back launches keep the gap.  On most boxes 128 CTAs are 5-6 % faster than one
+// per SM -- but the position of the jump moves from chip to chip, on one box of seven 128 CTAs
+// sat on the wrong side of it (5.61 instead of 5.75 TB/s), and with all 8 GPUs of a box busy
+// the slowest GPU does too (1.125 instead of 1.084 ms per step).  So the number is MEASURED:
+// the first launch of a process with >= 2^22 rows on a contiguous [N] / no-weight layout times
+// the launch it was asked for on both grids (gd_loss_api.cu: calibrate_grid, ~13 ms once per
+// device, host-synchronising) and keeps the faster one.  No calibration -- one CTA per SM --
+//   * for the instantiations with fewer, heavier warps per CTA ([N,7] weights, row-strided /
+//     unaligned inputs): bound by their instruction stream, they lose bandwidth with every SM
+//     taken away, no jump (profiles/r03_grid.md);
+//   * for ranks of a multi-process job (WORLD_SIZE > 1, as torchrun / dist_train.sh export it);
+//   * while the stream is being captured into a CUDA graph, and for smaller launches as long as
+//     nothing has been calibrated;
+//   * when gd_set_loss_grid(n > 0) pins the grid.
+extern std::atomic<int> g_loss_grid;                      // gd_set_loss_grid
+extern std::atomic<int> g_loss_grid_cal[kMaxDevices];     // calibrated CTAs per device, 0 = not yet
+extern thread_local int t_loss_grid_try;                  // set by the calibration around its launches
+inline bool loss_multi_process() {
+  static const bool multi = [] {
     const char* e = getenv("WORLD_SIZE");
     return e != nullptr && atoi(e) > 1;
   }();
-  if (!light || multi_process) return sms;
-  const long long g = sms * 32 / 37;
-  return g < 1 ? 1 : g;
+  return multi;
+}
+inline long long warp_kernel_ctas(long long sms, bool light) {
+  if (t_loss_grid_try > 0) return t_loss_grid_try < sms ? t_loss_grid_try : sms;
+  const int forced = g_loss_grid.load(std::memory_order_relaxed);
+  if (forced > 0) return forced < sms ? forced : sms;
+  if (!light || loss_multi_process()) return sms;
+  const int cal = g_loss_grid_cal[current_device()].load(std::memory_order_relaxed);
+  return cal > 0 && cal < sms ? cal : sms;
 }
 
 template <int LOSS, bool GRAD, int R, int SPEC, int WM, bool PACK = false, bool ANY = false>
