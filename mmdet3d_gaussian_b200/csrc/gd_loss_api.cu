@@ -107,20 +107,26 @@ thread_local int t_loss_grid_try = 0;
 static std::mutex g_cal_mutex;
 
 // Times `launch` (the launch the caller asked for: idempotent, it writes its outputs) on one CTA
-// per SM and on 32/37 of the SMs, twice each and interleaved, and keeps the faster grid for the
-// device.  Host-synchronising, once per device and process; any failure keeps one CTA per SM.
+// per SM and on a ladder of smaller grids (the bandwidth jump sat at 138, 132, 130, < 128 and 120
+// CTAs on the boxes it was looked for: profiles/r03_grid.md), two interleaved rounds of 2 + 8
+// launches each, and keeps the fastest grid for the device.  Host-synchronising, ~35 ms once per
+// device and process; any failure keeps one CTA per SM.
 template <typename F>
 static void calibrate_grid(F&& launch, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_cal_mutex);
   const int dev = current_device();
   if (g_loss_grid_cal[dev].load(std::memory_order_relaxed) > 0) return;
   const int sms = device_info().sm_count;
-  const int cand[2] = {sms, sms * 32 / 37 > 0 ? sms * 32 / 37 : 1};
-  float ms[2] = {0.0f, 0.0f};
+  constexpr int kCand = 7;
+  const int ladder[kCand] = {148, 136, 132, 128, 124, 120, 116};   // of 148 SMs
+  int cand[kCand];
+  for (int c = 0; c < kCand; ++c) cand[c] = ladder[c] * sms / 148 > 0 ? ladder[c] * sms / 148 : 1;
+  float ms[kCand] = {};
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool ok = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
   for (int round = 0; ok && round < 2; ++round) {
-    for (int c = 0; ok && c < 2; ++c) {
+    for (int k = 0; ok && k < kCand; ++k) {
+      const int c = round == 0 ? k : kCand - 1 - k;          // second round in reverse order
       t_loss_grid_try = cand[c];
       for (int i = 0; ok && i < 2; ++i) ok = launch() == 0;
       ok = ok && cudaEventRecord(e0, st) == cudaSuccess;
@@ -134,8 +140,14 @@ static void calibrate_grid(F&& launch, cudaStream_t st) {
   t_loss_grid_try = 0;
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  if (!ok) (void)cudaGetLastError();
-  g_loss_grid_cal[dev].store(ok && ms[1] < ms[0] ? cand[1] : cand[0], std::memory_order_relaxed);
+  int best = 0;
+  if (ok) {
+    for (int c = 1; c < kCand; ++c)
+      if (ms[c] < ms[best] * 0.995f) best = c;               // a smaller grid has to win by 0.5 %
+  } else {
+    (void)cudaGetLastError();
+  }
+  g_loss_grid_cal[dev].store(cand[best], std::memory_order_relaxed);
 }
 
 extern template int launch_loss<gd::kGwd>(const LossArgs&, int, int, cudaStream_t);
