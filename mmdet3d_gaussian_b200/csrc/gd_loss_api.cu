@@ -108,9 +108,12 @@ static std::mutex g_cal_mutex;
 
 // Times `launch` (the launch the caller asked for: idempotent, it writes its outputs) on one CTA
 // per SM and on a ladder of smaller grids (the bandwidth jump sat at 138, 132, 130, < 128 and 120
-// CTAs on the boxes it was looked for: profiles/r03_grid.md), two interleaved rounds of 2 + 8
-// launches each, and keeps the fastest grid for the device.  Host-synchronising, ~35 ms once per
-// device and process; any failure keeps one CTA per SM.
+// CTAs on the boxes it was looked for: profiles/r03_grid.md) and keeps the fastest grid for the
+// device.  What is to be measured is the power-capped steady state, which a cold board only
+// reaches after tens of milliseconds of work (a first version that measured straight away kept
+// 148 CTAs on a cold box: everything is fast before the cap bites): ~100 ms of launches first,
+// then two interleaved rounds of ~5 ms per grid.  Host-synchronising, ~0.25 s once per device
+// and process; any failure keeps one CTA per SM.
 template <typename F>
 static void calibrate_grid(F&& launch, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_cal_mutex);
@@ -124,16 +127,31 @@ static void calibrate_grid(F&& launch, cudaStream_t st) {
   float ms[kCand] = {};
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool ok = cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+  auto timed = [&](int reps, float* out) {       // `reps` launches, elapsed ms
+    ok = ok && cudaEventRecord(e0, st) == cudaSuccess;
+    for (int i = 0; ok && i < reps; ++i) ok = launch() == 0;
+    ok = ok && cudaEventRecord(e1, st) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
+    ok = ok && cudaEventElapsedTime(out, e0, e1) == cudaSuccess;
+  };
+  // into the steady state, and how long one launch takes
+  t_loss_grid_try = cand[0];
+  float warm = 0.0f, one = 0.0f;
+  timed(4, &one);
+  one = one > 0.0f ? one / 4.0f : 1.0f;
+  for (int batch = 0; ok && warm < 100.0f && batch < 64; ++batch) {
+    float t = 0.0f;
+    timed(16, &t);
+    warm += t;
+  }
+  int reps = (int)(5.0f / one);                  // ~5 ms per measurement
+  reps = reps < 4 ? 4 : (reps > 64 ? 64 : reps);
   for (int round = 0; ok && round < 2; ++round) {
     for (int k = 0; ok && k < kCand; ++k) {
       const int c = round == 0 ? k : kCand - 1 - k;          // second round in reverse order
       t_loss_grid_try = cand[c];
       for (int i = 0; ok && i < 2; ++i) ok = launch() == 0;
-      ok = ok && cudaEventRecord(e0, st) == cudaSuccess;
-      for (int i = 0; ok && i < 8; ++i) ok = launch() == 0;
-      ok = ok && cudaEventRecord(e1, st) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
       float t = 0.0f;
-      ok = ok && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess;
+      timed(reps, &t);
       ms[c] += t;
     }
   }
