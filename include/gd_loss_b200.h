@@ -443,8 +443,9 @@ GD_API int64_t gd_launch_count(void);
  * runs this kernel at its power cap and on most chips 128 of the 148 SMs deliver 5-6 % more
  * bandwidth than all of them, on some they deliver less (profiles/r03_grid.md) -- so the first
  * launch of a process with >= 2^22 rows on a contiguous [N] / no-weight layout TIMES the launch it
- * was asked for on a ladder of grids (148, 136, 132, 128, 124, 120, 116 CTAs; ~35 ms once per device;
- * this one call synchronises with the host) and keeps the fastest.  Never calibrated, one CTA per SM: [N,7] weights, row-strided /
+ * was asked for on a ladder of grids (148, 136, 132, 128, 124, 120, 116 CTAs) after ~100 ms of
+ * launches that bring the board into its power-capped steady state (~0.25 s once per device; this
+ * one call synchronises with the host) and keeps the fastest.  Never calibrated, one CTA per SM: [N,7] weights, row-strided /
  * unaligned inputs, ranks of a multi-process job (WORLD_SIZE > 1), launches captured into a CUDA
  * graph.  A positive value pins the grid for every later launch of the process and switches the
  * calibration off (measurements: tools/ab_grid.py; latency-critical callers). */
