@@ -17,6 +17,11 @@ def main():
     n = 1 << 24
     torch.cuda.set_device(0)
     lib = _lib.load()
+    # The library measures the grid of the headline kernel at the first large launch (hundreds of
+    # calibration launches, which `ncu -c 10` would capture instead of the cases below): pin it.
+    # 128 CTAs is what the calibration keeps on most boxes (profiles/r03_grid.md); GD_NCU_GRID=148
+    # captures one CTA per SM.
+    lib.gd_set_loss_grid(int(os.environ.get('GD_NCU_GRID', '128')))
     pred, target, w = synth.make_pairs(n, 'kitti', seed=0, device='cuda')
     w7 = w[:, None].expand(n, 7).contiguous()
     wide_p = torch.zeros(n, 9, device='cuda')
